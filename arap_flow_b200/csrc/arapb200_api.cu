@@ -1,0 +1,342 @@
+// arapb200_api.cu -- the flat C ABI of include/arapb200.h (host buffers in, host buffers out).
+#include "../../include/arapb200.h"
+#include "pipeline.cuh"
+
+#include <cstring>
+#include <memory>
+#include <vector>
+
+using namespace arapb200;
+
+namespace {
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    explicit DevBuf(size_t count) : n(count) { ARAP_CUDA_OR_EXIT(cudaMalloc(&p, (count ? count : 1) * sizeof(T))); }
+    ~DevBuf() { cudaFree(p); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    void up(const T* h, cudaStream_t s = nullptr)
+    {
+        ARAP_CUDA_OR_EXIT(cudaMemcpyAsync(p, h, n * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    void down(T* h, cudaStream_t s = nullptr)
+    {
+        ARAP_CUDA_OR_EXIT(cudaMemcpyAsync(h, p, n * sizeof(T), cudaMemcpyDeviceToHost, s));
+    }
+};
+
+int warp_common(int W, int H, const float* pos_or_flow, bool is_flow, const uint8_t* rgb, const uint8_t* mask_red,
+                uint8_t* out_rgb, uint8_t* out_mask, uint32_t* out_splat)
+{
+    if (W <= 0 || H <= 0 || !pos_or_flow || !rgb || !mask_red || !out_rgb || !out_mask) return 1;
+    const size_t N = (size_t)W * H;
+    DevBuf<float2> d_in(N), d_pos(is_flow ? N : 0);
+    DevBuf<unsigned char> d_rgb(3 * N), d_m(N), d_orgb(3 * N), d_om(N);
+    DevBuf<unsigned> d_z(N);
+    d_in.up((const float2*)pos_or_flow);
+    d_rgb.up(rgb);
+    d_m.up(mask_red);
+    const float2* pos = d_in.p;
+    if (is_flow) {
+        enqueue_flow_to_pos(W, H, d_in.p, d_pos.p, nullptr);
+        pos = d_pos.p;
+    }
+    enqueue_warp(W, H, pos, d_rgb.p, d_m.p, d_z.p, d_orgb.p, d_om.p, nullptr);
+    d_orgb.down(out_rgb);
+    d_om.down(out_mask);
+    if (out_splat) d_z.down(out_splat);
+    ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
+    return 0;
+}
+
+} // namespace
+
+struct arapb200_batch {
+    int maxW, maxH, max_problems, nCont, nGN, nPCG, backend;
+    std::unique_ptr<DeformPipeline> pipe;
+    std::vector<HostProblem> slots;
+    std::vector<char> pending;
+    float ms[3] = {0, 0, 0};
+    long long launches = 0;
+};
+
+extern "C" {
+
+const char* arapb200_version(void) { return "arapb200 0.1.0 (sm_100a)"; }
+
+int arapb200_device_info(int* sm_count, size_t* l2_bytes, int* cc_major, int* cc_minor)
+{
+    int dev = 0;
+    ARAP_CUDA_OR_RETURN(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    ARAP_CUDA_OR_RETURN(cudaGetDeviceProperties(&p, dev));
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (l2_bytes) *l2_bytes = (size_t)p.l2CacheSize;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    return 0;
+}
+
+int arapb200_warp(int W, int H, const float* pos, const uint8_t* rgb, const uint8_t* mask_red, uint8_t* out_rgb,
+                  uint8_t* out_mask, uint32_t* out_splat)
+{
+    return warp_common(W, H, pos, false, rgb, mask_red, out_rgb, out_mask, out_splat);
+}
+
+int arapb200_warp_flow(int W, int H, const float* flow, const uint8_t* rgb, const uint8_t* mask_red,
+                       uint8_t* out_rgb, uint8_t* out_mask, uint32_t* out_splat)
+{
+    return warp_common(W, H, flow, true, rgb, mask_red, out_rgb, out_mask, out_splat);
+}
+
+int arapb200_deform(int W, int H, const uint8_t* rgb, const uint8_t* mask_red, const int32_t* matches, int n_matches,
+                    int nCont, int nGN, int nPCG, int backend, float* out_flow, uint8_t* out_rgb, uint8_t* out_mask,
+                    float* out_costs)
+{
+    if (W <= 0 || H <= 0 || !rgb || !mask_red || (n_matches > 0 && !matches)) return 1;
+    DeformPipeline pipe(W, H, nCont, nGN, nPCG, backend);
+    HostProblem hp;
+    hp.W = W; hp.H = H; hp.rgb = rgb; hp.mask_red = mask_red; hp.matches = matches; hp.n_matches = n_matches;
+    hp.out_flow = out_flow; hp.out_rgb = out_rgb; hp.out_mask = out_mask; hp.out_costs = out_costs;
+    return pipe.run(hp);
+}
+
+arapb200_batch* arapb200_batch_create(int maxW, int maxH, int max_problems, int nCont, int nGN, int nPCG, int backend)
+{
+    if (maxW <= 0 || maxH <= 0 || max_problems <= 0) return nullptr;
+    arapb200_batch* b = new arapb200_batch;
+    b->maxW = maxW; b->maxH = maxH; b->max_problems = max_problems;
+    b->nCont = nCont; b->nGN = nGN; b->nPCG = nPCG; b->backend = backend;
+    b->pipe.reset(new DeformPipeline(maxW, maxH, nCont, nGN, nPCG, backend));
+    b->slots.resize(max_problems);
+    b->pending.assign(max_problems, 0);
+    return b;
+}
+
+void arapb200_batch_destroy(arapb200_batch* b) { delete b; }
+
+int arapb200_batch_submit(arapb200_batch* b, int slot, int W, int H, const uint8_t* rgb, const uint8_t* mask_red,
+                          const int32_t* matches, int n_matches, float* out_flow, uint8_t* out_rgb,
+                          uint8_t* out_mask, float* out_costs)
+{
+    if (!b || slot < 0 || slot >= b->max_problems) return 1;
+    HostProblem& hp = b->slots[slot];
+    hp.W = W; hp.H = H; hp.rgb = rgb; hp.mask_red = mask_red; hp.matches = matches; hp.n_matches = n_matches;
+    hp.out_flow = out_flow; hp.out_rgb = out_rgb; hp.out_mask = out_mask; hp.out_costs = out_costs;
+    b->pending[slot] = 1;
+    return 0;
+}
+
+int arapb200_batch_run(arapb200_batch* b)
+{
+    if (!b) return 1;
+    b->ms[0] = b->ms[1] = b->ms[2] = 0.f;
+    const long long l0 = b->pipe->launches();
+    for (int s = 0; s < b->max_problems; ++s) {
+        if (!b->pending[s]) continue;
+        int rc = b->pipe->run(b->slots[s]);
+        b->pending[s] = 0;
+        if (rc) return rc;
+        b->ms[0] += b->pipe->last_ms_total();
+        b->ms[1] += b->pipe->last_ms_solve();
+        b->ms[2] += b->pipe->last_ms_warp();
+    }
+    b->launches = b->pipe->launches() - l0;
+    return 0;
+}
+
+int arapb200_batch_timing(arapb200_batch* b, float* ms3)
+{
+    if (!b || !ms3) return 1;
+    ms3[0] = b->ms[0]; ms3[1] = b->ms[1]; ms3[2] = b->ms[2];
+    return 0;
+}
+
+long long arapb200_batch_launches(arapb200_batch* b) { return b ? b->launches : 0; }
+
+// ------------------------------------------------------------------------------------ debug / parity
+int arapb200_debug_gn_solve(int W, int H, float* X, float* A, const float* U, const float* C, const float* M,
+                            float wf, float wr, int nGN, int nPCG, int backend, float* costs, float* scal)
+{
+    const size_t N = (size_t)W * H;
+    DevBuf<float2> dX(N), dU(N), dC(N);
+    DevBuf<float> dA(N), dM(N);
+    DevBuf<float> dtr(scal ? (size_t)3 * nGN * nPCG : 0);
+    dX.up((const float2*)X); dU.up((const float2*)U); dC.up((const float2*)C); dA.up(A); dM.up(M);
+    ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
+    GnPlan plan(W, H, 0, backend);
+    plan.set_parameter("nIterations", &nGN);
+    plan.set_parameter("lIterations", &nPCG);
+    if (scal) plan.set_trace(dtr.p);
+    void* pp[7] = {dX.p, dA.p, dU.p, dC.p, dM.p, &wf, &wr};
+    plan.init(pp);
+    if (costs) costs[0] = (float)plan.current_cost();
+    int g = 0;
+    while (plan.step(pp)) {
+        ++g;
+        if (costs) costs[g] = (float)plan.current_cost();
+    }
+    dX.down((float2*)X);
+    dA.down(A);
+    if (scal) dtr.down(scal);
+    ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
+    return 0;
+}
+
+static int debug_setup(int W, int H, const float* X, const float* A, const float* U, const float* C, const float* M,
+                       float wf, float wr, StreamSolver& s, DevBuf<float2>& dX, DevBuf<float2>& dU, DevBuf<float2>& dC,
+                       DevBuf<float>& dA, DevBuf<float>& dM)
+{
+    const size_t N = (size_t)W * H;
+    std::vector<float> zeros(2 * N, 0.f);
+    dX.up((const float2*)(X ? X : zeros.data()));
+    dU.up((const float2*)U);
+    dC.up((const float2*)C);
+    dA.up(A);
+    dM.up(M);
+    ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
+    s.bind(dX.p, dA.p, dU.p, dC.p, dM.p, wf, wr, nullptr);
+    s.enqueue_prep(nullptr);
+    return 0;
+}
+
+static void gather3(const StreamDev& v, float* const planes[3], size_t N, float* out3, const std::vector<unsigned char>& flags)
+{
+    std::vector<float> tmp(N);
+    for (int k = 0; k < 3; ++k) {
+        ARAP_CUDA_OR_EXIT(cudaMemcpy(tmp.data(), planes[k], N * sizeof(float), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < N; ++i) out3[3 * i + k] = (flags[i] & FLAG_ACTIVE) ? tmp[i] : 0.f;
+    }
+    (void)v;
+}
+
+int arapb200_debug_eval_jtf(int W, int H, const float* X, const float* A, const float* U, const float* C,
+                            const float* M, float wf, float wr, float* r3, float* pre3)
+{
+    const size_t N = (size_t)W * H;
+    DevBuf<float2> dX(N), dU(N), dC(N);
+    DevBuf<float> dA(N), dM(N);
+    StreamSolver s(W, H);
+    if (int rc = debug_setup(W, H, X, A, U, C, M, wf, wr, s, dX, dU, dC, dA, dM)) return rc;
+    s.enqueue_pcg_init(nullptr);
+    ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
+    const StreamDev& v = s.host_view();
+    std::vector<unsigned char> flags(N);
+    ARAP_CUDA_OR_RETURN(cudaMemcpy(flags.data(), v.flags, N, cudaMemcpyDeviceToHost));
+    gather3(v, v.r, N, r3, flags);
+    float* pre_planes[3] = {v.pre[0], v.pre[0], v.pre[1]};
+    gather3(v, pre_planes, N, pre3, flags);
+    return 0;
+}
+
+int arapb200_debug_apply_jtj(int W, int H, const float* A, const float* U, const float* C, const float* M, float wf,
+                             float wr, const float* p3, float* q3, float* dot)
+{
+    const size_t N = (size_t)W * H;
+    DevBuf<float2> dX(N), dU(N), dC(N);
+    DevBuf<float> dA(N), dM(N);
+    StreamSolver s(W, H);
+    if (int rc = debug_setup(W, H, nullptr, A, U, C, M, wf, wr, s, dX, dU, dC, dA, dM)) return rc;
+    const StreamDev& v = s.host_view();
+    std::vector<float> tmp(N);
+    for (int k = 0; k < 3; ++k) {
+        for (size_t i = 0; i < N; ++i) tmp[i] = p3[3 * i + k];
+        ARAP_CUDA_OR_RETURN(cudaMemcpy(v.p[0][k], tmp.data(), N * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    s.enqueue_step_a(true, 0, nullptr);
+    ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
+    std::vector<unsigned char> flags(N);
+    ARAP_CUDA_OR_RETURN(cudaMemcpy(flags.data(), v.flags, N, cudaMemcpyDeviceToHost));
+    gather3(v, v.q, N, q3, flags);
+    StreamScalars sc;
+    ARAP_CUDA_OR_RETURN(cudaMemcpy(&sc, v.sc, sizeof(sc), cudaMemcpyDeviceToHost));
+    if (dot) *dot = sc.den;
+    return 0;
+}
+
+int arapb200_debug_cost(int W, int H, const float* X, const float* A, const float* U, const float* C, const float* M,
+                        float wf, float wr, float* cost)
+{
+    const size_t N = (size_t)W * H;
+    DevBuf<float2> dX(N), dU(N), dC(N);
+    DevBuf<float> dA(N), dM(N);
+    dX.up((const float2*)X); dU.up((const float2*)U); dC.up((const float2*)C); dA.up(A); dM.up(M);
+    ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
+    StreamSolver s(W, H);
+    s.bind(dX.p, dA.p, dU.p, dC.p, dM.p, wf, wr, nullptr);
+    s.enqueue_init(nullptr);
+    s.read_back(nullptr, cost, nullptr);
+    return 0;
+}
+
+} // extern "C"
+
+// device-side sincos / exact-sum probes
+namespace {
+__global__ void k_dbg_sincos(int n, const float* a, float* s, float* c)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) contract_sincos(a[i], s[i], c[i]);
+}
+// one block; thread t sums terms t, t+B, ... sequentially in binary32?  No: each term is its own
+// "group term": the block folds them exactly in chunks of blockDim.x.
+__global__ void k_dbg_exact_sum(size_t n, const float* t, float* out)
+{
+    __shared__ double red[64];
+    // level 1: per-chunk block sums; level 2: chunk results are folded with a second exact pass below
+    extern __shared__ double chunks[]; // 2 * nchunks
+    const size_t nchunks = (n + blockDim.x - 1) / blockDim.x;
+    for (size_t c = 0; c < nchunks; ++c) {
+        size_t i = c * blockDim.x + threadIdx.x;
+        float g = (i < n) ? t[i] : 0.f;
+        HL b = block_exact_sum(g, red);
+        if (threadIdx.x == 0) {
+            chunks[2 * c] = b.h;
+            chunks[2 * c + 1] = b.l;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 32) {
+        // fold the chunk partials 32 at a time, carrying the running (h, l) in lane 0's slot
+        HL run = {0.0, 0.0};
+        for (size_t base = 0; base < nchunks; base += 31) {
+            HL v = {0.0, 0.0};
+            const size_t idx = base + threadIdx.x;
+            if (threadIdx.x < 31 && idx < nchunks) { v.h = chunks[2 * idx]; v.l = chunks[2 * idx + 1]; }
+            if (threadIdx.x == 31) v = run;
+            run = warp_combine(v);
+        }
+        if (threadIdx.x == 0) *out = hl_to_float(run);
+    }
+}
+} // namespace
+
+extern "C" {
+
+int arapb200_debug_sincos(int n, const float* a, float* s, float* c)
+{
+    DevBuf<float> da(n), ds(n), dc(n);
+    da.up(a);
+    k_dbg_sincos<<<(n + 255) / 256, 256>>>(n, da.p, ds.p, dc.p);
+    ds.down(s);
+    dc.down(c);
+    ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
+    return 0;
+}
+
+int arapb200_debug_exact_sum(size_t n, const float* t, float* sum)
+{
+    if (n > (size_t)256 * 2048) return 1;
+    DevBuf<float> dt(n), dsum(1);
+    dt.up(t);
+    const size_t nchunks = (n + 255) / 256;
+    k_dbg_exact_sum<<<1, 256, 2 * nchunks * sizeof(double)>>>(n, dt.p, dsum.p);
+    dsum.down(sum);
+    ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,114 @@
+// opt_api.cu -- the 10 Opt_* entry points of include/Opt.h over the hand-written solver back-ends.
+//
+// Reference behaviour being replaced: ARAP/API/src/createwrapper.t:124-220 (thunks),
+// ARAP/API/src/o.t:2521-2558 (API bodies), ARAP/API/src/solverGPUGaussNewton.t:956-1007 (init),
+// :1016-1177 (step), :1179-1182 (cost), :1205-1221 (setSolverParameter), :1223-1284 (free/makePlan).
+#include "../../include/Opt.h"
+#include "plan.cuh"
+
+#include <cstring>
+#include <string>
+
+using namespace arapb200;
+
+struct Opt_State {
+    Opt_InitializationParameters params;
+};
+
+struct Opt_Problem {
+    std::string filename;
+};
+
+struct Opt_Plan {
+    GnPlan* plan;
+};
+
+extern "C" {
+
+Opt_State* Opt_NewState(Opt_InitializationParameters params)
+{
+    if (params.doublePrecision) {
+        fprintf(stderr, "arapb200: doublePrecision is not supported (the ARAP app never enables it: "
+                        "CombinedSolverParameters.h:14)\n");
+        return nullptr;
+    }
+    Opt_State* s = new Opt_State;
+    s->params = params;
+    return s;
+}
+
+// The energy file is identified, not interpreted: it must exist and declare the ARAP unknowns.
+static bool looks_like_arap_plan(const char* filename)
+{
+    FILE* f = fopen(filename, "rb");
+    if (!f) return false;
+    std::string txt;
+    char buf[4096];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof(buf), f)) > 0 && txt.size() < (1u << 20)) txt.append(buf, n);
+    fclose(f);
+    const char* need[] = {"Offset", "Angle", "UrShape", "Constraints", "Mask", "w_fitSqrt", "w_regSqrt", "Rotate2D"};
+    for (const char* k : need)
+        if (txt.find(k) == std::string::npos) return false;
+    return true;
+}
+
+Opt_Problem* Opt_ProblemDefine(Opt_State* state, const char* filename, const char* solverkind)
+{
+    if (!state || !filename || !solverkind) return nullptr;
+    if (strcmp(solverkind, "gaussNewtonGPU") != 0) {
+        // o.t:121-124 asserts gaussNewtonGPU or LMGPU; the app only ever asks for the former
+        fprintf(stderr, "arapb200: solver kind '%s' not supported (only gaussNewtonGPU)\n", solverkind);
+        return nullptr;
+    }
+    if (!looks_like_arap_plan(filename)) {
+        fprintf(stderr, "arapb200: '%s' is missing or is not the ARAP energy (arap_plan.t)\n", filename);
+        return nullptr;
+    }
+    Opt_Problem* p = new Opt_Problem;
+    p->filename = filename;
+    return p;
+}
+
+void Opt_ProblemDelete(Opt_State*, Opt_Problem* problem) { delete problem; }
+
+Opt_Plan* Opt_ProblemPlan(Opt_State* state, Opt_Problem* problem, unsigned int* dimensions)
+{
+    if (!state || !problem || !dimensions) return nullptr;
+    const unsigned W = dimensions[0], H = dimensions[1];
+    if (W == 0 || H == 0 || W > 65535u || H > 65535u) {
+        fprintf(stderr, "arapb200: bad plan dimensions %u x %u\n", W, H);
+        return nullptr;
+    }
+    Opt_Plan* pl = new Opt_Plan;
+    pl->plan = new GnPlan((int)W, (int)H, state->params.verbosityLevel, ARAPB200_BACKEND_AUTO);
+    return pl;
+}
+
+void Opt_PlanFree(Opt_State*, Opt_Plan* plan)
+{
+    if (!plan) return;
+    delete plan->plan;
+    delete plan;
+}
+
+void Opt_SetSolverParameter(Opt_State* state, Opt_Plan* plan, const char* name, void* value)
+{
+    if (!plan || !name || !value) return;
+    if (!plan->plan->set_parameter(name, value) && state && state->params.verbosityLevel > 0)
+        fprintf(stderr, "Warning: tried to set nonexistent solver parameter %s\n", name); // :1220
+}
+
+void Opt_ProblemInit(Opt_State*, Opt_Plan* plan, void** problemparams) { plan->plan->init(problemparams); }
+
+int Opt_ProblemStep(Opt_State*, Opt_Plan* plan, void** problemparams) { return plan->plan->step(problemparams); }
+
+void Opt_ProblemSolve(Opt_State*, Opt_Plan* plan, void** problemparams)
+{
+    // o.t:2548-2551: init, then step until it reports completion
+    plan->plan->solve(problemparams);
+}
+
+double Opt_ProblemCurrentCost(Opt_State*, Opt_Plan* plan) { return plan->plan->current_cost(); }
+
+} // extern "C"

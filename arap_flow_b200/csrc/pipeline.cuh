@@ -1,0 +1,76 @@
+// pipeline.cuh -- per-image path of arap_deform on the device: what CombinedSolver (ARAP/deformation/
+// src/CombinedSolver.h:139-242, 280-366) and CombinedSolverBase::singleSolve (ARAP/shared/
+// CombinedSolverBase.h:99-120) do around the solver, with every host<->device hop removed except the
+// upload of the inputs and the download of the outputs.
+#pragma once
+#include "plan.cuh"
+#include "warp.cuh"
+#include <vector>
+
+namespace arapb200 {
+
+struct HostProblem {
+    int W = 0, H = 0;
+    const unsigned char* rgb = nullptr;      // uint8x3[N]
+    const unsigned char* mask_red = nullptr; // uint8[N]
+    const int* matches = nullptr;            // int32[4*n], without border pins
+    int n_matches = 0;
+    float* out_flow = nullptr;               // float2[N]
+    unsigned char* out_rgb = nullptr;        // uint8x3[N]
+    unsigned char* out_mask = nullptr;       // uint8[N]
+    float* out_costs = nullptr;              // float[nCont*(nGN+1)] or null
+};
+
+// compact constraint record: source pixel index and the match, after the reference's filtering
+// (mask(src) == 0, later entries override earlier ones, border pins appended: main.cpp:130-136,
+// CombinedSolver.h:223-242)
+struct MatchRec {
+    int idx;
+    float x1, y1, x2, y2;
+};
+
+// host-side: filter + dedupe the match list exactly like setConstraintImage would resolve it
+void build_match_records(int W, int H, const unsigned char* mask_red, const int* matches, int n_matches,
+                         std::vector<MatchRec>& out);
+
+class DeformPipeline {
+public:
+    DeformPipeline(int maxW, int maxH, int nCont, int nGN, int nPCG, int backend);
+    ~DeformPipeline();
+    DeformPipeline(const DeformPipeline&) = delete;
+    DeformPipeline& operator=(const DeformPipeline&) = delete;
+    // upload, solve (all continuation steps), flow, warp, download.  Blocking.
+    int run(const HostProblem& hp);
+    long long launches() const { return launches_; }
+    float last_ms_total() const { return ms_total_; }
+    float last_ms_solve() const { return ms_solve_; }
+    float last_ms_warp() const { return ms_warp_; }
+
+private:
+    int maxW_, maxH_, nCont_, nGN_, nPCG_, backend_;
+    int curW_ = 0, curH_ = 0;
+    StreamSolver* solver_ = nullptr;
+    cudaStream_t stream_ = nullptr;
+    cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
+    // device images
+    float2 *d_X_ = nullptr, *d_U_ = nullptr, *d_C_ = nullptr, *d_flow_ = nullptr;
+    float *d_A_ = nullptr, *d_M_ = nullptr, *d_costs_ = nullptr;
+    unsigned char *d_rgb_ = nullptr, *d_mask_ = nullptr, *d_orgb_ = nullptr, *d_omask_ = nullptr;
+    unsigned* d_z_ = nullptr;
+    MatchRec* d_matches_ = nullptr;
+    size_t matches_cap_ = 0;
+    // pinned staging
+    unsigned char* h_in_ = nullptr;
+    unsigned char* h_out_ = nullptr;
+    size_t h_in_bytes_ = 0, h_out_bytes_ = 0;
+    long long launches_ = 0;
+    float ms_total_ = 0, ms_solve_ = 0, ms_warp_ = 0;
+};
+
+// shared small kernels
+void enqueue_reset_state(int W, int H, const unsigned char* d_mask_red, float2* d_X, float2* d_U, float* d_A,
+                         float* d_M, cudaStream_t stream);
+void enqueue_constraint_image(int W, int H, const MatchRec* d_matches, int n, float alpha, float2* d_C,
+                              cudaStream_t stream);
+
+} // namespace arapb200

@@ -1,0 +1,513 @@
+// solver_stream.cu -- streaming Gauss-Newton / PCG back-end.
+//
+// Replaces the generated kernels PCGInit1 / PCGStep1 / PCGStep2 / PCGStep3 / PCGLinearUpdate /
+// computeCost and the host loop of ARAP/API/src/solverGPUGaussNewton.t:361-397, 421-434, 446-489,
+// 537-557, 580-592, 1016-1177 with:
+//   k_prep    flags (validity of the 4 neighbours, fit, active), cos/sin table, UrShape check
+//   k_init    r = -J^T F, pre, p = pre*r, delta = 0, sum r.p                    (PCGInit1)
+//   k_step_a  p = pre*r + beta*p (recomputed on the halo), q = J^T J p, sum p.q  (PCGStep3 + PCGStep1)
+//   k_step_b  alpha; delta += alpha p; r -= alpha q; sum (pre*r).r              (PCGStep2)
+//   k_update  X += delta, refresh cos/sin                                        (PCGLinearUpdate)
+//   k_cost    0.5 * sum residual^2                                               (computeCost)
+// Scalars (alpha/beta numerators and denominators) never leave the device; every reduction is the
+// deterministic exact sum of contract C3; a whole GN step (2*nPCG + 3 kernels) is one graph launch.
+#include "solver_stream.cuh"
+#include "grid_math.cuh"
+
+namespace arapb200 {
+
+namespace {
+
+constexpr int TS = ST_TILE + 2; // staged tile pitch (1-pixel halo)
+
+__device__ __forceinline__ int clog2_u32(unsigned n)
+{
+    return (n <= 1) ? 0 : 32 - __clz(n - 1);
+}
+
+// Block result (valid in warp 0) -> per-tile partial; the last tile to arrive folds all partials
+// exactly and returns true in thread 0 with the total in `total`.
+__device__ bool finalize_partial(const StreamDev* dp, HL blockval, double* smem, float& total)
+{
+    __shared__ bool s_last;
+    const unsigned nb = gridDim.x;
+    if (threadIdx.x == 0) {
+        dp->partials[blockIdx.x] = make_double2(blockval.h, blockval.l);
+        __threadfence();
+        unsigned t = atomicInc(dp->counter, nb - 1);
+        s_last = (t == nb - 1);
+    }
+    __syncthreads();
+    if (!s_last) return false;
+    __threadfence();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    // pass 1: max |h|
+    double m = 0.0;
+    for (unsigned i = threadIdx.x; i < nb; i += blockDim.x) m = fmax(m, fabs(__ldcg(&dp->partials[i].x)));
+    m = warp_max(m);
+    if (lane == 0) smem[wid] = m;
+    __syncthreads();
+    m = 0.0;
+    for (int w = 0; w < nw; ++w) m = fmax(m, smem[w]);
+    __syncthreads();
+    const double B = bin_base(ilogb_f64(m) + clog2_u32(nb) + 2);
+    // pass 2: binned accumulation
+    double hs = 0.0, ls = 0.0;
+    for (unsigned i = threadIdx.x; i < nb; i += blockDim.x) {
+        double2 v = __ldcg(&dp->partials[i]);
+        double hi, lo;
+        bin_split(B, v.x, hi, lo);
+        hs = __dadd_rn(hs, hi);
+        ls = __dadd_rn(ls, __dadd_rn(lo, v.y));
+    }
+    hs = warp_sum(hs);
+    ls = warp_sum(ls);
+    if (lane == 0) {
+        smem[wid] = hs;
+        smem[32 + wid] = ls;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double H = 0.0, L = 0.0;
+        for (int w = 0; w < nw; ++w) {
+            H = __dadd_rn(H, smem[w]);
+            L = __dadd_rn(L, smem[32 + w]);
+        }
+        total = (float)__dadd_rn(H, L);
+        return true;
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ST_THREADS) k_prep(const StreamDev* __restrict__ dpp)
+{
+    const StreamDev& dp = *dpp;
+    const int W = dp.W, H = dp.H;
+    const int x = (blockIdx.x % dp.tx) * ST_TILE + (threadIdx.x & 31);
+    const int yb = (blockIdx.x / dp.tx) * ST_TILE + (threadIdx.x >> 5) * 4;
+    if (x >= W) return;
+    unsigned bad = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int y = yb + r;
+        if (y >= H) break;
+        const size_t i = (size_t)y * W + x;
+        unsigned f = 0;
+        if (dp.M[i] == 0.0f) {
+            f = FLAG_ACTIVE;
+            if (x + 1 < W && dp.M[i + 1] == 0.0f) f |= 1u;
+            if (x > 0 && dp.M[i - 1] == 0.0f) f |= 2u;
+            if (y + 1 < H && dp.M[i + W] == 0.0f) f |= 4u;
+            if (y > 0 && dp.M[i - W] == 0.0f) f |= 8u;
+            const float2 c = dp.C[i];
+            if (c.x >= 0.0f && c.y >= 0.0f) f |= FLAG_FIT; // arap_plan.t:22
+            float s, co;
+            contract_sincos(dp.A[i], s, co);
+            dp.cs[0][i] = co;
+            dp.cs[1][i] = s;
+            const float2 u = dp.U[i];
+            if (u.x != (float)x || u.y != (float)y) bad = 1;
+        }
+        dp.flags[i] = (unsigned char)f;
+    }
+    if (bad) atomicAdd(&dp.sc->bad_u, 1u);
+}
+
+// Stage (X_x, X_y, cos, sin) of a tile + halo.  Inactive / out-of-image entries are never used.
+__device__ __forceinline__ void stage_x_tile(const StreamDev& dp, float4 (*T)[TS], int x0, int y0)
+{
+    for (int e = threadIdx.x; e < TS * TS; e += ST_THREADS) {
+        const int ly = e / TS, lx = e - ly * TS;
+        const int x = x0 + lx - 1, y = y0 + ly - 1;
+        float4 v = make_float4(0.f, 0.f, 1.f, 0.f);
+        if (x >= 0 && x < dp.W && y >= 0 && y < dp.H) {
+            const size_t i = (size_t)y * dp.W + x;
+            if (dp.flags[i] & FLAG_ACTIVE) {
+                const float2 X = dp.X[i];
+                v = make_float4(X.x, X.y, dp.cs[0][i], dp.cs[1][i]);
+            }
+        }
+        T[ly][lx] = v;
+    }
+}
+
+// PCGInit1 (solverGPUGaussNewton.t:361-397)
+__global__ void __launch_bounds__(ST_THREADS) k_init(const StreamDev* __restrict__ dpp)
+{
+    __shared__ float4 T[TS][TS];
+    __shared__ double red[64];
+    const StreamDev& dp = *dpp;
+    const int W = dp.W, H = dp.H;
+    const int x0 = (blockIdx.x % dp.tx) * ST_TILE, y0 = (blockIdx.x / dp.tx) * ST_TILE;
+    stage_x_tile(dp, T, x0, y0);
+    __syncthreads();
+    const int lx = threadIdx.x & 31, lyb = (threadIdx.x >> 5) * 4;
+    const int x = x0 + lx;
+    float g = 0.0f;
+    if (x < W) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int ly = lyb + r, y = y0 + ly;
+            if (y >= H) break;
+            const size_t i = (size_t)y * W + x;
+            const unsigned f = dp.flags[i];
+            if (!(f & FLAG_ACTIVE)) continue;
+            const float4 Ei = T[ly + 1][lx + 1];
+            JtfAcc a;
+            jtf_zero(a);
+            if (f & 1u) jtf_nb<0>(a, Ei.x, Ei.y, Ei.z, Ei.w, T[ly + 1][lx + 2]);
+            if (f & 2u) jtf_nb<1>(a, Ei.x, Ei.y, Ei.z, Ei.w, T[ly + 1][lx]);
+            if (f & 4u) jtf_nb<2>(a, Ei.x, Ei.y, Ei.z, Ei.w, T[ly + 2][lx + 1]);
+            if (f & 8u) jtf_nb<3>(a, Ei.x, Ei.y, Ei.z, Ei.w, T[ly][lx + 1]);
+            const bool fit = (f & FLAG_FIT) != 0;
+            float2 c = make_float2(0.f, 0.f);
+            if (fit) c = dp.C[i];
+            float g0, g1, ga, DX, DA;
+            jtf_finish(a, Ei.x, Ei.y, fit, c.x, c.y, dp.wr2, dp.wf2, g0, g1, ga, DX, DA);
+            const float pX = guarded_invert(DX), pA = guarded_invert(DA);
+            const float r0 = -g0, r1 = -g1, r2 = -ga;
+            const float p0 = pX * r0, p1 = pX * r1, p2 = pA * r2;
+            dp.pre[0][i] = pX;
+            dp.pre[1][i] = pA;
+            dp.r[0][i] = r0; dp.r[1][i] = r1; dp.r[2][i] = r2;
+            dp.p[0][0][i] = p0; dp.p[0][1][i] = p1; dp.p[0][2][i] = p2;
+            dp.d[0][i] = 0.f; dp.d[1][i] = 0.f; dp.d[2][i] = 0.f;
+            g = g + dot3(r0, r1, r2, p0, p1, p2);
+        }
+    }
+    HL b = block_exact_sum(g, red);
+    float total;
+    __syncthreads();
+    if (finalize_partial(dpp, b, red, total)) dp.sc->num = total;
+}
+
+// PCGStep3 of the previous iteration fused with PCGStep1 (solverGPUGaussNewton.t:537-550, 421-434)
+template <bool FIRST>
+__global__ void __launch_bounds__(ST_THREADS) k_step_a(const StreamDev* __restrict__ dpp, int it)
+{
+    __shared__ float4 T[TS][TS];
+    __shared__ double red[64];
+    const StreamDev& dp = *dpp;
+    const int W = dp.W, H = dp.H;
+    const int x0 = (blockIdx.x % dp.tx) * ST_TILE, y0 = (blockIdx.x / dp.tx) * ST_TILE;
+    float beta = 0.0f;
+    if (!FIRST) {
+        const float num = dp.sc->num, bnum = dp.sc->bnum;
+        beta = (num > 0.0f) ? bnum / num : 0.0f; // :544-547
+    }
+    // p is ping-ponged between two buffers: the halo of a tile needs the OLD direction of pixels that
+    // the neighbouring tile is updating in this very kernel.
+    float* const* __restrict__ psrc = dp.p[FIRST ? 0 : ((it - 1) & 1)];
+    float* const* __restrict__ pdst = dp.p[it & 1];
+    // stage (p_x, p_y, sin*p_a, cos*p_a) of tile + halo, p being the NEW direction
+    for (int e = threadIdx.x; e < TS * TS; e += ST_THREADS) {
+        const int ly = e / TS, lx = e - ly * TS;
+        const int x = x0 + lx - 1, y = y0 + ly - 1;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (x >= 0 && x < W && y >= 0 && y < H) {
+            const size_t i = (size_t)y * W + x;
+            if (dp.flags[i] & FLAG_ACTIVE) {
+                float p0 = psrc[0][i], p1 = psrc[1][i], p2 = psrc[2][i];
+                if (!FIRST) {
+                    const float pX = dp.pre[0][i], pA = dp.pre[1][i];
+                    p0 = fmaf(beta, p0, pX * dp.r[0][i]);
+                    p1 = fmaf(beta, p1, pX * dp.r[1][i]);
+                    p2 = fmaf(beta, p2, pA * dp.r[2][i]);
+                    const bool interior = (lx >= 1 && lx <= ST_TILE && ly >= 1 && ly <= ST_TILE);
+                    if (interior) { pdst[0][i] = p0; pdst[1][i] = p1; pdst[2][i] = p2; }
+                }
+                v = make_float4(p0, p1, dp.cs[1][i] * p2, dp.cs[0][i] * p2);
+            }
+        }
+        T[ly][lx] = v;
+    }
+    __syncthreads();
+    const int lx = threadIdx.x & 31, lyb = (threadIdx.x >> 5) * 4;
+    const int x = x0 + lx;
+    float g = 0.0f;
+    if (x < W) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int ly = lyb + r, y = y0 + ly;
+            if (y >= H) break;
+            const size_t i = (size_t)y * W + x;
+            const unsigned f = dp.flags[i];
+            if (!(f & FLAG_ACTIVE)) continue;
+            const float4 Pi = T[ly + 1][lx + 1];
+            float pa = psrc[2][i];
+            if (!FIRST) pa = fmaf(beta, pa, dp.pre[1][i] * dp.r[2][i]);
+            JtjAcc a;
+            jtj_zero(a);
+            if (f & 1u) jtj_nb<0>(a, Pi.x, Pi.y, T[ly + 1][lx + 2]);
+            if (f & 2u) jtj_nb<1>(a, Pi.x, Pi.y, T[ly + 1][lx]);
+            if (f & 4u) jtj_nb<2>(a, Pi.x, Pi.y, T[ly + 2][lx + 1]);
+            if (f & 8u) jtj_nb<3>(a, Pi.x, Pi.y, T[ly][lx + 1]);
+            float q0, q1, qa;
+            jtj_finish(a, dp.cs[0][i], dp.cs[1][i], Pi.x, Pi.y, pa, (f & FLAG_FIT) != 0, dp.wr2, dp.wf2, q0, q1, qa);
+            dp.q[0][i] = q0; dp.q[1][i] = q1; dp.q[2][i] = qa;
+            g = g + dot3(Pi.x, Pi.y, pa, q0, q1, qa);
+        }
+    }
+    HL b = block_exact_sum(g, red);
+    float total;
+    __syncthreads();
+    if (finalize_partial(dpp, b, red, total)) {
+        if (!FIRST) dp.sc->num = dp.sc->bnum; // :1091
+        dp.sc->den = total;
+        if (dp.trace) {
+            dp.trace[3 * it] = total;
+            dp.trace[3 * it + 1] = dp.sc->num;
+        }
+    }
+}
+
+// PCGStep2 (solverGPUGaussNewton.t:446-489)
+__global__ void __launch_bounds__(ST_THREADS) k_step_b(const StreamDev* __restrict__ dpp, int it)
+{
+    __shared__ double red[64];
+    const StreamDev& dp = *dpp;
+    const int W = dp.W, H = dp.H;
+    const int x = (blockIdx.x % dp.tx) * ST_TILE + (threadIdx.x & 31);
+    const int yb = (blockIdx.x / dp.tx) * ST_TILE + (threadIdx.x >> 5) * 4;
+    const float num = dp.sc->num, den = dp.sc->den;
+    const float alpha = (den > 0.0f) ? num / den : 0.0f; // :456-459
+    float g = 0.0f;
+    if (x < W) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int y = yb + r;
+            if (y >= H) break;
+            const size_t i = (size_t)y * W + x;
+            if (!(dp.flags[i] & FLAG_ACTIVE)) continue;
+            const float pX = dp.pre[0][i], pA = dp.pre[1][i];
+            float rr[3], zz[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float pk = dp.p[it & 1][k][i];
+                dp.d[k][i] = fmaf(alpha, pk, dp.d[k][i]);
+                rr[k] = fmaf(-alpha, dp.q[k][i], dp.r[k][i]);
+                dp.r[k][i] = rr[k];
+                zz[k] = ((k < 2) ? pX : pA) * rr[k];
+            }
+            g = g + dot3(zz[0], zz[1], zz[2], rr[0], rr[1], rr[2]);
+        }
+    }
+    HL b = block_exact_sum(g, red);
+    float total;
+    __syncthreads();
+    if (finalize_partial(dpp, b, red, total)) {
+        dp.sc->bnum = total;
+        if (dp.trace) dp.trace[3 * it + 2] = total;
+    }
+}
+
+// PCGLinearUpdate (solverGPUGaussNewton.t:552-557) + cos/sin refresh for the new angles
+__global__ void __launch_bounds__(ST_THREADS) k_update(const StreamDev* __restrict__ dpp)
+{
+    const StreamDev& dp = *dpp;
+    const int W = dp.W, H = dp.H;
+    const int x = (blockIdx.x % dp.tx) * ST_TILE + (threadIdx.x & 31);
+    const int yb = (blockIdx.x / dp.tx) * ST_TILE + (threadIdx.x >> 5) * 4;
+    if (x >= W) return;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int y = yb + r;
+        if (y >= H) break;
+        const size_t i = (size_t)y * W + x;
+        if (!(dp.flags[i] & FLAG_ACTIVE)) continue;
+        float2 X = dp.X[i];
+        X.x = X.x + dp.d[0][i];
+        X.y = X.y + dp.d[1][i];
+        dp.X[i] = X;
+        const float a = dp.A[i] + dp.d[2][i];
+        dp.A[i] = a;
+        float s, c;
+        contract_sincos(a, s, c);
+        dp.cs[0][i] = c;
+        dp.cs[1][i] = s;
+    }
+}
+
+// computeCost (solverGPUGaussNewton.t:580-592, o.t:2375-2385)
+__global__ void __launch_bounds__(ST_THREADS) k_cost(const StreamDev* __restrict__ dpp)
+{
+    __shared__ float4 T[TS][TS];
+    __shared__ double red[64];
+    const StreamDev& dp = *dpp;
+    const int W = dp.W, H = dp.H;
+    const int x0 = (blockIdx.x % dp.tx) * ST_TILE, y0 = (blockIdx.x / dp.tx) * ST_TILE;
+    stage_x_tile(dp, T, x0, y0);
+    __syncthreads();
+    const int lx = threadIdx.x & 31, lyb = (threadIdx.x >> 5) * 4;
+    const int x = x0 + lx;
+    float g = 0.0f;
+    if (x < W) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int ly = lyb + r, y = y0 + ly;
+            if (y >= H) break;
+            const size_t i = (size_t)y * W + x;
+            const unsigned f = dp.flags[i];
+            if (!(f & FLAG_ACTIVE)) continue;
+            const float4 Ei = T[ly + 1][lx + 1];
+            float acc = 0.0f;
+            if (f & 1u) acc = cost_nb<0>(acc, Ei.x, Ei.y, Ei.z, Ei.w, T[ly + 1][lx + 2], dp.wr);
+            if (f & 2u) acc = cost_nb<1>(acc, Ei.x, Ei.y, Ei.z, Ei.w, T[ly + 1][lx], dp.wr);
+            if (f & 4u) acc = cost_nb<2>(acc, Ei.x, Ei.y, Ei.z, Ei.w, T[ly + 2][lx + 1], dp.wr);
+            if (f & 8u) acc = cost_nb<3>(acc, Ei.x, Ei.y, Ei.z, Ei.w, T[ly][lx + 1], dp.wr);
+            if (f & FLAG_FIT) {
+                const float2 c = dp.C[i];
+                acc = cost_fit(acc, Ei.x, Ei.y, c.x, c.y, dp.wf);
+            }
+            g = g + acc;
+        }
+    }
+    HL b = block_exact_sum(g, red);
+    float total;
+    __syncthreads();
+    if (finalize_partial(dpp, b, red, total)) dp.sc->cost = 0.5f * total;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------ host
+StreamSolver::StreamSolver(int W, int H)
+{
+    h_.W = W;
+    h_.H = H;
+    h_.tx = (W + ST_TILE - 1) / ST_TILE;
+    h_.ty = (H + ST_TILE - 1) / ST_TILE;
+    h_.ntiles = h_.tx * h_.ty;
+    const size_t N = (size_t)W * H;
+    const size_t Np = (N + 63) & ~(size_t)63; // keep every plane 256-byte aligned
+    ARAP_CUDA_OR_EXIT(cudaMalloc(&planes_, 19 * Np * sizeof(float)));
+    ARAP_CUDA_OR_EXIT(cudaMemset(planes_, 0, 19 * Np * sizeof(float)));
+    float* b = planes_;
+    for (int k = 0; k < 3; ++k) { h_.r[k] = b; b += Np; }
+    for (int k = 0; k < 3; ++k) { h_.p[0][k] = b; b += Np; }
+    for (int k = 0; k < 3; ++k) { h_.p[1][k] = b; b += Np; }
+    for (int k = 0; k < 3; ++k) { h_.q[k] = b; b += Np; }
+    for (int k = 0; k < 3; ++k) { h_.d[k] = b; b += Np; }
+    for (int k = 0; k < 2; ++k) { h_.cs[k] = b; b += Np; }
+    for (int k = 0; k < 2; ++k) { h_.pre[k] = b; b += Np; }
+    ARAP_CUDA_OR_EXIT(cudaMalloc(&h_.flags, Np));
+    ARAP_CUDA_OR_EXIT(cudaMemset(h_.flags, 0, Np));
+    ARAP_CUDA_OR_EXIT(cudaMalloc(&h_.partials, (size_t)h_.ntiles * sizeof(double2)));
+    ARAP_CUDA_OR_EXIT(cudaMalloc(&h_.counter, sizeof(unsigned)));
+    ARAP_CUDA_OR_EXIT(cudaMemset(h_.counter, 0, sizeof(unsigned)));
+    ARAP_CUDA_OR_EXIT(cudaMalloc(&h_.sc, sizeof(StreamScalars)));
+    ARAP_CUDA_OR_EXIT(cudaMemset(h_.sc, 0, sizeof(StreamScalars)));
+    ARAP_CUDA_OR_EXIT(cudaMalloc(&d_, sizeof(StreamDev)));
+    h_.trace = nullptr;
+}
+
+StreamSolver::~StreamSolver()
+{
+    if (graph_) cudaGraphExecDestroy(graph_);
+    cudaFree(planes_);
+    cudaFree(h_.flags);
+    cudaFree(h_.partials);
+    cudaFree(h_.counter);
+    cudaFree(h_.sc);
+    cudaFree(d_);
+}
+
+void StreamSolver::upload(cudaStream_t stream)
+{
+    ARAP_CUDA_OR_EXIT(cudaMemcpyAsync(d_, &h_, sizeof(StreamDev), cudaMemcpyHostToDevice, stream));
+}
+
+void StreamSolver::bind(float2* X, float* A, const float2* U, const float2* C, const float* M, float wf,
+                        float wr, cudaStream_t stream)
+{
+    h_.X = X; h_.A = A; h_.U = U; h_.C = C; h_.M = M;
+    h_.wf = wf; h_.wr = wr; h_.wf2 = wf * wf; h_.wr2 = wr * wr;
+    h_.trace = nullptr;
+    upload(stream);
+}
+
+void StreamSolver::enqueue_prep(cudaStream_t stream)
+{
+    k_prep<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
+    ++launches_;
+}
+
+void StreamSolver::enqueue_pcg_init(cudaStream_t stream)
+{
+    k_init<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
+    ++launches_;
+}
+
+void StreamSolver::enqueue_step_a(bool first, int it, cudaStream_t stream)
+{
+    if (first) k_step_a<true><<<h_.ntiles, ST_THREADS, 0, stream>>>(d_, it);
+    else k_step_a<false><<<h_.ntiles, ST_THREADS, 0, stream>>>(d_, it);
+    ++launches_;
+}
+
+void StreamSolver::enqueue_init(cudaStream_t stream)
+{
+    ARAP_CUDA_OR_EXIT(cudaMemsetAsync(&h_.sc->bad_u, 0, sizeof(unsigned), stream));
+    enqueue_prep(stream);
+    k_cost<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
+    ++launches_;
+    ARAP_CUDA_OR_EXIT(cudaGetLastError());
+}
+
+void StreamSolver::launch_gn_body(int nPCG, cudaStream_t stream, bool tracing)
+{
+    // the caller may have changed the constraint image / mask between steps (Opt.h:58-60): refresh flags
+    k_prep<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
+    k_init<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
+    for (int it = 0; it < nPCG; ++it) {
+        if (it == 0) k_step_a<true><<<h_.ntiles, ST_THREADS, 0, stream>>>(d_, it);
+        else k_step_a<false><<<h_.ntiles, ST_THREADS, 0, stream>>>(d_, it);
+        k_step_b<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_, it);
+    }
+    k_update<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
+    k_cost<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
+    (void)tracing;
+}
+
+void StreamSolver::enqueue_gn_step(int nPCG, cudaStream_t stream, float* d_trace)
+{
+    const long long nodes = 2LL * nPCG + 4;
+    if (d_trace) {
+        h_.trace = d_trace;
+        upload(stream);
+        launch_gn_body(nPCG, stream, true);
+        ARAP_CUDA_OR_EXIT(cudaGetLastError());
+        h_.trace = nullptr;
+        upload(stream);
+        launches_ += nodes;
+        return;
+    }
+    if (!graph_ || graph_npcg_ != nPCG) {
+        if (graph_) { cudaGraphExecDestroy(graph_); graph_ = nullptr; }
+        cudaStream_t cap;
+        ARAP_CUDA_OR_EXIT(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+        cudaGraph_t g;
+        ARAP_CUDA_OR_EXIT(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+        launch_gn_body(nPCG, cap, false);
+        ARAP_CUDA_OR_EXIT(cudaStreamEndCapture(cap, &g));
+        ARAP_CUDA_OR_EXIT(cudaGraphInstantiate(&graph_, g, 0));
+        ARAP_CUDA_OR_EXIT(cudaGraphDestroy(g));
+        ARAP_CUDA_OR_EXIT(cudaStreamDestroy(cap));
+        graph_npcg_ = nPCG;
+        graph_nodes_ = nodes;
+    }
+    ARAP_CUDA_OR_EXIT(cudaGraphLaunch(graph_, stream));
+    launches_ += graph_nodes_;
+}
+
+void StreamSolver::read_back(cudaStream_t stream, float* cost, unsigned* bad_u)
+{
+    StreamScalars s;
+    ARAP_CUDA_OR_EXIT(cudaMemcpyAsync(&s, h_.sc, sizeof(s), cudaMemcpyDeviceToHost, stream));
+    ARAP_CUDA_OR_EXIT(cudaStreamSynchronize(stream));
+    if (cost) *cost = s.cost;
+    if (bad_u) *bad_u = s.bad_u;
+}
+
+} // namespace arapb200

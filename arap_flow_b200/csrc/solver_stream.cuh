@@ -1,0 +1,84 @@
+// solver_stream.cuh -- the streaming Gauss-Newton/PCG back-end (state in L2/HBM, two kernels per
+// PCG iteration, a whole GN step captured in one CUDA graph).  Used for problems whose PCG state
+// does not fit on chip (1920x1080) and as the general-size path behind Opt.h.
+#pragma once
+#include "common.cuh"
+#include <vector>
+
+namespace arapb200 {
+
+constexpr int ST_TILE = 32;                 // 32 x 32 pixel tiles
+constexpr int ST_THREADS = 256;             // thread = one aligned vertical quad (contract C3 group)
+constexpr unsigned FLAG_FIT = 0x10u;        // bits 0..3: neighbour n valid (order +x,-x,+y,-y)
+constexpr unsigned FLAG_ACTIVE = 0x20u;
+
+struct StreamScalars {
+    float num, den, bnum, cost;
+    unsigned bad_u; // number of pixels whose UrShape is not the pixel grid
+    unsigned pad[3];
+};
+
+// Everything the kernels need, resident in device memory; kernels take a pointer to it so that a
+// captured graph stays valid when the caller re-binds its images (Opt_ProblemInit/Step re-bind on
+// every call: ARAP/API/src/util.t:664-692).
+struct StreamDev {
+    int W, H, tx, ty, ntiles;
+    float2* X;            // Offset  (in/out)
+    float* A;             // Angle   (in/out)
+    const float2* U;      // UrShape
+    const float2* C;      // Constraints
+    const float* M;       // Mask
+    float wf, wr, wf2, wr2;
+    float* r[3];
+    float* p[2][3];       // search direction, ping-ponged per PCG iteration (buffer it & 1)
+    float* q[3];
+    float* d[3];
+    float* cs[2];         // cos, sin of Angle, refreshed per GN step
+    float* pre[2];        // guarded-inverted diagonal: X part (both comps), angle part
+    unsigned char* flags;
+    double2* partials;    // one (h, l) pair per tile
+    unsigned* counter;
+    StreamScalars* sc;
+    float* trace;         // optional: (den, num, bnum) per PCG iteration of the current GN step
+};
+
+class StreamSolver {
+public:
+    StreamSolver(int W, int H);
+    ~StreamSolver();
+    StreamSolver(const StreamSolver&) = delete;
+    StreamSolver& operator=(const StreamSolver&) = delete;
+
+    // bind the caller's device images + weights (== util.initParameters in the reference)
+    void bind(float2* X, float* A, const float2* U, const float2* C, const float* M, float wf, float wr,
+              cudaStream_t stream);
+    // flags + cos/sin + UrShape check, then cost.  Enqueue only.
+    void enqueue_init(cudaStream_t stream);
+    // one Gauss-Newton step: PCGInit, nPCG iterations, update, cos/sin refresh, cost.  Enqueue only.
+    // trace (device, 3*nPCG floats) may be null; tracing bypasses the graph.
+    void enqueue_gn_step(int nPCG, cudaStream_t stream, float* d_trace = nullptr);
+    // blocking read of (cost, bad_u) after the enqueued work
+    void read_back(cudaStream_t stream, float* cost, unsigned* bad_u);
+    // unit-level pieces for the parity tests (enqueue only)
+    void enqueue_prep(cudaStream_t stream);
+    void enqueue_pcg_init(cudaStream_t stream);
+    void enqueue_step_a(bool first, int it, cudaStream_t stream);
+    const StreamDev& host_view() const { return h_; }
+    StreamScalars* d_scalars() const { return h_.sc; }
+    long long launches() const { return launches_; }
+    int W() const { return h_.W; }
+    int H() const { return h_.H; }
+
+private:
+    void upload(cudaStream_t stream);
+    void launch_gn_body(int nPCG, cudaStream_t stream, bool tracing);
+    StreamDev h_{};
+    StreamDev* d_ = nullptr;
+    float* planes_ = nullptr;
+    cudaGraphExec_t graph_ = nullptr;
+    int graph_npcg_ = -1;
+    long long graph_nodes_ = 0;
+    long long launches_ = 0;
+};
+
+} // namespace arapb200

@@ -1,0 +1,249 @@
+"""ctypes binding of libarapb200.so (include/Opt.h + include/arapb200.h).
+
+The shared library is the product; this module only marshals numpy buffers into its C ABI.  There is no
+fallback of any kind: if the library is missing or no CUDA device is present, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libarapb200.so")
+
+BACKEND_AUTO, BACKEND_STREAM, BACKEND_RESIDENT = 0, 1, 2
+
+# every symbol include/Opt.h and include/arapb200.h declare
+OPT_SYMBOLS = [
+    "Opt_NewState", "Opt_ProblemDefine", "Opt_ProblemDelete", "Opt_ProblemPlan", "Opt_PlanFree",
+    "Opt_SetSolverParameter", "Opt_ProblemSolve", "Opt_ProblemInit", "Opt_ProblemStep", "Opt_ProblemCurrentCost",
+]
+ARAP_SYMBOLS = [
+    "arapb200_device_info", "arapb200_version", "arapb200_warp", "arapb200_warp_flow", "arapb200_deform",
+    "arapb200_batch_create", "arapb200_batch_destroy", "arapb200_batch_submit", "arapb200_batch_run",
+    "arapb200_batch_timing", "arapb200_batch_launches", "arapb200_debug_gn_solve", "arapb200_debug_eval_jtf",
+    "arapb200_debug_apply_jtj", "arapb200_debug_cost", "arapb200_debug_sincos", "arapb200_debug_exact_sum",
+]
+
+
+class OptInitializationParameters(C.Structure):
+    _fields_ = [("doublePrecision", C.c_int), ("verbosityLevel", C.c_int),
+                ("collectPerKernelTimingInfo", C.c_int), ("threadsPerBlock", C.c_int)]
+
+
+_f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+_lib = None
+
+
+def load():
+    """Load the library (raises if it has not been built: run `python -c 'import __graft_entry__ as g; g.build()'`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with arap_flow_b200/csrc/Makefile (no CPU fallback exists)")
+    L = C.CDLL(LIB_PATH)
+    L.arapb200_version.restype = C.c_char_p
+    L.arapb200_device_info.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.arapb200_warp.argtypes = [C.c_int, C.c_int, _f32p, _u8p, _u8p, _u8p, _u8p, C.c_void_p]
+    L.arapb200_warp_flow.argtypes = [C.c_int, C.c_int, _f32p, _u8p, _u8p, _u8p, _u8p, C.c_void_p]
+    L.arapb200_deform.argtypes = [C.c_int, C.c_int, _u8p, _u8p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  _f32p, _u8p, _u8p, C.c_void_p]
+    L.arapb200_batch_create.argtypes = [C.c_int] * 7
+    L.arapb200_batch_create.restype = C.c_void_p
+    L.arapb200_batch_destroy.argtypes = [C.c_void_p]
+    L.arapb200_batch_destroy.restype = None
+    L.arapb200_batch_submit.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.arapb200_batch_run.argtypes = [C.c_void_p]
+    L.arapb200_batch_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.arapb200_batch_launches.argtypes = [C.c_void_p]
+    L.arapb200_batch_launches.restype = C.c_longlong
+    L.arapb200_debug_gn_solve.argtypes = [C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_float, C.c_float,
+                                          C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.arapb200_debug_eval_jtf.argtypes = [C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_float, C.c_float,
+                                          _f32p, _f32p]
+    L.arapb200_debug_apply_jtj.argtypes = [C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p, C.c_float, C.c_float,
+                                           _f32p, _f32p, C.POINTER(C.c_float)]
+    L.arapb200_debug_cost.argtypes = [C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_float, C.c_float,
+                                      C.POINTER(C.c_float)]
+    L.arapb200_debug_sincos.argtypes = [C.c_int, _f32p, _f32p, _f32p]
+    L.arapb200_debug_exact_sum.argtypes = [C.c_size_t, _f32p, C.POINTER(C.c_float)]
+    # Opt.h
+    L.Opt_NewState.argtypes = [OptInitializationParameters]
+    L.Opt_NewState.restype = C.c_void_p
+    L.Opt_ProblemDefine.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+    L.Opt_ProblemDefine.restype = C.c_void_p
+    L.Opt_ProblemDelete.argtypes = [C.c_void_p, C.c_void_p]
+    L.Opt_ProblemDelete.restype = None
+    L.Opt_ProblemPlan.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint)]
+    L.Opt_ProblemPlan.restype = C.c_void_p
+    L.Opt_PlanFree.argtypes = [C.c_void_p, C.c_void_p]
+    L.Opt_PlanFree.restype = None
+    L.Opt_SetSolverParameter.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p]
+    L.Opt_SetSolverParameter.restype = None
+    for n in ("Opt_ProblemSolve", "Opt_ProblemInit"):
+        getattr(L, n).argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        getattr(L, n).restype = None
+    L.Opt_ProblemStep.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.Opt_ProblemStep.restype = C.c_int
+    L.Opt_ProblemCurrentCost.argtypes = [C.c_void_p, C.c_void_p]
+    L.Opt_ProblemCurrentCost.restype = C.c_double
+    _lib = L
+    return L
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed with code {rc}")
+
+
+def device_info():
+    sm, l2, ma, mi = C.c_int(), C.c_size_t(), C.c_int(), C.c_int()
+    _check(load().arapb200_device_info(C.byref(sm), C.byref(l2), C.byref(ma), C.byref(mi)), "arapb200_device_info")
+    return dict(sm_count=sm.value, l2_bytes=l2.value, cc=(ma.value, mi.value))
+
+
+def warp(pos, rgb, mask_red, want_splat=True):
+    """Forward warp from absolute positions (== CombinedSolver::copyResultToCPU).  Returns (rgb, mask, splat)."""
+    H, W = mask_red.shape
+    o_rgb = np.zeros((H, W, 3), np.uint8)
+    o_m = np.zeros((H, W), np.uint8)
+    sp = np.zeros((H, W), np.uint32) if want_splat else None
+    _check(load().arapb200_warp(W, H, _c(pos, np.float32), _c(rgb, np.uint8), _c(mask_red, np.uint8), o_rgb, o_m,
+                                sp.ctypes.data if want_splat else None), "arapb200_warp")
+    return o_rgb, o_m, sp
+
+
+def warp_flow(flow, rgb, mask_red, want_splat=True):
+    """warp_image: forward warp from a flow field (ARAP/warping/src/main.cpp:145-225)."""
+    H, W = mask_red.shape
+    o_rgb = np.zeros((H, W, 3), np.uint8)
+    o_m = np.zeros((H, W), np.uint8)
+    sp = np.zeros((H, W), np.uint32) if want_splat else None
+    _check(load().arapb200_warp_flow(W, H, _c(flow, np.float32), _c(rgb, np.uint8), _c(mask_red, np.uint8), o_rgb, o_m,
+                                     sp.ctypes.data if want_splat else None), "arapb200_warp_flow")
+    return o_rgb, o_m, sp
+
+
+def deform(rgb, mask_red, matches, nCont=19, nGN=8, nPCG=400, backend=BACKEND_AUTO):
+    """arap_deform for one image/segment: returns (flow[H,W,2], warped_rgb, warped_mask, costs[nCont,nGN+1])."""
+    H, W = mask_red.shape
+    m = _c(matches, np.int32).reshape(-1, 4)
+    flow = np.zeros((H, W, 2), np.float32)
+    o_rgb = np.zeros((H, W, 3), np.uint8)
+    o_m = np.zeros((H, W), np.uint8)
+    costs = np.zeros((nCont, nGN + 1), np.float32)
+    _check(load().arapb200_deform(W, H, _c(rgb, np.uint8), _c(mask_red, np.uint8), m, len(m), nCont, nGN, nPCG,
+                                  backend, flow, o_rgb, o_m, costs.ctypes.data), "arapb200_deform")
+    return flow, o_rgb, o_m, costs
+
+
+class Batch:
+    """Many independent (image, segment) problems on the current device (arapb200_batch_*)."""
+
+    def __init__(self, maxW, maxH, max_problems, nCont=19, nGN=8, nPCG=400, backend=BACKEND_AUTO):
+        self.L = load()
+        self.nCont, self.nGN = nCont, nGN
+        self.h = self.L.arapb200_batch_create(maxW, maxH, max_problems, nCont, nGN, nPCG, backend)
+        if not self.h:
+            raise RuntimeError("arapb200_batch_create failed")
+        self._keep = {}
+
+    def submit(self, slot, rgb, mask_red, matches):
+        H, W = mask_red.shape
+        rgb = _c(rgb, np.uint8)
+        mask_red = _c(mask_red, np.uint8)
+        m = _c(matches, np.int32).reshape(-1, 4)
+        out = dict(flow=np.zeros((H, W, 2), np.float32), rgb=np.zeros((H, W, 3), np.uint8),
+                   mask=np.zeros((H, W), np.uint8), costs=np.zeros((self.nCont, self.nGN + 1), np.float32))
+        self._keep[slot] = (rgb, mask_red, m, out)
+        _check(self.L.arapb200_batch_submit(self.h, slot, W, H, rgb.ctypes.data, mask_red.ctypes.data, m.ctypes.data,
+                                            len(m), out["flow"].ctypes.data, out["rgb"].ctypes.data,
+                                            out["mask"].ctypes.data, out["costs"].ctypes.data), "arapb200_batch_submit")
+        return out
+
+    def run(self):
+        _check(self.L.arapb200_batch_run(self.h), "arapb200_batch_run")
+
+    def timing_ms(self):
+        ms = (C.c_float * 3)()
+        self.L.arapb200_batch_timing(self.h, ms)
+        return dict(total=ms[0], solve=ms[1], warp=ms[2])
+
+    def launches(self):
+        return int(self.L.arapb200_batch_launches(self.h))
+
+    def close(self):
+        if self.h:
+            self.L.arapb200_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- unit-level parity entry points -----------------------------------------------------------------
+def debug_gn_solve(X, A, U, Cn, M, nGN, nPCG, wf, wr, backend=BACKEND_AUTO, trace=False):
+    H, W = M.shape
+    X = _c(X, np.float32).copy()
+    A = _c(A, np.float32).copy()
+    costs = np.zeros(nGN + 1, np.float32)
+    scal = np.zeros((nGN, nPCG, 3), np.float32) if trace else None
+    _check(load().arapb200_debug_gn_solve(W, H, X, A, _c(U, np.float32), _c(Cn, np.float32), _c(M, np.float32),
+                                          wf, wr, nGN, nPCG, backend, costs.ctypes.data,
+                                          scal.ctypes.data if trace else None), "arapb200_debug_gn_solve")
+    return X, A, costs, scal
+
+
+def debug_eval_jtf(X, A, U, Cn, M, wf, wr):
+    H, W = M.shape
+    r = np.zeros((H, W, 3), np.float32)
+    pre = np.zeros((H, W, 3), np.float32)
+    _check(load().arapb200_debug_eval_jtf(W, H, _c(X, np.float32), _c(A, np.float32), _c(U, np.float32),
+                                          _c(Cn, np.float32), _c(M, np.float32), wf, wr, r, pre), "debug_eval_jtf")
+    return r, pre
+
+
+def debug_apply_jtj(A, U, Cn, M, p, wf, wr):
+    H, W = M.shape
+    q = np.zeros((H, W, 3), np.float32)
+    d = C.c_float()
+    _check(load().arapb200_debug_apply_jtj(W, H, _c(A, np.float32), _c(U, np.float32), _c(Cn, np.float32),
+                                           _c(M, np.float32), wf, wr, _c(p, np.float32), q, C.byref(d)), "debug_apply_jtj")
+    return q, np.float32(d.value)
+
+
+def debug_cost(X, A, U, Cn, M, wf, wr):
+    H, W = M.shape
+    c = C.c_float()
+    _check(load().arapb200_debug_cost(W, H, _c(X, np.float32), _c(A, np.float32), _c(U, np.float32),
+                                      _c(Cn, np.float32), _c(M, np.float32), wf, wr, C.byref(c)), "debug_cost")
+    return np.float32(c.value)
+
+
+def debug_sincos(a):
+    a = _c(a, np.float32).ravel()
+    s = np.zeros_like(a)
+    c = np.zeros_like(a)
+    _check(load().arapb200_debug_sincos(a.size, a, s, c), "debug_sincos")
+    return s, c
+
+
+def debug_exact_sum(t):
+    t = _c(t, np.float32).ravel()
+    out = C.c_float()
+    _check(load().arapb200_debug_exact_sum(t.size, t, C.byref(out)), "debug_exact_sum")
+    return np.float32(out.value)

@@ -1,0 +1,89 @@
+/*
+ * arapb200.h -- flat C ABI above the Opt.h level: what the reference's L3/L4 code does around the
+ * solver (ARAP/deformation/src/CombinedSolver.h, ARAP/deformation/src/main.cpp,
+ * ARAP/warping/src/main.cpp), as whole-image calls with plain pointers and sizes.  This is the
+ * surface a Terra host reaches with terralib.includec and the one bench.py / the
+ * Python mirror bind with ctypes.  All functions return 0 on success, non-zero on failure (message on
+ * stderr); CUDA errors inside the Opt_* entry points follow the reference instead and exit
+ * (solverGPUGaussNewton.t:59-73).
+ */
+#ifndef ARAPB200_H
+#define ARAPB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifndef ARAPB200_API
+#define ARAPB200_API __attribute__((visibility("default")))
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARAPB200_BACKEND_AUTO 0     /* resident when the problem fits on chip, else streaming */
+#define ARAPB200_BACKEND_STREAM 1   /* graph-captured 2-kernel PCG iteration, state in L2/HBM */
+#define ARAPB200_BACKEND_RESIDENT 2 /* persistent cooperative kernel, state in registers/smem */
+
+/* library / device info: fills sm_count, l2_bytes, cc_major, cc_minor (any may be NULL) */
+ARAPB200_API int arapb200_device_info(int* sm_count, size_t* l2_bytes, int* cc_major, int* cc_minor);
+ARAPB200_API const char* arapb200_version(void);
+
+/* ---- forward warp (replaces ARAP/warping/src/main.cpp:145-225 == CombinedSolver.h:280-342) ----
+ * Host buffers.  pos float2[W*H] absolute positions, rgb uint8x3[W*H], mask_red uint8[W*H]
+ * (0 = object).  Outputs: out_rgb uint8x3[W*H], out_mask uint8[W*H] (255 where something landed),
+ * out_splat uint32[W*H] = 1 + 2*(y*W+x) + t of the winning triangle (0 = empty); out_splat may be NULL. */
+ARAPB200_API int arapb200_warp(int W, int H, const float* pos, const uint8_t* rgb, const uint8_t* mask_red,
+                  uint8_t* out_rgb, uint8_t* out_mask, uint32_t* out_splat);
+/* warp tool front half (warping/src/main.cpp:160-166): positions = grid + flow, then warp */
+ARAPB200_API int arapb200_warp_flow(int W, int H, const float* flow, const uint8_t* rgb, const uint8_t* mask_red,
+                       uint8_t* out_rgb, uint8_t* out_mask, uint32_t* out_splat);
+
+/* ---- one image / segment, end to end (replaces deformSingle, deformation/src/main.cpp:140-160:
+ * border pins :130-136, resetGPU + continuation CombinedSolver.h:172-242, solve, warp, flow :352-366).
+ * Host buffers in, host buffers out.  matches int32[4*n] (x1 y1 x2 y2) WITHOUT the border pins.
+ * out_flow float2[W*H]; out_rgb/out_mask as arapb200_warp; out_costs float[nCont*(nGN+1)] (may be
+ * NULL): cost at init and after every Gauss-Newton step of every continuation step. */
+ARAPB200_API int arapb200_deform(int W, int H, const uint8_t* rgb, const uint8_t* mask_red, const int32_t* matches,
+                    int n_matches, int nCont, int nGN, int nPCG, int backend, float* out_flow,
+                    uint8_t* out_rgb, uint8_t* out_mask, float* out_costs);
+
+/* ---- batched, pipelined variant: many independent (image, segment) problems per GPU --------- */
+typedef struct arapb200_batch arapb200_batch;
+/* max_problems problems of at most maxW x maxH in flight on the current device */
+ARAPB200_API arapb200_batch* arapb200_batch_create(int maxW, int maxH, int max_problems, int nCont, int nGN, int nPCG,
+                                      int backend);
+ARAPB200_API void arapb200_batch_destroy(arapb200_batch* b);
+/* enqueue problem `slot` (0 <= slot < max_problems); host pointers must stay valid until _wait */
+ARAPB200_API int arapb200_batch_submit(arapb200_batch* b, int slot, int W, int H, const uint8_t* rgb,
+                          const uint8_t* mask_red, const int32_t* matches, int n_matches, float* out_flow,
+                          uint8_t* out_rgb, uint8_t* out_mask, float* out_costs);
+/* run everything submitted since the last run; returns after all outputs are in host memory */
+ARAPB200_API int arapb200_batch_run(arapb200_batch* b);
+/* device milliseconds of the last run: [0] total, [1] solve kernels only, [2] warp kernels only */
+ARAPB200_API int arapb200_batch_timing(arapb200_batch* b, float* ms3);
+/* number of kernel launches issued by the last run */
+ARAPB200_API long long arapb200_batch_launches(arapb200_batch* b);
+
+/* ---- debug / parity entry points (unit-level comparison against the oracle) ----------------- */
+/* one Opt_ProblemSolve on host buffers: X float2[N] and A float[N] in/out; U, C float2[N]; M float[N];
+ * costs float[nGN+1] (may be NULL); scal float[nGN*nPCG*3] (den, num, bnum per PCG iteration; may be NULL) */
+ARAPB200_API int arapb200_debug_gn_solve(int W, int H, float* X, float* A, const float* U, const float* C, const float* M,
+                            float wf, float wr, int nGN, int nPCG, int backend, float* costs, float* scal);
+/* r = -J^T F and pre (float3[N] each, zero on inactive pixels) */
+ARAPB200_API int arapb200_debug_eval_jtf(int W, int H, const float* X, const float* A, const float* U, const float* C,
+                            const float* M, float wf, float wr, float* r3, float* pre3);
+/* q = J^T J p (float3[N]); *dot = p.q per the summation contract */
+ARAPB200_API int arapb200_debug_apply_jtj(int W, int H, const float* A, const float* U, const float* C, const float* M,
+                             float wf, float wr, const float* p3, float* q3, float* dot);
+/* cost per the contract */
+ARAPB200_API int arapb200_debug_cost(int W, int H, const float* X, const float* A, const float* U, const float* C,
+                        const float* M, float wf, float wr, float* cost);
+/* contract sincos and exact sum on the device */
+ARAPB200_API int arapb200_debug_sincos(int n, const float* a, float* s, float* c);
+ARAPB200_API int arapb200_debug_exact_sum(size_t n, const float* t, float* sum);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

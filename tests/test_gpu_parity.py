@@ -1,0 +1,221 @@
+"""CUDA path vs the CPU oracle, through the C ABI (libarapb200.so).  Bit-exact unless stated otherwise."""
+import os
+
+import numpy as np
+import pytest
+
+from arap_flow_b200 import flowio, lib, synth
+from tests.helpers import epe, random_problem, synth_gn_problem
+
+pytestmark = pytest.mark.gpu
+
+
+def _eq(a, b):
+    """value equality (treats -0 == +0), NaN-free"""
+    return np.array_equal(np.asarray(a), np.asarray(b))
+
+
+# ------------------------------------------------------------------------------------- scalar contract
+def test_contract_sincos_bit_exact(oracle):
+    rng = np.random.default_rng(1)
+    a = np.concatenate([rng.uniform(-10, 10, 20000), rng.uniform(-1e-3, 1e-3, 2000), [0.0, 1e4, -3e4]]).astype(np.float32)
+    s, c = lib.debug_sincos(a)
+    ref = np.array([oracle.sincos(float(x)) for x in a])
+    assert _eq(s, ref[:, 0]) and _eq(c, ref[:, 1])
+
+
+def test_exact_sum_bit_exact(oracle):
+    rng = np.random.default_rng(2)
+    for n in (1, 33, 256, 5000, 200000):
+        t = (rng.standard_normal(n) * 10.0 ** rng.uniform(-6, 6, n)).astype(np.float32)
+        assert lib.debug_exact_sum(t) == oracle.exact_sum(t)
+
+
+# ------------------------------------------------------------------------------------- single kernels
+@pytest.mark.parametrize("W,H,seed", [(37, 29, 0), (64, 64, 1), (100, 70, 2), (33, 5, 3), (1, 9, 4)])
+def test_kernels_bit_exact(oracle, W, H, seed):
+    pr = random_problem(W, H, seed)
+    wf, wr = oracle.WF, oracle.WR
+    r_o, pre_o = oracle.eval_jtf(pr["X"], pr["A"], pr["U"], pr["C"], pr["M"])
+    r_g, pre_g = lib.debug_eval_jtf(pr["X"], pr["A"], pr["U"], pr["C"], pr["M"], wf, wr)
+    assert _eq(r_g, r_o) and _eq(pre_g, pre_o)
+    q_o, d_o = oracle.apply_jtj(pr["A"], pr["U"], pr["C"], pr["M"], pr["p"])
+    q_g, d_g = lib.debug_apply_jtj(pr["A"], pr["U"], pr["C"], pr["M"], pr["p"], wf, wr)
+    assert _eq(q_g, q_o) and d_g == d_o
+    assert lib.debug_cost(pr["X"], pr["A"], pr["U"], pr["C"], pr["M"], wf, wr) == \
+        oracle.cost(pr["X"], pr["A"], pr["U"], pr["C"], pr["M"])
+
+
+def test_kernels_empty_and_full_masks(oracle):
+    for p_in in (0.0, 1.0):
+        pr = random_problem(40, 33, 7, p_inactive=p_in)
+        q_o, d_o = oracle.apply_jtj(pr["A"], pr["U"], pr["C"], pr["M"], pr["p"])
+        q_g, d_g = lib.debug_apply_jtj(pr["A"], pr["U"], pr["C"], pr["M"], pr["p"], oracle.WF, oracle.WR)
+        assert _eq(q_g, q_o) and d_g == d_o
+
+
+# ------------------------------------------------------------------------------------- Opt_ProblemSolve level
+@pytest.mark.parametrize("backend", [lib.BACKEND_STREAM, lib.BACKEND_RESIDENT])
+@pytest.mark.parametrize("W,H,seed,nGN,nPCG", [(64, 64, 0, 3, 40), (150, 97, 1, 2, 60), (96, 128, 2, 2, 25)])
+def test_gn_solve_bit_exact(oracle, backend, W, H, seed, nGN, nPCG):
+    pr = synth_gn_problem(oracle, W, H, seed, fd=2)
+    Xo, Ao, co, so = oracle.gn_solve(pr["X"], pr["A"], pr["U"], pr["C"], pr["M"], nGN, nPCG, trace=True)
+    Xg, Ag, cg, sg = lib.debug_gn_solve(pr["X"], pr["A"], pr["U"], pr["C"], pr["M"], nGN, nPCG, oracle.WF, oracle.WR,
+                                        backend=backend, trace=True)
+    assert _eq(sg, so), "per-iteration PCG scalars (den, num, bnum) differ"
+    assert _eq(cg, co) and _eq(Xg, Xo) and _eq(Ag, Ao)
+
+
+def test_gn_solve_random_state_bit_exact(oracle):
+    """start from a perturbed state with non-zero angles (exercises every sin/cos path)"""
+    pr = random_problem(80, 60, 11, p_inactive=0.2, n_cstr=40)
+    Xo, Ao, co, so = oracle.gn_solve(pr["X"], pr["A"], pr["U"], pr["C"], pr["M"], 2, 30, trace=True)
+    Xg, Ag, cg, sg = lib.debug_gn_solve(pr["X"], pr["A"], pr["U"], pr["C"], pr["M"], 2, 30, oracle.WF, oracle.WR,
+                                        backend=lib.BACKEND_STREAM, trace=True)
+    assert _eq(sg, so) and _eq(cg, co) and _eq(Xg, Xo) and _eq(Ag, Ao)
+
+
+# ------------------------------------------------------------------------------------- whole arap_deform path
+@pytest.mark.parametrize("backend", [lib.BACKEND_STREAM, lib.BACKEND_RESIDENT])
+def test_deform_c0_full_schedule(oracle, backend):
+    """BASELINE config C0 (64x64, fd=1), the full 19 x 8 x 400 schedule."""
+    sp = synth.config("C0")
+    mask = sp.masks[0]
+    Xo, Ao, co = oracle.solve(mask, sp.matches)
+    flo_o = oracle.flow(Xo)
+    rgb_o, m_o, sp_o = oracle.warp(Xo, sp.rgb, mask)
+    flo_g, rgb_g, m_g, cg = lib.deform(sp.rgb, mask, sp.matches, backend=backend)
+    act = mask == 0
+    # north_star tolerances, stated: flow within 1e-3 px mean EPE, final energy within 1e-4 relative
+    assert epe(flo_g, flo_o, act).mean() < 1e-3
+    assert abs(float(cg[-1, -1]) - float(co[-1, -1])) <= 1e-4 * abs(float(co[-1, -1]))
+    # ... and in fact the contract makes it exact
+    assert _eq(flo_g, flo_o) and _eq(cg, co)
+    assert _eq(rgb_g, rgb_o) and _eq(m_g, m_o)
+    assert (flo_g[~act] == 0).all()
+
+
+def test_deform_multiseg_shared_constraints(oracle):
+    """--multseg quirk (para_gen.py:523-536): every segment run gets the SAME constraint file; foreign matches
+    are dropped by the mask test.  Reduced schedule."""
+    sp = synth.synth(128, 96, 4, 3, 2000)
+    for mask in sp.masks:
+        Xo, Ao, co = oracle.solve(mask, sp.matches, nCont=3, nGN=2, nPCG=40)
+        flo_g, rgb_g, m_g, cg = lib.deform(sp.rgb, mask, sp.matches, nCont=3, nGN=2, nPCG=40)
+        assert _eq(flo_g, oracle.flow(Xo)) and _eq(cg, co)
+        rgb_o, m_o, _ = oracle.warp(Xo, sp.rgb, mask)
+        assert _eq(rgb_g, rgb_o) and _eq(m_g, m_o)
+
+
+def test_deform_edge_cases(oracle):
+    sp = synth.synth(40, 36, 1, 1, 3)
+    # empty object: nothing moves, nothing lands
+    none = np.full((36, 40), 255, np.uint8)
+    flo, rgb, m, c = lib.deform(sp.rgb, none, sp.matches, nCont=2, nGN=1, nPCG=5)
+    assert not flo.any() and not rgb.any() and not m.any() and not c.any()
+    # no matches at all; object touching the border gets pinned there
+    mask = sp.masks[0].copy()
+    mask[:, :6] = 0
+    Xo, Ao, co = oracle.solve(mask, np.zeros((0, 4), np.int32), nCont=2, nGN=2, nPCG=10)
+    flo, rgb, m, c = lib.deform(sp.rgb, mask, np.zeros((0, 4), np.int32), nCont=2, nGN=2, nPCG=10)
+    assert _eq(flo, oracle.flow(Xo)) and _eq(c, co)
+    # duplicate sources (later wins) and off-object / out-of-image sources are ignored
+    mm = np.array([[20, 18, 23, 18], [20, 18, 21, 20], [0, 0, 5, 5], [39, 35, 30, 30], [-3, 2, 1, 1]], np.int32)
+    Xo, Ao, co = oracle.solve(sp.masks[0], mm, nCont=2, nGN=2, nPCG=30)
+    flo, rgb, m, c = lib.deform(sp.rgb, sp.masks[0], mm, nCont=2, nGN=2, nPCG=30)
+    assert _eq(flo, oracle.flow(Xo)) and _eq(c, co)
+
+
+# ------------------------------------------------------------------------------------- forward warp
+def test_warp_golden_cat512(oracle, gold):
+    rgb = flowio.read_png_rgb(os.path.join(gold, "cat512_iRGB.png"))
+    msk = flowio.read_png_mask_red(os.path.join(gold, "cat512_iMsk.png"))
+    flo = flowio.read_flo(os.path.join(gold, "cat512_iFlo.flo"))
+    r, m, sp = lib.warp_flow(flo, rgb, msk)
+    assert _eq(m, flowio.read_png_rgb(os.path.join(gold, "cat512_wMsk.png"))[..., 0])          # shipped golden
+    assert _eq(r, flowio.read_png_rgb(os.path.join(gold, "cat512_reftool_wRGB.png")))          # reference tool
+    ro, mo, spo = oracle.warp(oracle.flow_to_pos(flo), rgb, msk)
+    assert _eq(sp, spo) and _eq(r, ro) and _eq(m, mo)                                          # splat indices
+
+
+def test_warp_reference_tool_cases(oracle, gold):
+    z = np.load(os.path.join(gold, "warp_reftool_cases.npz"))
+    for name in ("warp_a", "warp_b", "warp_c"):
+        r, m, sp = lib.warp_flow(z[f"{name}__flow"], z[f"{name}__rgb"], z[f"{name}__mask"])
+        assert _eq(r, z[f"{name}__ref_rgb"]) and _eq(m, z[f"{name}__ref_mask"]), name
+        _, _, spo = oracle.warp(oracle.flow_to_pos(z[f"{name}__flow"]), z[f"{name}__rgb"], z[f"{name}__mask"])
+        assert _eq(sp, spo), name
+
+
+@pytest.mark.parametrize("W,H,amp,seed", [(97, 61, 4.0, 0), (200, 120, 40.0, 1), (64, 64, 0.0, 2), (3, 2, 1.0, 3)])
+def test_warp_random_vs_oracle(oracle, W, H, amp, seed):
+    rng = np.random.default_rng(seed)
+    rgb = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    mask = np.where(rng.random((H, W)) < 0.2, 255, 0).astype(np.uint8)
+    pos = (oracle.grid(W, H) + rng.standard_normal((H, W, 2)) * amp).astype(np.float32)
+    if amp > 10:  # degenerate + non-finite corners
+        pos[5, 5] = pos[5, 6]
+        pos[10, 10] = np.nan
+        pos[12, 12] = np.inf
+    r, m, sp = lib.warp(pos, rgb, mask)
+    ro, mo, spo = oracle.warp(pos, rgb, mask)
+    assert _eq(sp, spo) and _eq(r, ro) and _eq(m, mo)
+
+
+def test_warp_full_size_properties():
+    """1920x1080 (C4 shape): identity flow reproduces the interior of the object exactly; deterministic."""
+    sp = synth.config("C4")
+    mask = sp.masks[0]
+    zero = np.zeros((1080, 1920, 2), np.float32)
+    r1, m1, s1 = lib.warp_flow(zero, sp.rgb, mask)
+    r2, m2, s2 = lib.warp_flow(zero, sp.rgb, mask)
+    assert _eq(r1, r2) and _eq(m1, m2) and _eq(s1, s2)
+    act = mask == 0
+    quad = act[:-1, :-1] & act[1:, :-1] & act[:-1, 1:] & act[1:, 1:]
+    cov = np.zeros_like(act)
+    for dy in (0, 1):
+        for dx in (0, 1):
+            cov[dy:1080 - 1 + dy, dx:1920 - 1 + dx] |= quad
+    assert _eq(m1 == 255, cov)
+    assert _eq(r1[cov], sp.rgb[cov])
+
+
+# ------------------------------------------------------------------------------------- Opt.h boundary
+def test_opt_h_boundary_through_ctypes(oracle):
+    """Drive the library exactly as OptSolver does (ARAP/shared/OptSolver.h:43-91) with torch-owned device images."""
+    import ctypes as C
+    import torch
+    L = lib.load()
+    pr = synth_gn_problem(oracle, 72, 56, seed=4, fd=2)
+    dev = torch.device("cuda:0")
+    t = {k: torch.from_numpy(np.ascontiguousarray(pr[k])).to(dev) for k in ("X", "A", "U", "C", "M")}
+    torch.cuda.synchronize()
+    st = L.Opt_NewState(lib.OptInitializationParameters(0, 0, 0, 0))
+    plan_file = os.path.join(os.path.dirname(lib.LIB_PATH), "arap_plan.t").encode()
+    prob = L.Opt_ProblemDefine(st, plan_file, b"gaussNewtonGPU")
+    dims = (C.c_uint * 2)(72, 56)
+    plan = L.Opt_ProblemPlan(st, prob, dims)
+    assert st and prob and plan
+    nGN, nPCG = C.c_uint(3), C.c_uint(35)
+    L.Opt_SetSolverParameter(st, plan, b"nIterations", C.byref(nGN))
+    L.Opt_SetSolverParameter(st, plan, b"lIterations", C.byref(nPCG))
+    L.Opt_SetSolverParameter(st, plan, b"no_such_parameter", C.byref(nGN))  # warns at most
+    wf, wr = C.c_float(float(oracle.WF)), C.c_float(float(oracle.WR))
+    pp = (C.c_void_p * 7)(t["X"].data_ptr(), t["A"].data_ptr(), t["U"].data_ptr(), t["C"].data_ptr(),
+                          t["M"].data_ptr(), C.cast(C.byref(wf), C.c_void_p), C.cast(C.byref(wr), C.c_void_p))
+    L.Opt_ProblemSolve(st, plan, pp)
+    cost = L.Opt_ProblemCurrentCost(st, plan)
+    Xo, Ao, co, _ = oracle.gn_solve(pr["X"], pr["A"], pr["U"], pr["C"], pr["M"], 3, 35)
+    assert _eq(t["X"].cpu().numpy(), Xo) and _eq(t["A"].cpu().numpy(), Ao) and np.float32(cost) == co[-1]
+    # stepwise API (launchProfiledSolve, OptUtils.h:47-64) on a fresh state gives the same trajectory
+    t2 = {k: torch.from_numpy(np.ascontiguousarray(pr[k])).to(dev) for k in ("X", "A")}
+    torch.cuda.synchronize()
+    pp[0], pp[1] = t2["X"].data_ptr(), t2["A"].data_ptr()
+    L.Opt_ProblemInit(st, plan, pp)
+    costs = [L.Opt_ProblemCurrentCost(st, plan)]
+    while L.Opt_ProblemStep(st, plan, pp):
+        costs.append(L.Opt_ProblemCurrentCost(st, plan))
+    assert _eq(np.float32(costs), co) and L.Opt_ProblemStep(st, plan, pp) == 0
+    assert _eq(t2["X"].cpu().numpy(), Xo)
+    L.Opt_PlanFree(st, plan)
+    L.Opt_ProblemDelete(st, prob)

@@ -1,0 +1,81 @@
+"""The oracle against the reference's own golden vectors -- CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from arap_flow_b200 import flowio
+
+
+def _cat(gold):
+    rgb = flowio.read_png_rgb(os.path.join(gold, "cat512_iRGB.png"))
+    msk = flowio.read_png_mask_red(os.path.join(gold, "cat512_iMsk.png"))
+    flo = flowio.read_flo(os.path.join(gold, "cat512_iFlo.flo"))
+    return rgb, msk, flo
+
+
+def test_warp_oracle_matches_shipped_golden_mask(oracle, gold):
+    rgb, msk, flo = _cat(gold)
+    o_rgb, o_m, sp = oracle.warp(oracle.flow_to_pos(flo), rgb, msk)
+    g_m = flowio.read_png_rgb(os.path.join(gold, "cat512_wMsk.png"))
+    assert np.array_equal(o_m, g_m[..., 0]) and np.array_equal(g_m[..., 0], g_m[..., 2])
+    assert int((sp != 0).sum()) == int((o_m == 255).sum()) == 105530
+    # shipped RGB golden was rasterised from un-rounded positions: +-1 level on < 0.5 % of pixels
+    g_rgb = flowio.read_png_rgb(os.path.join(gold, "cat512_wRGB.png")).astype(int)
+    d = np.abs(o_rgb.astype(int) - g_rgb)
+    assert d.max() <= 1 and (d.max(-1) > 0).mean() < 0.005
+
+
+def test_warp_oracle_bit_exact_vs_reference_tool(oracle, gold):
+    """cat512 RGB and three synthetic cases (folds, out-of-frame motion, ragged masks, identity) produced by the
+    reference's own warp_image binary (tools/make_golden.py)."""
+    rgb, msk, flo = _cat(gold)
+    o_rgb, _, _ = oracle.warp(oracle.flow_to_pos(flo), rgb, msk)
+    assert np.array_equal(o_rgb, flowio.read_png_rgb(os.path.join(gold, "cat512_reftool_wRGB.png")))
+    z = np.load(os.path.join(gold, "warp_reftool_cases.npz"))
+    for name in ("warp_a", "warp_b", "warp_c"):
+        r, m, sp = oracle.warp(oracle.flow_to_pos(z[f"{name}__flow"]), z[f"{name}__rgb"], z[f"{name}__mask"])
+        assert np.array_equal(r, z[f"{name}__ref_rgb"]), name
+        assert np.array_equal(m, z[f"{name}__ref_mask"]), name
+
+
+def test_warp_oracle_live_reference_binary(oracle, gold, tmp_path):
+    """When oracle/_ref/warp_image_ref is present (build container, or shipped prebuilt), run it live."""
+    if not os.path.exists(oracle.REF_WARP_BIN):
+        pytest.skip("reference warp binary not built")
+    import subprocess
+    from arap_flow_b200 import synth
+    sp = synth.synth(80, 60, 1, 3, 77)
+    rng = np.random.default_rng(5)
+    fl = (rng.standard_normal((60, 80, 2)) * 2.0).astype(np.float32)
+    p = {k: str(tmp_path / k) for k in ("i.png", "m.png", "f.flo", "o.png", "om.png")}
+    flowio.write_png(p["i.png"], sp.rgb)
+    flowio.write_png(p["m.png"], np.repeat(sp.masks[0][..., None], 3, 2))
+    flowio.write_flo(p["f.flo"], fl)
+    subprocess.check_call([oracle.REF_WARP_BIN, p["i.png"], p["m.png"], p["f.flo"], p["o.png"], p["om.png"]],
+                          stdout=subprocess.DEVNULL)
+    r, m, _ = oracle.warp(oracle.flow_to_pos(fl), sp.rgb, sp.masks[0])
+    assert np.array_equal(r, flowio.read_png_rgb(p["o.png"]))
+    assert np.array_equal(m, flowio.read_png_rgb(p["om.png"])[..., 0])
+
+
+def test_solve_pin_record(gold):
+    """The recorded full-schedule oracle solve on cat512 (tools/make_golden.py --solve): weak end-to-end pin."""
+    with open(os.path.join(gold, "cat512_oracle_pin.json")) as f:
+        pin = json.load(f)
+    assert pin["active_px"] == 101406
+    assert pin["off_object_max_abs_flow"] == 0.0
+    assert pin["constraint_err_px_max"] < 5e-3          # golden itself: 3.9e-3
+    assert pin["mean_epe_px"] < 0.35                      # chaotic regime, SURVEY.md 8c expects 0.2-0.3
+    assert pin["median_epe_px"] < 0.12
+
+
+@pytest.mark.slow
+def test_solve_cat512_full(oracle, gold):
+    rgb, msk, flo = _cat(gold)
+    cstr = flowio.read_constraints(os.path.join(gold, "cat512_iCstr.txt"))
+    X, A, costs = oracle.solve(msk, cstr)
+    fl = oracle.flow(X)
+    z = np.load(os.path.join(gold, "cat512_oracle_flow.npz"))
+    assert np.array_equal(fl, z["flow"])  # the oracle is deterministic
