@@ -70,6 +70,20 @@ __global__ void __launch_bounds__(256) k_scatter_c(const MatchRec* __restrict__ 
     C[r.idx] = make_float2(om * r.x1 + alpha * r.x2, om * r.y1 + alpha * r.y2);
 }
 
+// resident back-end: per-pixel match TARGET image; the kernel applies the continuation lerp itself
+__global__ void __launch_bounds__(256) k_fill_t(size_t N, float2* __restrict__ C)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) C[i] = make_float2(-1e30f, -1e30f);
+}
+__global__ void __launch_bounds__(256) k_scatter_t(const MatchRec* __restrict__ m, int n, float2* __restrict__ C)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const MatchRec r = m[k];
+    C[r.idx] = make_float2(r.x2, r.y2);
+}
+
 __global__ void k_copy_cost(const StreamScalars* __restrict__ sc, float* __restrict__ dst) { *dst = sc->cost; }
 
 } // namespace
@@ -117,6 +131,7 @@ DeformPipeline::~DeformPipeline()
 {
     cudaStreamSynchronize(stream_);
     delete solver_;
+    delete resident_;
     cudaFree(d_X_); cudaFree(d_U_); cudaFree(d_C_); cudaFree(d_flow_); cudaFree(d_A_); cudaFree(d_M_);
     cudaFree(d_costs_); cudaFree(d_rgb_); cudaFree(d_mask_); cudaFree(d_orgb_); cudaFree(d_omask_);
     cudaFree(d_z_); cudaFree(d_matches_);
@@ -133,13 +148,14 @@ int DeformPipeline::run(const HostProblem& hp)
         return 1;
     }
     const size_t N = (size_t)W * H;
-    if (!solver_ || curW_ != W || curH_ != H) { // re-plan on a size change (CombinedSolver.h:149-160)
+    if (curW_ != W || curH_ != H) { // re-plan on a size change (CombinedSolver.h:149-160)
         delete solver_;
-        solver_ = new StreamSolver(W, H);
+        solver_ = nullptr;
         curW_ = W;
         curH_ = H;
     }
-    const long long l0 = solver_->launches();
+    if (backend_ != ARAPB200_BACKEND_STREAM && !resident_) resident_ = new ResidentSolver(maxW_, maxH_);
+    const long long l0 = (solver_ ? solver_->launches() : 0) + (resident_ ? resident_->launches() : 0);
     std::vector<MatchRec> recs;
     build_match_records(W, H, hp.mask_red, hp.matches, hp.n_matches, recs);
     if (recs.size() > matches_cap_) {
@@ -160,9 +176,27 @@ int DeformPipeline::run(const HostProblem& hp)
     launches_ += 1;
     // weights: CombinedSolver.h:172-177
     const float wf = sqrtf(100.0f), wr = sqrtf(0.01f);
-    solver_->bind(d_X_, d_A_, d_U_, d_C_, d_M_, wf, wr, stream_);
+    bool use_res = false;
+    if (backend_ != ARAPB200_BACKEND_STREAM) {
+        use_res = resident_->prepare(W, H, d_M_, stream_);
+        if (!use_res && backend_ == ARAPB200_BACKEND_RESIDENT) {
+            fprintf(stderr, "arapb200: problem %dx%d (%d strips) does not fit the resident back-end\n", W, H,
+                    resident_->n_strips());
+            return 3;
+        }
+    }
+    last_resident_ = use_res;
+    if (!use_res && !solver_) solver_ = new StreamSolver(W, H);
+    if (!use_res) solver_->bind(d_X_, d_A_, d_U_, d_C_, d_M_, wf, wr, stream_);
     ARAP_CUDA_OR_RETURN(cudaEventRecord(ev_[1], stream_));
-    for (int t = 0; t < nCont_; ++t) {
+    if (use_res) {
+        // the whole continuation schedule (CombinedSolverBase.h:99-120) is ONE kernel launch
+        k_fill_t<<<(unsigned)((N + 255) / 256), 256, 0, stream_>>>(N, d_C_);
+        if (!recs.empty()) k_scatter_t<<<((int)recs.size() + 255) / 256, 256, 0, stream_>>>(d_matches_, (int)recs.size(), d_C_);
+        launches_ += recs.empty() ? 1 : 2;
+        resident_->enqueue(d_X_, d_A_, d_C_, 1, wf, wr, nCont_, nGN_, nPCG_, d_costs_, nullptr, stream_);
+    }
+    for (int t = 0; t < nCont_ && !use_res; ++t) {
         const float alpha = (float)(t + 1) / (float)nCont_; // CombinedSolver.h:199-201
         enqueue_constraint_image(W, H, d_matches_, (int)recs.size(), alpha, d_C_, stream_);
         launches_ += recs.empty() ? 1 : 2;
@@ -186,17 +220,24 @@ int DeformPipeline::run(const HostProblem& hp)
     const size_t cbytes = (size_t)nCont_ * (nGN_ + 1) * sizeof(float);
     ARAP_CUDA_OR_RETURN(cudaMemcpyAsync(o + 12 * N, d_costs_, cbytes, cudaMemcpyDeviceToHost, stream_));
     ARAP_CUDA_OR_RETURN(cudaStreamSynchronize(stream_));
-    unsigned bad = 0;
-    solver_->read_back(stream_, nullptr, &bad);
-    if (bad) {
-        fprintf(stderr, "arapb200: internal error: UrShape check failed\n");
-        return 2;
+    if (use_res) {
+        if (int st = resident_->status(stream_)) {
+            fprintf(stderr, "arapb200: resident solver aborted (watchdog, code %d)\n", st);
+            return 4;
+        }
+    } else {
+        unsigned bad = 0;
+        solver_->read_back(stream_, nullptr, &bad);
+        if (bad) {
+            fprintf(stderr, "arapb200: internal error: UrShape check failed\n");
+            return 2;
+        }
     }
     if (hp.out_flow) memcpy(hp.out_flow, o, N * sizeof(float2));
     if (hp.out_rgb) memcpy(hp.out_rgb, o + 8 * N, 3 * N);
     if (hp.out_mask) memcpy(hp.out_mask, o + 11 * N, N);
     if (hp.out_costs) memcpy(hp.out_costs, o + 12 * N, cbytes);
-    launches_ += solver_->launches() - l0;
+    launches_ += (solver_ ? solver_->launches() : 0) + (resident_ ? resident_->launches() : 0) - l0;
     cudaEventElapsedTime(&ms_total_, ev_[0], ev_[3]);
     cudaEventElapsedTime(&ms_solve_, ev_[1], ev_[2]);
     cudaEventElapsedTime(&ms_warp_, ev_[2], ev_[3]);

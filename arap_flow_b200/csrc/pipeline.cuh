@@ -45,11 +45,14 @@ public:
     float last_ms_total() const { return ms_total_; }
     float last_ms_solve() const { return ms_solve_; }
     float last_ms_warp() const { return ms_warp_; }
+    bool last_used_resident() const { return last_resident_; }
 
 private:
     int maxW_, maxH_, nCont_, nGN_, nPCG_, backend_;
     int curW_ = 0, curH_ = 0;
     StreamSolver* solver_ = nullptr;
+    ResidentSolver* resident_ = nullptr;
+    bool last_resident_ = false;
     cudaStream_t stream_ = nullptr;
     cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
     // device images

@@ -4,6 +4,8 @@
 #pragma once
 #include "../../include/arapb200.h"
 #include "solver_stream.cuh"
+#include "solver_resident.cuh"
+#include <memory>
 
 namespace arapb200 {
 
@@ -17,7 +19,8 @@ public:
     int step(void** problemparams);   // :1016-1177
     void solve(void** problemparams); // o.t:2548-2551, with a single host sync at the end
     double current_cost() const { return (double)prev_cost_; }
-    long long launches() const { return stream_.launches(); }
+    long long launches() const;
+    bool using_resident() const { return use_resident_; }
     // parity/debug: device buffer of 3*lIterations floats per GN step, or null
     void set_trace(float* d_trace) { d_trace_ = d_trace; }
 
@@ -29,8 +32,15 @@ private:
     int n_iter_ = 0;
     float prev_cost_ = 0.f;
     cudaStream_t stream_h_ = nullptr;
-    StreamSolver stream_;
+    std::unique_ptr<StreamSolver> stream_;      // created on first use
+    std::unique_ptr<ResidentSolver> resident_;  // created on first use
+    bool use_resident_ = false;
+    void** last_params_ = nullptr;
+    float* d_costs_ = nullptr;                  // resident: cost log of the current launch
+    unsigned* d_bad_u_ = nullptr;
     float* d_trace_ = nullptr;
+    void choose_backend(void** problemparams);
+    float run_resident(void** problemparams, int nGN, float* trace);
 };
 
 } // namespace arapb200

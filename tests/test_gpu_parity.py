@@ -219,3 +219,43 @@ def test_opt_h_boundary_through_ctypes(oracle):
     assert _eq(t2["X"].cpu().numpy(), Xo)
     L.Opt_PlanFree(st, plan)
     L.Opt_ProblemDelete(st, prob)
+
+
+# ------------------------------------------------------------------------------------- full-size configs
+@pytest.mark.parametrize("cfg,kw", [("C1", dict(nCont=2, nGN=2, nPCG=60)), ("C3", dict(nCont=1, nGN=2, nPCG=40))])
+def test_full_size_backends_and_oracle_agree(oracle, cfg, kw):
+    """854x480 (C1) and 1024x436 (C3) at a reduced schedule: oracle == streaming == resident, bit for bit."""
+    sp = synth.config(cfg)
+    mask = sp.masks[0]
+    Xo, Ao, co = oracle.solve(mask, sp.matches, **kw)
+    for backend in (lib.BACKEND_STREAM, lib.BACKEND_RESIDENT):
+        flo, rgb, m, c = lib.deform(sp.rgb, mask, sp.matches, backend=backend, **kw)
+        assert _eq(c, co), (cfg, backend)
+        assert _eq(flo, oracle.flow(Xo)), (cfg, backend)
+    rgb_o, m_o, _ = oracle.warp(Xo, sp.rgb, mask)
+    assert _eq(rgb, rgb_o) and _eq(m, m_o)
+
+
+def test_c4_streams_and_matches_oracle(oracle):
+    """1920x1080 (C4): too large for the on-chip state, AUTO falls back to streaming; still exact."""
+    sp = synth.config("C4")
+    mask = sp.masks[0]
+    kw = dict(nCont=1, nGN=1, nPCG=12)
+    Xo, Ao, co = oracle.solve(mask, sp.matches, **kw)
+    flo, rgb, m, c = lib.deform(sp.rgb, mask, sp.matches, backend=lib.BACKEND_AUTO, **kw)
+    assert _eq(c, co) and _eq(flo, oracle.flow(Xo))
+
+
+def test_full_schedule_size_independent_properties():
+    """C1 at the full 19x8x400 schedule through the default (resident) path: deterministic run to run,
+    zero flow off the object, matches met, cost trajectory finite and decreasing within each continuation step."""
+    sp = synth.config("C1")
+    mask = sp.masks[0]
+    f1, r1, m1, c1 = lib.deform(sp.rgb, mask, sp.matches)
+    f2, r2, m2, c2 = lib.deform(sp.rgb, mask, sp.matches)
+    assert _eq(f1, f2) and _eq(c1, c2) and _eq(r1, r2) and _eq(m1, m2)
+    act = mask == 0
+    assert (f1[~act] == 0).all() and np.isfinite(f1).all() and np.isfinite(c1).all()
+    err = np.array([np.hypot(*(f1[y1, x1] - (x2 - x1, y2 - y1))) for x1, y1, x2, y2 in sp.matches])
+    assert err.max() < 0.05, err.max()
+    assert (c1[:, -1] <= c1[:, 0]).all()
