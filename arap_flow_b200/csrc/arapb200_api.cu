@@ -2,6 +2,7 @@
 #include "../../include/arapb200.h"
 #include "pipeline.cuh"
 
+#include <cmath>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -269,6 +270,46 @@ int arapb200_debug_cost(int W, int H, const float* X, const float* A, const floa
     s.bind(dX.p, dA.p, dU.p, dC.p, dM.p, wf, wr, nullptr);
     s.enqueue_init(nullptr);
     s.read_back(nullptr, cost, nullptr);
+    return 0;
+}
+
+// Cycle accounting of the resident kernel on one problem (see solver_resident.cu, RS_TICK):
+// prof[cta][8] = cycles in {phase1, phase2, phase3, other, barrier skew, barrier poll, barrier fold}, epochs.
+// info = {n_strips, ctas, warps per cta}; *ms = device time of the launch.
+int arapb200_debug_resident_profile(int W, int H, const uint8_t* mask_red, const int32_t* matches, int n_matches,
+                                    int nCont, int nGN, int nPCG, unsigned long long* prof, int* info, float* ms)
+{
+    const size_t N = (size_t)W * H;
+    std::vector<MatchRec> recs;
+    build_match_records(W, H, mask_red, matches, n_matches, recs);
+    DevBuf<unsigned char> dmask(N);
+    DevBuf<float2> dX(N), dU(N), dC(N);
+    DevBuf<float> dA(N), dM(N), dcost((size_t)nCont * (nGN + 1));
+    DevBuf<MatchRec> dm(recs.size());
+    DevBuf<unsigned long long> dprof(RS_MAX_CTAS * 8);
+    dmask.up(mask_red);
+    if (!recs.empty()) dm.up(recs.data());
+    ARAP_CUDA_OR_RETURN(cudaMemset(dprof.p, 0, RS_MAX_CTAS * 8 * sizeof(unsigned long long)));
+    enqueue_reset_state(W, H, dmask.p, dX.p, dU.p, dA.p, dM.p, nullptr);
+    enqueue_target_image(W, H, dm.p, (int)recs.size(), dC.p, nullptr);
+    ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
+    ResidentSolver rs(W, H);
+    if (!rs.prepare(W, H, dM.p, nullptr)) return 3;
+    rs.set_profile(dprof.p);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, nullptr);
+    rs.enqueue(dX.p, dA.p, dC.p, 1, sqrtf(100.f), sqrtf(0.01f), nCont, nGN, nPCG, dcost.p, nullptr, nullptr);
+    cudaEventRecord(e1, nullptr);
+    ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
+    if (ms) cudaEventElapsedTime(ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (int st = rs.status(nullptr)) return 100 + st;
+    dprof.down(prof);
+    ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
+    if (info) { info[0] = rs.n_strips(); info[1] = rs.ctas(); info[2] = rs.warps(); }
     return 0;
 }
 

@@ -103,6 +103,13 @@ void enqueue_constraint_image(int W, int H, const MatchRec* d_matches, int n, fl
     if (n > 0) k_scatter_c<<<(n + 255) / 256, 256, 0, stream>>>(d_matches, n, alpha, d_C);
 }
 
+void enqueue_target_image(int W, int H, const MatchRec* d_matches, int n, float2* d_C, cudaStream_t stream)
+{
+    const size_t N = (size_t)W * H;
+    k_fill_t<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(N, d_C);
+    if (n > 0) k_scatter_t<<<(n + 255) / 256, 256, 0, stream>>>(d_matches, n, d_C);
+}
+
 DeformPipeline::DeformPipeline(int maxW, int maxH, int nCont, int nGN, int nPCG, int backend)
     : maxW_(maxW), maxH_(maxH), nCont_(nCont), nGN_(nGN), nPCG_(nPCG), backend_(backend)
 {
@@ -191,8 +198,7 @@ int DeformPipeline::run(const HostProblem& hp)
     ARAP_CUDA_OR_RETURN(cudaEventRecord(ev_[1], stream_));
     if (use_res) {
         // the whole continuation schedule (CombinedSolverBase.h:99-120) is ONE kernel launch
-        k_fill_t<<<(unsigned)((N + 255) / 256), 256, 0, stream_>>>(N, d_C_);
-        if (!recs.empty()) k_scatter_t<<<((int)recs.size() + 255) / 256, 256, 0, stream_>>>(d_matches_, (int)recs.size(), d_C_);
+        enqueue_target_image(W, H, d_matches_, (int)recs.size(), d_C_, stream_);
         launches_ += recs.empty() ? 1 : 2;
         resident_->enqueue(d_X_, d_A_, d_C_, 1, wf, wr, nCont_, nGN_, nPCG_, d_costs_, nullptr, stream_);
     }

@@ -73,6 +73,8 @@ private:
 // shared small kernels
 void enqueue_reset_state(int W, int H, const unsigned char* d_mask_red, float2* d_X, float2* d_U, float* d_A,
                          float* d_M, cudaStream_t stream);
+// resident back-end: per-pixel match target image ((-1e30, -1e30) = none); the kernel does the lerp
+void enqueue_target_image(int W, int H, const MatchRec* d_matches, int n, float2* d_C, cudaStream_t stream);
 void enqueue_constraint_image(int W, int H, const MatchRec* d_matches, int n, float alpha, float2* d_C,
                               cudaStream_t stream);
 

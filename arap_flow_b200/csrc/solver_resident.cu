@@ -71,6 +71,9 @@ struct Cta {
     Ctl* ctl;
     int cta, G, lane, wid, nw;
     unsigned epoch;
+    // optional cycle accounting (thread 0 only): [0] arrive skew, [1] publish+poll, [2] fold+broadcast
+    unsigned long long acc[3];
+    bool prof;
 };
 
 // ---- grid barrier carrying an exact sum ----------------------------------------------------------
@@ -79,6 +82,8 @@ struct Cta {
 __device__ __noinline__ float grid_sum(Cta& c, float g0, float g1, bool& ok)
 {
     Ctl* ctl = c.ctl;
+    long long t0 = 0, t1 = 0, t2 = 0;
+    if (c.prof) t0 = clock64();
     // warp: exact sum of 64 terms
     float m = warp_max(fmaxf(fabsf(g0), fabsf(g1)));
     const double B = bin_base(ilogb_f32(m) + 6 + 2);
@@ -92,6 +97,7 @@ __device__ __noinline__ float grid_sum(Cta& c, float g0, float g1, bool& ok)
         ctl->red[32 + c.wid] = ls;
     }
     __syncthreads();
+    if (c.prof) t1 = clock64();
     if (c.wid == 0) {
         HL v;
         v.h = (c.lane < c.nw) ? ctl->red[c.lane] : 0.0;
@@ -138,6 +144,7 @@ __device__ __noinline__ float grid_sum(Cta& c, float g0, float g1, bool& ok)
                 }
             }
         } while (!done);
+        if (c.prof) t2 = clock64();
         __threadfence();
         // exact fold of the G partials, identical in every CTA
         double mm = 0.0;
@@ -158,6 +165,12 @@ __device__ __noinline__ float grid_sum(Cta& c, float g0, float g1, bool& ok)
         if (c.lane == 0) ctl->bc = (float)__dadd_rn(H, L);
     }
     __syncthreads();
+    if (c.prof && threadIdx.x == 0) {
+        const long long t3 = clock64();
+        c.acc[0] += (unsigned long long)(t1 - t0);
+        c.acc[1] += (unsigned long long)(t2 - t1);
+        c.acc[2] += (unsigned long long)(t3 - t2);
+    }
     ++c.epoch;
     ok = (ctl->abort == 0);
     return ctl->bc;
@@ -271,6 +284,11 @@ __global__ void __launch_bounds__(RS_THREADS_MAX, 1) k_resident(const ResProb* _
     Cta c;
     c.P = &P; c.ctl = &ctl; c.cta = blockIdx.x; c.G = P.G;
     c.lane = threadIdx.x & 31; c.wid = threadIdx.x >> 5; c.nw = blockDim.x >> 5; c.epoch = 0;
+    c.acc[0] = c.acc[1] = c.acc[2] = 0; c.prof = (P.prof != nullptr);
+    unsigned long long ph[4] = {0, 0, 0, 0}; // cycles in PCG phase 1, 2, 3 and everything else (thread 0)
+    long long tk = c.prof ? clock64() : 0;
+#define RS_TICK(slot) do { if (c.prof && threadIdx.x == 0) { const long long tn = clock64(); ph[slot] += (unsigned long long)(tn - tk); tk = tn; } } while (0)
+#define RS_TOCK() do { if (c.prof && threadIdx.x == 0) tk = clock64(); } while (0)
     const int lane = c.lane, wid = c.wid;
     const int W = P.W, H = P.H;
     const float wr = P.wr, wf = P.wf, wr2 = P.wr2, wf2 = P.wf2;
@@ -463,6 +481,7 @@ __global__ void __launch_bounds__(RS_THREADS_MAX, 1) k_resident(const ResProb* _
             }
 
             // ======== PCG iterations ========
+            RS_TICK(3);
             for (int it = 0; it < P.nPCG; ++it) {
                 // ---- PCGStep1: q = J^T J p, den = sum p.q ----
                 float gs0 = 0.f, gs1 = 0.f;
@@ -490,7 +509,9 @@ __global__ void __launch_bounds__(RS_THREADS_MAX, 1) k_resident(const ResProb* _
                         cur = dn;
                     }
                 }
+                RS_TICK(0);
                 const float den = grid_sum(c, gs0, gs1, ok);
+                RS_TOCK();
                 if (!ok) break;
                 const float alpha = (den > 0.0f) ? num / den : 0.0f; // :456-459
 
@@ -519,7 +540,9 @@ __global__ void __launch_bounds__(RS_THREADS_MAX, 1) k_resident(const ResProb* _
                     if (s.has && it + 1 < P.nPCG)
                         publish_rowcol(s, lane, k, pub_top, pub_bot, pub_left, pub_right, v0, v1, true);
                 }
+                RS_TICK(1);
                 const float bnum = grid_sum(c, gs0, gs1, ok);
+                RS_TOCK();
                 if (!ok) break;
                 if (P.trace && c.cta == 0 && threadIdx.x == 0) {
                     float* tr = P.trace + ((size_t)(t * P.nGN + g) * P.nPCG + it) * 3;
@@ -545,6 +568,7 @@ __global__ void __launch_bounds__(RS_THREADS_MAX, 1) k_resident(const ResProb* _
                 }
                 if (s.has) recv_p(P, s, lane, beta);
                 __syncthreads();
+                RS_TICK(2);
             }
             if (!ok) break;
 
@@ -563,6 +587,13 @@ __global__ void __launch_bounds__(RS_THREADS_MAX, 1) k_resident(const ResProb* _
             __syncthreads(); // tile entries (p) are overwritten by the next prologue
         }
     }
+    if (c.prof && threadIdx.x == 0) {
+        unsigned long long* o = P.prof + (size_t)c.cta * 8;
+        o[0] = ph[0]; o[1] = ph[1]; o[2] = ph[2]; o[3] = ph[3];
+        o[4] = c.acc[0]; o[5] = c.acc[1]; o[6] = c.acc[2]; o[7] = c.epoch;
+    }
+#undef RS_TICK
+#undef RS_TOCK
 }
 
 // ---- strip table construction -------------------------------------------------------------------------
@@ -692,6 +723,7 @@ void ResidentSolver::enqueue(float2* X, float* A, const float2* C, int lerp_mode
     p.strip_xy = d_strip_xy_; p.slot_of_strip = d_slot_of_strip_;
     p.outbox = d_outbox_; p.slots = d_slots_; p.costs = d_costs; p.trace = d_trace; p.status = d_status_;
     p.nCont = nCont; p.nGN = nGN; p.nPCG = nPCG;
+    p.prof = d_prof_;
     ARAP_CUDA_OR_EXIT(cudaMemcpyAsync(d_prob_, &p, sizeof(p), cudaMemcpyHostToDevice, stream));
     ARAP_CUDA_OR_EXIT(cudaMemsetAsync(d_slots_, 0xFF, 3 * RS_MAX_CTAS * sizeof(double2), stream));
     const int threads = NW_ * 32;

@@ -33,6 +33,7 @@ struct ResProb {
     float* trace;              // optional [nCont*nGN][nPCG][3]
     int* status;               // [0] abort flag, [1] error code
     int nCont, nGN, nPCG;
+    unsigned long long* prof;  // optional [G][8] cycle counters (debug)
 };
 
 class ResidentSolver {
@@ -56,6 +57,8 @@ public:
     int n_strips() const { return n_strips_; }
     int ctas() const { return G_; }
     int warps() const { return NW_; }
+    // debug: per-CTA cycle accounting of the next launches into d_prof ([ctas()][8] u64), or null to disable
+    void set_profile(unsigned long long* d_prof) { d_prof_ = d_prof; }
 
 private:
     int maxW_, maxH_;
@@ -71,6 +74,7 @@ private:
     ResProb* d_prob_ = nullptr;
     int sm_count_ = 0;
     long long launches_ = 0;
+    unsigned long long* d_prof_ = nullptr;
 };
 
 } // namespace arapb200

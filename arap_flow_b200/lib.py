@@ -25,6 +25,7 @@ ARAP_SYMBOLS = [
     "arapb200_batch_create", "arapb200_batch_destroy", "arapb200_batch_submit", "arapb200_batch_run",
     "arapb200_batch_timing", "arapb200_batch_launches", "arapb200_debug_gn_solve", "arapb200_debug_eval_jtf",
     "arapb200_debug_apply_jtj", "arapb200_debug_cost", "arapb200_debug_sincos", "arapb200_debug_exact_sum",
+    "arapb200_debug_resident_profile",
 ]
 
 
@@ -232,6 +233,22 @@ def debug_cost(X, A, U, Cn, M, wf, wr):
     _check(load().arapb200_debug_cost(W, H, _c(X, np.float32), _c(A, np.float32), _c(U, np.float32),
                                       _c(Cn, np.float32), _c(M, np.float32), wf, wr, C.byref(c)), "debug_cost")
     return np.float32(c.value)
+
+
+def debug_resident_profile(mask_red, matches, nCont, nGN, nPCG):
+    """Cycle accounting of the resident kernel (thread 0 of every CTA).  Returns (prof[G, 8], info, ms)."""
+    H, W = mask_red.shape
+    m = _c(matches, np.int32).reshape(-1, 4)
+    prof = np.zeros((160, 8), np.uint64)
+    info = (C.c_int * 3)()
+    ms = C.c_float()
+    L = load()
+    L.arapb200_debug_resident_profile.argtypes = [C.c_int, C.c_int, _u8p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                  C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)]
+    _check(L.arapb200_debug_resident_profile(W, H, _c(mask_red, np.uint8), m, len(m), nCont, nGN, nPCG,
+                                             prof.ctypes.data, info, C.byref(ms)), "debug_resident_profile")
+    G = info[1]
+    return prof[:G], dict(strips=info[0], ctas=info[1], warps=info[2]), ms.value
 
 
 def debug_sincos(a):
