@@ -6,15 +6,26 @@
 // back-end and to oracle/arap_oracle.c.
 //
 // Decomposition: the active part of the image is cut into 32x8-pixel strips; a warp owns one strip, a lane
-// one column of 8 pixels (two contract-C3 groups).  r, delta, p_angle, cos/sin and the neighbour flags live
-// in registers for the whole PCG loop; (p_x, p_y, sin*p_a, cos*p_a) of every pixel sits in a shared-memory
-// tile with a one-pixel ring.  Strips of the same CTA read each other's tiles directly; strips of other
-// CTAs exchange their boundary through a 2.5 KB global "outbox" per strip, piggy-backed on the grid barrier.
+// one column of 8 pixels (two contract-C3 groups).  r, p_angle, cos/sin and the neighbour flags live in
+// registers for the whole PCG loop, delta in shared memory; (p_x, p_y, sin*p_a, cos*p_a) of every pixel sits
+// in a shared-memory tile with a one-pixel ring.  Strips of the same CTA read each other's tiles directly;
+// strips of other CTAs exchange their boundary through a small global "outbox" per strip.
 //
-// Per PCG iteration there are exactly two grid-wide barriers, each carrying the exact (h, l) partial sum of
-// the dot product (sum p.Ap, then sum z.r).  The direction update p = z + beta p that follows the second
-// barrier needs the neighbours' NEW p; instead of a third barrier, every strip publishes (z, p_old) of its
-// boundary pixels before the second barrier and the receiver applies beta itself.
+// Everything that crosses CTAs is FENCE-FREE (a __threadfence is MEMBAR.SC + CCTL.IVALL, > 1 us here):
+//  * Grid barrier + all-reduce.  A dot product is accumulated in fixed point: every group term is split
+//    against a common scale 2^S into four 24-bit limbs (exact for terms within 2^-67 of 2^S); a CTA adds its
+//    limb sums into four 64-bit words with red.global.add.u64, the upper 16 bits of each contribution
+//    counting the arrival (+ an overflow flag).  A word is complete when its count reaches G, so value and
+//    "everybody arrived" travel in the same 8-byte word and integer addition makes the result independent
+//    of arrival order.  Two buffers alternate; they are never reset inside a launch (readers subtract the
+//    total they saw two barriers ago).  S is predicted from the previous result of the same reduction and
+//    verified (overflow flag / magnitude of the result); a wrong guess costs one extra barrier.
+//  * Halo.  Outbox words are (float, tag) pairs written with plain 16-byte stores; the receiver spins until
+//    the tag equals the publication sequence number, so the data validates itself.
+//
+// Per PCG iteration there are exactly two grid barriers (sum p.Ap, sum z.r).  The direction update
+// p = z + beta p that follows the second one needs the neighbours' NEW p; instead of a third barrier every
+// strip publishes (z, p_old) of its boundary pixels before the second barrier and the receiver applies beta.
 #include "solver_resident.cuh"
 #include "grid_math.cuh"
 #include "solver_stream.cuh" // FLAG_* bit layout
@@ -24,46 +35,94 @@ namespace {
 
 constexpr int TW = RS_STRIP_W + 2, TH = RS_STRIP_H + 2;
 constexpr int RS_THREADS_MAX = 384;
-constexpr unsigned long long SENTINEL = 0xFFFFFFFFFFFFFFFFull;
+constexpr long long LIMB_BIAS = 1ll << 36;
+constexpr int S_MIN = -300, S_MAX = 300;
 
 struct __align__(16) StripSmem {
-    float4 T[TH][TW];                  // tile + ring
-    float2 rcs[RS_OUTBOX_ENTRIES];     // cos/sin of the ring pixels (remote sides only)
+    float4 T[TH][TW];              // tile + ring: (p_x, p_y, sin*p_a, cos*p_a) or (X_x, X_y, cos, sin)
+    float D[3][RS_STRIP_H][32];    // delta
+    float2 rcs[RS_OUTBOX_ENTRIES]; // cos/sin of the ring pixels (remote sides only)
 };
 
 struct Ctl {
-    double red[64];
-    float bc;
+    int limb[RS_THREADS_MAX / 32][4];
+    int ovf[RS_THREADS_MAX / 32];
+    unsigned long long prev[2][4]; // totals last seen in each barrier buffer
+    float bc;                      // broadcast result
+    int bc_code;                   // 0 accept, 1 redo with bc_S
+    int bc_S;
     int abort;
     float preX[10];
     float preA[5];
 };
 
-__device__ __forceinline__ double2 ld_slot(const double2* p)
+__device__ __forceinline__ unsigned long long ld_u64_volatile(const unsigned long long* p)
 {
-    double2 v;
-    asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_slot(double2* p, double a, double b)
+__device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v)
 {
-    asm volatile("st.volatile.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ float4 ldcg4(const float4* p) { return __ldcg(p); }
+__device__ __forceinline__ uint4 ld_u4_volatile(const uint4* p)
+{
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_u4(uint4* p, uint4 v)
+{
+    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ double pow2_f64(int e) // 2^e, e in the normal range
+{
+    return __hiloint2double((e + 1023) << 20, 0);
+}
+
+// exact 128-bit integer (units of 2^e_unit) -> binary32, round to nearest even
+__device__ float i128_to_float_rn(__int128 T, int e_unit)
+{
+    if (T == 0) return 0.0f;
+    const bool neg = T < 0;
+    unsigned __int128 m = neg ? (unsigned __int128)(-T) : (unsigned __int128)T;
+    const unsigned long long hi = (unsigned long long)(m >> 64), lo = (unsigned long long)m;
+    const int nbits = hi ? 128 - __clzll((long long)hi) : 64 - __clzll((long long)lo);
+    unsigned long long mant;
+    int e = e_unit;
+    if (nbits > 24) {
+        const int sh = nbits - 24;
+        mant = (unsigned long long)(m >> sh);
+        const unsigned __int128 rem = m & ((((unsigned __int128)1) << sh) - 1);
+        const unsigned __int128 half = ((unsigned __int128)1) << (sh - 1);
+        if (rem > half || (rem == half && (mant & 1ull))) ++mant;
+        e += sh;
+    } else {
+        mant = lo;
+    }
+    e = max(-1000, min(1000, e));
+    const double d = (double)(long long)mant * pow2_f64(e); // exact: mant <= 2^24
+    const float f = (float)d;
+    return neg ? -f : f;
+}
 
 // Everything a warp needs to know about its strip
 struct StripCtx {
-    bool has;                 // this warp owns a strip
-    int slot;                 // global strip id
-    int x, y0;                // lane's column, first row
-    float4* own;              // &T[0][0] of the own tile
-    const float4* up_row;     // row y = -1, indexed by lane
-    const float4* down_row;   // row y = 8
-    const float4* lptr;       // pixel to the left of (lane, row 0); row stride TW
-    const float4* rptr;       // pixel to the right
+    bool has;               // this warp owns a strip
+    int x, y0;              // lane's column, first row
+    float4* own;            // &T[0][0] of the own tile
+    const float4* up_row;   // row y = -1, indexed by lane
+    const float4* down_row; // row y = 8
+    const float4* lptr;     // pixel to the left of (lane, row 0); row stride TW
+    const float4* rptr;     // pixel to the right
+    float* D;               // &D[0][0][lane]
     float2* rcs;
-    int rem[4];               // remote neighbour strip id per side (0 up, 1 down, 2 left, 3 right) or -1
-    float4* outbox;           // own outbox
+    int rem[4];             // remote neighbour strip id per side (0 up, 1 down, 2 left, 3 right) or -1
+    uint4* outbox;          // own outbox: [RS_OUTBOX_ENTRIES][3]
 };
 
 struct Cta {
@@ -71,192 +130,226 @@ struct Cta {
     Ctl* ctl;
     int cta, G, lane, wid, nw;
     unsigned epoch;
-    // optional cycle accounting (thread 0 only): [0] arrive skew, [1] publish+poll, [2] fold+broadcast
-    unsigned long long acc[3];
+    unsigned long long acc[3]; // optional cycle accounting (thread 0): reduce+arrive, poll, decode+broadcast
     bool prof;
 };
 
 // ---- grid barrier carrying an exact sum ----------------------------------------------------------
-// g0/g1: this thread's two group terms.  Returns the exact sum over the whole problem, rounded to
-// binary32; *ok = false when the watchdog fired (every thread of every CTA then leaves the kernel).
-__device__ __noinline__ float grid_sum(Cta& c, float g0, float g1, bool& ok)
+// g0/g1: this thread's two group terms.  S: scale exponent of this reduction kind (in/out).  Returns the
+// exact sum over the whole problem, rounded once to binary32.  ok = false: watchdog fired / peer aborted.
+__device__ __noinline__ float grid_sum(Cta& c, float g0, float g1, int& S, bool& ok)
 {
     Ctl* ctl = c.ctl;
-    long long t0 = 0, t1 = 0, t2 = 0;
-    if (c.prof) t0 = clock64();
-    // warp: exact sum of 64 terms
-    float m = warp_max(fmaxf(fabsf(g0), fabsf(g1)));
-    const double B = bin_base(ilogb_f32(m) + 6 + 2);
-    double h0, l0, h1, l1;
-    bin_split(B, (double)g0, h0, l0);
-    bin_split(B, (double)g1, h1, l1);
-    double hs = warp_sum(__dadd_rn(h0, h1));
-    double ls = warp_sum(__dadd_rn(l0, l1));
-    if (c.lane == 0) {
-        ctl->red[c.wid] = hs;
-        ctl->red[32 + c.wid] = ls;
-    }
-    __syncthreads();
-    if (c.prof) t1 = clock64();
-    if (c.wid == 0) {
-        HL v;
-        v.h = (c.lane < c.nw) ? ctl->red[c.lane] : 0.0;
-        v.l = (c.lane < c.nw) ? ctl->red[32 + c.lane] : 0.0;
-        HL cta_sum = warp_combine(v);
-        const ResProb& P = *c.P;
-        double2* buf = P.slots + (size_t)(c.epoch % 3u) * c.G;
-        double2* nxt = P.slots + (size_t)((c.epoch + 1u) % 3u) * c.G;
+    const ResProb& P = *c.P;
+    bool grown = false;
+    for (;;) {
+        long long t0 = 0, t1 = 0, t2 = 0;
+        if (c.prof) t0 = clock64();
+        // ---- thread -> limbs (units 2^(S-42) and 2^(S-90)) ----
+        const double sc = pow2_f64(42 - S);
+        const double a0 = (double)g0 * sc, a1 = (double)g1 * sc;
+        const bool ovf = !(fabs(a0) < 281474976710656.0) || !(fabs(a1) < 281474976710656.0); // |g| >= 2^(S+6), NaN
+        const long long A0 = __double2ll_rn(a0), A1 = __double2ll_rn(a1);
+        const double r0 = __dadd_rn(a0, -__ll2double_rn(A0)), r1 = __dadd_rn(a1, -__ll2double_rn(A1));
+        const long long B0 = __double2ll_rn(r0 * 281474976710656.0), B1 = __double2ll_rn(r1 * 281474976710656.0);
+        // an overflowing thread contributes nothing (its limbs would spill into the arrival counts)
+        const long long A = ovf ? 0ll : A0 + A1, B = ovf ? 0ll : B0 + B1;
+        const int l0 = (int)(A >> 24), l2 = (int)(B >> 24);
+        const unsigned l1 = (unsigned)(A & 0xFFFFFF), l3 = (unsigned)(B & 0xFFFFFF);
+        const int s0 = __reduce_add_sync(0xffffffffu, l0);
+        const unsigned s1 = __reduce_add_sync(0xffffffffu, l1);
+        const int s2 = __reduce_add_sync(0xffffffffu, l2);
+        const unsigned s3 = __reduce_add_sync(0xffffffffu, l3);
+        const bool wovf = __any_sync(0xffffffffu, ovf);
         if (c.lane == 0) {
-            // recycle next epoch's slot first: whoever sees this epoch's value also sees the reset
-            st_slot(nxt + c.cta, __longlong_as_double((long long)SENTINEL), __longlong_as_double((long long)SENTINEL));
-            __threadfence();
-            st_slot(buf + c.cta, cta_sum.h, cta_sum.l);
+            ctl->limb[c.wid][0] = s0;
+            ctl->limb[c.wid][1] = (int)s1;
+            ctl->limb[c.wid][2] = s2;
+            ctl->limb[c.wid][3] = (int)s3;
+            ctl->ovf[c.wid] = wovf ? 1 : 0;
         }
-        // gather every CTA's partial (<= 5 per lane)
-        double2 v5[5];
-        unsigned spins = 0;
-        bool done;
-        do {
-            done = true;
-#pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                const int i = c.lane + 32 * j;
-                if (i < c.G) {
-                    v5[j] = ld_slot(buf + i);
-                    if ((unsigned long long)__double_as_longlong(v5[j].x) == SENTINEL ||
-                        (unsigned long long)__double_as_longlong(v5[j].y) == SENTINEL)
-                        done = false;
-                } else {
-                    v5[j] = make_double2(0.0, 0.0);
+        __syncthreads();
+        if (c.wid == 0) {
+            unsigned long long* buf = P.bar + (c.epoch & 1u) * 4;
+            if (c.lane < 4) {
+                long long sum = 0;
+                int any = 0;
+                for (int w = 0; w < c.nw; ++w) {
+                    const int v = ctl->limb[w][c.lane];
+                    sum += (c.lane & 1) ? (long long)(unsigned)v : (long long)v;
+                    any |= ctl->ovf[w];
                 }
+                unsigned long long contrib = (1ull << 48) + (unsigned long long)(sum + LIMB_BIAS);
+                if (c.lane == 0 && any) contrib += (1ull << 56);
+                red_add_u64(buf + c.lane, contrib);
             }
-            done = __all_sync(0xffffffffu, done);
-            if (!done && ((++spins & 0x3ffu) == 0)) {
-                // watchdog: ~4M polls (seconds) or a peer's abort => bail out instead of hanging the GPU
-                int ab = *(volatile int*)P.status;
-                if (ab || spins > (1u << 22)) {
-                    if (c.lane == 0) {
-                        atomicExch(P.status, 1);
-                        atomicCAS(P.status + 1, 0, 100 + (int)(c.epoch & 0xffff));
+            if (c.prof) t1 = clock64();
+            if (c.lane == 0) {
+                unsigned long long* prev = ctl->prev[c.epoch & 1u];
+                unsigned long long d[4];
+                unsigned spins = 0;
+                for (;;) {
+                    bool done = true;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        d[j] = ld_u64_volatile(buf + j) - prev[j];
+                        if ((int)((d[j] >> 48) & 0xFF) != c.G) done = false;
                     }
-                    ctl->abort = 1;
-                    done = true;
+                    if (done) break;
+                    if ((++spins & 0xffu) == 0) {
+                        // watchdog: a peer's abort or ~seconds of polling => leave instead of hanging the GPU
+                        if (*(volatile int*)P.status || spins > (1u << 23)) {
+                            atomicExch(P.status, 1);
+                            atomicCAS(P.status + 1, 0, 100 + (int)(c.epoch & 0xffff));
+                            ctl->abort = 1;
+                            break;
+                        }
+                    }
                 }
+                if (c.prof) t2 = clock64();
+                long long L[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    prev[j] += d[j];
+                    L[j] = (long long)(d[j] & ((1ull << 48) - 1)) - (long long)c.G * LIMB_BIAS;
+                }
+                const int novf = (int)((d[0] >> 56) & 0xFF);
+                const __int128 T = ((__int128)L[0] << 72) + ((__int128)L[1] << 48) + ((__int128)L[2] << 24) + (__int128)L[3];
+                const float res = i128_to_float_rn(T, S - 90);
+                int code = 0, newS = S;
+                if (novf) {
+                    code = 1; newS = min(S + 24, S_MAX);
+                    if (S >= S_MAX) code = 0; // Inf/NaN terms: give up, the result is garbage anyway
+                } else if (T == 0) {
+                    if (!grown && S > S_MIN) { code = 1; newS = max(S - 64, S_MIN); }
+                } else {
+                    const int e = ilogb_f32(fabsf(res));
+                    if (!grown && e < S - 24 && S > S_MIN) { code = 1; newS = max(e + 4, S_MIN); }
+                    else newS = max(min(e + 4, S_MAX), S_MIN);
+                }
+                ctl->bc = res;
+                ctl->bc_code = code;
+                ctl->bc_S = newS;
             }
-        } while (!done);
-        if (c.prof) t2 = clock64();
-        __threadfence();
-        // exact fold of the G partials, identical in every CTA
-        double mm = 0.0;
-#pragma unroll
-        for (int j = 0; j < 5; ++j) mm = fmax(mm, fabs(v5[j].x));
-        mm = warp_max(mm);
-        const double B2 = bin_base(ilogb_f64(mm) + 8 + 2); // <= 160 partials
-        double H = 0.0, L = 0.0;
-#pragma unroll
-        for (int j = 0; j < 5; ++j) {
-            double hi, lo;
-            bin_split(B2, v5[j].x, hi, lo);
-            H = __dadd_rn(H, hi);
-            L = __dadd_rn(L, __dadd_rn(lo, v5[j].y));
         }
-        H = warp_sum(H);
-        L = warp_sum(L);
-        if (c.lane == 0) ctl->bc = (float)__dadd_rn(H, L);
+        __syncthreads();
+        if (c.prof && threadIdx.x == 0) {
+            const long long t3 = clock64();
+            c.acc[0] += (unsigned long long)(t1 - t0);
+            c.acc[1] += (unsigned long long)(t2 - t1);
+            c.acc[2] += (unsigned long long)(t3 - t2);
+        }
+        ++c.epoch;
+        if (ctl->abort) { ok = false; return 0.f; }
+        const int code = ctl->bc_code;
+        const int newS = ctl->bc_S;
+        const float res = ctl->bc;
+        if (newS > S) grown = true;
+        S = newS;
+        if (code == 0) return res;
+        __syncthreads(); // everybody has read the broadcast before the redo overwrites it
     }
-    __syncthreads();
-    if (c.prof && threadIdx.x == 0) {
-        const long long t3 = clock64();
-        c.acc[0] += (unsigned long long)(t1 - t0);
-        c.acc[1] += (unsigned long long)(t2 - t1);
-        c.acc[2] += (unsigned long long)(t3 - t2);
-    }
-    ++c.epoch;
-    ok = (ctl->abort == 0);
-    return ctl->bc;
 }
 
 // ---- halo publication / reception ----------------------------------------------------------------
-// Entry layout in the outbox: two float4 per boundary pixel.
-__device__ __forceinline__ void publish_rowcol(const StripCtx& s, int lane, int k, bool top, bool bottom, bool left,
-                                               bool right, float4 v0, float4 v1, bool two)
+// An outbox entry is 3 x uint4 = six (float, tag) words: (z0, z1 | z2, p0 | p1, pa) or (X0, X1 | c, s | -, -).
+__device__ __forceinline__ void put_entry(uint4* e, unsigned tag, float a, float b, float c2, float d, float e2, float f,
+                                          bool three)
 {
-    // called once per row k (fully unrolled); v0/v1 are the entry of pixel (lane, k)
-    if (top && k == 0) {
-        s.outbox[2 * lane] = v0;
-        if (two) s.outbox[2 * lane + 1] = v1;
-    }
-    if (bottom && k == RS_STRIP_H - 1) {
-        s.outbox[2 * (32 + lane)] = v0;
-        if (two) s.outbox[2 * (32 + lane) + 1] = v1;
-    }
-    if (left && lane == 0) {
-        s.outbox[2 * (64 + k)] = v0;
-        if (two) s.outbox[2 * (64 + k) + 1] = v1;
-    }
-    if (right && lane == 31) {
-        s.outbox[2 * (72 + k)] = v0;
-        if (two) s.outbox[2 * (72 + k) + 1] = v1;
+    st_u4(e, make_uint4(__float_as_uint(a), tag, __float_as_uint(b), tag));
+    st_u4(e + 1, make_uint4(__float_as_uint(c2), tag, __float_as_uint(d), tag));
+    if (three) st_u4(e + 2, make_uint4(__float_as_uint(e2), tag, __float_as_uint(f), tag));
+}
+
+// called once per row k (fully unrolled) with the entry of pixel (lane, k)
+__device__ __forceinline__ void publish_rowcol(const StripCtx& s, int lane, int k, unsigned tag, float a, float b, float c2,
+                                               float d, float e2, float f, bool three)
+{
+    if (s.rem[0] >= 0 && k == 0) put_entry(s.outbox + 3 * lane, tag, a, b, c2, d, e2, f, three);
+    if (s.rem[1] >= 0 && k == RS_STRIP_H - 1) put_entry(s.outbox + 3 * (32 + lane), tag, a, b, c2, d, e2, f, three);
+    if (s.rem[2] >= 0 && lane == 0) put_entry(s.outbox + 3 * (64 + k), tag, a, b, c2, d, e2, f, three);
+    if (s.rem[3] >= 0 && lane == 31) put_entry(s.outbox + 3 * (72 + k), tag, a, b, c2, d, e2, f, three);
+}
+
+// spin until the entry carries `tag` (normally the first read succeeds: it was published a barrier ago)
+__device__ __forceinline__ bool get_entry(const ResProb& P, Ctl* ctl, int nslot, int e, unsigned tag, bool three, float v[6])
+{
+    const uint4* p = P.outbox + ((size_t)nslot * RS_OUTBOX_ENTRIES + e) * 3;
+    unsigned spins = 0;
+    for (;;) {
+        const uint4 w0 = ld_u4_volatile(p), w1 = ld_u4_volatile(p + 1);
+        uint4 w2 = make_uint4(0u, tag, 0u, tag);
+        if (three) w2 = ld_u4_volatile(p + 2);
+        if (w0.y == tag && w0.w == tag && w1.y == tag && w1.w == tag && w2.y == tag && w2.w == tag) {
+            v[0] = __uint_as_float(w0.x); v[1] = __uint_as_float(w0.z);
+            v[2] = __uint_as_float(w1.x); v[3] = __uint_as_float(w1.z);
+            v[4] = __uint_as_float(w2.x); v[5] = __uint_as_float(w2.z);
+            return true;
+        }
+        if ((++spins & 0xffu) == 0 && (*(volatile int*)P.status || spins > (1u << 22))) {
+            atomicExch(P.status, 1);
+            atomicCAS(P.status + 1, 0, 200);
+            ctl->abort = 1;
+            v[0] = v[1] = v[2] = v[3] = v[4] = v[5] = 0.f;
+            return false;
+        }
     }
 }
 
-__device__ __forceinline__ const float4* remote_entry(const ResProb& P, int nslot, int e)
+// ring <- neighbours' (X_x, X_y, cos, sin).  Up/down rows: every lane; left column: lanes 0..7; right: 8..15.
+__device__ __forceinline__ void recv_x(const ResProb& P, Ctl* ctl, const StripCtx& s, int lane, unsigned tag)
 {
-    return P.outbox + ((size_t)nslot * RS_OUTBOX_ENTRIES + e) * 2;
-}
-
-// ring <- neighbours' (X_x, X_y, cos, sin)
-__device__ __forceinline__ void recv_x(const ResProb& P, const StripCtx& s, int lane)
-{
-    if (s.rem[0] >= 0) { // up neighbour: its bottom row
-        float4 v = ldcg4(remote_entry(P, s.rem[0], 32 + lane));
-        s.own[0 * TW + lane + 1] = v;
-        s.rcs[lane] = make_float2(v.z, v.w);
+    float v[6];
+    if (s.rem[0] >= 0) {
+        get_entry(P, ctl, s.rem[0], 32 + lane, tag, false, v);
+        s.own[0 * TW + lane + 1] = make_float4(v[0], v[1], v[2], v[3]);
+        s.rcs[lane] = make_float2(v[2], v[3]);
     }
-    if (s.rem[1] >= 0) { // down neighbour: its top row
-        float4 v = ldcg4(remote_entry(P, s.rem[1], lane));
-        s.own[(TH - 1) * TW + lane + 1] = v;
-        s.rcs[32 + lane] = make_float2(v.z, v.w);
+    if (s.rem[1] >= 0) {
+        get_entry(P, ctl, s.rem[1], lane, tag, false, v);
+        s.own[(TH - 1) * TW + lane + 1] = make_float4(v[0], v[1], v[2], v[3]);
+        s.rcs[32 + lane] = make_float2(v[2], v[3]);
     }
-    if (s.rem[2] >= 0 && lane < 8) { // left neighbour: its right column
-        float4 v = ldcg4(remote_entry(P, s.rem[2], 72 + lane));
-        s.own[(lane + 1) * TW + 0] = v;
-        s.rcs[64 + lane] = make_float2(v.z, v.w);
+    if (s.rem[2] >= 0 && lane < 8) {
+        get_entry(P, ctl, s.rem[2], 72 + lane, tag, false, v);
+        s.own[(lane + 1) * TW + 0] = make_float4(v[0], v[1], v[2], v[3]);
+        s.rcs[64 + lane] = make_float2(v[2], v[3]);
     }
-    if (s.rem[3] >= 0 && lane >= 8 && lane < 16) { // right neighbour: its left column
-        float4 v = ldcg4(remote_entry(P, s.rem[3], 64 + lane - 8));
-        s.own[(lane - 8 + 1) * TW + TW - 1] = v;
-        s.rcs[72 + lane - 8] = make_float2(v.z, v.w);
+    if (s.rem[3] >= 0 && lane >= 8 && lane < 16) {
+        get_entry(P, ctl, s.rem[3], 64 + lane - 8, tag, false, v);
+        s.own[(lane - 8 + 1) * TW + TW - 1] = make_float4(v[0], v[1], v[2], v[3]);
+        s.rcs[72 + lane - 8] = make_float2(v[2], v[3]);
     }
 }
 
-__device__ __forceinline__ float4 p_entry_from(const float4 v0, const float4 v1, float beta, float2 cs)
+__device__ __forceinline__ float4 p_entry_from(const float v[6], float beta, float2 cs)
 {
-    // v0 = (z0, z1, z2, p0_old), v1 = (p1_old, pa_old, -, -); cs = (cos, sin)
-    const float p0 = fmaf(beta, v0.w, v0.x);
-    const float p1 = fmaf(beta, v1.x, v0.y);
-    const float pa = fmaf(beta, v1.y, v0.z);
+    // v = (z0, z1, z2, p0_old, p1_old, pa_old); cs = (cos, sin)
+    const float p0 = fmaf(beta, v[3], v[0]);
+    const float p1 = fmaf(beta, v[4], v[1]);
+    const float pa = fmaf(beta, v[5], v[2]);
     return make_float4(p0, p1, cs.y * pa, cs.x * pa);
 }
 
 // ring <- neighbours' new direction, computed from their published (z, p_old)
-__device__ __forceinline__ void recv_p(const ResProb& P, const StripCtx& s, int lane, float beta)
+__device__ __forceinline__ void recv_p(const ResProb& P, Ctl* ctl, const StripCtx& s, int lane, unsigned tag, float beta)
 {
+    float v[6];
     if (s.rem[0] >= 0) {
-        const float4* e = remote_entry(P, s.rem[0], 32 + lane);
-        s.own[0 * TW + lane + 1] = p_entry_from(ldcg4(e), ldcg4(e + 1), beta, s.rcs[lane]);
+        get_entry(P, ctl, s.rem[0], 32 + lane, tag, true, v);
+        s.own[0 * TW + lane + 1] = p_entry_from(v, beta, s.rcs[lane]);
     }
     if (s.rem[1] >= 0) {
-        const float4* e = remote_entry(P, s.rem[1], lane);
-        s.own[(TH - 1) * TW + lane + 1] = p_entry_from(ldcg4(e), ldcg4(e + 1), beta, s.rcs[32 + lane]);
+        get_entry(P, ctl, s.rem[1], lane, tag, true, v);
+        s.own[(TH - 1) * TW + lane + 1] = p_entry_from(v, beta, s.rcs[32 + lane]);
     }
     if (s.rem[2] >= 0 && lane < 8) {
-        const float4* e = remote_entry(P, s.rem[2], 72 + lane);
-        s.own[(lane + 1) * TW + 0] = p_entry_from(ldcg4(e), ldcg4(e + 1), beta, s.rcs[64 + lane]);
+        get_entry(P, ctl, s.rem[2], 72 + lane, tag, true, v);
+        s.own[(lane + 1) * TW + 0] = p_entry_from(v, beta, s.rcs[64 + lane]);
     }
     if (s.rem[3] >= 0 && lane >= 8 && lane < 16) {
-        const float4* e = remote_entry(P, s.rem[3], 64 + lane - 8);
-        s.own[(lane - 8 + 1) * TW + TW - 1] = p_entry_from(ldcg4(e), ldcg4(e + 1), beta, s.rcs[72 + lane - 8]);
+        get_entry(P, ctl, s.rem[3], 64 + lane - 8, tag, true, v);
+        s.own[(lane - 8 + 1) * TW + TW - 1] = p_entry_from(v, beta, s.rcs[72 + lane - 8]);
     }
 }
 
@@ -270,6 +363,12 @@ __device__ __forceinline__ float2 constraint_of(const ResProb& P, size_t i, int 
         c.y = om * (float)y + alpha * c.y;
     }
     return c;
+}
+
+// flags of pixel k out of the two packed words
+__device__ __forceinline__ unsigned flag_of(unsigned flo, unsigned fhi, int k)
+{
+    return ((k < 4 ? flo : fhi) >> (8 * (k & 3))) & 0xffu;
 }
 
 // =====================================================================================================
@@ -294,6 +393,7 @@ __global__ void __launch_bounds__(RS_THREADS_MAX, 1) k_resident(const ResProb* _
     const float wr = P.wr, wf = P.wf, wr2 = P.wr2, wf2 = P.wf2;
 
     if (threadIdx.x == 0) ctl.abort = 0;
+    if (threadIdx.x < 8) ctl.prev[threadIdx.x >> 2][threadIdx.x & 3] = 0ull; // the host zeroes P.bar before the launch
     if (threadIdx.x < 10) { // preconditioner values by (number of valid neighbours, fit)
         const int nv = threadIdx.x % 5, fit = threadIdx.x / 5;
         float DX = (wr2 + wr2) * (float)nv;
@@ -306,9 +406,10 @@ __global__ void __launch_bounds__(RS_THREADS_MAX, 1) k_resident(const ResProb* _
     const int n = P.n_strips;
     const int s_begin = (int)(((long long)c.cta * n) / c.G), s_end = (int)(((long long)(c.cta + 1) * n) / c.G);
     StripCtx s;
-    s.slot = s_begin + wid;
-    s.has = s.slot < s_end;
+    const int slot = s_begin + wid;
+    s.has = slot < s_end;
     s.own = &S[wid].T[0][0];
+    s.D = &S[wid].D[0][0][lane];
     s.rcs = S[wid].rcs;
     s.up_row = s.own + 0 * TW + 1;
     s.down_row = s.own + (TH - 1) * TW + 1;
@@ -318,9 +419,9 @@ __global__ void __launch_bounds__(RS_THREADS_MAX, 1) k_resident(const ResProb* _
     s.outbox = nullptr;
     int sx = 0, sy = 0;
     if (s.has) {
-        const int2 xy = P.strip_xy[s.slot];
+        const int2 xy = P.strip_xy[slot];
         sx = xy.x; sy = xy.y;
-        s.outbox = P.outbox + (size_t)s.slot * RS_OUTBOX_ENTRIES * 2;
+        s.outbox = P.outbox + (size_t)slot * RS_OUTBOX_ENTRIES * 3;
         const int nu = (sy > 0) ? P.slot_of_strip[(sy - 1) * P.SX + sx] : -1;
         const int nd = (sy + 1 < P.SY) ? P.slot_of_strip[(sy + 1) * P.SX + sx] : -1;
         const int nl = (sx > 0) ? P.slot_of_strip[sy * P.SX + sx - 1] : -1;
@@ -332,10 +433,9 @@ __global__ void __launch_bounds__(RS_THREADS_MAX, 1) k_resident(const ResProb* _
     }
     s.x = sx * RS_STRIP_W + lane;
     s.y0 = sy * RS_STRIP_H;
-    const bool pub_top = s.rem[0] >= 0, pub_bot = s.rem[1] >= 0, pub_left = s.rem[2] >= 0, pub_right = s.rem[3] >= 0;
 
     // ---- flags from the mask (constant for the whole launch except the fit bit) ----
-    unsigned fl[RS_STRIP_H];
+    unsigned flo = 0, fhi = 0;
 #pragma unroll
     for (int k = 0; k < RS_STRIP_H; ++k) {
         unsigned f = 0;
@@ -350,14 +450,17 @@ __global__ void __launch_bounds__(RS_THREADS_MAX, 1) k_resident(const ResProb* _
                 if (y > 0 && P.M[i - W] == 0.0f) f |= 8u;
             }
         }
-        fl[k] = f;
+        if (k < 4) flo |= f << (8 * k); else fhi |= f << (8 * (k - 4));
     }
 
     // registers that live across the PCG loop
     float r0[RS_STRIP_H], r1[RS_STRIP_H], r2[RS_STRIP_H];
-    float d0[RS_STRIP_H], d1[RS_STRIP_H], d2[RS_STRIP_H];
     float pa[RS_STRIP_H], cc[RS_STRIP_H], ss[RS_STRIP_H];
     float q0[RS_STRIP_H], q1[RS_STRIP_H], qa[RS_STRIP_H];
+#pragma unroll
+    for (int k = 0; k < RS_STRIP_H; ++k) { r0[k] = r1[k] = r2[k] = pa[k] = 0.f; cc[k] = 1.f; ss[k] = 0.f; q0[k] = q1[k] = qa[k] = 0.f; }
+    int S_cost = 0, S_num = 0, S_den = 0, S_bnum = 0, S_sync = S_MIN;
+    unsigned seq = 0; // publication sequence number == halo tag
     bool ok = true;
     __syncthreads();
 
@@ -365,10 +468,11 @@ __global__ void __launch_bounds__(RS_THREADS_MAX, 1) k_resident(const ResProb* _
         const float alpha_c = (float)(t + 1) / (float)P.nCont; // CombinedSolver.h:199-201
         for (int g = 0; g <= P.nGN && ok; ++g) {
             // ======== prologue: tile <- (X, cos, sin), ring exchange, cost of the current state ========
+            ++seq;
 #pragma unroll
             for (int k = 0; k < RS_STRIP_H; ++k) {
                 float4 e = make_float4(0.f, 0.f, 1.f, 0.f);
-                if (fl[k] & FLAG_ACTIVE) {
+                if (flag_of(flo, fhi, k) & FLAG_ACTIVE) {
                     const size_t i = (size_t)(s.y0 + k) * W + s.x;
                     const float2 X = P.X[i];
                     float sn, cs;
@@ -377,11 +481,11 @@ __global__ void __launch_bounds__(RS_THREADS_MAX, 1) k_resident(const ResProb* _
                     e = make_float4(X.x, X.y, cs, sn);
                 }
                 s.own[(k + 1) * TW + lane + 1] = e;
-                if (s.has) publish_rowcol(s, lane, k, pub_top, pub_bot, pub_left, pub_right, e, e, false);
+                if (s.has) publish_rowcol(s, lane, k, seq, e.x, e.y, e.z, e.w, 0.f, 0.f, false);
             }
-            (void)grid_sum(c, 0.f, 0.f, ok);
+            (void)grid_sum(c, 0.f, 0.f, S_sync, ok);
             if (!ok) break;
-            if (s.has) recv_x(P, s, lane);
+            if (s.has) recv_x(P, &ctl, s, lane, seq);
             __syncthreads();
             {
                 float gs0 = 0.f, gs1 = 0.f;
@@ -389,7 +493,7 @@ __global__ void __launch_bounds__(RS_THREADS_MAX, 1) k_resident(const ResProb* _
 #pragma unroll
                 for (int k = 0; k < RS_STRIP_H; ++k) {
                     const float4 dn = (k < RS_STRIP_H - 1) ? s.own[(k + 2) * TW + lane + 1] : s.down_row[lane];
-                    const unsigned f = fl[k];
+                    const unsigned f = flag_of(flo, fhi, k);
                     if (f & FLAG_ACTIVE) {
                         const float4 lf = s.lptr[k * TW], rt = s.rptr[k * TW];
                         float acc = 0.f;
@@ -405,7 +509,7 @@ __global__ void __launch_bounds__(RS_THREADS_MAX, 1) k_resident(const ResProb* _
                     up = cur;
                     cur = dn;
                 }
-                const float tot = grid_sum(c, gs0, gs1, ok);
+                const float tot = grid_sum(c, gs0, gs1, S_cost, ok);
                 if (!ok) break;
                 if (c.cta == 0 && threadIdx.x == 0) P.costs[(size_t)t * (P.nGN + 1) + g] = 0.5f * tot;
             }
@@ -416,13 +520,16 @@ __global__ void __launch_bounds__(RS_THREADS_MAX, 1) k_resident(const ResProb* _
             {
                 float gs0 = 0.f, gs1 = 0.f;
                 float4 up = s.up_row[lane], cur = s.own[1 * TW + lane + 1];
+                unsigned nflo = 0, nfhi = 0;
 #pragma unroll
                 for (int k = 0; k < RS_STRIP_H; ++k) {
                     const float4 dn = (k < RS_STRIP_H - 1) ? s.own[(k + 2) * TW + lane + 1] : s.down_row[lane];
-                    unsigned f = fl[k] & ~FLAG_FIT;
+                    unsigned f = flag_of(flo, fhi, k) & ~FLAG_FIT;
                     r0[k] = r1[k] = r2[k] = 0.f;
-                    d0[k] = d1[k] = d2[k] = 0.f;
                     pa[k] = 0.f;
+                    s.D[(0 * RS_STRIP_H + k) * 32] = 0.f;
+                    s.D[(1 * RS_STRIP_H + k) * 32] = 0.f;
+                    s.D[(2 * RS_STRIP_H + k) * 32] = 0.f;
                     if (f & FLAG_ACTIVE) {
                         const float4 lf = s.lptr[k * TW], rt = s.rptr[k * TW];
                         JtfAcc a;
@@ -443,105 +550,103 @@ __global__ void __launch_bounds__(RS_THREADS_MAX, 1) k_resident(const ResProb* _
                         const float term = dot3(r0[k], r1[k], r2[k], z0, z1, z2);
                         if (k < 4) gs0 = gs0 + term; else gs1 = gs1 + term;
                     }
-                    fl[k] = f;
+                    if (k < 4) nflo |= f << (8 * k); else nfhi |= f << (8 * (k - 4));
                     up = cur;
                     cur = dn;
                 }
+                flo = nflo; fhi = nfhi;
                 // publish (z = p_0, p_old = 0) of the boundary so that neighbours rebuild p_0 with beta = 0
+                ++seq;
 #pragma unroll
                 for (int k = 0; k < RS_STRIP_H; ++k) {
                     if (s.has) {
-                        const unsigned f = fl[k];
-                        const int ix = __popc(f & 15u) + ((f & FLAG_FIT) ? 5 : 0);
-                        const float pX = ctl.preX[ix], pA = ctl.preA[__popc(f & 15u)];
-                        const float4 v0 = (f & FLAG_ACTIVE) ? make_float4(pX * r0[k], pX * r1[k], pA * r2[k], 0.f)
-                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
-                        publish_rowcol(s, lane, k, pub_top, pub_bot, pub_left, pub_right, v0,
-                                       make_float4(0.f, 0.f, 0.f, 0.f), true);
+                        const unsigned f = flag_of(flo, fhi, k);
+                        const int nv = __popc(f & 15u);
+                        const float pX = ctl.preX[nv + ((f & FLAG_FIT) ? 5 : 0)], pA = ctl.preA[nv];
+                        publish_rowcol(s, lane, k, seq, pX * r0[k], pX * r1[k], pA * r2[k], 0.f, 0.f, 0.f, true);
                     }
                 }
-                num = grid_sum(c, gs0, gs1, ok); // solverGPUGaussNewton.t:395 scanAlphaNumerator
+                num = grid_sum(c, gs0, gs1, S_num, ok); // solverGPUGaussNewton.t:395 scanAlphaNumerator
                 if (!ok) break;
                 // p_0 = z_0 into the tile (all warps are past their J^T F reads: grid_sum synchronised)
 #pragma unroll
                 for (int k = 0; k < RS_STRIP_H; ++k) {
-                    const unsigned f = fl[k];
-                    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (f & FLAG_ACTIVE) {
-                        const int ix = __popc(f & 15u) + ((f & FLAG_FIT) ? 5 : 0);
-                        const float pX = ctl.preX[ix], pA = ctl.preA[__popc(f & 15u)];
-                        const float p0 = pX * r0[k], p1 = pX * r1[k];
-                        pa[k] = pA * r2[k];
-                        e = make_float4(p0, p1, ss[k] * pa[k], cc[k] * pa[k]);
-                    }
-                    s.own[(k + 1) * TW + lane + 1] = e;
+                    const unsigned f = flag_of(flo, fhi, k);
+                    const int nv = __popc(f & 15u);
+                    const float pX = ctl.preX[nv + ((f & FLAG_FIT) ? 5 : 0)], pA = ctl.preA[nv];
+                    const float p0 = pX * r0[k], p1 = pX * r1[k];
+                    pa[k] = pA * r2[k];
+                    s.own[(k + 1) * TW + lane + 1] = make_float4(p0, p1, ss[k] * pa[k], cc[k] * pa[k]);
                 }
-                if (s.has) recv_p(P, s, lane, 0.0f);
+                if (s.has) recv_p(P, &ctl, s, lane, seq, 0.0f);
                 __syncthreads();
             }
 
             // ======== PCG iterations ========
             RS_TICK(3);
             for (int it = 0; it < P.nPCG; ++it) {
-                // ---- PCGStep1: q = J^T J p, den = sum p.q ----
+                // ---- PCGStep1: q = J^T J p, den = sum p.q.  Branch-free: an invalid neighbour is replaced by
+                // (own p_x, own p_y, 0, 0), which contributes exact zeros; inactive pixels hold zeros throughout.
                 float gs0 = 0.f, gs1 = 0.f;
                 {
                     float4 up = s.up_row[lane], cur = s.own[1 * TW + lane + 1];
 #pragma unroll
                     for (int k = 0; k < RS_STRIP_H; ++k) {
                         const float4 dn = (k < RS_STRIP_H - 1) ? s.own[(k + 2) * TW + lane + 1] : s.down_row[lane];
-                        const unsigned f = fl[k];
-                        q0[k] = q1[k] = qa[k] = 0.f;
-                        if (f & FLAG_ACTIVE) {
-                            const float4 lf = s.lptr[k * TW], rt = s.rptr[k * TW];
-                            JtjAcc a;
-                            jtj_zero(a);
-                            if (f & 1u) jtj_nb<0>(a, cur.x, cur.y, rt);
-                            if (f & 2u) jtj_nb<1>(a, cur.x, cur.y, lf);
-                            if (f & 4u) jtj_nb<2>(a, cur.x, cur.y, dn);
-                            if (f & 8u) jtj_nb<3>(a, cur.x, cur.y, up);
-                            jtj_finish(a, cc[k], ss[k], cur.x, cur.y, pa[k], (f & FLAG_FIT) != 0, wr2, wf2, q0[k], q1[k],
-                                       qa[k]);
-                            const float term = dot3(cur.x, cur.y, pa[k], q0[k], q1[k], qa[k]);
-                            if (k < 4) gs0 = gs0 + term; else gs1 = gs1 + term;
-                        }
+                        float4 lf = s.lptr[k * TW], rt = s.rptr[k * TW];
+                        const unsigned f = flag_of(flo, fhi, k);
+                        const bool v0 = (f & 1u) != 0, v1 = (f & 2u) != 0, v2 = (f & 4u) != 0, v3 = (f & 8u) != 0;
+                        rt.x = v0 ? rt.x : cur.x; rt.y = v0 ? rt.y : cur.y; rt.z = v0 ? rt.z : 0.f; rt.w = v0 ? rt.w : 0.f;
+                        lf.x = v1 ? lf.x : cur.x; lf.y = v1 ? lf.y : cur.y; lf.z = v1 ? lf.z : 0.f; lf.w = v1 ? lf.w : 0.f;
+                        const float4 dnn = make_float4(v2 ? dn.x : cur.x, v2 ? dn.y : cur.y, v2 ? dn.z : 0.f, v2 ? dn.w : 0.f);
+                        const float4 upp = make_float4(v3 ? up.x : cur.x, v3 ? up.y : cur.y, v3 ? up.z : 0.f, v3 ? up.w : 0.f);
+                        JtjAcc a;
+                        jtj_zero(a);
+                        jtj_nb<0>(a, cur.x, cur.y, rt);
+                        jtj_nb<1>(a, cur.x, cur.y, lf);
+                        jtj_nb<2>(a, cur.x, cur.y, dnn);
+                        jtj_nb<3>(a, cur.x, cur.y, upp);
+                        // sums of d over the VALID neighbours only (jtj_nb counted all four)
+                        a.Sx = (v1 ? 1.0f : 0.0f) - (v0 ? 1.0f : 0.0f);
+                        a.Sy = (v3 ? 1.0f : 0.0f) - (v2 ? 1.0f : 0.0f);
+                        a.nd = (float)__popc(f & 15u);
+                        jtj_finish(a, cc[k], ss[k], cur.x, cur.y, pa[k], (f & FLAG_FIT) != 0, wr2, wf2, q0[k], q1[k], qa[k]);
+                        const float term = dot3(cur.x, cur.y, pa[k], q0[k], q1[k], qa[k]);
+                        if (k < 4) gs0 = gs0 + term; else gs1 = gs1 + term;
                         up = cur;
                         cur = dn;
                     }
                 }
                 RS_TICK(0);
-                const float den = grid_sum(c, gs0, gs1, ok);
+                const float den = grid_sum(c, gs0, gs1, S_den, ok);
                 RS_TOCK();
                 if (!ok) break;
                 const float alpha = (den > 0.0f) ? num / den : 0.0f; // :456-459
 
                 // ---- PCGStep2: delta += alpha p, r -= alpha q, z = pre r, bnum = sum z.r ----
                 gs0 = 0.f; gs1 = 0.f;
+                const bool pub = s.has && (it + 1 < P.nPCG);
+                ++seq;
 #pragma unroll
                 for (int k = 0; k < RS_STRIP_H; ++k) {
-                    const unsigned f = fl[k];
-                    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-                    if (f & FLAG_ACTIVE) {
-                        const float4 e = s.own[(k + 1) * TW + lane + 1];
-                        d0[k] = fmaf(alpha, e.x, d0[k]);
-                        d1[k] = fmaf(alpha, e.y, d1[k]);
-                        d2[k] = fmaf(alpha, pa[k], d2[k]);
-                        r0[k] = fmaf(-alpha, q0[k], r0[k]);
-                        r1[k] = fmaf(-alpha, q1[k], r1[k]);
-                        r2[k] = fmaf(-alpha, qa[k], r2[k]);
-                        const int ix = __popc(f & 15u) + ((f & FLAG_FIT) ? 5 : 0);
-                        const float pX = ctl.preX[ix], pA = ctl.preA[__popc(f & 15u)];
-                        const float z0 = pX * r0[k], z1 = pX * r1[k], z2 = pA * r2[k];
-                        const float term = dot3(z0, z1, z2, r0[k], r1[k], r2[k]);
-                        if (k < 4) gs0 = gs0 + term; else gs1 = gs1 + term;
-                        v0 = make_float4(z0, z1, z2, e.x);
-                        v1 = make_float4(e.y, pa[k], 0.f, 0.f);
-                    }
-                    if (s.has && it + 1 < P.nPCG)
-                        publish_rowcol(s, lane, k, pub_top, pub_bot, pub_left, pub_right, v0, v1, true);
+                    const unsigned f = flag_of(flo, fhi, k);
+                    const float4 e = s.own[(k + 1) * TW + lane + 1];
+                    float* Dk = s.D + k * 32;
+                    Dk[0 * RS_STRIP_H * 32] = fmaf(alpha, e.x, Dk[0 * RS_STRIP_H * 32]);
+                    Dk[1 * RS_STRIP_H * 32] = fmaf(alpha, e.y, Dk[1 * RS_STRIP_H * 32]);
+                    Dk[2 * RS_STRIP_H * 32] = fmaf(alpha, pa[k], Dk[2 * RS_STRIP_H * 32]);
+                    r0[k] = fmaf(-alpha, q0[k], r0[k]);
+                    r1[k] = fmaf(-alpha, q1[k], r1[k]);
+                    r2[k] = fmaf(-alpha, qa[k], r2[k]);
+                    const int nv = __popc(f & 15u);
+                    const float pX = ctl.preX[nv + ((f & FLAG_FIT) ? 5 : 0)], pA = ctl.preA[nv];
+                    const float z0 = pX * r0[k], z1 = pX * r1[k], z2 = pA * r2[k];
+                    const float term = dot3(z0, z1, z2, r0[k], r1[k], r2[k]);
+                    if (k < 4) gs0 = gs0 + term; else gs1 = gs1 + term;
+                    if (pub) publish_rowcol(s, lane, k, seq, z0, z1, z2, e.x, e.y, pa[k], true);
                 }
                 RS_TICK(1);
-                const float bnum = grid_sum(c, gs0, gs1, ok);
+                const float bnum = grid_sum(c, gs0, gs1, S_bnum, ok);
                 RS_TOCK();
                 if (!ok) break;
                 if (P.trace && c.cta == 0 && threadIdx.x == 0) {
@@ -555,18 +660,16 @@ __global__ void __launch_bounds__(RS_THREADS_MAX, 1) k_resident(const ResProb* _
                 // ---- PCGStep3: p = z + beta p (own pixels, then the remote ring) ----
 #pragma unroll
                 for (int k = 0; k < RS_STRIP_H; ++k) {
-                    const unsigned f = fl[k];
-                    if (f & FLAG_ACTIVE) {
-                        const float4 e = s.own[(k + 1) * TW + lane + 1];
-                        const int ix = __popc(f & 15u) + ((f & FLAG_FIT) ? 5 : 0);
-                        const float pX = ctl.preX[ix], pA = ctl.preA[__popc(f & 15u)];
-                        const float p0 = fmaf(beta, e.x, pX * r0[k]);
-                        const float p1 = fmaf(beta, e.y, pX * r1[k]);
-                        pa[k] = fmaf(beta, pa[k], pA * r2[k]);
-                        s.own[(k + 1) * TW + lane + 1] = make_float4(p0, p1, ss[k] * pa[k], cc[k] * pa[k]);
-                    }
+                    const unsigned f = flag_of(flo, fhi, k);
+                    const float4 e = s.own[(k + 1) * TW + lane + 1];
+                    const int nv = __popc(f & 15u);
+                    const float pX = ctl.preX[nv + ((f & FLAG_FIT) ? 5 : 0)], pA = ctl.preA[nv];
+                    const float p0 = fmaf(beta, e.x, pX * r0[k]);
+                    const float p1 = fmaf(beta, e.y, pX * r1[k]);
+                    pa[k] = fmaf(beta, pa[k], pA * r2[k]);
+                    s.own[(k + 1) * TW + lane + 1] = make_float4(p0, p1, ss[k] * pa[k], cc[k] * pa[k]);
                 }
-                if (s.has) recv_p(P, s, lane, beta);
+                if (s.has) recv_p(P, &ctl, s, lane, seq, beta);
                 __syncthreads();
                 RS_TICK(2);
             }
@@ -575,13 +678,13 @@ __global__ void __launch_bounds__(RS_THREADS_MAX, 1) k_resident(const ResProb* _
             // ======== PCGLinearUpdate ========
 #pragma unroll
             for (int k = 0; k < RS_STRIP_H; ++k) {
-                if (fl[k] & FLAG_ACTIVE) {
+                if (flag_of(flo, fhi, k) & FLAG_ACTIVE) {
                     const size_t i = (size_t)(s.y0 + k) * W + s.x;
                     float2 X = P.X[i];
-                    X.x = X.x + d0[k];
-                    X.y = X.y + d1[k];
+                    X.x = X.x + s.D[(0 * RS_STRIP_H + k) * 32];
+                    X.y = X.y + s.D[(1 * RS_STRIP_H + k) * 32];
                     P.X[i] = X;
-                    P.A[i] = P.A[i] + d2[k];
+                    P.A[i] = P.A[i] + s.D[(2 * RS_STRIP_H + k) * 32];
                 }
             }
             __syncthreads(); // tile entries (p) are overwritten by the next prologue
@@ -670,20 +773,19 @@ ResidentSolver::ResidentSolver(int maxW, int maxH) : maxW_(maxW), maxH_(maxH)
     ARAP_CUDA_OR_EXIT(cudaMalloc(&d_slot_of_strip_, ns * sizeof(int) + ns)); // + the active bytes
     ARAP_CUDA_OR_EXIT(cudaMalloc(&d_count_, sizeof(int)));
     outbox_cap_ = ns;
-    ARAP_CUDA_OR_EXIT(cudaMalloc(&d_outbox_, ns * RS_OUTBOX_ENTRIES * 2 * sizeof(float4)));
-    ARAP_CUDA_OR_EXIT(cudaMemset(d_outbox_, 0, ns * RS_OUTBOX_ENTRIES * 2 * sizeof(float4)));
-    ARAP_CUDA_OR_EXIT(cudaMalloc(&d_slots_, 3 * RS_MAX_CTAS * sizeof(double2)));
+    ARAP_CUDA_OR_EXIT(cudaMalloc(&d_outbox_, ns * RS_OUTBOX_ENTRIES * 3 * sizeof(uint4)));
+    ARAP_CUDA_OR_EXIT(cudaMalloc(&d_bar_, 8 * sizeof(unsigned long long)));
     ARAP_CUDA_OR_EXIT(cudaMalloc(&d_status_, 2 * sizeof(int)));
     ARAP_CUDA_OR_EXIT(cudaMemset(d_status_, 0, 2 * sizeof(int)));
     ARAP_CUDA_OR_EXIT(cudaMalloc(&d_prob_, sizeof(ResProb)));
     ARAP_CUDA_OR_EXIT(cudaFuncSetAttribute(k_resident, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)(RS_MAX_WARPS * sizeof(StripSmem))));
+                                           (int)((RS_THREADS_MAX / 32) * sizeof(StripSmem))));
 }
 
 ResidentSolver::~ResidentSolver()
 {
     cudaFree(d_strip_xy_); cudaFree(d_slot_of_strip_); cudaFree(d_count_); cudaFree(d_outbox_);
-    cudaFree(d_slots_); cudaFree(d_status_); cudaFree(d_prob_);
+    cudaFree(d_bar_); cudaFree(d_status_); cudaFree(d_prob_);
 }
 
 bool ResidentSolver::prepare(int W, int H, const float* d_M, cudaStream_t stream)
@@ -721,11 +823,14 @@ void ResidentSolver::enqueue(float2* X, float* A, const float2* C, int lerp_mode
     p.X = X; p.A = A; p.C = C; p.M = d_M_; p.lerp_mode = lerp_mode;
     p.wf = wf; p.wr = wr; p.wf2 = wf * wf; p.wr2 = wr * wr;
     p.strip_xy = d_strip_xy_; p.slot_of_strip = d_slot_of_strip_;
-    p.outbox = d_outbox_; p.slots = d_slots_; p.costs = d_costs; p.trace = d_trace; p.status = d_status_;
+    p.outbox = d_outbox_; p.bar = d_bar_; p.costs = d_costs; p.trace = d_trace; p.status = d_status_;
     p.nCont = nCont; p.nGN = nGN; p.nPCG = nPCG;
     p.prof = d_prof_;
     ARAP_CUDA_OR_EXIT(cudaMemcpyAsync(d_prob_, &p, sizeof(p), cudaMemcpyHostToDevice, stream));
-    ARAP_CUDA_OR_EXIT(cudaMemsetAsync(d_slots_, 0xFF, 3 * RS_MAX_CTAS * sizeof(double2), stream));
+    // barrier words start at zero; halo tags start at 1, so a zeroed outbox is "nothing published yet"
+    ARAP_CUDA_OR_EXIT(cudaMemsetAsync(d_bar_, 0, 8 * sizeof(unsigned long long), stream));
+    ARAP_CUDA_OR_EXIT(cudaMemsetAsync(d_outbox_, 0, (size_t)(n_strips_ > 0 ? n_strips_ : 1) * RS_OUTBOX_ENTRIES * 3 * sizeof(uint4),
+                                      stream));
     const int threads = NW_ * 32;
     const size_t smem = (size_t)NW_ * sizeof(StripSmem);
     int per_sm = 0;

@@ -11,8 +11,8 @@ namespace arapb200 {
 constexpr int RS_STRIP_W = 32;   // a strip is 32 x 8 pixels: one warp, lane = column, 8 rows per lane
 constexpr int RS_STRIP_H = 8;
 constexpr int RS_MAX_WARPS = 16; // strips per CTA
-constexpr int RS_MAX_CTAS = 160; // CTAs per problem (barrier slots are gathered 5 per lane)
-constexpr int RS_OUTBOX_ENTRIES = 80; // 32 top + 32 bottom + 8 left + 8 right, 32 bytes each
+constexpr int RS_MAX_CTAS = 160; // CTAs per problem (8-bit arrival count per barrier word)
+constexpr int RS_OUTBOX_ENTRIES = 80; // 32 top + 32 bottom + 8 left + 8 right, 48 bytes each
 
 // One problem as the kernel sees it (device memory, one per blockIdx.y)
 struct ResProb {
@@ -27,8 +27,8 @@ struct ResProb {
     float wf, wr, wf2, wr2;
     const int2* strip_xy;      // [n_strips] strip coordinates (sx, sy), column-major order
     const int* slot_of_strip;  // [SY*SX] -> slot or -1
-    float4* outbox;            // [n_strips][RS_OUTBOX_ENTRIES][2]
-    double2* slots;            // [3][G] barrier slots (Lamport-style, sentinel = all ones)
+    uint4* outbox;             // [n_strips][RS_OUTBOX_ENTRIES][3]: six (float, tag) words per boundary pixel
+    unsigned long long* bar;   // [2][4] barrier words: 16-bit arrival count | 48-bit fixed-point limb sum
     float* costs;              // [nCont][nGN+1]
     float* trace;              // optional [nCont*nGN][nPCG][3]
     int* status;               // [0] abort flag, [1] error code
@@ -67,9 +67,9 @@ private:
     int2* d_strip_xy_ = nullptr;
     int* d_slot_of_strip_ = nullptr;
     int* d_count_ = nullptr;
-    float4* d_outbox_ = nullptr;
+    uint4* d_outbox_ = nullptr;
     size_t outbox_cap_ = 0;
-    double2* d_slots_ = nullptr;
+    unsigned long long* d_bar_ = nullptr;
     int* d_status_ = nullptr;
     ResProb* d_prob_ = nullptr;
     int sm_count_ = 0;
