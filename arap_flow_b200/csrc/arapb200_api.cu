@@ -57,9 +57,10 @@ int warp_common(int W, int H, const float* pos_or_flow, bool is_flow, const uint
 
 struct arapb200_batch {
     int maxW, maxH, max_problems, nCont, nGN, nPCG, backend;
-    std::unique_ptr<DeformPipeline> pipe;
+    std::unique_ptr<BatchPipeline> pipe;
     std::vector<HostProblem> slots;
     std::vector<char> pending;
+    std::vector<HostProblem> todo;
     float ms[3] = {0, 0, 0};
     long long launches = 0;
 };
@@ -98,11 +99,11 @@ int arapb200_deform(int W, int H, const uint8_t* rgb, const uint8_t* mask_red, c
                     float* out_costs)
 {
     if (W <= 0 || H <= 0 || !rgb || !mask_red || (n_matches > 0 && !matches)) return 1;
-    DeformPipeline pipe(W, H, nCont, nGN, nPCG, backend);
+    BatchPipeline pipe(W, H, 1, nCont, nGN, nPCG, backend);
     HostProblem hp;
     hp.W = W; hp.H = H; hp.rgb = rgb; hp.mask_red = mask_red; hp.matches = matches; hp.n_matches = n_matches;
     hp.out_flow = out_flow; hp.out_rgb = out_rgb; hp.out_mask = out_mask; hp.out_costs = out_costs;
-    return pipe.run(hp);
+    return pipe.run(&hp, 1);
 }
 
 arapb200_batch* arapb200_batch_create(int maxW, int maxH, int max_problems, int nCont, int nGN, int nPCG, int backend)
@@ -111,7 +112,7 @@ arapb200_batch* arapb200_batch_create(int maxW, int maxH, int max_problems, int 
     arapb200_batch* b = new arapb200_batch;
     b->maxW = maxW; b->maxH = maxH; b->max_problems = max_problems;
     b->nCont = nCont; b->nGN = nGN; b->nPCG = nPCG; b->backend = backend;
-    b->pipe.reset(new DeformPipeline(maxW, maxH, nCont, nGN, nPCG, backend));
+    b->pipe.reset(new BatchPipeline(maxW, maxH, max_problems, nCont, nGN, nPCG, backend));
     b->slots.resize(max_problems);
     b->pending.assign(max_problems, 0);
     return b;
@@ -136,15 +137,17 @@ int arapb200_batch_run(arapb200_batch* b)
     if (!b) return 1;
     b->ms[0] = b->ms[1] = b->ms[2] = 0.f;
     const long long l0 = b->pipe->launches();
-    for (int s = 0; s < b->max_problems; ++s) {
-        if (!b->pending[s]) continue;
-        int rc = b->pipe->run(b->slots[s]);
-        b->pending[s] = 0;
-        if (rc) return rc;
-        b->ms[0] += b->pipe->last_ms_total();
-        b->ms[1] += b->pipe->last_ms_solve();
-        b->ms[2] += b->pipe->last_ms_warp();
-    }
+    b->todo.clear();
+    for (int s = 0; s < b->max_problems; ++s)
+        if (b->pending[s]) {
+            b->todo.push_back(b->slots[s]);
+            b->pending[s] = 0;
+        }
+    const int rc = b->pipe->run(b->todo.data(), (int)b->todo.size());
+    if (rc) return rc;
+    b->ms[0] = b->pipe->last_ms_total();
+    b->ms[1] = b->pipe->last_ms_solve();
+    b->ms[2] = b->pipe->last_ms_warp();
     b->launches = b->pipe->launches() - l0;
     return 0;
 }

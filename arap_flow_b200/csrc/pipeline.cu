@@ -110,128 +110,185 @@ void enqueue_target_image(int W, int H, const MatchRec* d_matches, int n, float2
     if (n > 0) k_scatter_t<<<(n + 255) / 256, 256, 0, stream>>>(d_matches, n, d_C);
 }
 
-DeformPipeline::DeformPipeline(int maxW, int maxH, int nCont, int nGN, int nPCG, int backend)
+BatchPipeline::BatchPipeline(int maxW, int maxH, int max_problems, int nCont, int nGN, int nPCG, int backend)
     : maxW_(maxW), maxH_(maxH), nCont_(nCont), nGN_(nGN), nPCG_(nPCG), backend_(backend)
 {
     const size_t N = (size_t)maxW * maxH;
     ARAP_CUDA_OR_EXIT(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     for (auto& e : ev_) ARAP_CUDA_OR_EXIT(cudaEventCreate(&e));
-    ARAP_CUDA_OR_EXIT(cudaMalloc(&d_X_, N * sizeof(float2)));
-    ARAP_CUDA_OR_EXIT(cudaMalloc(&d_U_, N * sizeof(float2)));
-    ARAP_CUDA_OR_EXIT(cudaMalloc(&d_C_, N * sizeof(float2)));
-    ARAP_CUDA_OR_EXIT(cudaMalloc(&d_flow_, N * sizeof(float2)));
-    ARAP_CUDA_OR_EXIT(cudaMalloc(&d_A_, N * sizeof(float)));
-    ARAP_CUDA_OR_EXIT(cudaMalloc(&d_M_, N * sizeof(float)));
-    ARAP_CUDA_OR_EXIT(cudaMalloc(&d_costs_, (size_t)nCont * (nGN + 1) * sizeof(float)));
-    ARAP_CUDA_OR_EXIT(cudaMalloc(&d_rgb_, 3 * N));
-    ARAP_CUDA_OR_EXIT(cudaMalloc(&d_mask_, N));
-    ARAP_CUDA_OR_EXIT(cudaMalloc(&d_orgb_, 3 * N));
-    ARAP_CUDA_OR_EXIT(cudaMalloc(&d_omask_, N));
-    ARAP_CUDA_OR_EXIT(cudaMalloc(&d_z_, N * sizeof(unsigned)));
-    h_in_bytes_ = 4 * N;
-    h_out_bytes_ = N * sizeof(float2) + 4 * N + (size_t)nCont * (nGN + 1) * sizeof(float);
-    ARAP_CUDA_OR_EXIT(cudaMallocHost(&h_in_, h_in_bytes_));
-    ARAP_CUDA_OR_EXIT(cudaMallocHost(&h_out_, h_out_bytes_));
+    dev_.resize(max_problems > 0 ? max_problems : 1);
+    const size_t cbytes = (size_t)nCont * (nGN + 1) * sizeof(float);
+    for (Dev& d : dev_) {
+        ARAP_CUDA_OR_EXIT(cudaMalloc(&d.X, N * sizeof(float2)));
+        ARAP_CUDA_OR_EXIT(cudaMalloc(&d.U, N * sizeof(float2)));
+        ARAP_CUDA_OR_EXIT(cudaMalloc(&d.C, N * sizeof(float2)));
+        ARAP_CUDA_OR_EXIT(cudaMalloc(&d.flow, N * sizeof(float2)));
+        ARAP_CUDA_OR_EXIT(cudaMalloc(&d.A, N * sizeof(float)));
+        ARAP_CUDA_OR_EXIT(cudaMalloc(&d.M, N * sizeof(float)));
+        ARAP_CUDA_OR_EXIT(cudaMalloc(&d.costs, cbytes));
+        ARAP_CUDA_OR_EXIT(cudaMalloc(&d.rgb, 3 * N));
+        ARAP_CUDA_OR_EXIT(cudaMalloc(&d.mask, N));
+        ARAP_CUDA_OR_EXIT(cudaMalloc(&d.orgb, 3 * N));
+        ARAP_CUDA_OR_EXIT(cudaMalloc(&d.omask, N));
+        ARAP_CUDA_OR_EXIT(cudaMalloc(&d.z, N * sizeof(unsigned)));
+        ARAP_CUDA_OR_EXIT(cudaMallocHost(&d.h_in, 4 * N));
+        ARAP_CUDA_OR_EXIT(cudaMallocHost(&d.h_out, 12 * N + cbytes));
+    }
+    if (backend_ != ARAPB200_BACKEND_STREAM) resident_ = new ResidentSolver(maxW, maxH, (int)dev_.size());
 }
 
-DeformPipeline::~DeformPipeline()
+BatchPipeline::~BatchPipeline()
 {
     cudaStreamSynchronize(stream_);
     delete solver_;
     delete resident_;
-    cudaFree(d_X_); cudaFree(d_U_); cudaFree(d_C_); cudaFree(d_flow_); cudaFree(d_A_); cudaFree(d_M_);
-    cudaFree(d_costs_); cudaFree(d_rgb_); cudaFree(d_mask_); cudaFree(d_orgb_); cudaFree(d_omask_);
-    cudaFree(d_z_); cudaFree(d_matches_);
-    cudaFreeHost(h_in_); cudaFreeHost(h_out_);
+    for (Dev& d : dev_) {
+        cudaFree(d.X); cudaFree(d.U); cudaFree(d.C); cudaFree(d.flow); cudaFree(d.A); cudaFree(d.M);
+        cudaFree(d.costs); cudaFree(d.rgb); cudaFree(d.mask); cudaFree(d.orgb); cudaFree(d.omask);
+        cudaFree(d.z); cudaFree(d.matches);
+        cudaFreeHost(d.h_in); cudaFreeHost(d.h_out);
+    }
     for (auto& e : ev_) cudaEventDestroy(e);
     cudaStreamDestroy(stream_);
 }
 
-int DeformPipeline::run(const HostProblem& hp)
+// the streaming back-end: one graph launch per Gauss-Newton step (problems too large for the chip)
+void BatchPipeline::solve_streaming(const HostProblem& hp, Dev& d)
 {
     const int W = hp.W, H = hp.H;
-    if (W <= 0 || H <= 0 || (size_t)W * H > (size_t)maxW_ * maxH_) {
-        fprintf(stderr, "arapb200: problem %dx%d does not fit the pipeline (%dx%d)\n", W, H, maxW_, maxH_);
-        return 1;
-    }
-    const size_t N = (size_t)W * H;
-    if (curW_ != W || curH_ != H) { // re-plan on a size change (CombinedSolver.h:149-160)
+    if (!solver_ || solverW_ != W || solverH_ != H) { // re-plan on a size change (CombinedSolver.h:149-160)
+        if (solver_) launches_ += solver_->launches();
         delete solver_;
-        solver_ = nullptr;
-        curW_ = W;
-        curH_ = H;
+        solver_ = new StreamSolver(W, H);
+        solverW_ = W;
+        solverH_ = H;
     }
-    if (backend_ != ARAPB200_BACKEND_STREAM && !resident_) resident_ = new ResidentSolver(maxW_, maxH_);
-    const long long l0 = (solver_ ? solver_->launches() : 0) + (resident_ ? resident_->launches() : 0);
-    std::vector<MatchRec> recs;
-    build_match_records(W, H, hp.mask_red, hp.matches, hp.n_matches, recs);
-    if (recs.size() > matches_cap_) {
-        cudaFree(d_matches_);
-        matches_cap_ = recs.size() * 2 + 1024;
-        ARAP_CUDA_OR_RETURN(cudaMalloc(&d_matches_, matches_cap_ * sizeof(MatchRec)));
-    }
-    // stage inputs through pinned memory
-    memcpy(h_in_, hp.rgb, 3 * N);
-    memcpy(h_in_ + 3 * N, hp.mask_red, N);
-    ARAP_CUDA_OR_RETURN(cudaEventRecord(ev_[0], stream_));
-    ARAP_CUDA_OR_RETURN(cudaMemcpyAsync(d_rgb_, h_in_, 3 * N, cudaMemcpyHostToDevice, stream_));
-    ARAP_CUDA_OR_RETURN(cudaMemcpyAsync(d_mask_, h_in_ + 3 * N, N, cudaMemcpyHostToDevice, stream_));
-    if (!recs.empty())
-        ARAP_CUDA_OR_RETURN(cudaMemcpyAsync(d_matches_, recs.data(), recs.size() * sizeof(MatchRec),
-                                            cudaMemcpyHostToDevice, stream_));
-    enqueue_reset_state(W, H, d_mask_, d_X_, d_U_, d_A_, d_M_, stream_);
-    launches_ += 1;
-    // weights: CombinedSolver.h:172-177
-    const float wf = sqrtf(100.0f), wr = sqrtf(0.01f);
-    bool use_res = false;
-    if (backend_ != ARAPB200_BACKEND_STREAM) {
-        use_res = resident_->prepare(W, H, d_M_, stream_);
-        if (!use_res && backend_ == ARAPB200_BACKEND_RESIDENT) {
-            fprintf(stderr, "arapb200: problem %dx%d (%d strips) does not fit the resident back-end\n", W, H,
-                    resident_->n_strips());
-            return 3;
-        }
-    }
-    last_resident_ = use_res;
-    if (!use_res && !solver_) solver_ = new StreamSolver(W, H);
-    if (!use_res) solver_->bind(d_X_, d_A_, d_U_, d_C_, d_M_, wf, wr, stream_);
-    ARAP_CUDA_OR_RETURN(cudaEventRecord(ev_[1], stream_));
-    if (use_res) {
-        // the whole continuation schedule (CombinedSolverBase.h:99-120) is ONE kernel launch
-        enqueue_target_image(W, H, d_matches_, (int)recs.size(), d_C_, stream_);
-        launches_ += recs.empty() ? 1 : 2;
-        resident_->enqueue(d_X_, d_A_, d_C_, 1, wf, wr, nCont_, nGN_, nPCG_, d_costs_, nullptr, stream_);
-    }
-    for (int t = 0; t < nCont_ && !use_res; ++t) {
+    const long long l0 = solver_->launches();
+    const float wf = sqrtf(100.0f), wr = sqrtf(0.01f); // CombinedSolver.h:172-177
+    solver_->bind(d.X, d.A, d.U, d.C, d.M, wf, wr, stream_);
+    for (int t = 0; t < nCont_; ++t) {
         const float alpha = (float)(t + 1) / (float)nCont_; // CombinedSolver.h:199-201
-        enqueue_constraint_image(W, H, d_matches_, (int)recs.size(), alpha, d_C_, stream_);
-        launches_ += recs.empty() ? 1 : 2;
+        enqueue_constraint_image(W, H, d.matches, (int)d.recs.size(), alpha, d.C, stream_);
+        launches_ += d.recs.empty() ? 1 : 2;
         solver_->enqueue_init(stream_);
-        k_copy_cost<<<1, 1, 0, stream_>>>(solver_->d_scalars(), d_costs_ + (size_t)t * (nGN_ + 1));
+        k_copy_cost<<<1, 1, 0, stream_>>>(solver_->d_scalars(), d.costs + (size_t)t * (nGN_ + 1));
         for (int g = 0; g < nGN_; ++g) {
             solver_->enqueue_gn_step(nPCG_, stream_);
-            k_copy_cost<<<1, 1, 0, stream_>>>(solver_->d_scalars(), d_costs_ + (size_t)t * (nGN_ + 1) + g + 1);
+            k_copy_cost<<<1, 1, 0, stream_>>>(solver_->d_scalars(), d.costs + (size_t)t * (nGN_ + 1) + g + 1);
         }
         launches_ += 1 + nGN_;
     }
-    ARAP_CUDA_OR_RETURN(cudaEventRecord(ev_[2], stream_));
-    enqueue_pos_to_flow(W, H, d_X_, d_flow_, stream_);
-    enqueue_warp(W, H, d_X_, d_rgb_, d_mask_, d_z_, d_orgb_, d_omask_, stream_);
-    launches_ += 1 + warp_launches_per_call();
-    ARAP_CUDA_OR_RETURN(cudaEventRecord(ev_[3], stream_));
-    unsigned char* o = h_out_;
-    ARAP_CUDA_OR_RETURN(cudaMemcpyAsync(o, d_flow_, N * sizeof(float2), cudaMemcpyDeviceToHost, stream_));
-    ARAP_CUDA_OR_RETURN(cudaMemcpyAsync(o + 8 * N, d_orgb_, 3 * N, cudaMemcpyDeviceToHost, stream_));
-    ARAP_CUDA_OR_RETURN(cudaMemcpyAsync(o + 11 * N, d_omask_, N, cudaMemcpyDeviceToHost, stream_));
+    launches_ += solver_->launches() - l0;
+}
+
+int BatchPipeline::run(const HostProblem* problems, int count)
+{
+    if (count <= 0) return 0;
+    if (count > (int)dev_.size()) {
+        fprintf(stderr, "arapb200: %d problems submitted, pipeline holds %d\n", count, (int)dev_.size());
+        return 1;
+    }
     const size_t cbytes = (size_t)nCont_ * (nGN_ + 1) * sizeof(float);
-    ARAP_CUDA_OR_RETURN(cudaMemcpyAsync(o + 12 * N, d_costs_, cbytes, cudaMemcpyDeviceToHost, stream_));
+    const float wf = sqrtf(100.0f), wr = sqrtf(0.01f); // CombinedSolver.h:172-177
+    const long long r0 = resident_ ? resident_->launches() : 0;
+    // ---- stage + upload every problem, reset its state (resetGPU), build its strip tables ----
+    for (int i = 0; i < count; ++i) {
+        const HostProblem& hp = problems[i];
+        Dev& d = dev_[i];
+        if (hp.W <= 0 || hp.H <= 0 || (size_t)hp.W * hp.H > (size_t)maxW_ * maxH_) {
+            fprintf(stderr, "arapb200: problem %dx%d does not fit the pipeline (%dx%d)\n", hp.W, hp.H, maxW_, maxH_);
+            return 1;
+        }
+        const size_t N = (size_t)hp.W * hp.H;
+        build_match_records(hp.W, hp.H, hp.mask_red, hp.matches, hp.n_matches, d.recs);
+        if (d.recs.size() > d.matches_cap) {
+            cudaFree(d.matches);
+            d.matches_cap = d.recs.size() * 2 + 1024;
+            ARAP_CUDA_OR_RETURN(cudaMalloc(&d.matches, d.matches_cap * sizeof(MatchRec)));
+        }
+        memcpy(d.h_in, hp.rgb, 3 * N);
+        memcpy(d.h_in + 3 * N, hp.mask_red, N);
+    }
+    ARAP_CUDA_OR_RETURN(cudaEventRecord(ev_[0], stream_));
+    for (int i = 0; i < count; ++i) {
+        const HostProblem& hp = problems[i];
+        Dev& d = dev_[i];
+        const size_t N = (size_t)hp.W * hp.H;
+        ARAP_CUDA_OR_RETURN(cudaMemcpyAsync(d.rgb, d.h_in, 3 * N, cudaMemcpyHostToDevice, stream_));
+        ARAP_CUDA_OR_RETURN(cudaMemcpyAsync(d.mask, d.h_in + 3 * N, N, cudaMemcpyHostToDevice, stream_));
+        if (!d.recs.empty())
+            ARAP_CUDA_OR_RETURN(cudaMemcpyAsync(d.matches, d.recs.data(), d.recs.size() * sizeof(MatchRec),
+                                                cudaMemcpyHostToDevice, stream_));
+        enqueue_reset_state(hp.W, hp.H, d.mask, d.X, d.U, d.A, d.M, stream_);
+        launches_ += 1;
+        d.resident = false;
+        if (resident_) resident_->prepare_enqueue(i, hp.W, hp.H, d.M, stream_);
+    }
+    n_resident_ = 0;
+    if (resident_) {
+        ARAP_CUDA_OR_RETURN(cudaStreamSynchronize(stream_)); // strip counts are needed to size the launches
+        for (int i = 0; i < count; ++i) {
+            dev_[i].resident = resident_->prepare_finish(i);
+            if (!dev_[i].resident && backend_ == ARAPB200_BACKEND_RESIDENT) {
+                fprintf(stderr, "arapb200: problem %dx%d (%d strips) does not fit the resident back-end\n", problems[i].W,
+                        problems[i].H, resident_->n_strips(i));
+                return 3;
+            }
+            n_resident_ += dev_[i].resident ? 1 : 0;
+        }
+    }
+    ARAP_CUDA_OR_RETURN(cudaEventRecord(ev_[1], stream_));
+    // ---- solve.  Resident problems: whole continuation schedules, several problems per cooperative launch ----
+    group_size_ = 0;
+    for (int i = 0; i < count;) {
+        Dev& d = dev_[i];
+        if (!d.resident) {
+            solve_streaming(problems[i], d);
+            ++i;
+            continue;
+        }
+        int run_len = 0; // consecutive resident problems
+        while (i + run_len < count && dev_[i + run_len].resident) ++run_len;
+        const int gsz = resident_->group_size(i, run_len);
+        for (int j = 0; j < gsz; ++j) {
+            Dev& dj = dev_[i + j];
+            const HostProblem& hp = problems[i + j];
+            enqueue_target_image(hp.W, hp.H, dj.matches, (int)dj.recs.size(), dj.C, stream_);
+            launches_ += dj.recs.empty() ? 1 : 2;
+            resident_->set_problem(i + j, dj.X, dj.A, dj.C, 1, wf, wr, dj.costs, nullptr);
+        }
+        resident_->enqueue_group(i, gsz, nCont_, nGN_, nPCG_, stream_);
+        if (gsz > group_size_) group_size_ = gsz;
+        i += gsz;
+    }
+    ARAP_CUDA_OR_RETURN(cudaEventRecord(ev_[2], stream_));
+    // ---- flow extraction + forward warp + download ----
+    for (int i = 0; i < count; ++i) {
+        const HostProblem& hp = problems[i];
+        Dev& d = dev_[i];
+        enqueue_pos_to_flow(hp.W, hp.H, d.X, d.flow, stream_);
+        enqueue_warp(hp.W, hp.H, d.X, d.rgb, d.mask, d.z, d.orgb, d.omask, stream_);
+        launches_ += 1 + warp_launches_per_call();
+    }
+    ARAP_CUDA_OR_RETURN(cudaEventRecord(ev_[3], stream_));
+    for (int i = 0; i < count; ++i) {
+        const HostProblem& hp = problems[i];
+        Dev& d = dev_[i];
+        const size_t N = (size_t)hp.W * hp.H;
+        unsigned char* o = d.h_out;
+        ARAP_CUDA_OR_RETURN(cudaMemcpyAsync(o, d.flow, N * sizeof(float2), cudaMemcpyDeviceToHost, stream_));
+        ARAP_CUDA_OR_RETURN(cudaMemcpyAsync(o + 8 * N, d.orgb, 3 * N, cudaMemcpyDeviceToHost, stream_));
+        ARAP_CUDA_OR_RETURN(cudaMemcpyAsync(o + 11 * N, d.omask, N, cudaMemcpyDeviceToHost, stream_));
+        ARAP_CUDA_OR_RETURN(cudaMemcpyAsync(o + 12 * N, d.costs, cbytes, cudaMemcpyDeviceToHost, stream_));
+    }
     ARAP_CUDA_OR_RETURN(cudaStreamSynchronize(stream_));
-    if (use_res) {
+    if (resident_ && n_resident_ > 0) {
         if (int st = resident_->status(stream_)) {
             fprintf(stderr, "arapb200: resident solver aborted (watchdog, code %d)\n", st);
             return 4;
         }
-    } else {
+    }
+    if (solver_ && n_resident_ < count) {
         unsigned bad = 0;
         solver_->read_back(stream_, nullptr, &bad);
         if (bad) {
@@ -239,11 +296,17 @@ int DeformPipeline::run(const HostProblem& hp)
             return 2;
         }
     }
-    if (hp.out_flow) memcpy(hp.out_flow, o, N * sizeof(float2));
-    if (hp.out_rgb) memcpy(hp.out_rgb, o + 8 * N, 3 * N);
-    if (hp.out_mask) memcpy(hp.out_mask, o + 11 * N, N);
-    if (hp.out_costs) memcpy(hp.out_costs, o + 12 * N, cbytes);
-    launches_ += (solver_ ? solver_->launches() : 0) + (resident_ ? resident_->launches() : 0) - l0;
+    for (int i = 0; i < count; ++i) {
+        const HostProblem& hp = problems[i];
+        Dev& d = dev_[i];
+        const size_t N = (size_t)hp.W * hp.H;
+        const unsigned char* o = d.h_out;
+        if (hp.out_flow) memcpy(hp.out_flow, o, N * sizeof(float2));
+        if (hp.out_rgb) memcpy(hp.out_rgb, o + 8 * N, 3 * N);
+        if (hp.out_mask) memcpy(hp.out_mask, o + 11 * N, N);
+        if (hp.out_costs) memcpy(hp.out_costs, o + 12 * N, cbytes);
+    }
+    if (resident_) launches_ += resident_->launches() - r0;
     cudaEventElapsedTime(&ms_total_, ev_[0], ev_[3]);
     cudaEventElapsedTime(&ms_solve_, ev_[1], ev_[2]);
     cudaEventElapsedTime(&ms_warp_, ev_[2], ev_[3]);

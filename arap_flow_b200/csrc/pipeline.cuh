@@ -1,7 +1,7 @@
-// pipeline.cuh -- per-image path of arap_deform on the device: what CombinedSolver (ARAP/deformation/
-// src/CombinedSolver.h:139-242, 280-366) and CombinedSolverBase::singleSolve (ARAP/shared/
-// CombinedSolverBase.h:99-120) do around the solver, with every host<->device hop removed except the
-// upload of the inputs and the download of the outputs.
+// pipeline.cuh -- per-image path of arap_deform on the device, batched: what CombinedSolver (ARAP/
+// deformation/src/CombinedSolver.h:139-242, 280-366) and CombinedSolverBase::singleSolve (ARAP/shared/
+// CombinedSolverBase.h:99-120) do around the solver, for many independent (image, segment) problems at once,
+// with every host<->device hop removed except the upload of the inputs and the download of the outputs.
 #pragma once
 #include "plan.cuh"
 #include "warp.cuh"
@@ -33,41 +33,46 @@ struct MatchRec {
 void build_match_records(int W, int H, const unsigned char* mask_red, const int* matches, int n_matches,
                          std::vector<MatchRec>& out);
 
-class DeformPipeline {
+class BatchPipeline {
 public:
-    DeformPipeline(int maxW, int maxH, int nCont, int nGN, int nPCG, int backend);
-    ~DeformPipeline();
-    DeformPipeline(const DeformPipeline&) = delete;
-    DeformPipeline& operator=(const DeformPipeline&) = delete;
-    // upload, solve (all continuation steps), flow, warp, download.  Blocking.
-    int run(const HostProblem& hp);
+    // up to max_problems problems of at most maxW x maxH in flight
+    BatchPipeline(int maxW, int maxH, int max_problems, int nCont, int nGN, int nPCG, int backend);
+    ~BatchPipeline();
+    BatchPipeline(const BatchPipeline&) = delete;
+    BatchPipeline& operator=(const BatchPipeline&) = delete;
+    // upload, solve (all continuation steps), flow, warp, download -- for every problem given.  Blocking.
+    int run(const HostProblem* problems, int count);
     long long launches() const { return launches_; }
     float last_ms_total() const { return ms_total_; }
     float last_ms_solve() const { return ms_solve_; }
     float last_ms_warp() const { return ms_warp_; }
-    bool last_used_resident() const { return last_resident_; }
+    int last_resident_count() const { return n_resident_; }
+    int last_group_size() const { return group_size_; }
+    int max_problems() const { return (int)dev_.size(); }
 
 private:
+    struct Dev { // device + pinned staging of one problem slot
+        float2 *X = nullptr, *U = nullptr, *C = nullptr, *flow = nullptr;
+        float *A = nullptr, *M = nullptr, *costs = nullptr;
+        unsigned char *rgb = nullptr, *mask = nullptr, *orgb = nullptr, *omask = nullptr;
+        unsigned* z = nullptr;
+        MatchRec* matches = nullptr;
+        size_t matches_cap = 0;
+        unsigned char *h_in = nullptr, *h_out = nullptr;
+        std::vector<MatchRec> recs;
+        bool resident = false;
+    };
+    void solve_streaming(const HostProblem& hp, Dev& d);
     int maxW_, maxH_, nCont_, nGN_, nPCG_, backend_;
-    int curW_ = 0, curH_ = 0;
+    std::vector<Dev> dev_;
     StreamSolver* solver_ = nullptr;
+    int solverW_ = 0, solverH_ = 0;
     ResidentSolver* resident_ = nullptr;
-    bool last_resident_ = false;
     cudaStream_t stream_ = nullptr;
     cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
-    // device images
-    float2 *d_X_ = nullptr, *d_U_ = nullptr, *d_C_ = nullptr, *d_flow_ = nullptr;
-    float *d_A_ = nullptr, *d_M_ = nullptr, *d_costs_ = nullptr;
-    unsigned char *d_rgb_ = nullptr, *d_mask_ = nullptr, *d_orgb_ = nullptr, *d_omask_ = nullptr;
-    unsigned* d_z_ = nullptr;
-    MatchRec* d_matches_ = nullptr;
-    size_t matches_cap_ = 0;
-    // pinned staging
-    unsigned char* h_in_ = nullptr;
-    unsigned char* h_out_ = nullptr;
-    size_t h_in_bytes_ = 0, h_out_bytes_ = 0;
     long long launches_ = 0;
     float ms_total_ = 0, ms_solve_ = 0, ms_warp_ = 0;
+    int n_resident_ = 0, group_size_ = 0;
 };
 
 // shared small kernels

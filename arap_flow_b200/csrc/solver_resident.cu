@@ -29,14 +29,17 @@
 #include "solver_resident.cuh"
 #include "grid_math.cuh"
 #include "solver_stream.cuh" // FLAG_* bit layout
+#include <algorithm>
 
 namespace arapb200 {
 namespace {
 
 constexpr int TW = RS_STRIP_W + 2, TH = RS_STRIP_H + 2;
-constexpr int RS_THREADS_MAX = 384;
+constexpr int RS_THREADS_MAX = (RS_STRIP_H == 8) ? 384 : 512;
+constexpr int OB_LEFT = 64, OB_RIGHT = 64 + RS_STRIP_H;
+static_assert(RS_STRIP_H == 4 || RS_STRIP_H == 8, "strip height must be 4 or 8");
 constexpr long long LIMB_BIAS = 1ll << 36;
-constexpr int S_MIN = -300, S_MAX = 300;
+constexpr int S_MIN = -100, S_MAX = 100;
 
 struct __align__(16) StripSmem {
     float4 T[TH][TW];              // tile + ring: (p_x, p_y, sin*p_a, cos*p_a) or (X_x, X_y, cos, sin)
@@ -59,7 +62,7 @@ struct Ctl {
 __device__ __forceinline__ unsigned long long ld_u64_volatile(const unsigned long long* p)
 {
     unsigned long long v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v)
@@ -69,7 +72,7 @@ __device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long
 __device__ __forceinline__ uint4 ld_u4_volatile(const uint4* p)
 {
     uint4 v;
-    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                  : "l"(p)
                  : "memory");
@@ -84,30 +87,27 @@ __device__ __forceinline__ double pow2_f64(int e) // 2^e, e in the normal range
     return __hiloint2double((e + 1023) << 20, 0);
 }
 
-// exact 128-bit integer (units of 2^e_unit) -> binary32, round to nearest even
-__device__ float i128_to_float_rn(__int128 T, int e_unit)
+// exact 128-bit integer (units of 2^e_unit) -> binary32, round to nearest even.  The top 64 bits are
+// rounded to odd (sticky bit) and handed to the hardware u64 -> f32 conversion, which is then the single
+// rounding (64 >= 24 + 2).
+__device__ __forceinline__ float i128_to_float_rn(__int128 T, int e_unit)
 {
-    if (T == 0) return 0.0f;
     const bool neg = T < 0;
-    unsigned __int128 m = neg ? (unsigned __int128)(-T) : (unsigned __int128)T;
+    const unsigned __int128 m = neg ? (unsigned __int128)(-T) : (unsigned __int128)T;
     const unsigned long long hi = (unsigned long long)(m >> 64), lo = (unsigned long long)m;
-    const int nbits = hi ? 128 - __clzll((long long)hi) : 64 - __clzll((long long)lo);
-    unsigned long long mant;
+    unsigned long long top = lo;
     int e = e_unit;
-    if (nbits > 24) {
-        const int sh = nbits - 24;
-        mant = (unsigned long long)(m >> sh);
-        const unsigned __int128 rem = m & ((((unsigned __int128)1) << sh) - 1);
-        const unsigned __int128 half = ((unsigned __int128)1) << (sh - 1);
-        if (rem > half || (rem == half && (mant & 1ull))) ++mant;
+    if (hi) {
+        const int sh = 64 - __clzll((long long)hi); // 1..64
+        top = (sh == 64) ? hi : ((hi << (64 - sh)) | (lo >> sh));
+        const unsigned long long lost = (sh == 64) ? lo : (lo << (64 - sh));
+        top |= (lost != 0ull) ? 1ull : 0ull;
         e += sh;
-    } else {
-        mant = lo;
     }
+    const float f = __ull2float_rn(top);
     e = max(-1000, min(1000, e));
-    const double d = (double)(long long)mant * pow2_f64(e); // exact: mant <= 2^24
-    const float f = (float)d;
-    return neg ? -f : f;
+    const float r = (float)((double)f * pow2_f64(e)); // exact scaling (barring binary32 underflow)
+    return neg ? -r : r;
 }
 
 // Everything a warp needs to know about its strip
@@ -135,120 +135,159 @@ struct Cta {
 };
 
 // ---- grid barrier carrying an exact sum ----------------------------------------------------------
-// g0/g1: this thread's two group terms.  S: scale exponent of this reduction kind (in/out).  Returns the
-// exact sum over the whole problem, rounded once to binary32.  ok = false: watchdog fired / peer aborted.
-__device__ __noinline__ float grid_sum(Cta& c, float g0, float g1, int& S, bool& ok)
+// Split in two so that independent work (the halo fetch) can sit between arrival and completion.
+// grid_arrive: this thread's group terms g0 (and g1 when a lane holds two groups) are converted to limbs
+// against the scale 2^S, summed over the CTA and added to the barrier words.
+__device__ __forceinline__ void grid_arrive(Cta& c, float g0, float g1, int S, long long& t0, long long& t1)
+{
+    Ctl* ctl = c.ctl;
+    if (c.prof) t0 = clock64();
+    // ---- thread -> four signed 24-bit limbs in units 2^(S-18), 2^(S-42), 2^(S-66), 2^(S-90) ----
+    // (binary32 only: scaling by powers of two and the remainders are exact)
+    const float sc = __int_as_float((127 + 18 - S) << 23);
+    int l0, l1, l2, l3;
+    bool ovf;
+    {
+        const float v = g0 * sc;
+        ovf = !(fabsf(v) < 16777216.0f); // |g| >= 2^(S+6), Inf or NaN
+        const float vv = ovf ? 0.0f : v; // an overflowing term contributes nothing (its limbs would spill into the counts)
+        l0 = __float2int_rn(vv);
+        const float v1 = (vv - (float)l0) * 16777216.0f;
+        l1 = __float2int_rn(v1);
+        const float v2 = (v1 - (float)l1) * 16777216.0f;
+        l2 = __float2int_rn(v2);
+        const float v3 = (v2 - (float)l2) * 16777216.0f;
+        l3 = __float2int_rn(v3);
+    }
+    if (RS_STRIP_H == 8) {
+        const float v = g1 * sc;
+        const bool o1 = !(fabsf(v) < 16777216.0f);
+        ovf = ovf || o1;
+        const float vv = o1 ? 0.0f : v;
+        const int m0 = __float2int_rn(vv);
+        const float v1 = (vv - (float)m0) * 16777216.0f;
+        const int m1 = __float2int_rn(v1);
+        const float v2 = (v1 - (float)m1) * 16777216.0f;
+        const int m2 = __float2int_rn(v2);
+        const float v3 = (v2 - (float)m2) * 16777216.0f;
+        l0 += m0; l1 += m1; l2 += m2; l3 += __float2int_rn(v3);
+    }
+    const int s0 = __reduce_add_sync(0xffffffffu, l0);
+    const int s1 = __reduce_add_sync(0xffffffffu, l1);
+    const int s2 = __reduce_add_sync(0xffffffffu, l2);
+    const int s3 = __reduce_add_sync(0xffffffffu, l3);
+    const bool wovf = __any_sync(0xffffffffu, ovf);
+    if (c.lane == 0) {
+        ctl->limb[c.wid][0] = s0;
+        ctl->limb[c.wid][1] = s1;
+        ctl->limb[c.wid][2] = s2;
+        ctl->limb[c.wid][3] = s3;
+        ctl->ovf[c.wid] = wovf ? 1 : 0;
+    }
+    __syncthreads();
+    if (c.wid == 0 && c.lane < 4) {
+        unsigned long long* buf = c.P->bar + (c.epoch & 1u) * 4;
+        long long sum = 0;
+        int any = 0;
+        for (int w = 0; w < c.nw; ++w) {
+            sum += (long long)ctl->limb[w][c.lane];
+            any |= ctl->ovf[w];
+        }
+        unsigned long long contrib = (1ull << 48) + (unsigned long long)(sum + LIMB_BIAS);
+        if (c.lane == 0 && any) contrib += (1ull << 56);
+        red_add_u64(buf + c.lane, contrib);
+    }
+    if (c.prof) t1 = clock64();
+}
+
+// grid_wait: poll the barrier words until all G CTAs have arrived, decode, verify the scale, broadcast.
+// Returns 0 = accepted (result in res, S updated for the next reduction of this kind), 1 = redo with the new S.
+__device__ __forceinline__ int grid_wait(Cta& c, int& S, bool& grown, float& res, bool& ok, long long t0, long long t1)
 {
     Ctl* ctl = c.ctl;
     const ResProb& P = *c.P;
-    bool grown = false;
-    for (;;) {
-        long long t0 = 0, t1 = 0, t2 = 0;
-        if (c.prof) t0 = clock64();
-        // ---- thread -> limbs (units 2^(S-42) and 2^(S-90)) ----
-        const double sc = pow2_f64(42 - S);
-        const double a0 = (double)g0 * sc, a1 = (double)g1 * sc;
-        const bool ovf = !(fabs(a0) < 281474976710656.0) || !(fabs(a1) < 281474976710656.0); // |g| >= 2^(S+6), NaN
-        const long long A0 = __double2ll_rn(a0), A1 = __double2ll_rn(a1);
-        const double r0 = __dadd_rn(a0, -__ll2double_rn(A0)), r1 = __dadd_rn(a1, -__ll2double_rn(A1));
-        const long long B0 = __double2ll_rn(r0 * 281474976710656.0), B1 = __double2ll_rn(r1 * 281474976710656.0);
-        // an overflowing thread contributes nothing (its limbs would spill into the arrival counts)
-        const long long A = ovf ? 0ll : A0 + A1, B = ovf ? 0ll : B0 + B1;
-        const int l0 = (int)(A >> 24), l2 = (int)(B >> 24);
-        const unsigned l1 = (unsigned)(A & 0xFFFFFF), l3 = (unsigned)(B & 0xFFFFFF);
-        const int s0 = __reduce_add_sync(0xffffffffu, l0);
-        const unsigned s1 = __reduce_add_sync(0xffffffffu, l1);
-        const int s2 = __reduce_add_sync(0xffffffffu, l2);
-        const unsigned s3 = __reduce_add_sync(0xffffffffu, l3);
-        const bool wovf = __any_sync(0xffffffffu, ovf);
-        if (c.lane == 0) {
-            ctl->limb[c.wid][0] = s0;
-            ctl->limb[c.wid][1] = (int)s1;
-            ctl->limb[c.wid][2] = s2;
-            ctl->limb[c.wid][3] = (int)s3;
-            ctl->ovf[c.wid] = wovf ? 1 : 0;
-        }
-        __syncthreads();
-        if (c.wid == 0) {
-            unsigned long long* buf = P.bar + (c.epoch & 1u) * 4;
-            if (c.lane < 4) {
-                long long sum = 0;
-                int any = 0;
-                for (int w = 0; w < c.nw; ++w) {
-                    const int v = ctl->limb[w][c.lane];
-                    sum += (c.lane & 1) ? (long long)(unsigned)v : (long long)v;
-                    any |= ctl->ovf[w];
-                }
-                unsigned long long contrib = (1ull << 48) + (unsigned long long)(sum + LIMB_BIAS);
-                if (c.lane == 0 && any) contrib += (1ull << 56);
-                red_add_u64(buf + c.lane, contrib);
+    long long t2 = 0;
+    if (c.wid == 0 && c.lane == 0) {
+        unsigned long long* buf = P.bar + (c.epoch & 1u) * 4;
+        unsigned long long* prev = ctl->prev[c.epoch & 1u];
+        unsigned long long d[4];
+        unsigned spins = 0;
+        for (;;) {
+            bool done = true;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                d[j] = ld_u64_volatile(buf + j) - prev[j];
+                if ((int)((d[j] >> 48) & 0xFF) != c.G) done = false;
             }
-            if (c.prof) t1 = clock64();
-            if (c.lane == 0) {
-                unsigned long long* prev = ctl->prev[c.epoch & 1u];
-                unsigned long long d[4];
-                unsigned spins = 0;
-                for (;;) {
-                    bool done = true;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        d[j] = ld_u64_volatile(buf + j) - prev[j];
-                        if ((int)((d[j] >> 48) & 0xFF) != c.G) done = false;
-                    }
-                    if (done) break;
-                    if ((++spins & 0xffu) == 0) {
-                        // watchdog: a peer's abort or ~seconds of polling => leave instead of hanging the GPU
-                        if (*(volatile int*)P.status || spins > (1u << 23)) {
-                            atomicExch(P.status, 1);
-                            atomicCAS(P.status + 1, 0, 100 + (int)(c.epoch & 0xffff));
-                            ctl->abort = 1;
-                            break;
-                        }
-                    }
+            if (done) break;
+            if ((++spins & 0xffu) == 0) {
+                // watchdog: a peer's abort or ~seconds of polling => leave instead of hanging the GPU
+                if (*(volatile int*)P.status || spins > (1u << 23)) {
+                    atomicExch(P.status, 1);
+                    atomicCAS(P.status + 1, 0, 100 + (int)(c.epoch & 0xffff));
+                    ctl->abort = 1;
+                    break;
                 }
-                if (c.prof) t2 = clock64();
-                long long L[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    prev[j] += d[j];
-                    L[j] = (long long)(d[j] & ((1ull << 48) - 1)) - (long long)c.G * LIMB_BIAS;
-                }
-                const int novf = (int)((d[0] >> 56) & 0xFF);
-                const __int128 T = ((__int128)L[0] << 72) + ((__int128)L[1] << 48) + ((__int128)L[2] << 24) + (__int128)L[3];
-                const float res = i128_to_float_rn(T, S - 90);
-                int code = 0, newS = S;
-                if (novf) {
-                    code = 1; newS = min(S + 24, S_MAX);
-                    if (S >= S_MAX) code = 0; // Inf/NaN terms: give up, the result is garbage anyway
-                } else if (T == 0) {
-                    if (!grown && S > S_MIN) { code = 1; newS = max(S - 64, S_MIN); }
-                } else {
-                    const int e = ilogb_f32(fabsf(res));
-                    if (!grown && e < S - 24 && S > S_MIN) { code = 1; newS = max(e + 4, S_MIN); }
-                    else newS = max(min(e + 4, S_MAX), S_MIN);
-                }
-                ctl->bc = res;
-                ctl->bc_code = code;
-                ctl->bc_S = newS;
             }
         }
-        __syncthreads();
-        if (c.prof && threadIdx.x == 0) {
-            const long long t3 = clock64();
-            c.acc[0] += (unsigned long long)(t1 - t0);
-            c.acc[1] += (unsigned long long)(t2 - t1);
-            c.acc[2] += (unsigned long long)(t3 - t2);
+        if (c.prof) t2 = clock64();
+        long long L[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            prev[j] += d[j];
+            L[j] = (long long)(d[j] & ((1ull << 48) - 1)) - (long long)c.G * LIMB_BIAS;
         }
-        ++c.epoch;
-        if (ctl->abort) { ok = false; return 0.f; }
-        const int code = ctl->bc_code;
-        const int newS = ctl->bc_S;
-        const float res = ctl->bc;
-        if (newS > S) grown = true;
-        S = newS;
-        if (code == 0) return res;
-        __syncthreads(); // everybody has read the broadcast before the redo overwrites it
+        const int novf = (int)((d[0] >> 56) & 0xFF);
+        const __int128 T = ((__int128)L[0] << 72) + ((__int128)L[1] << 48) + ((__int128)L[2] << 24) + (__int128)L[3];
+        const float r = i128_to_float_rn(T, S - 90);
+        int code = 0, newS = S;
+        if (novf) {
+            code = 1; newS = min(S + 24, S_MAX);
+            if (S >= S_MAX) code = 0; // Inf/NaN terms: give up, the result is garbage anyway
+        } else if (T == 0) {
+            if (!grown && S > S_MIN) { code = 1; newS = max(S - 64, S_MIN); }
+        } else {
+            const int e = ilogb_f32(fabsf(r));
+            if (!grown && e < S - 24 && S > S_MIN) { code = 1; newS = max(e + 4, S_MIN); }
+            else newS = max(min(e + 4, S_MAX), S_MIN);
+        }
+        ctl->bc = r;
+        ctl->bc_code = code;
+        ctl->bc_S = newS;
     }
+    __syncthreads();
+    if (c.prof && threadIdx.x == 0) {
+        const long long t3 = clock64();
+        c.acc[0] += (unsigned long long)(t1 - t0);
+        c.acc[1] += (unsigned long long)(t2 - t1);
+        c.acc[2] += (unsigned long long)(t3 - t2);
+    }
+    ++c.epoch;
+    if (ctl->abort) { ok = false; res = 0.f; return 0; }
+    const int code = ctl->bc_code;
+    const int newS = ctl->bc_S;
+    res = ctl->bc;
+    if (newS > S) grown = true;
+    S = newS;
+    return code;
+}
+
+// arrive + wait (+ the rare redo with a corrected scale).  Returns the exact sum rounded once to binary32.
+__device__ __forceinline__ float grid_finish(Cta& c, float g0, float g1, int& S, bool& ok, long long t0, long long t1)
+{
+    bool grown = false;
+    float res;
+    while (grid_wait(c, S, grown, res, ok, t0, t1)) {
+        __syncthreads(); // everybody has read the broadcast before the redo overwrites it
+        grid_arrive(c, g0, g1, S, t0, t1);
+    }
+    return res;
+}
+__device__ __forceinline__ float grid_sum(Cta& c, float g0, float g1, int& S, bool& ok)
+{
+    long long t0 = 0, t1 = 0;
+    grid_arrive(c, g0, g1, S, t0, t1);
+    return grid_finish(c, g0, g1, S, ok, t0, t1);
 }
 
 // ---- halo publication / reception ----------------------------------------------------------------
@@ -267,58 +306,81 @@ __device__ __forceinline__ void publish_rowcol(const StripCtx& s, int lane, int 
 {
     if (s.rem[0] >= 0 && k == 0) put_entry(s.outbox + 3 * lane, tag, a, b, c2, d, e2, f, three);
     if (s.rem[1] >= 0 && k == RS_STRIP_H - 1) put_entry(s.outbox + 3 * (32 + lane), tag, a, b, c2, d, e2, f, three);
-    if (s.rem[2] >= 0 && lane == 0) put_entry(s.outbox + 3 * (64 + k), tag, a, b, c2, d, e2, f, three);
-    if (s.rem[3] >= 0 && lane == 31) put_entry(s.outbox + 3 * (72 + k), tag, a, b, c2, d, e2, f, three);
+    if (s.rem[2] >= 0 && lane == 0) put_entry(s.outbox + 3 * (OB_LEFT + k), tag, a, b, c2, d, e2, f, three);
+    if (s.rem[3] >= 0 && lane == 31) put_entry(s.outbox + 3 * (OB_RIGHT + k), tag, a, b, c2, d, e2, f, three);
 }
 
-// spin until the entry carries `tag` (normally the first read succeeds: it was published a barrier ago)
-__device__ __forceinline__ bool get_entry(const ResProb& P, Ctl* ctl, int nslot, int e, unsigned tag, bool three, float v[6])
+// What a lane receives: the pixel above / below its column (all lanes) and, for lanes 0..H-1 (left column)
+// or 8..8+H-1 (right column), one pixel beside the strip.
+struct Halo {
+    float up[6], dn[6], sd[6];
+};
+
+__device__ __forceinline__ bool entry_ok(const uint4 w0, const uint4 w1, const uint4 w2, unsigned tag)
 {
-    const uint4* p = P.outbox + ((size_t)nslot * RS_OUTBOX_ENTRIES + e) * 3;
+    return w0.y == tag && w0.w == tag && w1.y == tag && w1.w == tag && w2.y == tag && w2.w == tag;
+}
+__device__ __forceinline__ void entry_unpack(const uint4 w0, const uint4 w1, const uint4 w2, float v[6])
+{
+    v[0] = __uint_as_float(w0.x); v[1] = __uint_as_float(w0.z);
+    v[2] = __uint_as_float(w1.x); v[3] = __uint_as_float(w1.z);
+    v[4] = __uint_as_float(w2.x); v[5] = __uint_as_float(w2.z);
+}
+
+// Spin until every remote entry this lane needs carries `tag`.  All loads of a round are in flight together;
+// normally the first round succeeds because the neighbours published before they went into the barrier that
+// this warp is about to enter (the call sits BEFORE the grid barrier, so the latency hides behind it).
+__device__ __forceinline__ void fetch_halo(const ResProb& P, Ctl* ctl, const StripCtx& s, int lane, unsigned tag, bool three,
+                                           Halo& h)
+{
+    const bool left = s.rem[2] >= 0 && lane < RS_STRIP_H;
+    const bool right = s.rem[3] >= 0 && lane >= 8 && lane < 8 + RS_STRIP_H;
+    const uint4* pu = (s.rem[0] >= 0) ? P.outbox + ((size_t)s.rem[0] * RS_OUTBOX_ENTRIES + 32 + lane) * 3 : nullptr;
+    const uint4* pd = (s.rem[1] >= 0) ? P.outbox + ((size_t)s.rem[1] * RS_OUTBOX_ENTRIES + lane) * 3 : nullptr;
+    const uint4* ps = left ? P.outbox + ((size_t)s.rem[2] * RS_OUTBOX_ENTRIES + OB_RIGHT + lane) * 3
+                           : (right ? P.outbox + ((size_t)s.rem[3] * RS_OUTBOX_ENTRIES + OB_LEFT + lane - 8) * 3 : nullptr);
+    const uint4 fake = make_uint4(0u, tag, 0u, tag);
     unsigned spins = 0;
     for (;;) {
-        const uint4 w0 = ld_u4_volatile(p), w1 = ld_u4_volatile(p + 1);
-        uint4 w2 = make_uint4(0u, tag, 0u, tag);
-        if (three) w2 = ld_u4_volatile(p + 2);
-        if (w0.y == tag && w0.w == tag && w1.y == tag && w1.w == tag && w2.y == tag && w2.w == tag) {
-            v[0] = __uint_as_float(w0.x); v[1] = __uint_as_float(w0.z);
-            v[2] = __uint_as_float(w1.x); v[3] = __uint_as_float(w1.z);
-            v[4] = __uint_as_float(w2.x); v[5] = __uint_as_float(w2.z);
-            return true;
+        uint4 u0 = fake, u1 = fake, u2 = fake, d0 = fake, d1 = fake, d2 = fake, s0 = fake, s1 = fake, s2 = fake;
+        if (pu) { u0 = ld_u4_volatile(pu); u1 = ld_u4_volatile(pu + 1); if (three) u2 = ld_u4_volatile(pu + 2); }
+        if (pd) { d0 = ld_u4_volatile(pd); d1 = ld_u4_volatile(pd + 1); if (three) d2 = ld_u4_volatile(pd + 2); }
+        if (ps) { s0 = ld_u4_volatile(ps); s1 = ld_u4_volatile(ps + 1); if (three) s2 = ld_u4_volatile(ps + 2); }
+        if (entry_ok(u0, u1, u2, tag) && entry_ok(d0, d1, d2, tag) && entry_ok(s0, s1, s2, tag)) {
+            entry_unpack(u0, u1, u2, h.up);
+            entry_unpack(d0, d1, d2, h.dn);
+            entry_unpack(s0, s1, s2, h.sd);
+            return;
         }
         if ((++spins & 0xffu) == 0 && (*(volatile int*)P.status || spins > (1u << 22))) {
             atomicExch(P.status, 1);
             atomicCAS(P.status + 1, 0, 200);
             ctl->abort = 1;
-            v[0] = v[1] = v[2] = v[3] = v[4] = v[5] = 0.f;
-            return false;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) h.up[j] = h.dn[j] = h.sd[j] = 0.f;
+            return;
         }
     }
 }
 
-// ring <- neighbours' (X_x, X_y, cos, sin).  Up/down rows: every lane; left column: lanes 0..7; right: 8..15.
-__device__ __forceinline__ void recv_x(const ResProb& P, Ctl* ctl, const StripCtx& s, int lane, unsigned tag)
+// ring <- neighbours' (X_x, X_y, cos, sin)
+__device__ __forceinline__ void apply_x(const StripCtx& s, int lane, const Halo& h)
 {
-    float v[6];
     if (s.rem[0] >= 0) {
-        get_entry(P, ctl, s.rem[0], 32 + lane, tag, false, v);
-        s.own[0 * TW + lane + 1] = make_float4(v[0], v[1], v[2], v[3]);
-        s.rcs[lane] = make_float2(v[2], v[3]);
+        s.own[0 * TW + lane + 1] = make_float4(h.up[0], h.up[1], h.up[2], h.up[3]);
+        s.rcs[lane] = make_float2(h.up[2], h.up[3]);
     }
     if (s.rem[1] >= 0) {
-        get_entry(P, ctl, s.rem[1], lane, tag, false, v);
-        s.own[(TH - 1) * TW + lane + 1] = make_float4(v[0], v[1], v[2], v[3]);
-        s.rcs[32 + lane] = make_float2(v[2], v[3]);
+        s.own[(TH - 1) * TW + lane + 1] = make_float4(h.dn[0], h.dn[1], h.dn[2], h.dn[3]);
+        s.rcs[32 + lane] = make_float2(h.dn[2], h.dn[3]);
     }
-    if (s.rem[2] >= 0 && lane < 8) {
-        get_entry(P, ctl, s.rem[2], 72 + lane, tag, false, v);
-        s.own[(lane + 1) * TW + 0] = make_float4(v[0], v[1], v[2], v[3]);
-        s.rcs[64 + lane] = make_float2(v[2], v[3]);
+    if (s.rem[2] >= 0 && lane < RS_STRIP_H) {
+        s.own[(lane + 1) * TW + 0] = make_float4(h.sd[0], h.sd[1], h.sd[2], h.sd[3]);
+        s.rcs[OB_LEFT + lane] = make_float2(h.sd[2], h.sd[3]);
     }
-    if (s.rem[3] >= 0 && lane >= 8 && lane < 16) {
-        get_entry(P, ctl, s.rem[3], 64 + lane - 8, tag, false, v);
-        s.own[(lane - 8 + 1) * TW + TW - 1] = make_float4(v[0], v[1], v[2], v[3]);
-        s.rcs[72 + lane - 8] = make_float2(v[2], v[3]);
+    if (s.rem[3] >= 0 && lane >= 8 && lane < 8 + RS_STRIP_H) {
+        s.own[(lane - 8 + 1) * TW + TW - 1] = make_float4(h.sd[0], h.sd[1], h.sd[2], h.sd[3]);
+        s.rcs[OB_RIGHT + lane - 8] = make_float2(h.sd[2], h.sd[3]);
     }
 }
 
@@ -332,25 +394,13 @@ __device__ __forceinline__ float4 p_entry_from(const float v[6], float beta, flo
 }
 
 // ring <- neighbours' new direction, computed from their published (z, p_old)
-__device__ __forceinline__ void recv_p(const ResProb& P, Ctl* ctl, const StripCtx& s, int lane, unsigned tag, float beta)
+__device__ __forceinline__ void apply_p(const StripCtx& s, int lane, const Halo& h, float beta)
 {
-    float v[6];
-    if (s.rem[0] >= 0) {
-        get_entry(P, ctl, s.rem[0], 32 + lane, tag, true, v);
-        s.own[0 * TW + lane + 1] = p_entry_from(v, beta, s.rcs[lane]);
-    }
-    if (s.rem[1] >= 0) {
-        get_entry(P, ctl, s.rem[1], lane, tag, true, v);
-        s.own[(TH - 1) * TW + lane + 1] = p_entry_from(v, beta, s.rcs[32 + lane]);
-    }
-    if (s.rem[2] >= 0 && lane < 8) {
-        get_entry(P, ctl, s.rem[2], 72 + lane, tag, true, v);
-        s.own[(lane + 1) * TW + 0] = p_entry_from(v, beta, s.rcs[64 + lane]);
-    }
-    if (s.rem[3] >= 0 && lane >= 8 && lane < 16) {
-        get_entry(P, ctl, s.rem[3], 64 + lane - 8, tag, true, v);
-        s.own[(lane - 8 + 1) * TW + TW - 1] = p_entry_from(v, beta, s.rcs[72 + lane - 8]);
-    }
+    if (s.rem[0] >= 0) s.own[0 * TW + lane + 1] = p_entry_from(h.up, beta, s.rcs[lane]);
+    if (s.rem[1] >= 0) s.own[(TH - 1) * TW + lane + 1] = p_entry_from(h.dn, beta, s.rcs[32 + lane]);
+    if (s.rem[2] >= 0 && lane < RS_STRIP_H) s.own[(lane + 1) * TW + 0] = p_entry_from(h.sd, beta, s.rcs[OB_LEFT + lane]);
+    if (s.rem[3] >= 0 && lane >= 8 && lane < 8 + RS_STRIP_H)
+        s.own[(lane - 8 + 1) * TW + TW - 1] = p_entry_from(h.sd, beta, s.rcs[OB_RIGHT + lane - 8]);
 }
 
 // constraint of a pixel for the current continuation weight (CombinedSolver.h:236-239)
@@ -433,6 +483,7 @@ __global__ void __launch_bounds__(RS_THREADS_MAX, 1) k_resident(const ResProb* _
     }
     s.x = sx * RS_STRIP_W + lane;
     s.y0 = sy * RS_STRIP_H;
+    const bool any_rem = s.has && (s.rem[0] >= 0 || s.rem[1] >= 0 || s.rem[2] >= 0 || s.rem[3] >= 0); // warp-uniform
 
     // ---- flags from the mask (constant for the whole launch except the fit bit) ----
     unsigned flo = 0, fhi = 0;
@@ -459,7 +510,7 @@ __global__ void __launch_bounds__(RS_THREADS_MAX, 1) k_resident(const ResProb* _
     float q0[RS_STRIP_H], q1[RS_STRIP_H], qa[RS_STRIP_H];
 #pragma unroll
     for (int k = 0; k < RS_STRIP_H; ++k) { r0[k] = r1[k] = r2[k] = pa[k] = 0.f; cc[k] = 1.f; ss[k] = 0.f; q0[k] = q1[k] = qa[k] = 0.f; }
-    int S_cost = 0, S_num = 0, S_den = 0, S_bnum = 0, S_sync = S_MIN;
+    int S_cost = 0, S_num = 0, S_den = 0, S_bnum = 0;
     unsigned seq = 0; // publication sequence number == halo tag
     bool ok = true;
     __syncthreads();
@@ -481,11 +532,13 @@ __global__ void __launch_bounds__(RS_THREADS_MAX, 1) k_resident(const ResProb* _
                     e = make_float4(X.x, X.y, cs, sn);
                 }
                 s.own[(k + 1) * TW + lane + 1] = e;
-                if (s.has) publish_rowcol(s, lane, k, seq, e.x, e.y, e.z, e.w, 0.f, 0.f, false);
+                if (any_rem) publish_rowcol(s, lane, k, seq, e.x, e.y, e.z, e.w, 0.f, 0.f, false);
             }
-            (void)grid_sum(c, 0.f, 0.f, S_sync, ok);
-            if (!ok) break;
-            if (s.has) recv_x(P, &ctl, s, lane, seq);
+            if (any_rem) {
+                Halo h;
+                fetch_halo(P, &ctl, s, lane, seq, false, h);
+                apply_x(s, lane, h);
+            }
             __syncthreads();
             {
                 float gs0 = 0.f, gs1 = 0.f;
@@ -559,14 +612,18 @@ __global__ void __launch_bounds__(RS_THREADS_MAX, 1) k_resident(const ResProb* _
                 ++seq;
 #pragma unroll
                 for (int k = 0; k < RS_STRIP_H; ++k) {
-                    if (s.has) {
+                    if (any_rem) {
                         const unsigned f = flag_of(flo, fhi, k);
                         const int nv = __popc(f & 15u);
                         const float pX = ctl.preX[nv + ((f & FLAG_FIT) ? 5 : 0)], pA = ctl.preA[nv];
                         publish_rowcol(s, lane, k, seq, pX * r0[k], pX * r1[k], pA * r2[k], 0.f, 0.f, 0.f, true);
                     }
                 }
-                num = grid_sum(c, gs0, gs1, S_num, ok); // solverGPUGaussNewton.t:395 scanAlphaNumerator
+                Halo h0;
+                long long ta0 = 0, ta1 = 0;
+                grid_arrive(c, gs0, gs1, S_num, ta0, ta1);
+                if (any_rem) fetch_halo(P, &ctl, s, lane, seq, true, h0); // overlaps the barrier latency
+                num = grid_finish(c, gs0, gs1, S_num, ok, ta0, ta1); // solverGPUGaussNewton.t:395 scanAlphaNumerator
                 if (!ok) break;
                 // p_0 = z_0 into the tile (all warps are past their J^T F reads: grid_sum synchronised)
 #pragma unroll
@@ -578,7 +635,7 @@ __global__ void __launch_bounds__(RS_THREADS_MAX, 1) k_resident(const ResProb* _
                     pa[k] = pA * r2[k];
                     s.own[(k + 1) * TW + lane + 1] = make_float4(p0, p1, ss[k] * pa[k], cc[k] * pa[k]);
                 }
-                if (s.has) recv_p(P, &ctl, s, lane, seq, 0.0f);
+                if (any_rem) apply_p(s, lane, h0, 0.0f);
                 __syncthreads();
             }
 
@@ -625,7 +682,7 @@ __global__ void __launch_bounds__(RS_THREADS_MAX, 1) k_resident(const ResProb* _
 
                 // ---- PCGStep2: delta += alpha p, r -= alpha q, z = pre r, bnum = sum z.r ----
                 gs0 = 0.f; gs1 = 0.f;
-                const bool pub = s.has && (it + 1 < P.nPCG);
+                const bool pub = any_rem && (it + 1 < P.nPCG);
                 ++seq;
 #pragma unroll
                 for (int k = 0; k < RS_STRIP_H; ++k) {
@@ -645,8 +702,12 @@ __global__ void __launch_bounds__(RS_THREADS_MAX, 1) k_resident(const ResProb* _
                     if (k < 4) gs0 = gs0 + term; else gs1 = gs1 + term;
                     if (pub) publish_rowcol(s, lane, k, seq, z0, z1, z2, e.x, e.y, pa[k], true);
                 }
+                Halo h;
                 RS_TICK(1);
-                const float bnum = grid_sum(c, gs0, gs1, S_bnum, ok);
+                long long tb0 = 0, tb1 = 0;
+                grid_arrive(c, gs0, gs1, S_bnum, tb0, tb1);
+                if (pub) fetch_halo(P, &ctl, s, lane, seq, true, h); // overlaps the barrier latency
+                const float bnum = grid_finish(c, gs0, gs1, S_bnum, ok, tb0, tb1);
                 RS_TOCK();
                 if (!ok) break;
                 if (P.trace && c.cta == 0 && threadIdx.x == 0) {
@@ -669,7 +730,7 @@ __global__ void __launch_bounds__(RS_THREADS_MAX, 1) k_resident(const ResProb* _
                     pa[k] = fmaf(beta, pa[k], pA * r2[k]);
                     s.own[(k + 1) * TW + lane + 1] = make_float4(p0, p1, ss[k] * pa[k], cc[k] * pa[k]);
                 }
-                if (s.has) recv_p(P, &ctl, s, lane, seq, beta);
+                if (any_rem) apply_p(s, lane, h, beta);
                 __syncthreads();
                 RS_TICK(2);
             }
@@ -762,88 +823,151 @@ __global__ void __launch_bounds__(1024) k_strip_compact(int SX, int SY, const un
 } // namespace
 
 // ------------------------------------------------------------------------------------------------ host
-ResidentSolver::ResidentSolver(int maxW, int maxH) : maxW_(maxW), maxH_(maxH)
+ResidentSolver::ResidentSolver(int maxW, int maxH, int max_slots) : maxW_(maxW), maxH_(maxH)
 {
     int dev = 0;
     ARAP_CUDA_OR_EXIT(cudaGetDevice(&dev));
     ARAP_CUDA_OR_EXIT(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, dev));
     const int SX = (maxW + RS_STRIP_W - 1) / RS_STRIP_W, SY = (maxH + RS_STRIP_H - 1) / RS_STRIP_H;
-    const size_t ns = (size_t)SX * SY;
-    ARAP_CUDA_OR_EXIT(cudaMalloc(&d_strip_xy_, ns * sizeof(int2)));
-    ARAP_CUDA_OR_EXIT(cudaMalloc(&d_slot_of_strip_, ns * sizeof(int) + ns)); // + the active bytes
-    ARAP_CUDA_OR_EXIT(cudaMalloc(&d_count_, sizeof(int)));
-    outbox_cap_ = ns;
-    ARAP_CUDA_OR_EXIT(cudaMalloc(&d_outbox_, ns * RS_OUTBOX_ENTRIES * 3 * sizeof(uint4)));
-    ARAP_CUDA_OR_EXIT(cudaMalloc(&d_bar_, 8 * sizeof(unsigned long long)));
+    strip_cap_ = (size_t)SX * SY;
+    slots_.resize(max_slots > 0 ? max_slots : 1);
+    for (Slot& sl : slots_) {
+        ARAP_CUDA_OR_EXIT(cudaMalloc(&sl.d_strip_xy, strip_cap_ * sizeof(int2)));
+        ARAP_CUDA_OR_EXIT(cudaMalloc(&sl.d_slot_of_strip, strip_cap_ * sizeof(int) + strip_cap_)); // + the active bytes
+        ARAP_CUDA_OR_EXIT(cudaMalloc(&sl.d_count, sizeof(int)));
+        // the outbox only has to hold what can be resident: at most sm_count * max warps strips
+        const size_t ob = std::min(strip_cap_, (size_t)sm_count_ * (RS_THREADS_MAX / 32));
+        ARAP_CUDA_OR_EXIT(cudaMalloc(&sl.d_outbox, ob * RS_OUTBOX_ENTRIES * 3 * sizeof(uint4)));
+        ARAP_CUDA_OR_EXIT(cudaMalloc(&sl.d_bar, 8 * sizeof(unsigned long long)));
+    }
+    ARAP_CUDA_OR_EXIT(cudaMallocHost(&h_counts_, slots_.size() * sizeof(int)));
     ARAP_CUDA_OR_EXIT(cudaMalloc(&d_status_, 2 * sizeof(int)));
     ARAP_CUDA_OR_EXIT(cudaMemset(d_status_, 0, 2 * sizeof(int)));
-    ARAP_CUDA_OR_EXIT(cudaMalloc(&d_prob_, sizeof(ResProb)));
+    ARAP_CUDA_OR_EXIT(cudaMalloc(&d_probs_, slots_.size() * sizeof(ResProb)));
     ARAP_CUDA_OR_EXIT(cudaFuncSetAttribute(k_resident, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)((RS_THREADS_MAX / 32) * sizeof(StripSmem))));
 }
 
 ResidentSolver::~ResidentSolver()
 {
-    cudaFree(d_strip_xy_); cudaFree(d_slot_of_strip_); cudaFree(d_count_); cudaFree(d_outbox_);
-    cudaFree(d_bar_); cudaFree(d_status_); cudaFree(d_prob_);
+    for (Slot& sl : slots_) {
+        cudaFree(sl.d_strip_xy); cudaFree(sl.d_slot_of_strip); cudaFree(sl.d_count); cudaFree(sl.d_outbox); cudaFree(sl.d_bar);
+    }
+    cudaFreeHost(h_counts_);
+    cudaFree(d_status_); cudaFree(d_probs_);
+}
+
+void ResidentSolver::prepare_enqueue(int slot, int W, int H, const float* d_M, cudaStream_t stream)
+{
+    Slot& sl = slots_[slot];
+    sl.W = W; sl.H = H;
+    sl.SX = (W + RS_STRIP_W - 1) / RS_STRIP_W;
+    sl.SY = (H + RS_STRIP_H - 1) / RS_STRIP_H;
+    sl.d_M = d_M;
+    sl.fits = false;
+    sl.n_strips = 0;
+    if ((size_t)W * H > (size_t)maxW_ * maxH_ || (size_t)sl.SX * sl.SY > strip_cap_) { h_counts_[slot] = -1; return; }
+    unsigned char* d_active = reinterpret_cast<unsigned char*>(sl.d_slot_of_strip + (size_t)sl.SX * sl.SY);
+    k_strip_active<<<(sl.SX * sl.SY + 7) / 8, 256, 0, stream>>>(W, H, sl.SX, sl.SY, d_M, d_active);
+    k_strip_compact<<<1, 1024, 0, stream>>>(sl.SX, sl.SY, d_active, sl.d_strip_xy, sl.d_slot_of_strip, sl.d_count);
+    launches_ += 2;
+    ARAP_CUDA_OR_EXIT(cudaMemcpyAsync(&h_counts_[slot], sl.d_count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+}
+
+bool ResidentSolver::prepare_finish(int slot)
+{
+    Slot& sl = slots_[slot];
+    sl.fits = false;
+    if (h_counts_[slot] < 0) return false;
+    sl.n_strips = h_counts_[slot];
+    const int max_warps = RS_THREADS_MAX / 32;
+    if (sl.n_strips == 0) { sl.G = 1; sl.NW = 1; sl.fits = true; return true; }
+    sl.NW = (sl.n_strips + sm_count_ - 1) / sm_count_;
+    if (sl.NW < 4) sl.NW = 4;
+    if (sl.NW > max_warps) return false; // does not fit on chip
+    sl.G = (sl.n_strips + sl.NW - 1) / sl.NW;
+    if (sl.G > sm_count_) sl.G = sm_count_;
+    if (sl.G > RS_MAX_CTAS) return false;
+    if ((sl.n_strips + sl.G - 1) / sl.G > sl.NW) return false; // balanced split: ceil(n/G) strips per CTA
+    sl.fits = true;
+    return true;
 }
 
 bool ResidentSolver::prepare(int W, int H, const float* d_M, cudaStream_t stream)
 {
-    if ((size_t)W * H > (size_t)maxW_ * maxH_) return false;
-    W_ = W; H_ = H;
-    SX_ = (W + RS_STRIP_W - 1) / RS_STRIP_W;
-    SY_ = (H + RS_STRIP_H - 1) / RS_STRIP_H;
-    if ((size_t)SX_ * SY_ > outbox_cap_) return false;
-    d_M_ = d_M;
-    unsigned char* d_active = reinterpret_cast<unsigned char*>(d_slot_of_strip_ + (size_t)SX_ * SY_);
-    k_strip_active<<<(SX_ * SY_ + 7) / 8, 256, 0, stream>>>(W, H, SX_, SY_, d_M, d_active);
-    k_strip_compact<<<1, 1024, 0, stream>>>(SX_, SY_, d_active, d_strip_xy_, d_slot_of_strip_, d_count_);
-    launches_ += 2;
-    ARAP_CUDA_OR_EXIT(cudaMemcpyAsync(&n_strips_, d_count_, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    prepare_enqueue(0, W, H, d_M, stream);
     ARAP_CUDA_OR_EXIT(cudaStreamSynchronize(stream));
-    const int max_warps = RS_THREADS_MAX / 32;
-    if (n_strips_ == 0) { G_ = 1; NW_ = 1; return true; }
-    NW_ = (n_strips_ + sm_count_ - 1) / sm_count_;
-    if (NW_ < 4) NW_ = 4;
-    if (NW_ > max_warps) return false; // does not fit on chip
-    G_ = (n_strips_ + NW_ - 1) / NW_;
-    if (G_ > sm_count_) G_ = sm_count_;
-    if (G_ > RS_MAX_CTAS) return false;
-    // balanced split: ceil(n/G) strips at most per CTA
-    if ((n_strips_ + G_ - 1) / G_ > NW_) return false;
-    return true;
+    return prepare_finish(0);
+}
+
+void ResidentSolver::set_problem(int slot, float2* X, float* A, const float2* C, int lerp_mode, float wf, float wr,
+                                 float* d_costs, float* d_trace)
+{
+    Slot& sl = slots_[slot];
+    ResProb& p = sl.prob;
+    p = ResProb{};
+    p.W = sl.W; p.H = sl.H; p.SX = sl.SX; p.SY = sl.SY; p.n_strips = sl.n_strips; p.G = sl.G;
+    p.X = X; p.A = A; p.C = C; p.M = sl.d_M; p.lerp_mode = lerp_mode;
+    p.wf = wf; p.wr = wr; p.wf2 = wf * wf; p.wr2 = wr * wr;
+    p.strip_xy = sl.d_strip_xy; p.slot_of_strip = sl.d_slot_of_strip;
+    p.outbox = sl.d_outbox; p.bar = sl.d_bar; p.costs = d_costs; p.trace = d_trace; p.status = d_status_;
+}
+
+int ResidentSolver::group_size(int first, int limit) const
+{
+    int best = 1;
+    int gmax = 0, nwmax = 0;
+    for (int cnt = 1; cnt <= limit && first + cnt <= (int)slots_.size(); ++cnt) {
+        const Slot& sl = slots_[first + cnt - 1];
+        if (!sl.fits) break;
+        gmax = std::max(gmax, sl.G);
+        nwmax = std::max(nwmax, sl.NW);
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_resident, nwmax * 32,
+                                                          (size_t)nwmax * sizeof(StripSmem)) != cudaSuccess) break;
+        if ((long long)per_sm * sm_count_ < (long long)gmax * cnt) break;
+        best = cnt;
+    }
+    return best;
+}
+
+void ResidentSolver::enqueue_group(int first, int count, int nCont, int nGN, int nPCG, cudaStream_t stream)
+{
+    int gmax = 0, nwmax = 0;
+    std::vector<ResProb> host(count);
+    for (int i = 0; i < count; ++i) {
+        Slot& sl = slots_[first + i];
+        sl.prob.nCont = nCont; sl.prob.nGN = nGN; sl.prob.nPCG = nPCG;
+        sl.prob.prof = (i == 0) ? d_prof_ : nullptr;
+        host[i] = sl.prob;
+        gmax = std::max(gmax, sl.G);
+        nwmax = std::max(nwmax, sl.NW);
+        // barrier words start at zero; halo tags start at 1, so a zeroed outbox is "nothing published yet"
+        ARAP_CUDA_OR_EXIT(cudaMemsetAsync(sl.d_bar, 0, 8 * sizeof(unsigned long long), stream));
+        ARAP_CUDA_OR_EXIT(cudaMemsetAsync(sl.d_outbox, 0,
+                                          (size_t)(sl.n_strips > 0 ? sl.n_strips : 1) * RS_OUTBOX_ENTRIES * 3 * sizeof(uint4), stream));
+    }
+    ARAP_CUDA_OR_EXIT(cudaMemcpyAsync(d_probs_ + first, host.data(), count * sizeof(ResProb), cudaMemcpyHostToDevice, stream));
+    const int threads = nwmax * 32;
+    const size_t smem = (size_t)nwmax * sizeof(StripSmem);
+    int per_sm = 0;
+    ARAP_CUDA_OR_EXIT(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_resident, threads, smem));
+    if ((long long)per_sm * sm_count_ < (long long)gmax * count) {
+        fprintf(stderr, "arapb200: resident kernel cannot be co-resident (%d x %d CTAs, %d per SM)\n", gmax, count, per_sm);
+        exit(1);
+    }
+    const ResProb* dp = d_probs_ + first;
+    void* args[] = {(void*)&dp};
+    ARAP_CUDA_OR_EXIT(cudaLaunchCooperativeKernel((const void*)k_resident, dim3(gmax, count, 1), dim3(threads, 1, 1), args,
+                                                  smem, stream));
+    launches_ += 1;
 }
 
 void ResidentSolver::enqueue(float2* X, float* A, const float2* C, int lerp_mode, float wf, float wr, int nCont, int nGN,
                              int nPCG, float* d_costs, float* d_trace, cudaStream_t stream)
 {
-    ResProb p{};
-    p.W = W_; p.H = H_; p.SX = SX_; p.SY = SY_; p.n_strips = n_strips_; p.G = G_;
-    p.X = X; p.A = A; p.C = C; p.M = d_M_; p.lerp_mode = lerp_mode;
-    p.wf = wf; p.wr = wr; p.wf2 = wf * wf; p.wr2 = wr * wr;
-    p.strip_xy = d_strip_xy_; p.slot_of_strip = d_slot_of_strip_;
-    p.outbox = d_outbox_; p.bar = d_bar_; p.costs = d_costs; p.trace = d_trace; p.status = d_status_;
-    p.nCont = nCont; p.nGN = nGN; p.nPCG = nPCG;
-    p.prof = d_prof_;
-    ARAP_CUDA_OR_EXIT(cudaMemcpyAsync(d_prob_, &p, sizeof(p), cudaMemcpyHostToDevice, stream));
-    // barrier words start at zero; halo tags start at 1, so a zeroed outbox is "nothing published yet"
-    ARAP_CUDA_OR_EXIT(cudaMemsetAsync(d_bar_, 0, 8 * sizeof(unsigned long long), stream));
-    ARAP_CUDA_OR_EXIT(cudaMemsetAsync(d_outbox_, 0, (size_t)(n_strips_ > 0 ? n_strips_ : 1) * RS_OUTBOX_ENTRIES * 3 * sizeof(uint4),
-                                      stream));
-    const int threads = NW_ * 32;
-    const size_t smem = (size_t)NW_ * sizeof(StripSmem);
-    int per_sm = 0;
-    ARAP_CUDA_OR_EXIT(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_resident, threads, smem));
-    if (per_sm * sm_count_ < G_) {
-        fprintf(stderr, "arapb200: resident kernel cannot be co-resident (%d CTAs, %d per SM)\n", G_, per_sm);
-        exit(1);
-    }
-    const ResProb* dp = d_prob_;
-    void* args[] = {(void*)&dp};
-    ARAP_CUDA_OR_EXIT(cudaLaunchCooperativeKernel((const void*)k_resident, dim3(G_, 1, 1), dim3(threads, 1, 1), args,
-                                                  smem, stream));
-    launches_ += 1;
+    set_problem(0, X, A, C, lerp_mode, wf, wr, d_costs, d_trace);
+    enqueue_group(0, 1, nCont, nGN, nPCG, stream);
 }
 
 int ResidentSolver::status(cudaStream_t stream)

@@ -5,14 +5,18 @@
 // See DESIGN.md section 4 for the decomposition, the barrier and the halo protocol.
 #pragma once
 #include "common.cuh"
+#include <vector>
 
 namespace arapb200 {
 
-constexpr int RS_STRIP_W = 32;   // a strip is 32 x 8 pixels: one warp, lane = column, 8 rows per lane
-constexpr int RS_STRIP_H = 8;
+#ifndef ARAP_RS_STRIP_H
+#define ARAP_RS_STRIP_H 4
+#endif
+constexpr int RS_STRIP_W = 32;   // a strip is 32 x RS_STRIP_H pixels: one warp, lane = column
+constexpr int RS_STRIP_H = ARAP_RS_STRIP_H; // 4 (one contract-C3 group per lane) or 8 (two)
 constexpr int RS_MAX_WARPS = 16; // strips per CTA
 constexpr int RS_MAX_CTAS = 160; // CTAs per problem (8-bit arrival count per barrier word)
-constexpr int RS_OUTBOX_ENTRIES = 80; // 32 top + 32 bottom + 8 left + 8 right, 48 bytes each
+constexpr int RS_OUTBOX_ENTRIES = 64 + 2 * RS_STRIP_H; // top row, bottom row, left column, right column; 48 bytes each
 
 // One problem as the kernel sees it (device memory, one per blockIdx.y)
 struct ResProb {
@@ -38,12 +42,13 @@ struct ResProb {
 
 class ResidentSolver {
 public:
-    // capacity: largest image handled
-    ResidentSolver(int maxW, int maxH);
+    // capacity: largest image handled, number of problem slots that can be prepared / launched together
+    explicit ResidentSolver(int maxW, int maxH, int max_slots = 1);
     ~ResidentSolver();
     ResidentSolver(const ResidentSolver&) = delete;
     ResidentSolver& operator=(const ResidentSolver&) = delete;
 
+    // ---- single-problem convenience (slot 0) ----
     // Build the strip tables for mask M (device, float[N], 0 = active).  Blocking (4-byte read-back).
     // Returns false when the problem does not fit on chip (caller falls back to the streaming back-end).
     bool prepare(int W, int H, const float* d_M, cudaStream_t stream);
@@ -51,27 +56,44 @@ public:
     // (device, nCont*(nGN+1) floats) receives the cost before the first and after every GN step.
     void enqueue(float2* X, float* A, const float2* C, int lerp_mode, float wf, float wr, int nCont, int nGN,
                  int nPCG, float* d_costs, float* d_trace, cudaStream_t stream);
+
+    // ---- batched interface: several independent problems share ONE cooperative launch (blockIdx.y) ----
+    void prepare_enqueue(int slot, int W, int H, const float* d_M, cudaStream_t stream); // kernels + async read-back
+    bool prepare_finish(int slot);                                                       // after a stream sync
+    void set_problem(int slot, float2* X, float* A, const float2* C, int lerp_mode, float wf, float wr,
+                     float* d_costs, float* d_trace);
+    // how many of the prepared slots first, first+1, ... can be co-resident in one launch (>= 1)
+    int group_size(int first, int limit) const;
+    void enqueue_group(int first, int count, int nCont, int nGN, int nPCG, cudaStream_t stream);
+
     // after the stream has been synchronised: non-zero = the kernel bailed out (watchdog)
     int status(cudaStream_t stream);
     long long launches() const { return launches_; }
-    int n_strips() const { return n_strips_; }
-    int ctas() const { return G_; }
-    int warps() const { return NW_; }
+    int n_strips(int slot = 0) const { return slots_[slot].n_strips; }
+    int ctas(int slot = 0) const { return slots_[slot].G; }
+    int warps(int slot = 0) const { return slots_[slot].NW; }
+    int max_slots() const { return (int)slots_.size(); }
     // debug: per-CTA cycle accounting of the next launches into d_prof ([ctas()][8] u64), or null to disable
     void set_profile(unsigned long long* d_prof) { d_prof_ = d_prof; }
 
 private:
+    struct Slot {
+        int W = 0, H = 0, SX = 0, SY = 0, n_strips = 0, G = 0, NW = 0;
+        bool fits = false;
+        const float* d_M = nullptr;
+        int2* d_strip_xy = nullptr;
+        int* d_slot_of_strip = nullptr;
+        int* d_count = nullptr;
+        uint4* d_outbox = nullptr;
+        unsigned long long* d_bar = nullptr;
+        ResProb prob{};
+    };
     int maxW_, maxH_;
-    int W_ = 0, H_ = 0, SX_ = 0, SY_ = 0, n_strips_ = 0, G_ = 0, NW_ = 0;
-    const float* d_M_ = nullptr;
-    int2* d_strip_xy_ = nullptr;
-    int* d_slot_of_strip_ = nullptr;
-    int* d_count_ = nullptr;
-    uint4* d_outbox_ = nullptr;
-    size_t outbox_cap_ = 0;
-    unsigned long long* d_bar_ = nullptr;
-    int* d_status_ = nullptr;
-    ResProb* d_prob_ = nullptr;
+    size_t strip_cap_ = 0;
+    std::vector<Slot> slots_;
+    int* h_counts_ = nullptr;   // pinned
+    int* d_status_ = nullptr;   // shared by all slots
+    ResProb* d_probs_ = nullptr;
     int sm_count_ = 0;
     long long launches_ = 0;
     unsigned long long* d_prof_ = nullptr;
