@@ -39,6 +39,7 @@ constexpr int RS_THREADS_MAX = (RS_STRIP_H == 8) ? 384 : 512;
 constexpr int OB_LEFT = 64, OB_RIGHT = 64 + RS_STRIP_H;
 static_assert(RS_STRIP_H == 4 || RS_STRIP_H == 8, "strip height must be 4 or 8");
 constexpr long long LIMB_BIAS = 1ll << 36;
+constexpr int BAR_STRIDE = 128; // u64 words between barrier words (1 KiB): separate L2 slices, parallel atomics
 constexpr int S_MIN = -100, S_MAX = 100;
 
 struct __align__(16) StripSmem {
@@ -87,27 +88,35 @@ __device__ __forceinline__ double pow2_f64(int e) // 2^e, e in the normal range
     return __hiloint2double((e + 1023) << 20, 0);
 }
 
-// exact 128-bit integer (units of 2^e_unit) -> binary32, round to nearest even.  The top 64 bits are
-// rounded to odd (sticky bit) and handed to the hardware u64 -> f32 conversion, which is then the single
-// rounding (64 >= 24 + 2).
-__device__ __forceinline__ float i128_to_float_rn(__int128 T, int e_unit)
+// error-free a + b = s + e (Knuth)
+__device__ __forceinline__ void two_sum(double a, double b, double& s, double& e)
 {
-    const bool neg = T < 0;
-    const unsigned __int128 m = neg ? (unsigned __int128)(-T) : (unsigned __int128)T;
-    const unsigned long long hi = (unsigned long long)(m >> 64), lo = (unsigned long long)m;
-    unsigned long long top = lo;
-    int e = e_unit;
-    if (hi) {
-        const int sh = 64 - __clzll((long long)hi); // 1..64
-        top = (sh == 64) ? hi : ((hi << (64 - sh)) | (lo >> sh));
-        const unsigned long long lost = (sh == 64) ? lo : (lo << (64 - sh));
-        top |= (lost != 0ull) ? 1ull : 0ull;
-        e += sh;
-    }
-    const float f = __ull2float_rn(top);
-    e = max(-1000, min(1000, e));
-    const float r = (float)((double)f * pow2_f64(e)); // exact scaling (barring binary32 underflow)
-    return neg ? -r : r;
+    s = __dadd_rn(a, b);
+    const double bb = __dadd_rn(s, -a);
+    e = __dadd_rn(__dadd_rn(a, -__dadd_rn(s, -bb)), __dadd_rn(b, -bb));
+}
+
+// L0*2^72 + L1*2^48 + L2*2^24 + L3 (|Lj| < 2^45, units 2^e_unit) -> binary32 with ONE rounding: the four terms
+// are exact doubles; they are added error-free (s + e), s + e is rounded to odd in binary64 (53 >= 24 + 2 bits)
+// and only then to binary32.
+__device__ __forceinline__ float limbs_to_float_rn(const long long L[4], int e_unit, bool& is_zero)
+{
+    const double a = __ll2double_rn(L[0]) * 4722366482869645213696.0; // 2^72
+    const double b = __ll2double_rn(L[1]) * 281474976710656.0;        // 2^48
+    const double c = __ll2double_rn(L[2]) * 16777216.0;               // 2^24
+    const double d = __ll2double_rn(L[3]);
+    double s1, e1, s2, e2, s3, e3;
+    two_sum(c, d, s1, e1);   // low pair first: e1 is almost always 0
+    two_sum(b, s1, s2, e2);
+    two_sum(a, s2, s3, e3);
+    const double e = __dadd_rn(__dadd_rn(e3, e2), e1); // |e| < ulp(s3); only its sign and non-zero-ness matter
+    is_zero = (s3 == 0.0 && e == 0.0);
+    // round (s3 + e) to odd: truncate toward zero and, when inexact, set the last bit
+    const double zd = __dadd_rd(s3, e), zu = __dadd_ru(s3, e);
+    double z = (zu > 0.0) ? zd : zu;
+    if (zd != zu) z = __longlong_as_double(__double_as_longlong(z) | 1ll);
+    e_unit = max(-900, min(900, e_unit));
+    return (float)(z * pow2_f64(e_unit)); // exact scaling (barring binary32 underflow), single rounding
 }
 
 // Everything a warp needs to know about its strip
@@ -186,7 +195,7 @@ __device__ __forceinline__ void grid_arrive(Cta& c, float g0, float g1, int S, l
     }
     __syncthreads();
     if (c.wid == 0 && c.lane < 4) {
-        unsigned long long* buf = c.P->bar + (c.epoch & 1u) * 4;
+        unsigned long long* buf = c.P->bar + (size_t)(c.epoch & 1u) * 4 * BAR_STRIDE;
         long long sum = 0;
         int any = 0;
         for (int w = 0; w < c.nw; ++w) {
@@ -195,7 +204,7 @@ __device__ __forceinline__ void grid_arrive(Cta& c, float g0, float g1, int S, l
         }
         unsigned long long contrib = (1ull << 48) + (unsigned long long)(sum + LIMB_BIAS);
         if (c.lane == 0 && any) contrib += (1ull << 56);
-        red_add_u64(buf + c.lane, contrib);
+        red_add_u64(buf + (size_t)c.lane * BAR_STRIDE, contrib);
     }
     if (c.prof) t1 = clock64();
 }
@@ -208,7 +217,7 @@ __device__ __forceinline__ int grid_wait(Cta& c, int& S, bool& grown, float& res
     const ResProb& P = *c.P;
     long long t2 = 0;
     if (c.wid == 0 && c.lane == 0) {
-        unsigned long long* buf = P.bar + (c.epoch & 1u) * 4;
+        unsigned long long* buf = P.bar + (size_t)(c.epoch & 1u) * 4 * BAR_STRIDE;
         unsigned long long* prev = ctl->prev[c.epoch & 1u];
         unsigned long long d[4];
         unsigned spins = 0;
@@ -216,7 +225,7 @@ __device__ __forceinline__ int grid_wait(Cta& c, int& S, bool& grown, float& res
             bool done = true;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                d[j] = ld_u64_volatile(buf + j) - prev[j];
+                d[j] = ld_u64_volatile(buf + (size_t)j * BAR_STRIDE) - prev[j];
                 if ((int)((d[j] >> 48) & 0xFF) != c.G) done = false;
             }
             if (done) break;
@@ -238,13 +247,13 @@ __device__ __forceinline__ int grid_wait(Cta& c, int& S, bool& grown, float& res
             L[j] = (long long)(d[j] & ((1ull << 48) - 1)) - (long long)c.G * LIMB_BIAS;
         }
         const int novf = (int)((d[0] >> 56) & 0xFF);
-        const __int128 T = ((__int128)L[0] << 72) + ((__int128)L[1] << 48) + ((__int128)L[2] << 24) + (__int128)L[3];
-        const float r = i128_to_float_rn(T, S - 90);
+        bool T_is_zero;
+        const float r = limbs_to_float_rn(L, S - 90, T_is_zero);
         int code = 0, newS = S;
         if (novf) {
             code = 1; newS = min(S + 24, S_MAX);
             if (S >= S_MAX) code = 0; // Inf/NaN terms: give up, the result is garbage anyway
-        } else if (T == 0) {
+        } else if (T_is_zero) {
             if (!grown && S > S_MIN) { code = 1; newS = max(S - 64, S_MIN); }
         } else {
             const int e = ilogb_f32(fabsf(r));
@@ -422,7 +431,8 @@ __device__ __forceinline__ unsigned flag_of(unsigned flo, unsigned fhi, int k)
 }
 
 // =====================================================================================================
-__global__ void __launch_bounds__(RS_THREADS_MAX, 1) k_resident(const ResProb* __restrict__ probs)
+template <int MAXT, int MINB, bool PROF>
+__global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __restrict__ probs)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ Ctl ctl;
@@ -433,7 +443,7 @@ __global__ void __launch_bounds__(RS_THREADS_MAX, 1) k_resident(const ResProb* _
     Cta c;
     c.P = &P; c.ctl = &ctl; c.cta = blockIdx.x; c.G = P.G;
     c.lane = threadIdx.x & 31; c.wid = threadIdx.x >> 5; c.nw = blockDim.x >> 5; c.epoch = 0;
-    c.acc[0] = c.acc[1] = c.acc[2] = 0; c.prof = (P.prof != nullptr);
+    c.acc[0] = c.acc[1] = c.acc[2] = 0; c.prof = PROF && (P.prof != nullptr);
     unsigned long long ph[4] = {0, 0, 0, 0}; // cycles in PCG phase 1, 2, 3 and everything else (thread 0)
     long long tk = c.prof ? clock64() : 0;
 #define RS_TICK(slot) do { if (c.prof && threadIdx.x == 0) { const long long tn = clock64(); ph[slot] += (unsigned long long)(tn - tk); tk = tn; } } while (0)
@@ -760,6 +770,29 @@ __global__ void __launch_bounds__(RS_THREADS_MAX, 1) k_resident(const ResProb* _
 #undef RS_TOCK
 }
 
+// Instantiations: (max threads, min CTAs per SM).  More CTAs per SM = more problems interleaved on an SM,
+// which is what hides the barrier latency; the price is a tighter register budget.
+using KernelFn = void (*)(const ResProb*);
+struct KernelVariant {
+    int max_threads, min_blocks;
+    KernelFn fn, fn_prof;
+};
+#ifndef ARAP_RS_VARIANTS
+#if ARAP_RS_STRIP_H == 8
+#define ARAP_RS_VARIANTS {128, 4, k_resident_t<128, 4, false>, k_resident_t<128, 4, true>}, \
+                         {160, 3, k_resident_t<160, 3, false>, k_resident_t<160, 3, true>}, \
+                         {192, 2, k_resident_t<192, 2, false>, k_resident_t<192, 2, true>}, \
+                         {384, 1, k_resident_t<384, 1, false>, k_resident_t<384, 1, true>}
+#else
+#define ARAP_RS_VARIANTS {256, 4, k_resident_t<256, 4, false>, k_resident_t<256, 4, true>}, \
+                         {256, 3, k_resident_t<256, 3, false>, k_resident_t<256, 3, true>}, \
+                         {320, 3, k_resident_t<320, 3, false>, k_resident_t<320, 3, true>}, \
+                         {512, 1, k_resident_t<512, 1, false>, k_resident_t<512, 1, true>}
+#endif
+#endif
+const KernelVariant g_variants[] = {ARAP_RS_VARIANTS};
+constexpr int g_nvariants = sizeof(g_variants) / sizeof(g_variants[0]);
+
 // ---- strip table construction -------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_strip_active(int W, int H, int SX, int SY, const float* __restrict__ M,
                                                        unsigned char* __restrict__ active)
@@ -823,6 +856,21 @@ __global__ void __launch_bounds__(1024) k_strip_compact(int SX, int SY, const un
 } // namespace
 
 // ------------------------------------------------------------------------------------------------ host
+// The kernel variant with the most registers per thread that can keep `total_ctas` CTAs of nw warps resident;
+// -1 if none can.
+static int pick_variant(int nw, long long total_ctas, int sm_count)
+{
+    for (int v = g_nvariants - 1; v >= 0; --v) {
+        if (g_variants[v].max_threads < nw * 32) continue;
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)g_variants[v].fn, nw * 32,
+                                                          (size_t)nw * sizeof(StripSmem)) != cudaSuccess)
+            continue;
+        if ((long long)per_sm * sm_count >= total_ctas) return v;
+    }
+    return -1;
+}
+
 ResidentSolver::ResidentSolver(int maxW, int maxH, int max_slots) : maxW_(maxW), maxH_(maxH)
 {
     int dev = 0;
@@ -838,14 +886,17 @@ ResidentSolver::ResidentSolver(int maxW, int maxH, int max_slots) : maxW_(maxW),
         // the outbox only has to hold what can be resident: at most sm_count * max warps strips
         const size_t ob = std::min(strip_cap_, (size_t)sm_count_ * (RS_THREADS_MAX / 32));
         ARAP_CUDA_OR_EXIT(cudaMalloc(&sl.d_outbox, ob * RS_OUTBOX_ENTRIES * 3 * sizeof(uint4)));
-        ARAP_CUDA_OR_EXIT(cudaMalloc(&sl.d_bar, 8 * sizeof(unsigned long long)));
+        ARAP_CUDA_OR_EXIT(cudaMalloc(&sl.d_bar, 8 * BAR_STRIDE * sizeof(unsigned long long)));
     }
     ARAP_CUDA_OR_EXIT(cudaMallocHost(&h_counts_, slots_.size() * sizeof(int)));
     ARAP_CUDA_OR_EXIT(cudaMalloc(&d_status_, 2 * sizeof(int)));
     ARAP_CUDA_OR_EXIT(cudaMemset(d_status_, 0, 2 * sizeof(int)));
     ARAP_CUDA_OR_EXIT(cudaMalloc(&d_probs_, slots_.size() * sizeof(ResProb)));
-    ARAP_CUDA_OR_EXIT(cudaFuncSetAttribute(k_resident, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)((RS_THREADS_MAX / 32) * sizeof(StripSmem))));
+    for (int v = 0; v < g_nvariants; ++v) {
+        const int smem = (int)((g_variants[v].max_threads / 32) * sizeof(StripSmem));
+        ARAP_CUDA_OR_EXIT(cudaFuncSetAttribute((const void*)g_variants[v].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ARAP_CUDA_OR_EXIT(cudaFuncSetAttribute((const void*)g_variants[v].fn_prof, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    }
 }
 
 ResidentSolver::~ResidentSolver()
@@ -889,6 +940,7 @@ bool ResidentSolver::prepare_finish(int slot)
     if (sl.G > sm_count_) sl.G = sm_count_;
     if (sl.G > RS_MAX_CTAS) return false;
     if ((sl.n_strips + sl.G - 1) / sl.G > sl.NW) return false; // balanced split: ceil(n/G) strips per CTA
+    if (pick_variant(sl.NW, sl.G, sm_count_) < 0) return false;
     sl.fits = true;
     return true;
 }
@@ -915,17 +967,14 @@ void ResidentSolver::set_problem(int slot, float2* X, float* A, const float2* C,
 
 int ResidentSolver::group_size(int first, int limit) const
 {
-    int best = 1;
+    int best = 0;
     int gmax = 0, nwmax = 0;
     for (int cnt = 1; cnt <= limit && first + cnt <= (int)slots_.size(); ++cnt) {
         const Slot& sl = slots_[first + cnt - 1];
         if (!sl.fits) break;
         gmax = std::max(gmax, sl.G);
         nwmax = std::max(nwmax, sl.NW);
-        int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_resident, nwmax * 32,
-                                                          (size_t)nwmax * sizeof(StripSmem)) != cudaSuccess) break;
-        if ((long long)per_sm * sm_count_ < (long long)gmax * cnt) break;
+        if (pick_variant(nwmax, (long long)gmax * cnt, sm_count_) < 0) break;
         best = cnt;
     }
     return best;
@@ -943,23 +992,23 @@ void ResidentSolver::enqueue_group(int first, int count, int nCont, int nGN, int
         gmax = std::max(gmax, sl.G);
         nwmax = std::max(nwmax, sl.NW);
         // barrier words start at zero; halo tags start at 1, so a zeroed outbox is "nothing published yet"
-        ARAP_CUDA_OR_EXIT(cudaMemsetAsync(sl.d_bar, 0, 8 * sizeof(unsigned long long), stream));
+        ARAP_CUDA_OR_EXIT(cudaMemsetAsync(sl.d_bar, 0, 8 * BAR_STRIDE * sizeof(unsigned long long), stream));
         ARAP_CUDA_OR_EXIT(cudaMemsetAsync(sl.d_outbox, 0,
                                           (size_t)(sl.n_strips > 0 ? sl.n_strips : 1) * RS_OUTBOX_ENTRIES * 3 * sizeof(uint4), stream));
     }
     ARAP_CUDA_OR_EXIT(cudaMemcpyAsync(d_probs_ + first, host.data(), count * sizeof(ResProb), cudaMemcpyHostToDevice, stream));
-    const int threads = nwmax * 32;
-    const size_t smem = (size_t)nwmax * sizeof(StripSmem);
-    int per_sm = 0;
-    ARAP_CUDA_OR_EXIT(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_resident, threads, smem));
-    if ((long long)per_sm * sm_count_ < (long long)gmax * count) {
-        fprintf(stderr, "arapb200: resident kernel cannot be co-resident (%d x %d CTAs, %d per SM)\n", gmax, count, per_sm);
+    const int v = pick_variant(nwmax, (long long)gmax * count, sm_count_);
+    if (v < 0) {
+        fprintf(stderr, "arapb200: resident kernel cannot be co-resident (%d x %d CTAs of %d warps)\n", gmax, count, nwmax);
         exit(1);
     }
+    last_variant_ = v;
+    const int threads = nwmax * 32;
+    const size_t smem = (size_t)nwmax * sizeof(StripSmem);
     const ResProb* dp = d_probs_ + first;
     void* args[] = {(void*)&dp};
-    ARAP_CUDA_OR_EXIT(cudaLaunchCooperativeKernel((const void*)k_resident, dim3(gmax, count, 1), dim3(threads, 1, 1), args,
-                                                  smem, stream));
+    const void* fn = d_prof_ ? (const void*)g_variants[v].fn_prof : (const void*)g_variants[v].fn;
+    ARAP_CUDA_OR_EXIT(cudaLaunchCooperativeKernel(fn, dim3(gmax, count, 1), dim3(threads, 1, 1), args, smem, stream));
     launches_ += 1;
 }
 

@@ -10,7 +10,7 @@
 namespace arapb200 {
 
 #ifndef ARAP_RS_STRIP_H
-#define ARAP_RS_STRIP_H 4
+#define ARAP_RS_STRIP_H 8
 #endif
 constexpr int RS_STRIP_W = 32;   // a strip is 32 x RS_STRIP_H pixels: one warp, lane = column
 constexpr int RS_STRIP_H = ARAP_RS_STRIP_H; // 4 (one contract-C3 group per lane) or 8 (two)
@@ -73,6 +73,7 @@ public:
     int ctas(int slot = 0) const { return slots_[slot].G; }
     int warps(int slot = 0) const { return slots_[slot].NW; }
     int max_slots() const { return (int)slots_.size(); }
+    int last_variant() const { return last_variant_; }
     // debug: per-CTA cycle accounting of the next launches into d_prof ([ctas()][8] u64), or null to disable
     void set_profile(unsigned long long* d_prof) { d_prof_ = d_prof; }
 
@@ -97,6 +98,7 @@ private:
     int sm_count_ = 0;
     long long launches_ = 0;
     unsigned long long* d_prof_ = nullptr;
+    int last_variant_ = -1;
 };
 
 } // namespace arapb200
