@@ -259,3 +259,18 @@ def test_full_schedule_size_independent_properties():
     err = np.array([np.hypot(*(f1[y1, x1] - (x2 - x1, y2 - y1))) for x1, y1, x2, y2 in sp.matches])
     assert err.max() < 0.05, err.max()
     assert (c1[:, -1] <= c1[:, 0]).all()
+
+
+def test_batch_api_matches_single_problem_calls():
+    """arapb200_batch_*: problems that share one cooperative launch give exactly the single-problem results."""
+    sps = [synth.synth(160, 120, 1, 2, 300 + i) for i in range(4)] + [synth.synth(160, 120, 2, 3, 400)]
+    jobs = [(s, s.masks[0]) for s in sps] + [(sps[-1], sps[-1].masks[1])]
+    kw = dict(nCont=2, nGN=2, nPCG=40)
+    b = lib.Batch(160, 120, len(jobs), **kw)
+    outs = [b.submit(i, s.rgb, m, s.matches) for i, (s, m) in enumerate(jobs)]
+    b.run()
+    assert b.launches() > 0
+    for o, (s, m) in zip(outs, jobs):
+        flow, rgb, wm, costs = lib.deform(s.rgb, m, s.matches, **kw)
+        assert _eq(o["flow"], flow) and _eq(o["costs"], costs) and _eq(o["rgb"], rgb) and _eq(o["mask"], wm)
+    b.close()
