@@ -93,6 +93,8 @@ class ClockSampler:
 def cpu_leg(workload: str, cores_note=True):
     """Oracle (CPU port of the reference algorithm) on a bounded sample: ONE continuation step
     (8 GN x 400 PCG) of one pair, scaled x19 + one warp.  Returns (pairs_per_s, dict)."""
+    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU arm runs on rank 0 alone)
+    os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
     from oracle import pyoracle as O
     O.build()
     sp = make_pairs(workload, 1, 0)[0]
