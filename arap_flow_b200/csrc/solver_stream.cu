@@ -86,32 +86,37 @@ __global__ void __launch_bounds__(ST_THREADS) k_prep(const StreamDev* __restrict
     const int W = dp.W, H = dp.H;
     const int x = (blockIdx.x % dp.tx) * ST_TILE + (threadIdx.x & 31);
     const int yb = (blockIdx.x / dp.tx) * ST_TILE + (threadIdx.x >> 5) * 4;
-    if (x >= W) return;
     unsigned bad = 0;
+    int any = 0;
+    if (x < W) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int y = yb + r;
-        if (y >= H) break;
-        const size_t i = (size_t)y * W + x;
-        unsigned f = 0;
-        if (dp.M[i] == 0.0f) {
-            f = FLAG_ACTIVE;
-            if (x + 1 < W && dp.M[i + 1] == 0.0f) f |= 1u;
-            if (x > 0 && dp.M[i - 1] == 0.0f) f |= 2u;
-            if (y + 1 < H && dp.M[i + W] == 0.0f) f |= 4u;
-            if (y > 0 && dp.M[i - W] == 0.0f) f |= 8u;
-            const float2 c = dp.C[i];
-            if (c.x >= 0.0f && c.y >= 0.0f) f |= FLAG_FIT; // arap_plan.t:22
-            float s, co;
-            contract_sincos(dp.A[i], s, co);
-            dp.cs[0][i] = co;
-            dp.cs[1][i] = s;
-            const float2 u = dp.U[i];
-            if (u.x != (float)x || u.y != (float)y) bad = 1;
+        for (int r = 0; r < 4; ++r) {
+            const int y = yb + r;
+            if (y >= H) break;
+            const size_t i = (size_t)y * W + x;
+            unsigned f = 0;
+            if (dp.M[i] == 0.0f) {
+                f = FLAG_ACTIVE;
+                any = 1;
+                if (x + 1 < W && dp.M[i + 1] == 0.0f) f |= 1u;
+                if (x > 0 && dp.M[i - 1] == 0.0f) f |= 2u;
+                if (y + 1 < H && dp.M[i + W] == 0.0f) f |= 4u;
+                if (y > 0 && dp.M[i - W] == 0.0f) f |= 8u;
+                const float2 c = dp.C[i];
+                if (c.x >= 0.0f && c.y >= 0.0f) f |= FLAG_FIT; // arap_plan.t:22
+                float s, co;
+                contract_sincos(dp.A[i], s, co);
+                dp.cs[0][i] = co;
+                dp.cs[1][i] = s;
+                const float2 u = dp.U[i];
+                if (u.x != (float)x || u.y != (float)y) bad = 1;
+            }
+            dp.flags[i] = (unsigned char)f;
         }
-        dp.flags[i] = (unsigned char)f;
     }
     if (bad) atomicAdd(&dp.sc->bad_u, 1u);
+    any = __syncthreads_or(any);
+    if (threadIdx.x == 0) dp.tile_active[blockIdx.x] = any ? 1 : 0;
 }
 
 // Stage (X_x, X_y, cos, sin) of a tile + halo.  Inactive / out-of-image entries are never used.
@@ -152,7 +157,14 @@ __global__ void __launch_bounds__(ST_THREADS) k_init(const StreamDev* __restrict
             if (y >= H) break;
             const size_t i = (size_t)y * W + x;
             const unsigned f = dp.flags[i];
-            if (!(f & FLAG_ACTIVE)) continue;
+            if (!(f & FLAG_ACTIVE)) {
+                // the branch-free PCG kernels rely on zeros here; a previous problem may have left values behind
+                dp.pre[0][i] = 0.f; dp.pre[1][i] = 0.f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { dp.r[k][i] = 0.f; dp.p[0][k][i] = 0.f; dp.p[1][k][i] = 0.f; dp.q[k][i] = 0.f; dp.d[k][i] = 0.f; }
+                dp.cs[0][i] = 0.f; dp.cs[1][i] = 0.f;
+                continue;
+            }
             const float4 Ei = T[ly + 1][lx + 1];
             JtfAcc a;
             jtf_zero(a);
@@ -200,25 +212,27 @@ __global__ void __launch_bounds__(ST_THREADS) k_step_a(const StreamDev* __restri
     // the neighbouring tile is updating in this very kernel.
     float* const* __restrict__ psrc = dp.p[FIRST ? 0 : ((it - 1) & 1)];
     float* const* __restrict__ pdst = dp.p[it & 1];
+    const bool tile_on = dp.tile_active[blockIdx.x] != 0; // tiles without object pixels only take part in the reduction
     // stage (p_x, p_y, sin*p_a, cos*p_a) of tile + halo, p being the NEW direction
-    for (int e = threadIdx.x; e < TS * TS; e += ST_THREADS) {
+    for (int e = threadIdx.x; tile_on && e < TS * TS; e += ST_THREADS) {
         const int ly = e / TS, lx = e - ly * TS;
         const int x = x0 + lx - 1, y = y0 + ly - 1;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (x >= 0 && x < W && y >= 0 && y < H) {
+            // no activity test: every plane of an inactive pixel holds zeros, which flow through as zeros
             const size_t i = (size_t)y * W + x;
-            if (dp.flags[i] & FLAG_ACTIVE) {
-                float p0 = psrc[0][i], p1 = psrc[1][i], p2 = psrc[2][i];
-                if (!FIRST) {
-                    const float pX = dp.pre[0][i], pA = dp.pre[1][i];
-                    p0 = fmaf(beta, p0, pX * dp.r[0][i]);
-                    p1 = fmaf(beta, p1, pX * dp.r[1][i]);
-                    p2 = fmaf(beta, p2, pA * dp.r[2][i]);
-                    const bool interior = (lx >= 1 && lx <= ST_TILE && ly >= 1 && ly <= ST_TILE);
-                    if (interior) { pdst[0][i] = p0; pdst[1][i] = p1; pdst[2][i] = p2; }
-                }
-                v = make_float4(p0, p1, dp.cs[1][i] * p2, dp.cs[0][i] * p2);
+            float p0 = psrc[0][i], p1 = psrc[1][i], p2 = psrc[2][i];
+            const float c = dp.cs[0][i], sn = dp.cs[1][i];
+            if (!FIRST) {
+                const float pX = dp.pre[0][i], pA = dp.pre[1][i];
+                const float r0 = dp.r[0][i], r1 = dp.r[1][i], r2 = dp.r[2][i];
+                p0 = fmaf(beta, p0, pX * r0);
+                p1 = fmaf(beta, p1, pX * r1);
+                p2 = fmaf(beta, p2, pA * r2);
+                const bool interior = (lx >= 1 && lx <= ST_TILE && ly >= 1 && ly <= ST_TILE);
+                if (interior) { pdst[0][i] = p0; pdst[1][i] = p1; pdst[2][i] = p2; }
             }
+            v = make_float4(p0, p1, sn * p2, c * p2);
         }
         T[ly][lx] = v;
     }
@@ -226,7 +240,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_step_a(const StreamDev* __restri
     const int lx = threadIdx.x & 31, lyb = (threadIdx.x >> 5) * 4;
     const int x = x0 + lx;
     float g = 0.0f;
-    if (x < W) {
+    if (x < W && tile_on) {
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const int ly = lyb + r, y = y0 + ly;
@@ -262,7 +276,9 @@ __global__ void __launch_bounds__(ST_THREADS) k_step_a(const StreamDev* __restri
     }
 }
 
-// PCGStep2 (solverGPUGaussNewton.t:446-489)
+// PCGStep2 (solverGPUGaussNewton.t:446-489).  Branch-free: the planes of inactive pixels hold zeros (they are
+// zero-initialised and never written), so they flow through as exact zeros and add +0 to the group term;
+// every load of the four rows is issued before the first use.
 __global__ void __launch_bounds__(ST_THREADS) k_step_b(const StreamDev* __restrict__ dpp, int it)
 {
     __shared__ double red[64];
@@ -273,24 +289,36 @@ __global__ void __launch_bounds__(ST_THREADS) k_step_b(const StreamDev* __restri
     const float num = dp.sc->num, den = dp.sc->den;
     const float alpha = (den > 0.0f) ? num / den : 0.0f; // :456-459
     float g = 0.0f;
-    if (x < W) {
+    if (x < W && dp.tile_active[blockIdx.x]) {
+        const float* __restrict__ pk0 = dp.p[it & 1][0];
+        const float* __restrict__ pk1 = dp.p[it & 1][1];
+        const float* __restrict__ pk2 = dp.p[it & 1][2];
+        float pv[4][3], qv[4][3], rv[4][3], dv[4][3], pre[4][2];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int y = min(yb + r, H - 1); // rows past the image re-read the last row; they are not stored
+            const size_t i = (size_t)y * W + x;
+            pv[r][0] = pk0[i]; pv[r][1] = pk1[i]; pv[r][2] = pk2[i];
+            qv[r][0] = dp.q[0][i]; qv[r][1] = dp.q[1][i]; qv[r][2] = dp.q[2][i];
+            rv[r][0] = dp.r[0][i]; rv[r][1] = dp.r[1][i]; rv[r][2] = dp.r[2][i];
+            dv[r][0] = dp.d[0][i]; dv[r][1] = dp.d[1][i]; dv[r][2] = dp.d[2][i];
+            pre[r][0] = dp.pre[0][i]; pre[r][1] = dp.pre[1][i];
+        }
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const int y = yb + r;
-            if (y >= H) break;
-            const size_t i = (size_t)y * W + x;
-            if (!(dp.flags[i] & FLAG_ACTIVE)) continue;
-            const float pX = dp.pre[0][i], pA = dp.pre[1][i];
-            float rr[3], zz[3];
+            if (y < H) {
+                const size_t i = (size_t)y * W + x;
+                float rr[3], zz[3];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const float pk = dp.p[it & 1][k][i];
-                dp.d[k][i] = fmaf(alpha, pk, dp.d[k][i]);
-                rr[k] = fmaf(-alpha, dp.q[k][i], dp.r[k][i]);
-                dp.r[k][i] = rr[k];
-                zz[k] = ((k < 2) ? pX : pA) * rr[k];
+                for (int k = 0; k < 3; ++k) {
+                    dp.d[k][i] = fmaf(alpha, pv[r][k], dv[r][k]);
+                    rr[k] = fmaf(-alpha, qv[r][k], rv[r][k]);
+                    dp.r[k][i] = rr[k];
+                    zz[k] = ((k < 2) ? pre[r][0] : pre[r][1]) * rr[k];
+                }
+                g = g + dot3(zz[0], zz[1], zz[2], rr[0], rr[1], rr[2]);
             }
-            g = g + dot3(zz[0], zz[1], zz[2], rr[0], rr[1], rr[2]);
         }
     }
     HL b = block_exact_sum(g, red);
@@ -393,6 +421,8 @@ StreamSolver::StreamSolver(int W, int H)
     for (int k = 0; k < 2; ++k) { h_.pre[k] = b; b += Np; }
     ARAP_CUDA_OR_EXIT(cudaMalloc(&h_.flags, Np));
     ARAP_CUDA_OR_EXIT(cudaMemset(h_.flags, 0, Np));
+    ARAP_CUDA_OR_EXIT(cudaMalloc(&h_.tile_active, (size_t)h_.ntiles));
+    ARAP_CUDA_OR_EXIT(cudaMemset(h_.tile_active, 1, (size_t)h_.ntiles));
     ARAP_CUDA_OR_EXIT(cudaMalloc(&h_.partials, (size_t)h_.ntiles * sizeof(double2)));
     ARAP_CUDA_OR_EXIT(cudaMalloc(&h_.counter, sizeof(unsigned)));
     ARAP_CUDA_OR_EXIT(cudaMemset(h_.counter, 0, sizeof(unsigned)));
@@ -407,6 +437,7 @@ StreamSolver::~StreamSolver()
     if (graph_) cudaGraphExecDestroy(graph_);
     cudaFree(planes_);
     cudaFree(h_.flags);
+    cudaFree(h_.tile_active);
     cudaFree(h_.partials);
     cudaFree(h_.counter);
     cudaFree(h_.sc);

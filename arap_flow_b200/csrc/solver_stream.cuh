@@ -36,6 +36,7 @@ struct StreamDev {
     float* cs[2];         // cos, sin of Angle, refreshed per GN step
     float* pre[2];        // guarded-inverted diagonal: X part (both comps), angle part
     unsigned char* flags;
+    unsigned char* tile_active; // per 32x32 tile: any object pixel (set by k_prep)
     double2* partials;    // one (h, l) pair per tile
     unsigned* counter;
     StreamScalars* sc;
