@@ -25,7 +25,7 @@ ARAP_SYMBOLS = [
     "arapb200_batch_create", "arapb200_batch_destroy", "arapb200_batch_submit", "arapb200_batch_run",
     "arapb200_batch_timing", "arapb200_batch_launches", "arapb200_debug_gn_solve", "arapb200_debug_eval_jtf",
     "arapb200_debug_apply_jtj", "arapb200_debug_cost", "arapb200_debug_sincos", "arapb200_debug_exact_sum",
-    "arapb200_debug_resident_profile",
+    "arapb200_debug_resident_profile", "arapb200_flatten",
 ]
 
 
@@ -147,6 +147,27 @@ def deform(rgb, mask_red, matches, nCont=19, nGN=8, nPCG=400, backend=BACKEND_AU
     _check(load().arapb200_deform(W, H, _c(rgb, np.uint8), _c(mask_red, np.uint8), m, len(m), nCont, nGN, nPCG,
                                   backend, flow, o_rgb, o_m, costs.ctypes.data), "arapb200_deform")
     return flow, o_rgb, o_m, costs
+
+
+def flatten(flows, rgbs, masks, background=None):
+    """Layer the per-segment results of a --multseg pair and composite the background (para_gen.py:136-175, 50-61)."""
+    n = len(flows)
+    H, W = masks[0].shape
+    fl = [_c(f, np.float32) for f in flows]
+    rg = [_c(r, np.uint8) for r in rgbs]
+    mk = [_c(m, np.uint8) for m in masks]
+    P = C.c_void_p * n
+    bg = _c(background, np.uint8) if background is not None else None
+    o_f = np.zeros((H, W, 2), np.float32)
+    o_r = np.zeros((H, W, 3), np.uint8)
+    o_m = np.zeros((H, W), np.uint8)
+    L = load()
+    L.arapb200_flatten.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]
+    _check(L.arapb200_flatten(W, H, n, P(*[a.ctypes.data for a in fl]), P(*[a.ctypes.data for a in rg]),
+                              P(*[a.ctypes.data for a in mk]), bg.ctypes.data if bg is not None else None,
+                              o_f.ctypes.data, o_r.ctypes.data, o_m.ctypes.data), "arapb200_flatten")
+    return o_f, o_r, o_m
 
 
 class Batch:

@@ -48,6 +48,14 @@ ARAPB200_API int arapb200_deform(int W, int H, const uint8_t* rgb, const uint8_t
                     int n_matches, int nCont, int nGN, int nPCG, int backend, float* out_flow,
                     uint8_t* out_rgb, uint8_t* out_mask, float* out_costs);
 
+/* ---- "next" row N1: layer flatten + background composite (replaces para_gen.py:136-175 flatten and :50-61 add_bg).
+ * n_layers per-segment results of one --multseg pair, in segment order: flows[s] float2[W*H], rgbs[s] uint8x3[W*H],
+ * masks[s] uint8[W*H] (warped masks, non-zero = object).  Later segments overwrite earlier ones where their mask is
+ * non-zero; where the final mask is 0 the colour is taken from `background` (uint8x3[W*H], may be NULL). */
+ARAPB200_API int arapb200_flatten(int W, int H, int n_layers, const float* const* flows, const uint8_t* const* rgbs,
+                                  const uint8_t* const* masks, const uint8_t* background, float* out_flow,
+                                  uint8_t* out_rgb, uint8_t* out_mask);
+
 /* ---- batched, pipelined variant: many independent (image, segment) problems per GPU --------- */
 typedef struct arapb200_batch arapb200_batch;
 /* max_problems problems of at most maxW x maxH in flight on the current device */

@@ -274,3 +274,22 @@ def test_batch_api_matches_single_problem_calls():
         flow, rgb, wm, costs = lib.deform(s.rgb, m, s.matches, **kw)
         assert _eq(o["flow"], flow) and _eq(o["costs"], costs) and _eq(o["rgb"], rgb) and _eq(o["mask"], wm)
     b.close()
+
+
+def test_flatten_and_background_composite_vs_numpy_restatement():
+    """N1: para_gen.flatten + add_bg on the GPU vs oracle/pycomposite.py (line-by-line numpy restatement)."""
+    from oracle import pycomposite as PC
+    rng = np.random.default_rng(3)
+    H, W, n = 75, 131, 4
+    flows = [rng.standard_normal((H, W, 2)).astype(np.float32) for _ in range(n)]
+    rgbs = [rng.integers(0, 256, (H, W, 3), dtype=np.uint8) for _ in range(n)]
+    masks = [np.where(rng.random((H, W)) < 0.3, 255, 0).astype(np.uint8) for _ in range(n)]
+    bg = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    f_o, r_o, m_o = PC.flatten(flows, rgbs, masks)
+    f_g, r_g, m_g = lib.flatten(flows, rgbs, masks)
+    assert _eq(f_g, f_o) and _eq(r_g, r_o) and _eq(m_g, m_o)
+    f_g, r_g, m_g = lib.flatten(flows, rgbs, masks, background=bg)
+    assert _eq(r_g, PC.add_bg(r_o, m_o, bg)) and _eq(f_g, f_o) and _eq(m_g, m_o)
+    # single layer: flatten is the identity, background fills where nothing landed
+    f1, r1, m1 = lib.flatten(flows[:1], rgbs[:1], masks[:1], background=bg)
+    assert _eq(f1, flows[0]) and _eq(m1, masks[0]) and _eq(r1, PC.add_bg(rgbs[0], masks[0], bg))
