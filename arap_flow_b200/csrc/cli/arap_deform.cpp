@@ -34,7 +34,7 @@ static void usage()
     puts("warped_Mask \t [output] path to output warped mask (.png), all intermediate directories must exist");
     puts("\n./arap_deform LISTFILE   (one such 6-tuple per line)");
     puts("Environment: ARAP_PLAN = path of the ARAP energy file (default ./arap_plan.t); CUDA_VISIBLE_DEVICES selects the GPU;");
-    puts("             ARAP_BATCH = problems solved together (default 6)");
+    puts("             ARAP_BATCH = problems solved together (default 8)");
 }
 
 struct Loaded {
@@ -82,7 +82,7 @@ int main(int argc, const char* argv[])
     }
     // the solver budget is a compile-time constant of the reference: main.cpp:215-221
     const int nCont = 19, nGN = 8, nPCG = 400;
-    int batch = getenv("ARAP_BATCH") ? atoi(getenv("ARAP_BATCH")) : 6;
+    int batch = getenv("ARAP_BATCH") ? atoi(getenv("ARAP_BATCH")) : 8;
     if (batch < 1) batch = 1;
 
     arapb200_batch* ctx = NULL;

@@ -47,7 +47,7 @@ def shard(items: Sequence[Item], rank: int, world: int) -> List[Item]:
     return [it for i, it in enumerate(items) if i % world == rank]
 
 
-def do_arap(items: Sequence[Item], gpu: int, tmp_dir: str, arap_bin: str = ARAP_BIN, plan: str = PLAN, batch: int = 6):
+def do_arap(items: Sequence[Item], gpu: int, tmp_dir: str, arap_bin: str = ARAP_BIN, plan: str = PLAN, batch: int = 8):
     """para_gen.do_arap (para_gen.py:178-200): write a temporary list file, run the solver binary on one GPU, assert
     a zero exit code, always remove the list file.  Returns the elapsed seconds."""
     os.makedirs(tmp_dir, exist_ok=True)
@@ -81,7 +81,7 @@ def main(argv=None):
     ap.add_argument("listfile")
     ap.add_argument("--gpu", type=int, nargs="+", default=[0])
     ap.add_argument("--tmp", default=os.path.join(tempfile.gettempdir(), "arapb200"))
-    ap.add_argument("--batch", type=int, default=6)
+    ap.add_argument("--batch", type=int, default=8)
     a = ap.parse_args(argv)
     items = read_list_file(a.listfile)
     dt = run_sharded(items, a.gpu, a.tmp, batch=a.batch)

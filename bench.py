@@ -164,8 +164,8 @@ def main():
     lib.load()
     backend = {"auto": lib.BACKEND_AUTO, "stream": lib.BACKEND_STREAM, "resident": lib.BACKEND_RESIDENT}[args.backend]
     W, H = WORKLOADS[args.workload][:2]
-    # resident back-end: 3 problems share one cooperative launch (one CTA of each per SM); 6 = two such launches
-    B = args.batch if args.batch > 0 else (1 if args.backend == "stream" else 6)
+    # resident back-end: 4 problems share one cooperative launch (one CTA of each per SM); 8 = two such launches
+    B = args.batch if args.batch > 0 else (1 if args.backend == "stream" else 8)
     pairs = make_pairs(args.workload, B, first=rank * B)
     active_px = [int((p.masks[0] == 0).sum()) for p in pairs]
     batch = lib.Batch(W, H, B, NCONT, NGN, NPCG, backend)
