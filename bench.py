@@ -37,6 +37,15 @@ def make_pairs(workload: str, count: int, first: int):
     return [synth.synth(W, H, nseg, fd, seed0 + first + i) for i in range(count)]
 
 
+def measured_traffic():
+    """DRAM bytes per k_resident launch from the committed ncu capture (profiles/r1_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        return int(json.load(open(p))["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -228,7 +237,8 @@ def main():
             "gpu_launches": int(lt.cpu()[0]),
             "ms_per_gn_solve": solve_ms_max / (B * args.steps * NCONT * NGN),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": (measured_traffic() if args.backend != "stream" and B % 4 == 0 and args.workload == "C1" else None),
+                         "peak_source": peak_src,
                          "kernel": "k_resident (persistent fused GN/PCG solve; 156 B/active px/PCG iteration algorithmic, "
                                    "state on chip so a fraction > 1 of the STREAMING roofline is possible)" if args.backend != "stream"
                                    else "k_step_a + k_step_b (streaming PCG iteration; 156 B/active px/iteration algorithmic)"},
