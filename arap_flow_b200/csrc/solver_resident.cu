@@ -46,6 +46,7 @@ struct __align__(16) StripSmem {
     float4 T[TH][TW];              // tile + ring: (p_x, p_y, sin*p_a, cos*p_a) or (X_x, X_y, cos, sin)
     float D[3][RS_STRIP_H][32];    // delta
     float2 rcs[RS_OUTBOX_ENTRIES]; // cos/sin of the ring pixels (remote sides only)
+    float stage[RS_OUTBOX_ENTRIES][6]; // fetched (z, p_old) of the remote ring pixels, parked until beta is known
 };
 
 struct Ctl {
@@ -130,6 +131,7 @@ struct StripCtx {
     const float4* rptr;     // pixel to the right
     float* D;               // &D[0][0][lane]
     float2* rcs;
+    float* stage;           // &stage[0][0]
     int rem[4];             // remote neighbour strip id per side (0 up, 1 down, 2 left, 3 right) or -1
     uint4* outbox;          // own outbox: [RS_OUTBOX_ENTRIES][3]
 };
@@ -320,27 +322,23 @@ __device__ __forceinline__ void publish_rowcol(const StripCtx& s, int lane, int 
 }
 
 // What a lane receives: the pixel above / below its column (all lanes) and, for lanes 0..H-1 (left column)
-// or 8..8+H-1 (right column), one pixel beside the strip.
-struct Halo {
-    float up[6], dn[6], sd[6];
-};
-
+// or 8..8+H-1 (right column), one pixel beside the strip.  Fetched values are parked in shared memory
+// (stage[ring slot][6]) so that they do not occupy registers across the barrier.
 __device__ __forceinline__ bool entry_ok(const uint4 w0, const uint4 w1, const uint4 w2, unsigned tag)
 {
     return w0.y == tag && w0.w == tag && w1.y == tag && w1.w == tag && w2.y == tag && w2.w == tag;
 }
-__device__ __forceinline__ void entry_unpack(const uint4 w0, const uint4 w1, const uint4 w2, float v[6])
+__device__ __forceinline__ void entry_park(float* st, const uint4 w0, const uint4 w1, const uint4 w2)
 {
-    v[0] = __uint_as_float(w0.x); v[1] = __uint_as_float(w0.z);
-    v[2] = __uint_as_float(w1.x); v[3] = __uint_as_float(w1.z);
-    v[4] = __uint_as_float(w2.x); v[5] = __uint_as_float(w2.z);
+    *reinterpret_cast<float2*>(st) = make_float2(__uint_as_float(w0.x), __uint_as_float(w0.z));
+    *reinterpret_cast<float2*>(st + 2) = make_float2(__uint_as_float(w1.x), __uint_as_float(w1.z));
+    *reinterpret_cast<float2*>(st + 4) = make_float2(__uint_as_float(w2.x), __uint_as_float(w2.z));
 }
 
 // Spin until every remote entry this lane needs carries `tag`.  All loads of a round are in flight together;
 // normally the first round succeeds because the neighbours published before they went into the barrier that
-// this warp is about to enter (the call sits BEFORE the grid barrier, so the latency hides behind it).
-__device__ __forceinline__ void fetch_halo(const ResProb& P, Ctl* ctl, const StripCtx& s, int lane, unsigned tag, bool three,
-                                           Halo& h)
+// this warp has just arrived at (the call sits between arrival and completion, so its latency hides there).
+__device__ __forceinline__ void fetch_halo(const ResProb& P, Ctl* ctl, const StripCtx& s, int lane, unsigned tag, bool three)
 {
     const bool left = s.rem[2] >= 0 && lane < RS_STRIP_H;
     const bool right = s.rem[3] >= 0 && lane >= 8 && lane < 8 + RS_STRIP_H;
@@ -348,6 +346,7 @@ __device__ __forceinline__ void fetch_halo(const ResProb& P, Ctl* ctl, const Str
     const uint4* pd = (s.rem[1] >= 0) ? P.outbox + ((size_t)s.rem[1] * RS_OUTBOX_ENTRIES + lane) * 3 : nullptr;
     const uint4* ps = left ? P.outbox + ((size_t)s.rem[2] * RS_OUTBOX_ENTRIES + OB_RIGHT + lane) * 3
                            : (right ? P.outbox + ((size_t)s.rem[3] * RS_OUTBOX_ENTRIES + OB_LEFT + lane - 8) * 3 : nullptr);
+    const int side_slot = left ? OB_LEFT + lane : OB_RIGHT + lane - 8;
     const uint4 fake = make_uint4(0u, tag, 0u, tag);
     unsigned spins = 0;
     for (;;) {
@@ -356,44 +355,46 @@ __device__ __forceinline__ void fetch_halo(const ResProb& P, Ctl* ctl, const Str
         if (pd) { d0 = ld_u4_volatile(pd); d1 = ld_u4_volatile(pd + 1); if (three) d2 = ld_u4_volatile(pd + 2); }
         if (ps) { s0 = ld_u4_volatile(ps); s1 = ld_u4_volatile(ps + 1); if (three) s2 = ld_u4_volatile(ps + 2); }
         if (entry_ok(u0, u1, u2, tag) && entry_ok(d0, d1, d2, tag) && entry_ok(s0, s1, s2, tag)) {
-            entry_unpack(u0, u1, u2, h.up);
-            entry_unpack(d0, d1, d2, h.dn);
-            entry_unpack(s0, s1, s2, h.sd);
+            if (pu) entry_park(s.stage + 6 * lane, u0, u1, u2);
+            if (pd) entry_park(s.stage + 6 * (32 + lane), d0, d1, d2);
+            if (ps) entry_park(s.stage + 6 * side_slot, s0, s1, s2);
             return;
         }
         if ((++spins & 0xffu) == 0 && (*(volatile int*)P.status || spins > (1u << 22))) {
             atomicExch(P.status, 1);
             atomicCAS(P.status + 1, 0, 200);
             ctl->abort = 1;
-#pragma unroll
-            for (int j = 0; j < 6; ++j) h.up[j] = h.dn[j] = h.sd[j] = 0.f;
             return;
         }
     }
 }
 
 // ring <- neighbours' (X_x, X_y, cos, sin)
-__device__ __forceinline__ void apply_x(const StripCtx& s, int lane, const Halo& h)
+__device__ __forceinline__ void apply_x(const StripCtx& s, int lane)
 {
     if (s.rem[0] >= 0) {
-        s.own[0 * TW + lane + 1] = make_float4(h.up[0], h.up[1], h.up[2], h.up[3]);
-        s.rcs[lane] = make_float2(h.up[2], h.up[3]);
+        const float* v = s.stage + 6 * lane;
+        s.own[0 * TW + lane + 1] = make_float4(v[0], v[1], v[2], v[3]);
+        s.rcs[lane] = make_float2(v[2], v[3]);
     }
     if (s.rem[1] >= 0) {
-        s.own[(TH - 1) * TW + lane + 1] = make_float4(h.dn[0], h.dn[1], h.dn[2], h.dn[3]);
-        s.rcs[32 + lane] = make_float2(h.dn[2], h.dn[3]);
+        const float* v = s.stage + 6 * (32 + lane);
+        s.own[(TH - 1) * TW + lane + 1] = make_float4(v[0], v[1], v[2], v[3]);
+        s.rcs[32 + lane] = make_float2(v[2], v[3]);
     }
     if (s.rem[2] >= 0 && lane < RS_STRIP_H) {
-        s.own[(lane + 1) * TW + 0] = make_float4(h.sd[0], h.sd[1], h.sd[2], h.sd[3]);
-        s.rcs[OB_LEFT + lane] = make_float2(h.sd[2], h.sd[3]);
+        const float* v = s.stage + 6 * (OB_LEFT + lane);
+        s.own[(lane + 1) * TW + 0] = make_float4(v[0], v[1], v[2], v[3]);
+        s.rcs[OB_LEFT + lane] = make_float2(v[2], v[3]);
     }
     if (s.rem[3] >= 0 && lane >= 8 && lane < 8 + RS_STRIP_H) {
-        s.own[(lane - 8 + 1) * TW + TW - 1] = make_float4(h.sd[0], h.sd[1], h.sd[2], h.sd[3]);
-        s.rcs[OB_RIGHT + lane - 8] = make_float2(h.sd[2], h.sd[3]);
+        const float* v = s.stage + 6 * (OB_RIGHT + lane - 8);
+        s.own[(lane - 8 + 1) * TW + TW - 1] = make_float4(v[0], v[1], v[2], v[3]);
+        s.rcs[OB_RIGHT + lane - 8] = make_float2(v[2], v[3]);
     }
 }
 
-__device__ __forceinline__ float4 p_entry_from(const float v[6], float beta, float2 cs)
+__device__ __forceinline__ float4 p_entry_from(const float* v, float beta, float2 cs)
 {
     // v = (z0, z1, z2, p0_old, p1_old, pa_old); cs = (cos, sin)
     const float p0 = fmaf(beta, v[3], v[0]);
@@ -403,13 +404,14 @@ __device__ __forceinline__ float4 p_entry_from(const float v[6], float beta, flo
 }
 
 // ring <- neighbours' new direction, computed from their published (z, p_old)
-__device__ __forceinline__ void apply_p(const StripCtx& s, int lane, const Halo& h, float beta)
+__device__ __forceinline__ void apply_p(const StripCtx& s, int lane, float beta)
 {
-    if (s.rem[0] >= 0) s.own[0 * TW + lane + 1] = p_entry_from(h.up, beta, s.rcs[lane]);
-    if (s.rem[1] >= 0) s.own[(TH - 1) * TW + lane + 1] = p_entry_from(h.dn, beta, s.rcs[32 + lane]);
-    if (s.rem[2] >= 0 && lane < RS_STRIP_H) s.own[(lane + 1) * TW + 0] = p_entry_from(h.sd, beta, s.rcs[OB_LEFT + lane]);
+    if (s.rem[0] >= 0) s.own[0 * TW + lane + 1] = p_entry_from(s.stage + 6 * lane, beta, s.rcs[lane]);
+    if (s.rem[1] >= 0) s.own[(TH - 1) * TW + lane + 1] = p_entry_from(s.stage + 6 * (32 + lane), beta, s.rcs[32 + lane]);
+    if (s.rem[2] >= 0 && lane < RS_STRIP_H)
+        s.own[(lane + 1) * TW + 0] = p_entry_from(s.stage + 6 * (OB_LEFT + lane), beta, s.rcs[OB_LEFT + lane]);
     if (s.rem[3] >= 0 && lane >= 8 && lane < 8 + RS_STRIP_H)
-        s.own[(lane - 8 + 1) * TW + TW - 1] = p_entry_from(h.sd, beta, s.rcs[OB_RIGHT + lane - 8]);
+        s.own[(lane - 8 + 1) * TW + TW - 1] = p_entry_from(s.stage + 6 * (OB_RIGHT + lane - 8), beta, s.rcs[OB_RIGHT + lane - 8]);
 }
 
 // constraint of a pixel for the current continuation weight (CombinedSolver.h:236-239)
@@ -471,6 +473,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
     s.own = &S[wid].T[0][0];
     s.D = &S[wid].D[0][0][lane];
     s.rcs = S[wid].rcs;
+    s.stage = &S[wid].stage[0][0];
     s.up_row = s.own + 0 * TW + 1;
     s.down_row = s.own + (TH - 1) * TW + 1;
     s.lptr = s.own + 1 * TW + lane;
@@ -551,9 +554,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                 if (any_rem) publish_rowcol(s, lane, k, seq, e.x, e.y, e.z, e.w, 0.f, 0.f, false);
             }
             if (any_rem) {
-                Halo h;
-                fetch_halo(P, &ctl, s, lane, seq, false, h);
-                apply_x(s, lane, h);
+                fetch_halo(P, &ctl, s, lane, seq, false);
+                apply_x(s, lane);
             }
             __syncthreads();
             {
@@ -635,10 +637,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                         publish_rowcol(s, lane, k, seq, pX * r0[k], pX * r1[k], pA * r2[k], 0.f, 0.f, 0.f, true);
                     }
                 }
-                Halo h0;
                 long long ta0 = 0, ta1 = 0;
                 grid_arrive(c, gs0, gs1, S_num, ta0, ta1);
-                if (any_rem) fetch_halo(P, &ctl, s, lane, seq, true, h0); // overlaps the barrier latency
+                if (any_rem) fetch_halo(P, &ctl, s, lane, seq, true); // overlaps the barrier latency
                 num = grid_finish(c, gs0, gs1, S_num, ok, ta0, ta1); // solverGPUGaussNewton.t:395 scanAlphaNumerator
                 if (!ok) break;
                 // p_0 = z_0 into the tile (all warps are past their J^T F reads: grid_sum synchronised)
@@ -651,7 +652,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                     pa[k] = pA * r2[k];
                     s.own[(k + 1) * TW + lane + 1] = make_float4(p0, p1, ss[k] * pa[k], cc[k] * pa[k]);
                 }
-                if (any_rem) apply_p(s, lane, h0, 0.0f);
+                if (any_rem) apply_p(s, lane, 0.0f);
                 __syncthreads();
             }
 
@@ -752,11 +753,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                     if (k < 4) gs0 = gs0 + term; else gs1 = gs1 + term;
                     if (pub) publish_rowcol(s, lane, k, seq, z0, z1, z2, e.x, e.y, pa[k], true);
                 }
-                Halo h;
                 RS_TICK(1);
                 long long tb0 = 0, tb1 = 0;
                 grid_arrive(c, gs0, gs1, S_bnum, tb0, tb1);
-                if (pub) fetch_halo(P, &ctl, s, lane, seq, true, h); // overlaps the barrier latency
+                if (pub) fetch_halo(P, &ctl, s, lane, seq, true); // overlaps the barrier latency
                 const float bnum = grid_finish(c, gs0, gs1, S_bnum, ok, tb0, tb1);
                 RS_TOCK();
                 if (!ok) break;
@@ -787,7 +787,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                     pa[k] = fmaf(beta, pa[k], pA * r2[k]);
                     s.own[(k + 1) * TW + lane + 1] = make_float4(p0, p1, ss[k] * pa[k], cc[k] * pa[k]);
                 }
-                if (any_rem) apply_p(s, lane, h, beta);
+                if (any_rem) apply_p(s, lane, beta);
                 __syncthreads();
                 RS_TICK(2);
             }
