@@ -47,6 +47,7 @@ struct __align__(16) StripSmem {
     float D[3][RS_STRIP_H][32];    // delta
     float2 rcs[RS_OUTBOX_ENTRIES]; // cos/sin of the ring pixels (remote sides only)
     float stage[RS_OUTBOX_ENTRIES][6]; // fetched (z, p_old) of the remote ring pixels, parked until beta is known
+    float2 pre[RS_STRIP_H][32];        // (1/(1+sqrt(D_X))^2, 1/(1+sqrt(D_a))^2) per pixel, constant during a GN step
 };
 
 struct Ctl {
@@ -132,6 +133,7 @@ struct StripCtx {
     float* D;               // &D[0][0][lane]
     float2* rcs;
     float* stage;           // &stage[0][0]
+    float2* pre;            // &pre[0][lane]
     int rem[4];             // remote neighbour strip id per side (0 up, 1 down, 2 left, 3 right) or -1
     uint4* outbox;          // own outbox: [RS_OUTBOX_ENTRIES][3]
 };
@@ -474,6 +476,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
     s.D = &S[wid].D[0][0][lane];
     s.rcs = S[wid].rcs;
     s.stage = &S[wid].stage[0][0];
+    s.pre = &S[wid].pre[0][lane];
     s.up_row = s.own + 0 * TW + 1;
     s.down_row = s.own + (TH - 1) * TW + 1;
     s.lptr = s.own + 1 * TW + lane;
@@ -520,8 +523,6 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
     // warp-uniform: every pixel of the strip is active with four valid neighbours -> mask-free fast paths
     const bool interior = __all_sync(0xffffffffu, (flo & 0x2f2f2f2fu) == 0x2f2f2f2fu &&
                                                       (RS_STRIP_H == 4 || (fhi & 0x2f2f2f2fu) == 0x2f2f2f2fu));
-    const float preX4 = guarded_invert((wr2 + wr2) * 4.0f), preX4f = guarded_invert((wr2 + wr2) * 4.0f + wf2);
-    const float preA4 = guarded_invert(wr2 * 4.0f);
 
     // registers that live across the PCG loop
     float r0[RS_STRIP_H], r1[RS_STRIP_H], r2[RS_STRIP_H];
@@ -598,6 +599,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                     unsigned f = flag_of(flo, fhi, k) & ~FLAG_FIT;
                     r0[k] = r1[k] = r2[k] = 0.f;
                     pa[k] = 0.f;
+                    s.pre[k * 32] = make_float2(1.0f, 1.0f); // inactive pixels: r stays 0, any finite value works
                     s.D[(0 * RS_STRIP_H + k) * 32] = 0.f;
                     s.D[(1 * RS_STRIP_H + k) * 32] = 0.f;
                     s.D[(2 * RS_STRIP_H + k) * 32] = 0.f;
@@ -616,6 +618,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                         float g0, g1, ga, DX, DA;
                         jtf_finish(a, cur.x, cur.y, fit, ct.x, ct.y, wr2, wf2, g0, g1, ga, DX, DA);
                         const float pX = guarded_invert(DX), pA = guarded_invert(DA);
+                        s.pre[k * 32] = make_float2(pX, pA);
                         r0[k] = -g0; r1[k] = -g1; r2[k] = -ga;
                         const float z0 = pX * r0[k], z1 = pX * r1[k], z2 = pA * r2[k];
                         const float term = dot3(r0[k], r1[k], r2[k], z0, z1, z2);
@@ -631,10 +634,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
 #pragma unroll
                 for (int k = 0; k < RS_STRIP_H; ++k) {
                     if (any_rem) {
-                        const unsigned f = flag_of(flo, fhi, k);
-                        const int nv = __popc(f & 15u);
-                        const float pX = ctl.preX[nv + ((f & FLAG_FIT) ? 5 : 0)], pA = ctl.preA[nv];
-                        publish_rowcol(s, lane, k, seq, pX * r0[k], pX * r1[k], pA * r2[k], 0.f, 0.f, 0.f, true);
+                        const float2 pre = s.pre[k * 32];
+                        publish_rowcol(s, lane, k, seq, pre.x * r0[k], pre.x * r1[k], pre.y * r2[k], 0.f, 0.f, 0.f, true);
                     }
                 }
                 long long ta0 = 0, ta1 = 0;
@@ -645,9 +646,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                 // p_0 = z_0 into the tile (all warps are past their J^T F reads: grid_sum synchronised)
 #pragma unroll
                 for (int k = 0; k < RS_STRIP_H; ++k) {
-                    const unsigned f = flag_of(flo, fhi, k);
-                    const int nv = __popc(f & 15u);
-                    const float pX = ctl.preX[nv + ((f & FLAG_FIT) ? 5 : 0)], pA = ctl.preA[nv];
+                    const float2 pre = s.pre[k * 32];
+                    const float pX = pre.x, pA = pre.y;
                     const float p0 = pX * r0[k], p1 = pX * r1[k];
                     pa[k] = pA * r2[k];
                     s.own[(k + 1) * TW + lane + 1] = make_float4(p0, p1, ss[k] * pa[k], cc[k] * pa[k]);
@@ -739,15 +739,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                     r0[k] = fmaf(-alpha, q0[k], r0[k]);
                     r1[k] = fmaf(-alpha, q1[k], r1[k]);
                     r2[k] = fmaf(-alpha, qa[k], r2[k]);
-                    float pX, pA;
-                    if (interior) {
-                        pX = (f & FLAG_FIT) ? preX4f : preX4;
-                        pA = preA4;
-                    } else {
-                        const int nv = __popc(f & 15u);
-                        pX = ctl.preX[nv + ((f & FLAG_FIT) ? 5 : 0)];
-                        pA = ctl.preA[nv];
-                    }
+                    const float2 pre = s.pre[k * 32];
+                    const float pX = pre.x, pA = pre.y;
                     const float z0 = pX * r0[k], z1 = pX * r1[k], z2 = pA * r2[k];
                     const float term = dot3(z0, z1, z2, r0[k], r1[k], r2[k]);
                     if (k < 4) gs0 = gs0 + term; else gs1 = gs1 + term;
@@ -773,15 +766,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                 for (int k = 0; k < RS_STRIP_H; ++k) {
                     const unsigned f = flag_of(flo, fhi, k);
                     const float4 e = s.own[(k + 1) * TW + lane + 1];
-                    float pX, pA;
-                    if (interior) {
-                        pX = (f & FLAG_FIT) ? preX4f : preX4;
-                        pA = preA4;
-                    } else {
-                        const int nv = __popc(f & 15u);
-                        pX = ctl.preX[nv + ((f & FLAG_FIT) ? 5 : 0)];
-                        pA = ctl.preA[nv];
-                    }
+                    const float2 pre = s.pre[k * 32];
+                    const float pX = pre.x, pA = pre.y;
                     const float p0 = fmaf(beta, e.x, pX * r0[k]);
                     const float p1 = fmaf(beta, e.y, pX * r1[k]);
                     pa[k] = fmaf(beta, pa[k], pA * r2[k]);
