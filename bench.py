@@ -28,13 +28,15 @@ sys.path.insert(0, ROOT)
 B_ITER = 156.0            # algorithmic bytes / active pixel / PCG iteration
 B_GN_EXTRA = 132.0        # init + update + cost per GN step
 NCONT, NGN, NPCG = 19, 8, 400
-WORKLOADS = {"C1": (854, 480, 1, 1, 1000), "C3": (1024, 436, 1, 5, 3000), "C0": (64, 64, 1, 1, 0)}
+WORKLOADS = {"C1": (854, 480, 1, 1, 1000), "C3": (1024, 436, 1, 5, 3000), "C0": (64, 64, 1, 1, 0),
+             "C4": (1920, 1080, 1, 1, 4000)}
 
 
 def make_pairs(workload: str, count: int, first: int):
     from arap_flow_b200 import synth
     W, H, nseg, fd, seed0 = WORKLOADS[workload]
-    return [synth.synth(W, H, nseg, fd, seed0 + first + i) for i in range(count)]
+    axes = (0.46, 0.46) if workload == "C4" else None   # C4 enlarges the ellipse to 66 % coverage
+    return [synth.synth(W, H, nseg, fd, seed0 + first + i, axes=axes) for i in range(count)]
 
 
 def measured_traffic():
@@ -174,7 +176,7 @@ def main():
     backend = {"auto": lib.BACKEND_AUTO, "stream": lib.BACKEND_STREAM, "resident": lib.BACKEND_RESIDENT}[args.backend]
     W, H = WORKLOADS[args.workload][:2]
     # resident back-end: 4 problems share one cooperative launch (one CTA of each per SM); 8 = two such launches
-    B = args.batch if args.batch > 0 else (1 if args.backend == "stream" else 8)
+    B = args.batch if args.batch > 0 else (1 if (args.backend == "stream" or args.workload == "C4") else 8)
     pairs = make_pairs(args.workload, B, first=rank * B)
     active_px = [int((p.masks[0] == 0).sum()) for p in pairs]
     batch = lib.Batch(W, H, B, NCONT, NGN, NPCG, backend)
