@@ -58,8 +58,6 @@ struct Ctl {
     int bc_code;                   // 0 accept, 1 redo with bc_S
     int bc_S;
     int abort;
-    float preX[10];
-    float preA[5];
 };
 
 __device__ __forceinline__ unsigned long long ld_u64_volatile(const unsigned long long* p)
@@ -458,13 +456,6 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
 
     if (threadIdx.x == 0) ctl.abort = 0;
     if (threadIdx.x < 8) ctl.prev[threadIdx.x >> 2][threadIdx.x & 3] = 0ull; // the host zeroes P.bar before the launch
-    if (threadIdx.x < 10) { // preconditioner values by (number of valid neighbours, fit)
-        const int nv = threadIdx.x % 5, fit = threadIdx.x / 5;
-        float DX = (wr2 + wr2) * (float)nv;
-        if (fit) DX = DX + wf2;
-        ctl.preX[threadIdx.x] = guarded_invert(DX);
-        if (!fit) ctl.preA[nv] = guarded_invert(wr2 * (float)nv);
-    }
 
     // ---- which strip is mine, who are my neighbours ----
     const int n = P.n_strips;
@@ -730,7 +721,6 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                 ++seq;
 #pragma unroll
                 for (int k = 0; k < RS_STRIP_H; ++k) {
-                    const unsigned f = flag_of(flo, fhi, k);
                     const float4 e = s.own[(k + 1) * TW + lane + 1];
                     float* Dk = s.D + k * 32;
                     Dk[0 * RS_STRIP_H * 32] = fmaf(alpha, e.x, Dk[0 * RS_STRIP_H * 32]);
@@ -764,7 +754,6 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                 // ---- PCGStep3: p = z + beta p (own pixels, then the remote ring) ----
 #pragma unroll
                 for (int k = 0; k < RS_STRIP_H; ++k) {
-                    const unsigned f = flag_of(flo, fhi, k);
                     const float4 e = s.own[(k + 1) * TW + lane + 1];
                     const float2 pre = s.pre[k * 32];
                     const float pX = pre.x, pA = pre.y;
