@@ -10,6 +10,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
+#include <future>
+#include <memory>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -85,64 +87,108 @@ int main(int argc, const char* argv[])
     int batch = getenv("ARAP_BATCH") ? atoi(getenv("ARAP_BATCH")) : 8;
     if (batch < 1) batch = 1;
 
+    // Three overlapped stages: the main thread decodes group k+1 and encodes group k-1 while
+    // a worker thread runs group k on the GPU.  Output order and the "Saved" lines stay in list order.
+    struct Group {
+        size_t first = 0;
+        int W = 0, H = 0;
+        std::vector<Loaded> items;
+    };
     arapb200_batch* ctx = NULL;
     int ctxW = 0, ctxH = 0;
-    size_t i = 0;
-    while (i < lines.size()) {
-        // gather up to `batch` consecutive entries of one image size
-        std::vector<Loaded> group;
-        size_t j = i;
-        int W = 0, H = 0;
-        for (; j < lines.size() && (int)group.size() < batch; ++j) {
-            Loaded L;
-            ImageRGB m;
-            if (!read_constraints(lines[j].cstr, L.cstr) || !load_png_rgb(lines[j].rgb, L.rgb) || !load_png_rgb(lines[j].mask, m))
-                return 1;
-            if (m.W != L.rgb.W || m.H != L.rgb.H) {
-                fprintf(stderr, "mask %s and image %s differ in size\n", lines[j].mask.c_str(), lines[j].rgb.c_str());
-                return 1;
-            }
-            if (group.empty()) { W = L.rgb.W; H = L.rgb.H; }
-            else if (L.rgb.W != W || L.rgb.H != H) break; // next group
-            L.mask_red.resize((size_t)W * H);
-            for (size_t k = 0; k < L.mask_red.size(); ++k) L.mask_red[k] = m.px[3 * k]; // red channel only
-            L.flow.resize((size_t)2 * W * H);
-            L.wrgb.resize((size_t)3 * W * H);
-            L.wmask.resize((size_t)W * H);
-            group.push_back(std::move(L));
-        }
-        if (!ctx || W != ctxW || H != ctxH) {
+    auto gpu_stage = [&](std::shared_ptr<Group> g) -> int {
+        if (!ctx || g->W != ctxW || g->H != ctxH) {
             if (ctx) {
                 printf("Warning: Input image has different size to one in the prebuilt plan.\n"
                        "To avoid re-building the plan and to save time, put images of the "
                        "same size in the same list.\nStarting to re-build plan...\n");
                 arapb200_batch_destroy(ctx);
             }
-            ctx = arapb200_batch_create(W, H, batch, nCont, nGN, nPCG, ARAPB200_BACKEND_AUTO);
+            ctx = arapb200_batch_create(g->W, g->H, batch, nCont, nGN, nPCG, ARAPB200_BACKEND_AUTO);
             if (!ctx) return 1;
-            ctxW = W; ctxH = H;
+            ctxW = g->W; ctxH = g->H;
         }
-        for (size_t g = 0; g < group.size(); ++g) {
-            Loaded& L = group[g];
-            if (arapb200_batch_submit(ctx, (int)g, W, H, L.rgb.px.data(), L.mask_red.data(), L.cstr.data(),
+        for (size_t k = 0; k < g->items.size(); ++k) {
+            Loaded& L = g->items[k];
+            if (arapb200_batch_submit(ctx, (int)k, g->W, g->H, L.rgb.px.data(), L.mask_red.data(), L.cstr.data(),
                                       (int)(L.cstr.size() / 4), L.flow.data(), L.wrgb.data(), L.wmask.data(), NULL))
                 return 1;
         }
-        if (int rc = arapb200_batch_run(ctx)) {
-            fprintf(stderr, "arap_deform: solver failed (%d)\n", rc);
-            return rc;
-        }
-        for (size_t g = 0; g < group.size(); ++g) {
-            Loaded& L = group[g];
-            const InputPaths& p = lines[i + g];
-            std::vector<uint8_t> m3((size_t)3 * W * H); // warped mask as an RGB image, 255 = object (README.md:25-32)
-            for (size_t k = 0; k < L.wmask.size(); ++k) m3[3 * k] = m3[3 * k + 1] = m3[3 * k + 2] = L.wmask[k];
-            if (!save_png_rgb(p.wrgb, W, H, L.wrgb.data()) || !save_png_rgb(p.wmask, W, H, m3.data()) ||
-                !write_flo(p.flo, W, H, L.flow.data()))
-                return 1;
+        return arapb200_batch_run(ctx);
+    };
+    auto save_stage = [&](const Group& g) -> bool {
+        for (size_t k = 0; k < g.items.size(); ++k) {
+            const Loaded& L = g.items[k];
+            const InputPaths& p = lines[g.first + k];
+            std::vector<uint8_t> m3((size_t)3 * g.W * g.H); // warped mask as an RGB image, 255 = object (README.md:25-32)
+            for (size_t q = 0; q < L.wmask.size(); ++q) m3[3 * q] = m3[3 * q + 1] = m3[3 * q + 2] = L.wmask[q];
+            if (!save_png_rgb(p.wrgb, g.W, g.H, L.wrgb.data()) || !save_png_rgb(p.wmask, g.W, g.H, m3.data()) ||
+                !write_flo(p.flo, g.W, g.H, L.flow.data()))
+                return false;
             printf("Saved\n");
         }
-        i += group.size();
+        return true;
+    };
+
+    std::future<int> running;
+    std::shared_ptr<Group> in_flight, done;
+    size_t i = 0;
+    Loaded carry; // first entry of the next group when a size change ended the previous one
+    bool have_carry = false;
+    while (i < lines.size() || in_flight) {
+        // ---- decode the next group (up to `batch` consecutive entries of one image size) ----
+        std::shared_ptr<Group> next;
+        if (i < lines.size()) {
+            next = std::make_shared<Group>();
+            next->first = i;
+            while (i < lines.size() && (int)next->items.size() < batch) {
+                Loaded L;
+                if (have_carry) {
+                    L = std::move(carry);
+                    have_carry = false;
+                } else {
+                    ImageRGB m;
+                    if (!read_constraints(lines[i].cstr, L.cstr) || !load_png_rgb(lines[i].rgb, L.rgb) || !load_png_rgb(lines[i].mask, m))
+                        return 1;
+                    if (m.W != L.rgb.W || m.H != L.rgb.H) {
+                        fprintf(stderr, "mask %s and image %s differ in size\n", lines[i].mask.c_str(), lines[i].rgb.c_str());
+                        return 1;
+                    }
+                    const size_t N = (size_t)m.W * m.H;
+                    L.mask_red.resize(N);
+                    for (size_t q = 0; q < N; ++q) L.mask_red[q] = m.px[3 * q]; // red channel only
+                    L.flow.resize(2 * N);
+                    L.wrgb.resize(3 * N);
+                    L.wmask.resize(N);
+                }
+                if (next->items.empty()) { next->W = L.rgb.W; next->H = L.rgb.H; }
+                else if (L.rgb.W != next->W || L.rgb.H != next->H) { // belongs to the following group
+                    carry = std::move(L);
+                    have_carry = true;
+                    break;
+                }
+                next->items.push_back(std::move(L));
+                ++i;
+            }
+        }
+        // ---- wait for the group on the GPU, start the next one, then encode the finished one ----
+        if (in_flight) {
+            const int rc = running.get();
+            if (rc) {
+                fprintf(stderr, "arap_deform: solver failed (%d)\n", rc);
+                return rc;
+            }
+            done = in_flight;
+            in_flight.reset();
+        }
+        if (next) {
+            in_flight = next;
+            running = std::async(std::launch::async, gpu_stage, next);
+        }
+        if (done) {
+            if (!save_stage(*done)) return 1;
+            done.reset();
+        }
     }
     if (ctx) arapb200_batch_destroy(ctx);
     return 0;
