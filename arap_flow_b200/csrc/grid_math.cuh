@@ -65,6 +65,43 @@ __device__ __forceinline__ void jtj_nb(JtjAcc& a, float px, float py, const floa
     a.nd = a.nd + 1.0f;
 }
 
+// Masked variant for strips that touch the object boundary: m = 1.0f for a valid neighbour, 0.0f otherwise.
+// fmaf(1, x, acc) == acc + x and fmaf(0, x, acc) == acc exactly (x finite), so this is bit-identical to skipping
+// invalid neighbours; Sx, Sy and nd are accumulated from the masks themselves (exact small integers).
+template <int N>
+__device__ __forceinline__ void jtj_nb_masked(JtjAcc& a, float px, float py, const float4 Pj, float m)
+{
+    const float dp0 = px - Pj.x, dp1 = py - Pj.y;
+    a.sd0 = fmaf(m, dp0, a.sd0);
+    a.sd1 = fmaf(m, dp1, a.sd1);
+    if (N == 0) {
+        a.nb0 = fmaf(m, Pj.z, a.nb0);
+        a.nb1 = fmaf(-m, Pj.w, a.nb1);
+        a.dd = fmaf(-m, dp0, a.dd);
+        a.dc = fmaf(-m, dp1, a.dc);
+        a.Sx = a.Sx - m;
+    } else if (N == 1) {
+        a.nb0 = fmaf(-m, Pj.z, a.nb0);
+        a.nb1 = fmaf(m, Pj.w, a.nb1);
+        a.dd = fmaf(m, dp0, a.dd);
+        a.dc = fmaf(m, dp1, a.dc);
+        a.Sx = a.Sx + m;
+    } else if (N == 2) {
+        a.nb0 = fmaf(m, Pj.w, a.nb0);
+        a.nb1 = fmaf(m, Pj.z, a.nb1);
+        a.dd = fmaf(-m, dp1, a.dd);
+        a.dc = fmaf(m, dp0, a.dc);
+        a.Sy = a.Sy - m;
+    } else {
+        a.nb0 = fmaf(-m, Pj.w, a.nb0);
+        a.nb1 = fmaf(-m, Pj.z, a.nb1);
+        a.dd = fmaf(m, dp1, a.dd);
+        a.dc = fmaf(-m, dp0, a.dc);
+        a.Sy = a.Sy + m;
+    }
+    a.nd = a.nd + m;
+}
+
 __device__ __forceinline__ void jtj_finish(const JtjAcc& a, float ci, float si, float px, float py, float pa,
                                            bool fit, float wr2, float wf2, float& q0, float& q1, float& qa)
 {

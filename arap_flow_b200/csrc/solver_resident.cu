@@ -521,6 +521,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
     float q0[RS_STRIP_H], q1[RS_STRIP_H], qa[RS_STRIP_H];
 #pragma unroll
     for (int k = 0; k < RS_STRIP_H; ++k) { r0[k] = r1[k] = r2[k] = pa[k] = 0.f; cc[k] = 1.f; ss[k] = 0.f; q0[k] = q1[k] = qa[k] = 0.f; }
+    // every tile cell must hold finite data (the masked stencil multiplies invalid neighbours by 0)
+    for (int e = lane; e < TH * TW; e += 32) s.own[e] = make_float4(0.f, 0.f, 0.f, 0.f);
     int S_cost = 0, S_num = 0, S_den = 0, S_bnum = 0;
     unsigned seq = 0; // publication sequence number == halo tag
     bool ok = true;
@@ -685,23 +687,17 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
 #pragma unroll
                     for (int k = 0; k < RS_STRIP_H; ++k) {
                         const float4 dn = (k < RS_STRIP_H - 1) ? s.own[(k + 2) * TW + lane + 1] : s.down_row[lane];
-                        float4 lf = s.lptr[k * TW], rt = s.rptr[k * TW];
+                        const float4 lf = s.lptr[k * TW], rt = s.rptr[k * TW];
                         const unsigned f = flag_of(flo, fhi, k);
-                        const bool v0 = (f & 1u) != 0, v1 = (f & 2u) != 0, v2 = (f & 4u) != 0, v3 = (f & 8u) != 0;
-                        rt.x = v0 ? rt.x : cur.x; rt.y = v0 ? rt.y : cur.y; rt.z = v0 ? rt.z : 0.f; rt.w = v0 ? rt.w : 0.f;
-                        lf.x = v1 ? lf.x : cur.x; lf.y = v1 ? lf.y : cur.y; lf.z = v1 ? lf.z : 0.f; lf.w = v1 ? lf.w : 0.f;
-                        const float4 dnn = make_float4(v2 ? dn.x : cur.x, v2 ? dn.y : cur.y, v2 ? dn.z : 0.f, v2 ? dn.w : 0.f);
-                        const float4 upp = make_float4(v3 ? up.x : cur.x, v3 ? up.y : cur.y, v3 ? up.z : 0.f, v3 ? up.w : 0.f);
+                        // validity as 0/1 multipliers (every tile cell holds finite data: tiles are zeroed at start)
+                        const float m0 = (f & 1u) ? 1.0f : 0.0f, m1 = (f & 2u) ? 1.0f : 0.0f;
+                        const float m2 = (f & 4u) ? 1.0f : 0.0f, m3 = (f & 8u) ? 1.0f : 0.0f;
                         JtjAcc a;
                         jtj_zero(a);
-                        jtj_nb<0>(a, cur.x, cur.y, rt);
-                        jtj_nb<1>(a, cur.x, cur.y, lf);
-                        jtj_nb<2>(a, cur.x, cur.y, dnn);
-                        jtj_nb<3>(a, cur.x, cur.y, upp);
-                        // sums of d over the VALID neighbours only (jtj_nb counted all four)
-                        a.Sx = (v1 ? 1.0f : 0.0f) - (v0 ? 1.0f : 0.0f);
-                        a.Sy = (v3 ? 1.0f : 0.0f) - (v2 ? 1.0f : 0.0f);
-                        a.nd = (float)__popc(f & 15u);
+                        jtj_nb_masked<0>(a, cur.x, cur.y, rt, m0);
+                        jtj_nb_masked<1>(a, cur.x, cur.y, lf, m1);
+                        jtj_nb_masked<2>(a, cur.x, cur.y, dn, m2);
+                        jtj_nb_masked<3>(a, cur.x, cur.y, up, m3);
                         jtj_finish(a, cc[k], ss[k], cur.x, cur.y, pa[k], (f & FLAG_FIT) != 0, wr2, wf2, q0[k], q1[k], qa[k]);
                         const float term = dot3(cur.x, cur.y, pa[k], q0[k], q1[k], qa[k]);
                         if (k < 4) gs0 = gs0 + term; else gs1 = gs1 + term;
