@@ -29,7 +29,7 @@ B_ITER = 156.0            # algorithmic bytes / active pixel / PCG iteration (SU
 B_GN_EXTRA = 132.0        # init + update + cost per GN step
 NCONT, NGN, NPCG = 19, 8, 400
 WORKLOADS = {"C1": (854, 480, 1, 1, 1000), "C3": (1024, 436, 1, 5, 3000), "C0": (64, 64, 1, 1, 0),
-             "C4": (1920, 1080, 1, 1, 4000)}
+             "C4": (1920, 1080, 1, 1, 4000), "C2": (854, 480, 4, 3, 2000)}
 
 
 def make_pairs(workload: str, count: int, first: int):
@@ -109,20 +109,22 @@ def cpu_leg(workload: str, cores_note=True):
     from oracle import pyoracle as O
     O.build()
     sp = make_pairs(workload, 1, 0)[0]
-    mask = sp.masks[0]
     m = O.with_border_pins(sp.matches, sp.W, sp.H)
-    Cn = O.constraint_image(mask, m, 1.0 / NCONT)
     U = O.grid(sp.W, sp.H)
-    t0 = time.perf_counter()
-    X, A, costs, _ = O.gn_solve(U.copy(), np.zeros((sp.H, sp.W), np.float32), U, Cn, mask.astype(np.float32), NGN, NPCG)
-    t_cont = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    O.warp(X, sp.rgb, mask)
-    t_warp = time.perf_counter() - t0
+    t_cont = t_warp = 0.0
+    for mask in sp.masks:     # one independent solve + warp per segment (C2: 4, otherwise 1)
+        Cn = O.constraint_image(mask, m, 1.0 / NCONT)
+        t0 = time.perf_counter()
+        X, A, costs, _ = O.gn_solve(U.copy(), np.zeros((sp.H, sp.W), np.float32), U, Cn, mask.astype(np.float32), NGN, NPCG)
+        t_cont += time.perf_counter() - t0
+        t0 = time.perf_counter()
+        O.warp(X, sp.rgb, mask)
+        t_warp += time.perf_counter() - t0
     per_pair = NCONT * t_cont + t_warp
     info = {"value": 1.0 / per_pair, "unit": "pairs/s", "cores": O.num_threads(), "kind": "port",
-            "sample": f"{workload}: 1 of {NCONT} continuation steps ({NGN}x{NPCG} PCG iterations, {t_cont:.2f} s) "
-                      f"scaled x{NCONT} + 1 forward warp ({t_warp:.3f} s); oracle/arap_oracle.c, OpenMP"}
+            "sample": f"{workload}: 1 of {NCONT} continuation steps ({NGN}x{NPCG} PCG iterations) of each of the pair's "
+                      f"{len(sp.masks)} segment(s) ({t_cont:.2f} s) scaled x{NCONT} + forward warp(s) ({t_warp:.3f} s); "
+                      f"oracle/arap_oracle.c, OpenMP"}
     return 1.0 / per_pair, info
 
 
@@ -138,10 +140,10 @@ def run_reference_arm(args, rank, world):
             vals.append(v)
     v = float(np.mean(vals))
     info["value"] = v
-    line = {"impl": "reference", "metric": "flow pairs/sec @854x480", "value": v, "unit": "pairs/s",
+    line = {"impl": "reference", "metric": f"flow pairs/sec @{W}x{H}", "value": v, "unit": "pairs/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload} {W}x{H} single segment", "schedule": f"{NCONT}x{NGN}x{NPCG}",
+            "config": {"workload": f"{args.workload} {W}x{H} {WORKLOADS[args.workload][2]} segment(s) per pair", "schedule": f"{NCONT}x{NGN}x{NPCG}",
                        "note": "reference has no CPU path (SURVEY.md 8c); this is the oracle port on host cores"},
             "cpu_baseline": info,
             "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -176,10 +178,14 @@ def main():
     backend = {"auto": lib.BACKEND_AUTO, "stream": lib.BACKEND_STREAM, "resident": lib.BACKEND_RESIDENT}[args.backend]
     W, H = WORKLOADS[args.workload][:2]
     # resident back-end: 4 problems share one cooperative launch (one CTA of each per SM); 8 = two such launches
-    B = args.batch if args.batch > 0 else (1 if (args.backend == "stream" or args.workload == "C4") else 8)
+    B = args.batch if args.batch > 0 else (1 if (args.backend == "stream" or args.workload == "C4") else
+                                           (2 if args.workload == "C2" else 8))
     pairs = make_pairs(args.workload, B, first=rank * B)
-    active_px = [int((p.masks[0] == 0).sum()) for p in pairs]
-    batch = lib.Batch(W, H, B, NCONT, NGN, NPCG, backend)
+    nseg = WORKLOADS[args.workload][2]
+    # --multseg (C2): one independent problem per segment, all of them sharing the pair's constraint list
+    problems = [(p, m) for p in pairs for m in p.masks]
+    active_px = [int(sum((m == 0).sum() for m in p.masks)) for p in pairs]   # per pair
+    batch = lib.Batch(W, H, len(problems), NCONT, NGN, NPCG, backend)
 
     def barrier():
         torch.cuda.synchronize()
@@ -188,8 +194,12 @@ def main():
         torch.cuda.synchronize()
 
     def one_step():
-        outs = [batch.submit(i, p.rgb, p.masks[0], p.matches) for i, p in enumerate(pairs)]
+        outs = [batch.submit(i, p.rgb, m, p.matches) for i, (p, m) in enumerate(problems)]
         batch.run()
+        if nseg > 1:  # layer flatten of every pair (para_gen.py:136-175) belongs to the pair's end-to-end time
+            for k in range(len(pairs)):
+                o = outs[k * nseg:(k + 1) * nseg]
+                lib.flatten([x["flow"] for x in o], [x["rgb"] for x in o], [x["mask"] for x in o])
         return outs
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > the 126 MiB L2
@@ -232,17 +242,18 @@ def main():
         achieved = alg_bytes * B * args.steps / (solve_ms_max / 1000.0) / 1e9                  # this rank's GPU
         N = W * H
         line = {
-            "metric": "flow pairs/sec @854x480", "value": value, "unit": "pairs/s", "n_gpus": world,
+            "metric": f"flow pairs/sec @{W}x{H}", "value": value, "unit": "pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload} {W}x{H} single segment, synth seeds {WORKLOADS[args.workload][4]}+",
+            "config": {"workload": f"{args.workload} {W}x{H} {nseg} segment(s) per pair, synth seeds {WORKLOADS[args.workload][4]}+",
                        "pairs_per_gpu_per_step": B, "schedule": f"{NCONT}x{NGN}x{NPCG}", "backend": args.backend,
                        "active_px_mean": float(np.mean(active_px)), "parallelism": f"independent pairs x{world}, no collective",
                        "l2_policy": "L2 flushed between steps by writing a 256 MiB buffer; every step also re-uploads its inputs "
                                     "(host->device) and restarts from the reset grid, nothing is reused across steps; within a "
                                     "solve the PCG state lives in registers/shared memory"},
-            "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(B * (4 * N) + sum(16 * (len(p.matches) + 2 * (W + H)) for p in pairs)),
-                    "d2h_bytes_per_step": int(B * (12 * N + 4 * NCONT * (NGN + 1)))},
+            "e2e": {"value": e2e, "unit": "pairs/s",
+                    "h2d_bytes_per_step": int(len(problems) * (4 * N) + nseg * sum(16 * (len(p.matches) + 2 * (W + H)) for p in pairs)),
+                    "d2h_bytes_per_step": int(len(problems) * (12 * N + 4 * NCONT * (NGN + 1)))},
             "gpu_launches": int(lt.cpu()[0]),
             "ms_per_gn_solve": solve_ms_max / (B * args.steps * NCONT * NGN),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

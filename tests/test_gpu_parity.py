@@ -293,3 +293,63 @@ def test_flatten_and_background_composite_vs_numpy_restatement():
     # single layer: flatten is the identity, background fills where nothing landed
     f1, r1, m1 = lib.flatten(flows[:1], rgbs[:1], masks[:1], background=bg)
     assert _eq(f1, flows[0]) and _eq(m1, masks[0]) and _eq(r1, PC.add_bg(rgbs[0], masks[0], bg))
+
+
+def test_opt_h_multiple_live_states_and_plans(oracle):
+    """Opt_NewState has no matching free and is called again on every re-plan (CombinedSolver.h:155-159): several
+    states / plans of different sizes must coexist and interleave."""
+    import ctypes as C
+    import torch
+    L = lib.load()
+    plan_file = os.path.join(os.path.dirname(lib.LIB_PATH), "arap_plan.t").encode()
+    dev = torch.device("cuda:0")
+    jobs = []
+    for (W, H, seed) in ((64, 48, 21), (96, 40, 22)):
+        pr = synth_gn_problem(oracle, W, H, seed=seed, fd=2)
+        st = L.Opt_NewState(lib.OptInitializationParameters(0, 0, 0, 0))
+        prob = L.Opt_ProblemDefine(st, plan_file, b"gaussNewtonGPU")
+        plan = L.Opt_ProblemPlan(st, prob, (C.c_uint * 2)(W, H))
+        t = {k: torch.from_numpy(np.ascontiguousarray(pr[k])).to(dev) for k in ("X", "A", "U", "C", "M")}
+        jobs.append(dict(pr=pr, st=st, prob=prob, plan=plan, t=t))
+    torch.cuda.synchronize()
+    nGN, nPCG = C.c_uint(2), C.c_uint(25)
+    wf, wr = C.c_float(float(oracle.WF)), C.c_float(float(oracle.WR))
+    for rep in range(2):          # two Opt_ProblemSolve calls per plan, interleaved (= two continuation steps)
+        for j in jobs:
+            t = j["t"]
+            L.Opt_SetSolverParameter(j["st"], j["plan"], b"nIterations", C.byref(nGN))
+            L.Opt_SetSolverParameter(j["st"], j["plan"], b"lIterations", C.byref(nPCG))
+            pp = (C.c_void_p * 7)(t["X"].data_ptr(), t["A"].data_ptr(), t["U"].data_ptr(), t["C"].data_ptr(),
+                                  t["M"].data_ptr(), C.cast(C.byref(wf), C.c_void_p), C.cast(C.byref(wr), C.c_void_p))
+            L.Opt_ProblemSolve(j["st"], j["plan"], pp)
+            j.setdefault("costs", []).append(L.Opt_ProblemCurrentCost(j["st"], j["plan"]))
+    for j in jobs:
+        pr = j["pr"]
+        X, A, c1, _ = oracle.gn_solve(pr["X"], pr["A"], pr["U"], pr["C"], pr["M"], 2, 25)
+        X, A, c2, _ = oracle.gn_solve(X, A, pr["U"], pr["C"], pr["M"], 2, 25)
+        assert _eq(j["t"]["X"].cpu().numpy(), X) and _eq(j["t"]["A"].cpu().numpy(), A)
+        assert _eq(np.float32(j["costs"]), np.float32([c1[-1], c2[-1]]))
+        L.Opt_PlanFree(j["st"], j["plan"])
+        L.Opt_ProblemDelete(j["st"], j["prob"])
+
+
+def test_multiseg_pair_end_to_end_c2_shape(oracle):
+    """BASELINE config C2 (854x480, 4 segments, fd=3) at a reduced schedule: four independent per-segment solves share
+    one cooperative launch, every segment receives the SAME constraint file, then the layers are flattened."""
+    from oracle import pycomposite as PC
+    sp = synth.config("C2")
+    kw = dict(nCont=1, nGN=2, nPCG=30)
+    b = lib.Batch(sp.W, sp.H, 4, **kw)
+    outs = [b.submit(s, sp.rgb, sp.masks[s], sp.matches) for s in range(4)]
+    b.run()
+    flows, rgbs, masks = [], [], []
+    for s, o in enumerate(outs):
+        Xo, Ao, co = oracle.solve(sp.masks[s], sp.matches, **kw)
+        assert _eq(o["flow"], oracle.flow(Xo)) and _eq(o["costs"], co), s
+        r_o, m_o, _ = oracle.warp(Xo, sp.rgb, sp.masks[s])
+        assert _eq(o["rgb"], r_o) and _eq(o["mask"], m_o), s
+        flows.append(o["flow"]); rgbs.append(o["rgb"]); masks.append(o["mask"])
+    f_g, r_g, m_g = lib.flatten(flows, rgbs, masks)
+    f_o, r_o, m_o = PC.flatten(flows, rgbs, masks)
+    assert _eq(f_g, f_o) and _eq(r_g, r_o) and _eq(m_g, m_o)
+    b.close()
