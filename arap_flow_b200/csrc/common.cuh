@@ -186,6 +186,106 @@ __device__ __forceinline__ HL block_exact_sum(float g, double* smem)
     return out;
 }
 
+// ----------------------------------------------------------------------------------------------
+// Wide fixed-point accumulators (streaming back-end): a grid-wide exact sum WITHOUT a fence, a counter or a
+// "last block".  Every value this library sums is a multiple of 2^-149 of magnitude < 2^150, so a 320-bit
+// fixed-point number with LSB 2^-160 holds any such sum exactly.  It is kept as WA_LIMBS 32-bit limbs, each in its
+// own signed 64-bit word (2^31 contributions cannot overflow a word), WA_COPIES copies to spread same-address
+// atomics.  A producer adds the (at most three) non-zero limbs of a binary64 value with fire-and-forget
+// red.global.add.u64; integer addition commutes, so the total is independent of arrival order.  A consumer in a
+// LATER kernel sums the copies, propagates carries and rounds ONCE to binary32 (round-to-nearest-even).
+// ----------------------------------------------------------------------------------------------
+constexpr int WA_LIMBS = 10;
+constexpr int WA_COPIES = 8;
+constexpr int WA_WORDS = WA_LIMBS * WA_COPIES; // one accumulator, [copy][limb]
+constexpr int WA_LSB = -160;
+
+__device__ __forceinline__ void wide_add(unsigned long long* __restrict__ acc, unsigned copy, double v)
+{
+    if (v == 0.0) return;
+    const long long bits = __double_as_longlong(v);
+    const bool neg = bits < 0;
+    const int ex = (int)((bits >> 52) & 0x7ff);
+    unsigned long long mant = ((unsigned long long)bits & 0xfffffffffffffULL) | (ex ? (1ULL << 52) : 0ULL);
+    int pos = (ex ? ex : 1) - 1075 - WA_LSB; // bit position of the mantissa's LSB
+    if (pos < 0) {                           // multiples of 2^-149 have the trailing zeros to give
+        if (pos < -52) return;
+        mant >>= -pos;
+        pos = 0;
+    }
+    const int idx = pos >> 5, off = pos & 31;
+    const unsigned __int128 big = (unsigned __int128)mant << off;
+    unsigned long long* a = acc + (copy % WA_COPIES) * WA_LIMBS;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const unsigned long long w = (unsigned)(big >> (32 * k));
+        if (w != 0 && idx + k < WA_LIMBS) {
+            const unsigned long long c = neg ? (0ULL - w) : w;
+            asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(a + idx + k), "l"(c) : "memory");
+        }
+    }
+}
+
+// Read one accumulator.  Called by the 16 lanes of a half-warp (seg_lane = lane & 15): lanes 0..9 fetch one limb
+// each; the value is returned in every lane of the half-warp.  Both halves of a warp may decode different
+// accumulators in the same call (all 32 lanes must call).
+__device__ __forceinline__ long long wide_fetch(const unsigned long long* __restrict__ acc, int seg_lane)
+{
+    long long s = 0;
+    if (seg_lane < WA_LIMBS) {
+        unsigned long long v[WA_COPIES];
+#pragma unroll
+        for (int c = 0; c < WA_COPIES; ++c) v[c] = __ldcg(acc + c * WA_LIMBS + seg_lane);
+#pragma unroll
+        for (int c = 0; c < WA_COPIES; ++c) s += (long long)v[c];
+    }
+    return s;
+}
+__device__ __forceinline__ float wide_round(long long s_mine)
+{
+    unsigned limb[WA_LIMBS];
+    long long carry = 0;
+#pragma unroll
+    for (int k = 0; k < WA_LIMBS; ++k) {
+        const long long t = __shfl_sync(0xffffffffu, s_mine, k, 16) + carry;
+        limb[k] = (unsigned)t;
+        carry = t >> 32;
+    }
+    const bool neg = carry < 0;
+    if (neg) { // two's complement negate over the 320 bits
+        unsigned c = 1;
+#pragma unroll
+        for (int k = 0; k < WA_LIMBS; ++k) {
+            const unsigned v = ~limb[k];
+            limb[k] = v + c;
+            c = (c && v == 0xffffffffu) ? 1u : 0u;
+        }
+    }
+    int j = -1;
+    unsigned hi = 0, lo = 0;
+    bool sticky = false;
+#pragma unroll
+    for (int k = WA_LIMBS - 1; k >= 0; --k) {
+        if (j < 0) {
+            if (limb[k] != 0) {
+                j = k;
+                hi = limb[k];
+                lo = (k > 0) ? limb[k > 0 ? k - 1 : 0] : 0u;
+            }
+        } else if (k < j - 1) {
+            sticky = sticky || (limb[k] != 0);
+        }
+    }
+    if (j < 0) return 0.0f;
+    // >= 33 significant bits; the sticky bit is jammed far below binary32's rounding position (round to odd)
+    const unsigned long long top = ((unsigned long long)hi << 32) | lo | (sticky ? 1ULL : 0ULL);
+    const float f = __ull2float_rn(top);
+    const int e = 32 * (j - 1) + WA_LSB; // weight of top's LSB, in [-192, 96]
+    const double d = (double)f * __hiloint2double((e + 1023) << 20, 0);
+    const float r = (float)d; // exact for normal results; subnormal totals are exact multiples of 2^-149
+    return neg ? -r : r;
+}
+
 __device__ __forceinline__ float hl_to_float(HL v)
 {
     return (float)__dadd_rn(v.h, v.l);

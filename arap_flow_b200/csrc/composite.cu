@@ -7,7 +7,7 @@
 #include "../../include/arapb200.h"
 #include "common.cuh"
 
-#include <vector>
+#include <mutex>
 
 namespace arapb200 {
 namespace {
@@ -51,33 +51,47 @@ extern "C" int arapb200_flatten(int W, int H, int n_layers, const float* const* 
     const size_t N = (size_t)W * H;
     Layers L{};
     L.n = n_layers;
-    std::vector<void*> owned;
+    // One grow-only device arena per process (cudaMalloc / cudaFree of 15 multi-megabyte blocks per call cost far more
+    // than the kernel): [layers: flow, rgb, mask][background][outputs], every block 256-byte aligned.
+    static std::mutex mu;
+    static unsigned char* arena = nullptr;
+    static size_t arena_bytes = 0;
+    static int arena_dev = -1;
+    std::lock_guard<std::mutex> lock(mu);
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t per_layer = al(N * sizeof(float2)) + al(3 * N) + al(N);
+    const size_t need = (size_t)(n_layers + 1) * per_layer + al(3 * N);
+    int dev = 0;
+    int rc = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) rc = 2;
+    if (!rc && (need > arena_bytes || dev != arena_dev)) {
+        if (arena) { cudaFree(arena); arena = nullptr; arena_bytes = 0; }
+        if (cudaMalloc(&arena, need) != cudaSuccess) rc = 2;
+        else { arena_bytes = need; arena_dev = dev; }
+    }
+    unsigned char* cur = arena;
+    auto take = [&](size_t bytes) { unsigned char* p = cur; cur += al(bytes); return p; };
     auto up = [&](const void* h, size_t bytes) -> void* {
-        void* d = nullptr;
-        if (cudaMalloc(&d, bytes) != cudaSuccess) return nullptr;
-        owned.push_back(d);
-        if (cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, nullptr) != cudaSuccess) return nullptr;
+        void* d = take(bytes);
+        if (cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, nullptr) != cudaSuccess) rc = 2;
         return d;
     };
-    int rc = 0;
     for (int s = 0; s < n_layers && !rc; ++s) {
         L.flow[s] = (const float2*)up(flows[s], N * sizeof(float2));
         L.rgb[s] = (const unsigned char*)up(rgbs[s], 3 * N);
         L.mask[s] = (const unsigned char*)up(masks[s], N);
-        if (!L.flow[s] || !L.rgb[s] || !L.mask[s]) rc = 2;
     }
     const unsigned char* d_bg = nullptr;
-    if (!rc && background) { d_bg = (const unsigned char*)up(background, 3 * N); if (!d_bg) rc = 2; }
-    float2* d_of = nullptr; unsigned char *d_or = nullptr, *d_om = nullptr;
-    if (!rc && (cudaMalloc(&d_of, N * sizeof(float2)) || cudaMalloc(&d_or, 3 * N) || cudaMalloc(&d_om, N))) rc = 2;
+    if (!rc && background) d_bg = (const unsigned char*)up(background, 3 * N);
     if (!rc) {
+        float2* d_of = (float2*)take(N * sizeof(float2));
+        unsigned char* d_or = take(3 * N);
+        unsigned char* d_om = take(N);
         k_flatten<<<(unsigned)((N + 255) / 256), 256>>>(N, L, d_bg, d_of, d_or, d_om);
         if (cudaMemcpy(out_flow, d_of, N * sizeof(float2), cudaMemcpyDeviceToHost) ||
             cudaMemcpy(out_rgb, d_or, 3 * N, cudaMemcpyDeviceToHost) || cudaMemcpy(out_mask, d_om, N, cudaMemcpyDeviceToHost))
             rc = 3;
     }
     if (rc) fprintf(stderr, "arapb200_flatten: CUDA failure (%s)\n", cudaGetErrorString(cudaGetLastError()));
-    for (void* d : owned) cudaFree(d);
-    cudaFree(d_of); cudaFree(d_or); cudaFree(d_om);
     return rc;
 }

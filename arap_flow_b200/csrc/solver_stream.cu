@@ -20,63 +20,32 @@ namespace {
 
 constexpr int TS = ST_TILE + 2; // staged tile pitch (1-pixel halo)
 
-__device__ __forceinline__ int clog2_u32(unsigned n)
-{
-    return (n <= 1) ? 0 : 32 - __clz(n - 1);
-}
 
-// Block result (valid in warp 0) -> per-tile partial; the last tile to arrive folds all partials
-// exactly and returns true in thread 0 with the total in `total`.
-__device__ bool finalize_partial(const StreamDev* dp, HL blockval, double* smem, float& total)
+__device__ __forceinline__ unsigned long long* acc_set(const StreamPlanes& pl, int set)
 {
-    __shared__ bool s_last;
-    const unsigned nb = gridDim.x;
-    if (threadIdx.x == 0) {
-        dp->partials[blockIdx.x] = make_double2(blockval.h, blockval.l);
-        __threadfence();
-        unsigned t = atomicInc(dp->counter, nb - 1);
-        s_last = (t == nb - 1);
-    }
-    __syncthreads();
-    if (!s_last) return false;
-    __threadfence();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    // pass 1: max |h|
-    double m = 0.0;
-    for (unsigned i = threadIdx.x; i < nb; i += blockDim.x) m = fmax(m, fabs(__ldcg(&dp->partials[i].x)));
-    m = warp_max(m);
-    if (lane == 0) smem[wid] = m;
-    __syncthreads();
-    m = 0.0;
-    for (int w = 0; w < nw; ++w) m = fmax(m, smem[w]);
-    __syncthreads();
-    const double B = bin_base(ilogb_f64(m) + clog2_u32(nb) + 2);
-    // pass 2: binned accumulation
-    double hs = 0.0, ls = 0.0;
-    for (unsigned i = threadIdx.x; i < nb; i += blockDim.x) {
-        double2 v = __ldcg(&dp->partials[i]);
-        double hi, lo;
-        bin_split(B, v.x, hi, lo);
-        hs = __dadd_rn(hs, hi);
-        ls = __dadd_rn(ls, __dadd_rn(lo, v.y));
-    }
-    hs = warp_sum(hs);
-    ls = warp_sum(ls);
-    if (lane == 0) {
-        smem[wid] = hs;
-        smem[32 + wid] = ls;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double H = 0.0, L = 0.0;
-        for (int w = 0; w < nw; ++w) {
-            H = __dadd_rn(H, smem[w]);
-            L = __dadd_rn(L, smem[32 + w]);
-        }
-        total = (float)__dadd_rn(H, L);
-        return true;
-    }
-    return false;
+    return pl.acc + set * WA_WORDS;
+}
+__device__ __forceinline__ int bn_set(int j) // accumulator of r.z of PCG iteration j (j >= -2)
+{
+    return (j + 3) % 3;
+}
+// Block result (valid in warp 0) -> the grid-wide accumulator `set`.  Fire and forget: no fence, no counter; the
+// consumers run in a later kernel.
+__device__ __forceinline__ void publish(const StreamPlanes& pl, int set, HL blockval)
+{
+    if (threadIdx.x == 0) wide_add(acc_set(pl, set), blockIdx.x, blockval.h);
+    if (threadIdx.x == 1) wide_add(acc_set(pl, set), blockIdx.x, blockval.l);
+}
+// Warp 0 of a block reads two accumulators at once: lanes 0..15 `set_lo`, lanes 16..31 `set_hi`.
+__device__ __forceinline__ long long fetch2(const StreamPlanes& pl, int set_lo, int set_hi)
+{
+    const int lane = threadIdx.x & 31;
+    return wide_fetch(acc_set(pl, lane < 16 ? set_lo : set_hi), lane & 15);
+}
+__device__ __forceinline__ void zero_set(const StreamPlanes& pl, int set, int first_thread)
+{
+    const int t = (int)threadIdx.x - first_thread;
+    if (t >= 0 && t < WA_WORDS) acc_set(pl, set)[t] = 0ULL;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -188,31 +157,39 @@ __global__ void __launch_bounds__(ST_THREADS) k_init(const StreamDev* __restrict
             g = g + dot3(r0, r1, r2, p0, p1, p2);
         }
     }
-    HL b = block_exact_sum(g, red);
-    float total;
-    __syncthreads();
-    if (finalize_partial(dpp, b, red, total)) dp.sc->num = total;
+    publish(dp, bn_set(-1), block_exact_sum(g, red));
 }
 
 // PCGStep3 of the previous iteration fused with PCGStep1 (solverGPUGaussNewton.t:537-550, 421-434)
 template <bool FIRST>
-__global__ void __launch_bounds__(ST_THREADS) k_step_a(const StreamDev* __restrict__ dpp, int it)
+__global__ void __launch_bounds__(ST_THREADS) k_step_a(const __grid_constant__ StreamPlanes pl,
+                                                       const StreamDev* __restrict__ dpp, int it)
 {
     __shared__ float4 T[TS][TS];
     __shared__ double red[64];
-    const StreamDev& dp = *dpp;
-    const int W = dp.W, H = dp.H;
-    const int x0 = (blockIdx.x % dp.tx) * ST_TILE, y0 = (blockIdx.x / dp.tx) * ST_TILE;
+    __shared__ float s_beta;
+    const bool tile_on = pl.tile_active[blockIdx.x] != 0; // tiles without object pixels have nothing to add
+    if (!tile_on && blockIdx.x != 0) return;
+    const float wr2 = dpp->wr2, wf2 = dpp->wf2;
+    const int W = pl.W, H = pl.H;
+    const int x0 = (blockIdx.x % pl.tx) * ST_TILE, y0 = (blockIdx.x / pl.tx) * ST_TILE;
     float beta = 0.0f;
     if (!FIRST) {
-        const float num = dp.sc->num, bnum = dp.sc->bnum;
-        beta = (num > 0.0f) ? bnum / num : 0.0f; // :544-547
+        if (threadIdx.x < 32) {
+            const float v = wide_round(fetch2(pl, bn_set(it - 1), bn_set(it - 2)));
+            const float bnum = __shfl_sync(0xffffffffu, v, 0), num = __shfl_sync(0xffffffffu, v, 16);
+            if (threadIdx.x == 0) {
+                s_beta = (num > 0.0f) ? bnum / num : 0.0f; // :544-547
+                if (blockIdx.x == 0 && dpp->trace) dpp->trace[3 * (it - 1) + 2] = bnum;
+            }
+        }
+        __syncthreads();
+        beta = s_beta;
     }
     // p is ping-ponged between two buffers: the halo of a tile needs the OLD direction of pixels that
     // the neighbouring tile is updating in this very kernel.
-    float* const* __restrict__ psrc = dp.p[FIRST ? 0 : ((it - 1) & 1)];
-    float* const* __restrict__ pdst = dp.p[it & 1];
-    const bool tile_on = dp.tile_active[blockIdx.x] != 0; // tiles without object pixels only take part in the reduction
+    float* const* __restrict__ psrc = pl.p[FIRST ? 0 : ((it - 1) & 1)];
+    float* const* __restrict__ pdst = pl.p[it & 1];
     // stage (p_x, p_y, sin*p_a, cos*p_a) of tile + halo, p being the NEW direction
     for (int e = threadIdx.x; tile_on && e < TS * TS; e += ST_THREADS) {
         const int ly = e / TS, lx = e - ly * TS;
@@ -222,10 +199,10 @@ __global__ void __launch_bounds__(ST_THREADS) k_step_a(const StreamDev* __restri
             // no activity test: every plane of an inactive pixel holds zeros, which flow through as zeros
             const size_t i = (size_t)y * W + x;
             float p0 = psrc[0][i], p1 = psrc[1][i], p2 = psrc[2][i];
-            const float c = dp.cs[0][i], sn = dp.cs[1][i];
+            const float c = pl.cs[0][i], sn = pl.cs[1][i];
             if (!FIRST) {
-                const float pX = dp.pre[0][i], pA = dp.pre[1][i];
-                const float r0 = dp.r[0][i], r1 = dp.r[1][i], r2 = dp.r[2][i];
+                const float pX = pl.pre[0][i], pA = pl.pre[1][i];
+                const float r0 = pl.r[0][i], r1 = pl.r[1][i], r2 = pl.r[2][i];
                 p0 = fmaf(beta, p0, pX * r0);
                 p1 = fmaf(beta, p1, pX * r1);
                 p2 = fmaf(beta, p2, pA * r2);
@@ -246,11 +223,11 @@ __global__ void __launch_bounds__(ST_THREADS) k_step_a(const StreamDev* __restri
             const int ly = lyb + r, y = y0 + ly;
             if (y >= H) break;
             const size_t i = (size_t)y * W + x;
-            const unsigned f = dp.flags[i];
+            const unsigned f = pl.flags[i];
             if (!(f & FLAG_ACTIVE)) continue;
             const float4 Pi = T[ly + 1][lx + 1];
             float pa = psrc[2][i];
-            if (!FIRST) pa = fmaf(beta, pa, dp.pre[1][i] * dp.r[2][i]);
+            if (!FIRST) pa = fmaf(beta, pa, pl.pre[1][i] * pl.r[2][i]);
             JtjAcc a;
             jtj_zero(a);
             if (f & 1u) jtj_nb<0>(a, Pi.x, Pi.y, T[ly + 1][lx + 2]);
@@ -258,52 +235,66 @@ __global__ void __launch_bounds__(ST_THREADS) k_step_a(const StreamDev* __restri
             if (f & 4u) jtj_nb<2>(a, Pi.x, Pi.y, T[ly + 2][lx + 1]);
             if (f & 8u) jtj_nb<3>(a, Pi.x, Pi.y, T[ly][lx + 1]);
             float q0, q1, qa;
-            jtj_finish(a, dp.cs[0][i], dp.cs[1][i], Pi.x, Pi.y, pa, (f & FLAG_FIT) != 0, dp.wr2, dp.wf2, q0, q1, qa);
-            dp.q[0][i] = q0; dp.q[1][i] = q1; dp.q[2][i] = qa;
+            jtj_finish(a, pl.cs[0][i], pl.cs[1][i], Pi.x, Pi.y, pa, (f & FLAG_FIT) != 0, wr2, wf2, q0, q1, qa);
+            pl.q[0][i] = q0; pl.q[1][i] = q1; pl.q[2][i] = qa;
             g = g + dot3(Pi.x, Pi.y, pa, q0, q1, qa);
         }
     }
-    HL b = block_exact_sum(g, red);
-    float total;
-    __syncthreads();
-    if (finalize_partial(dpp, b, red, total)) {
-        if (!FIRST) dp.sc->num = dp.sc->bnum; // :1091
-        dp.sc->den = total;
-        if (dp.trace) {
-            dp.trace[3 * it] = total;
-            dp.trace[3 * it + 1] = dp.sc->num;
-        }
-    }
+    publish(pl, ST_ACC_D0 + (it & 1), block_exact_sum(g, red));
 }
 
 // PCGStep2 (solverGPUGaussNewton.t:446-489).  Branch-free: the planes of inactive pixels hold zeros (they are
 // zero-initialised and never written), so they flow through as exact zeros and add +0 to the group term;
 // every load of the four rows is issued before the first use.
-__global__ void __launch_bounds__(ST_THREADS) k_step_b(const StreamDev* __restrict__ dpp, int it)
+__global__ void __launch_bounds__(ST_THREADS) k_step_b(const __grid_constant__ StreamPlanes pl,
+                                                       const StreamDev* __restrict__ dpp, int it)
 {
     __shared__ double red[64];
-    const StreamDev& dp = *dpp;
-    const int W = dp.W, H = dp.H;
-    const int x = (blockIdx.x % dp.tx) * ST_TILE + (threadIdx.x & 31);
-    const int yb = (blockIdx.x / dp.tx) * ST_TILE + (threadIdx.x >> 5) * 4;
-    const float num = dp.sc->num, den = dp.sc->den;
-    const float alpha = (den > 0.0f) ? num / den : 0.0f; // :456-459
-    float g = 0.0f;
-    if (x < W && dp.tile_active[blockIdx.x]) {
-        const float* __restrict__ pk0 = dp.p[it & 1][0];
-        const float* __restrict__ pk1 = dp.p[it & 1][1];
-        const float* __restrict__ pk2 = dp.p[it & 1][2];
-        float pv[4][3], qv[4][3], rv[4][3], dv[4][3], pre[4][2];
+    __shared__ float s_alpha;
+    const bool tile_on = pl.tile_active[blockIdx.x] != 0;
+    if (!tile_on && blockIdx.x != 0) return;
+    const int W = pl.W, H = pl.H;
+    const int x = (blockIdx.x % pl.tx) * ST_TILE + (threadIdx.x & 31);
+    const int yb = (blockIdx.x / pl.tx) * ST_TILE + (threadIdx.x >> 5) * 4;
+    // warp 0: r.z of the previous iteration and this iteration's p.q; fetched before the planes, decoded after
+    long long raw = 0;
+    if (threadIdx.x < 32) raw = fetch2(pl, bn_set(it - 1), ST_ACC_D0 + (it & 1));
+    const bool on = tile_on && x < W;
+    const float* __restrict__ pk0 = pl.p[it & 1][0];
+    const float* __restrict__ pk1 = pl.p[it & 1][1];
+    const float* __restrict__ pk2 = pl.p[it & 1][2];
+    float pv[4][3], qv[4][3], rv[4][3], dv[4][3], pre[4][2];
+    if (on) {
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const int y = min(yb + r, H - 1); // rows past the image re-read the last row; they are not stored
             const size_t i = (size_t)y * W + x;
             pv[r][0] = pk0[i]; pv[r][1] = pk1[i]; pv[r][2] = pk2[i];
-            qv[r][0] = dp.q[0][i]; qv[r][1] = dp.q[1][i]; qv[r][2] = dp.q[2][i];
-            rv[r][0] = dp.r[0][i]; rv[r][1] = dp.r[1][i]; rv[r][2] = dp.r[2][i];
-            dv[r][0] = dp.d[0][i]; dv[r][1] = dp.d[1][i]; dv[r][2] = dp.d[2][i];
-            pre[r][0] = dp.pre[0][i]; pre[r][1] = dp.pre[1][i];
+            qv[r][0] = pl.q[0][i]; qv[r][1] = pl.q[1][i]; qv[r][2] = pl.q[2][i];
+            rv[r][0] = pl.r[0][i]; rv[r][1] = pl.r[1][i]; rv[r][2] = pl.r[2][i];
+            dv[r][0] = pl.d[0][i]; dv[r][1] = pl.d[1][i]; dv[r][2] = pl.d[2][i];
+            pre[r][0] = pl.pre[0][i]; pre[r][1] = pl.pre[1][i];
         }
+    }
+    if (threadIdx.x < 32) {
+        const float v = wide_round(raw);
+        const float num = __shfl_sync(0xffffffffu, v, 0), den = __shfl_sync(0xffffffffu, v, 16);
+        if (threadIdx.x == 0) {
+            s_alpha = (den > 0.0f) ? num / den : 0.0f; // :456-459
+            if (blockIdx.x == 0 && dpp->trace) {
+                dpp->trace[3 * it] = den;
+                dpp->trace[3 * it + 1] = num;
+            }
+        }
+    }
+    if (blockIdx.x == 0) { // recycle the accumulators nobody reads any more (their next writers are later kernels)
+        zero_set(pl, bn_set(it - 2), 64);
+        zero_set(pl, ST_ACC_D0 + ((it + 1) & 1), 160);
+    }
+    __syncthreads();
+    const float alpha = s_alpha;
+    float g = 0.0f;
+    if (on) {
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const int y = yb + r;
@@ -312,22 +303,16 @@ __global__ void __launch_bounds__(ST_THREADS) k_step_b(const StreamDev* __restri
                 float rr[3], zz[3];
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    dp.d[k][i] = fmaf(alpha, pv[r][k], dv[r][k]);
+                    pl.d[k][i] = fmaf(alpha, pv[r][k], dv[r][k]);
                     rr[k] = fmaf(-alpha, qv[r][k], rv[r][k]);
-                    dp.r[k][i] = rr[k];
+                    pl.r[k][i] = rr[k];
                     zz[k] = ((k < 2) ? pre[r][0] : pre[r][1]) * rr[k];
                 }
                 g = g + dot3(zz[0], zz[1], zz[2], rr[0], rr[1], rr[2]);
             }
         }
     }
-    HL b = block_exact_sum(g, red);
-    float total;
-    __syncthreads();
-    if (finalize_partial(dpp, b, red, total)) {
-        dp.sc->bnum = total;
-        if (dp.trace) dp.trace[3 * it + 2] = total;
-    }
+    publish(pl, bn_set(it), block_exact_sum(g, red));
 }
 
 // PCGLinearUpdate (solverGPUGaussNewton.t:552-557) + cos/sin refresh for the new angles
@@ -391,15 +376,30 @@ __global__ void __launch_bounds__(ST_THREADS) k_cost(const StreamDev* __restrict
             g = g + acc;
         }
     }
-    HL b = block_exact_sum(g, red);
-    float total;
-    __syncthreads();
-    if (finalize_partial(dpp, b, red, total)) dp.sc->cost = 0.5f * total;
+    publish(dp, ST_ACC_COST, block_exact_sum(g, red));
+}
+
+// Cost accumulator -> scalars; with tracing, also the last iteration's r.z
+__global__ void __launch_bounds__(32) k_finish(const __grid_constant__ StreamPlanes pl, const StreamDev* __restrict__ dpp,
+                                               int last_it)
+{
+    const float v = wide_round(fetch2(pl, ST_ACC_COST, bn_set(last_it < 0 ? 0 : last_it)));
+    if (threadIdx.x == 0) pl.sc->cost = 0.5f * v;
+    if (threadIdx.x == 16 && last_it >= 0 && dpp->trace) dpp->trace[3 * last_it + 2] = v;
+}
+
+// debug: one accumulator -> a float
+__global__ void __launch_bounds__(32) k_decode(const __grid_constant__ StreamPlanes pl, int set, float* dst)
+{
+    const float v = wide_round(fetch2(pl, set, set));
+    if (threadIdx.x == 0) *dst = v;
 }
 
 } // namespace
 
 // ------------------------------------------------------------------------------------------ host
+static constexpr size_t ACC_BYTES = (size_t)ST_ACC_SETS * WA_WORDS * sizeof(unsigned long long);
+
 StreamSolver::StreamSolver(int W, int H)
 {
     h_.W = W;
@@ -423,9 +423,8 @@ StreamSolver::StreamSolver(int W, int H)
     ARAP_CUDA_OR_EXIT(cudaMemset(h_.flags, 0, Np));
     ARAP_CUDA_OR_EXIT(cudaMalloc(&h_.tile_active, (size_t)h_.ntiles));
     ARAP_CUDA_OR_EXIT(cudaMemset(h_.tile_active, 1, (size_t)h_.ntiles));
-    ARAP_CUDA_OR_EXIT(cudaMalloc(&h_.partials, (size_t)h_.ntiles * sizeof(double2)));
-    ARAP_CUDA_OR_EXIT(cudaMalloc(&h_.counter, sizeof(unsigned)));
-    ARAP_CUDA_OR_EXIT(cudaMemset(h_.counter, 0, sizeof(unsigned)));
+    ARAP_CUDA_OR_EXIT(cudaMalloc(&h_.acc, ACC_BYTES));
+    ARAP_CUDA_OR_EXIT(cudaMemset(h_.acc, 0, ACC_BYTES));
     ARAP_CUDA_OR_EXIT(cudaMalloc(&h_.sc, sizeof(StreamScalars)));
     ARAP_CUDA_OR_EXIT(cudaMemset(h_.sc, 0, sizeof(StreamScalars)));
     ARAP_CUDA_OR_EXIT(cudaMalloc(&d_, sizeof(StreamDev)));
@@ -438,8 +437,7 @@ StreamSolver::~StreamSolver()
     cudaFree(planes_);
     cudaFree(h_.flags);
     cudaFree(h_.tile_active);
-    cudaFree(h_.partials);
-    cudaFree(h_.counter);
+    cudaFree(h_.acc);
     cudaFree(h_.sc);
     cudaFree(d_);
 }
@@ -460,6 +458,7 @@ void StreamSolver::bind(float2* X, float* A, const float2* U, const float2* C, c
 
 void StreamSolver::enqueue_prep(cudaStream_t stream)
 {
+    ARAP_CUDA_OR_EXIT(cudaMemsetAsync(h_.acc, 0, ACC_BYTES, stream));
     k_prep<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
     ++launches_;
 }
@@ -472,38 +471,45 @@ void StreamSolver::enqueue_pcg_init(cudaStream_t stream)
 
 void StreamSolver::enqueue_step_a(bool first, int it, cudaStream_t stream)
 {
-    if (first) k_step_a<true><<<h_.ntiles, ST_THREADS, 0, stream>>>(d_, it);
-    else k_step_a<false><<<h_.ntiles, ST_THREADS, 0, stream>>>(d_, it);
-    ++launches_;
+    const StreamPlanes& pl = h_;
+    if (first) k_step_a<true><<<h_.ntiles, ST_THREADS, 0, stream>>>(pl, d_, it);
+    else k_step_a<false><<<h_.ntiles, ST_THREADS, 0, stream>>>(pl, d_, it);
+    k_decode<<<1, 32, 0, stream>>>(pl, ST_ACC_D0 + (it & 1), &h_.sc->den);
+    launches_ += 2;
 }
 
 void StreamSolver::enqueue_init(cudaStream_t stream)
 {
+    const StreamPlanes& pl = h_;
     ARAP_CUDA_OR_EXIT(cudaMemsetAsync(&h_.sc->bad_u, 0, sizeof(unsigned), stream));
     enqueue_prep(stream);
     k_cost<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
-    ++launches_;
+    k_finish<<<1, 32, 0, stream>>>(pl, d_, -1);
+    launches_ += 2;
     ARAP_CUDA_OR_EXIT(cudaGetLastError());
 }
 
 void StreamSolver::launch_gn_body(int nPCG, cudaStream_t stream, bool tracing)
 {
+    const StreamPlanes& pl = h_;
+    ARAP_CUDA_OR_EXIT(cudaMemsetAsync(h_.acc, 0, ACC_BYTES, stream));
     // the caller may have changed the constraint image / mask between steps (Opt.h:58-60): refresh flags
     k_prep<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
     k_init<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
     for (int it = 0; it < nPCG; ++it) {
-        if (it == 0) k_step_a<true><<<h_.ntiles, ST_THREADS, 0, stream>>>(d_, it);
-        else k_step_a<false><<<h_.ntiles, ST_THREADS, 0, stream>>>(d_, it);
-        k_step_b<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_, it);
+        if (it == 0) k_step_a<true><<<h_.ntiles, ST_THREADS, 0, stream>>>(pl, d_, it);
+        else k_step_a<false><<<h_.ntiles, ST_THREADS, 0, stream>>>(pl, d_, it);
+        k_step_b<<<h_.ntiles, ST_THREADS, 0, stream>>>(pl, d_, it);
     }
     k_update<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
     k_cost<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
+    k_finish<<<1, 32, 0, stream>>>(pl, d_, nPCG - 1);
     (void)tracing;
 }
 
 void StreamSolver::enqueue_gn_step(int nPCG, cudaStream_t stream, float* d_trace)
 {
-    const long long nodes = 2LL * nPCG + 4;
+    const long long nodes = 2LL * nPCG + 5;
     if (d_trace) {
         h_.trace = d_trace;
         upload(stream);

@@ -18,17 +18,16 @@ struct StreamScalars {
     unsigned pad[3];
 };
 
-// Everything the kernels need, resident in device memory; kernels take a pointer to it so that a
-// captured graph stays valid when the caller re-binds its images (Opt_ProblemInit/Step re-bind on
-// every call: ARAP/API/src/util.t:664-692).
-struct StreamDev {
+// Accumulator sets (common.cuh: wide fixed-point accumulators).  r.z of PCG iteration j lives in set (j + 3) % 3
+// (j = -1: the initial r.p of PCGInit1), p.q of iteration j in set 3 + (j & 1); set 5 is the cost.
+constexpr int ST_ACC_D0 = 3;
+constexpr int ST_ACC_COST = 5;
+constexpr int ST_ACC_SETS = 6;
+
+// What the solver owns, fixed for its lifetime: passed to the kernels BY VALUE (constant bank), so that no block starts
+// with a chain of dependent pointer loads.
+struct StreamPlanes {
     int W, H, tx, ty, ntiles;
-    float2* X;            // Offset  (in/out)
-    float* A;             // Angle   (in/out)
-    const float2* U;      // UrShape
-    const float2* C;      // Constraints
-    const float* M;       // Mask
-    float wf, wr, wf2, wr2;
     float* r[3];
     float* p[2][3];       // search direction, ping-ponged per PCG iteration (buffer it & 1)
     float* q[3];
@@ -37,9 +36,19 @@ struct StreamDev {
     float* pre[2];        // guarded-inverted diagonal: X part (both comps), angle part
     unsigned char* flags;
     unsigned char* tile_active; // per 32x32 tile: any object pixel (set by k_prep)
-    double2* partials;    // one (h, l) pair per tile
-    unsigned* counter;
+    unsigned long long* acc;    // [ST_ACC_SETS][WA_COPIES][WA_LIMBS]
     StreamScalars* sc;
+};
+
+// Plus what the caller binds (Opt_ProblemInit/Step re-bind on every call: ARAP/API/src/util.t:664-692).  This part is
+// read through a pointer to a device copy, so that a captured graph stays valid across re-binds.
+struct StreamDev : StreamPlanes {
+    float2* X;            // Offset  (in/out)
+    float* A;             // Angle   (in/out)
+    const float2* U;      // UrShape
+    const float2* C;      // Constraints
+    const float* M;       // Mask
+    float wf, wr, wf2, wr2;
     float* trace;         // optional: (den, num, bnum) per PCG iteration of the current GN step
 };
 
@@ -63,7 +72,7 @@ public:
     // unit-level pieces for the parity tests (enqueue only)
     void enqueue_prep(cudaStream_t stream);
     void enqueue_pcg_init(cudaStream_t stream);
-    void enqueue_step_a(bool first, int it, cudaStream_t stream);
+    void enqueue_step_a(bool first, int it, cudaStream_t stream); // also decodes p.q into scalars().den
     const StreamDev& host_view() const { return h_; }
     StreamScalars* d_scalars() const { return h_.sc; }
     long long launches() const { return launches_; }

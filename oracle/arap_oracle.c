@@ -13,8 +13,10 @@
  *     (needs Terra release-2016-03-25 + CUDA 7.5 libdevice), and the tree holds no
  *     per-iteration vectors, so bit-level parity of the solve is UNPINNED.  It is anchored on the
  *     one end-to-end golden the tree ships (cat512_iCstr.txt -> cat512_iFlo.flo, weak because the
- *     fixed-budget GN/PCG trajectory is chaotic on 9 constraints) and on a finite-difference
- *     check of J^T F / J^T J p against the residual function (tests/test_oracle_solver.py).
+ *     fixed-budget GN/PCG trajectory is chaotic on 9 constraints; at energy level the shipped
+ *     result and the oracle's agree to 1.5 %: 44.76 vs 45.41, test_solve_energy_pin_vs_shipped_golden)
+ *     and on a finite-difference check of J^T F / J^T J p against the residual function
+ *     (tests/test_oracle_solver.py).
  *
  * What is restated (all paths relative to /root/reference):
  *   energy                      arap_plan.t:1-23, ARAP/API/src/lib.t:92-96 (Rotate2D)

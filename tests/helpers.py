@@ -35,3 +35,24 @@ def synth_gn_problem(oracle, W, H, seed, fd=2, alpha=1.0, nseg=1):
 def epe(a, b, sel=None):
     d = np.hypot(a[..., 0] - b[..., 0], a[..., 1] - b[..., 1])
     return d[sel] if sel is not None else d
+
+
+def optimal_angles(X, U, active):
+    """argmin over a_i of sum_j |(X_i - X_j) - R(a_i)(u_i - u_j)|^2 over valid 4-neighbours (arap_plan.t:16-20): the
+    energy is separable in the angles for fixed positions, a_i = atan2(sum d x e, sum d . e).  float64 numpy."""
+    H, W = active.shape
+    X = X.astype(np.float64)
+    Ud = U.astype(np.float64)
+    num = np.zeros((H, W))
+    den = np.zeros((H, W))
+    for dy, dx in ((0, 1), (0, -1), (1, 0), (-1, 0)):
+        ys = slice(max(0, -dy), H - max(0, dy)); xs = slice(max(0, -dx), W - max(0, dx))
+        yn = slice(max(0, dy), H - max(0, -dy)); xn = slice(max(0, dx), W - max(0, -dx))
+        v = np.zeros((H, W), bool)
+        v[ys, xs] = active[ys, xs] & active[yn, xn]
+        e = np.zeros((H, W, 2)); d = np.zeros((H, W, 2))
+        e[ys, xs] = X[ys, xs] - X[yn, xn]
+        d[ys, xs] = Ud[ys, xs] - Ud[yn, xn]
+        num += np.where(v, d[..., 0] * e[..., 1] - d[..., 1] * e[..., 0], 0.0)
+        den += np.where(v, d[..., 0] * e[..., 0] + d[..., 1] * e[..., 1], 0.0)
+    return np.arctan2(num, den)

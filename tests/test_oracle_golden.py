@@ -71,6 +71,32 @@ def test_solve_pin_record(gold):
     assert pin["median_epe_px"] < 0.12
 
 
+def test_solve_energy_pin_vs_shipped_golden(oracle, gold):
+    """Energy-level anchor for the solve (the trajectory-level one is chaotic, see test_solve_pin_record): evaluate the
+    ARAP energy AS DEFINED (arap_plan.t:13-23; float64 residuals, angles at their closed-form optimum for the given
+    positions) at the reference's shipped result cat512_iFlo.flo and at the oracle's recorded full-schedule result.  Both
+    must have minimised the same energy to the same level."""
+    from .helpers import optimal_angles
+    rgb, msk, flo_gold = _cat(gold)
+    flo_ours = np.load(os.path.join(gold, "cat512_oracle_flow.npz"))["flow"]
+    cstr = flowio.read_constraints(os.path.join(gold, "cat512_iCstr.txt"))
+    H, W = msk.shape
+    U = oracle.grid(W, H)
+    Cn = oracle.constraint_image(msk, oracle.with_border_pins(cstr, W, H), 1.0)
+    act = msk == 0
+    E = {}
+    for name, fl in (("golden", flo_gold), ("oracle", flo_ours)):
+        X = (U + np.where(act[..., None], fl, 0)).astype(np.float32)
+        A = optimal_angles(X, U, act)
+        r = oracle.residuals_f64(X, A, U, Cn, msk.astype(np.float32))
+        E[name] = (0.5 * float((r[..., :8] ** 2).sum()), 0.5 * float((r[..., 8:] ** 2).sum()))
+    (rg, fg), (ro, fo) = E["golden"], E["oracle"]
+    # recorded when the fixture was made: rigidity 44.762 vs 45.413, fit 2.78e-3 vs 2.73e-3
+    assert abs(ro - rg) / rg < 0.02, E
+    assert abs(fo - fg) / fg < 0.05, E
+    assert 40.0 < rg < 50.0 and fg < 5e-3, E
+
+
 @pytest.mark.slow
 def test_solve_cat512_full(oracle, gold):
     rgb, msk, flo = _cat(gold)
