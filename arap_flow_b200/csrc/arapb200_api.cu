@@ -207,14 +207,14 @@ static int debug_setup(int W, int H, const float* X, const float* A, const float
     return 0;
 }
 
-static void gather3(const StreamDev& v, float* const planes[3], size_t N, float* out3, const std::vector<unsigned char>& flags)
+// three planes (PL_* indices) -> interleaved [N][3], zero outside the object
+static void gather3(const StreamSolver& s, const int planes[3], size_t N, float* out3, const std::vector<unsigned char>& flags)
 {
     std::vector<float> tmp(N);
     for (int k = 0; k < 3; ++k) {
-        ARAP_CUDA_OR_EXIT(cudaMemcpy(tmp.data(), planes[k], N * sizeof(float), cudaMemcpyDeviceToHost));
+        s.download_plane(planes[k], tmp.data());
         for (size_t i = 0; i < N; ++i) out3[3 * i + k] = (flags[i] & FLAG_ACTIVE) ? tmp[i] : 0.f;
     }
-    (void)v;
 }
 
 int arapb200_debug_eval_jtf(int W, int H, const float* X, const float* A, const float* U, const float* C,
@@ -227,12 +227,12 @@ int arapb200_debug_eval_jtf(int W, int H, const float* X, const float* A, const 
     if (int rc = debug_setup(W, H, X, A, U, C, M, wf, wr, s, dX, dU, dC, dA, dM)) return rc;
     s.enqueue_pcg_init(nullptr);
     ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
-    const StreamDev& v = s.host_view();
     std::vector<unsigned char> flags(N);
-    ARAP_CUDA_OR_RETURN(cudaMemcpy(flags.data(), v.flags, N, cudaMemcpyDeviceToHost));
-    gather3(v, v.r, N, r3, flags);
-    float* pre_planes[3] = {v.pre[0], v.pre[0], v.pre[1]};
-    gather3(v, pre_planes, N, pre3, flags);
+    s.download_flags(flags.data());
+    const int r_planes[3] = {PL_R, PL_R + 1, PL_R + 2};
+    gather3(s, r_planes, N, r3, flags);
+    const int pre_planes[3] = {PL_PRE, PL_PRE, PL_PRE + 1};
+    gather3(s, pre_planes, N, pre3, flags);
     return 0;
 }
 
@@ -245,16 +245,18 @@ int arapb200_debug_apply_jtj(int W, int H, const float* A, const float* U, const
     StreamSolver s(W, H);
     if (int rc = debug_setup(W, H, nullptr, A, U, C, M, wf, wr, s, dX, dU, dC, dA, dM)) return rc;
     const StreamDev& v = s.host_view();
+    ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
     std::vector<float> tmp(N);
     for (int k = 0; k < 3; ++k) {
         for (size_t i = 0; i < N; ++i) tmp[i] = p3[3 * i + k];
-        ARAP_CUDA_OR_RETURN(cudaMemcpy(v.p[0][k], tmp.data(), N * sizeof(float), cudaMemcpyHostToDevice));
+        s.upload_plane(PL_P + k, tmp.data());
     }
     s.enqueue_step_a(true, 0, nullptr);
     ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
     std::vector<unsigned char> flags(N);
-    ARAP_CUDA_OR_RETURN(cudaMemcpy(flags.data(), v.flags, N, cudaMemcpyDeviceToHost));
-    gather3(v, v.q, N, q3, flags);
+    s.download_flags(flags.data());
+    const int q_planes[3] = {PL_Q, PL_Q + 1, PL_Q + 2};
+    gather3(s, q_planes, N, q3, flags);
     StreamScalars sc;
     ARAP_CUDA_OR_RETURN(cudaMemcpy(&sc, v.sc, sizeof(sc), cudaMemcpyDeviceToHost));
     if (dot) *dot = sc.den;

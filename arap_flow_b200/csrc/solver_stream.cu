@@ -10,7 +10,9 @@
 //   k_update  X += delta, refresh cos/sin                                        (PCGLinearUpdate)
 //   k_cost    0.5 * sum residual^2                                               (computeCost)
 // Scalars (alpha/beta numerators and denominators) never leave the device; every reduction is the
-// deterministic exact sum of contract C3; a whole GN step (2*nPCG + 3 kernels) is one graph launch.
+// deterministic exact sum of contract C3, accumulated without fences in wide fixed-point accumulators
+// (common.cuh) and decoded by the blocks of the next kernel; a whole GN step (2*nPCG + 5 kernels) is one
+// graph launch.  State layout: tile-interleaved planes (solver_stream.cuh).
 #include "solver_stream.cuh"
 #include "grid_math.cuh"
 
@@ -19,7 +21,6 @@ namespace arapb200 {
 namespace {
 
 constexpr int TS = ST_TILE + 2; // staged tile pitch (1-pixel halo)
-
 
 __device__ __forceinline__ unsigned long long* acc_set(const StreamPlanes& pl, int set)
 {
@@ -48,22 +49,41 @@ __device__ __forceinline__ void zero_set(const StreamPlanes& pl, int set, int fi
     if (t >= 0 && t < WA_WORDS) acc_set(pl, set)[t] = 0ULL;
 }
 
+// ---- tile-interleaved addressing ----
+__device__ __forceinline__ float* tile_ptr(const StreamPlanes& pl, int tile)
+{
+    return pl.planes + (size_t)tile * ST_TILE_FLOATS;
+}
+// float offset (plane 0) of image pixel (x, y)
+__device__ __forceinline__ size_t tiled_off(const StreamPlanes& pl, int x, int y)
+{
+    return (size_t)((y >> 5) * pl.tx + (x >> 5)) * ST_TILE_FLOATS + (size_t)(((y & 31) << 5) + (x & 31));
+}
+// flags of the pixel whose plane-0 address is `px` inside the tile starting at `tb`
+__device__ __forceinline__ unsigned char* flag_ptr(float* tb, int local)
+{
+    return reinterpret_cast<unsigned char*>(tb + PL_FLAGS * ST_TILE_PX) + local;
+}
+#define PLN(base, k) ((base)[(k) * ST_TILE_PX])
+
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ST_THREADS) k_prep(const StreamDev* __restrict__ dpp)
 {
     const StreamDev& dp = *dpp;
     const int W = dp.W, H = dp.H;
-    const int x = (blockIdx.x % dp.tx) * ST_TILE + (threadIdx.x & 31);
-    const int yb = (blockIdx.x / dp.tx) * ST_TILE + (threadIdx.x >> 5) * 4;
+    const int lx = threadIdx.x & 31, lyb = (threadIdx.x >> 5) * 4;
+    const int x = (blockIdx.x % dp.tx) * ST_TILE + lx;
+    const int yb = (blockIdx.x / dp.tx) * ST_TILE + lyb;
+    float* tb = tile_ptr(dp, blockIdx.x);
     unsigned bad = 0;
     int any = 0;
-    if (x < W) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int y = yb + r;
-            if (y >= H) break;
+    for (int r = 0; r < 4; ++r) {
+        const int y = yb + r;
+        const int loc = (lyb + r) * ST_TILE + lx;
+        unsigned f = 0;
+        if (x < W && y < H) {
             const size_t i = (size_t)y * W + x;
-            unsigned f = 0;
             if (dp.M[i] == 0.0f) {
                 f = FLAG_ACTIVE;
                 any = 1;
@@ -75,13 +95,13 @@ __global__ void __launch_bounds__(ST_THREADS) k_prep(const StreamDev* __restrict
                 if (c.x >= 0.0f && c.y >= 0.0f) f |= FLAG_FIT; // arap_plan.t:22
                 float s, co;
                 contract_sincos(dp.A[i], s, co);
-                dp.cs[0][i] = co;
-                dp.cs[1][i] = s;
+                PLN(tb + loc, PL_CS) = co;
+                PLN(tb + loc, PL_CS + 1) = s;
                 const float2 u = dp.U[i];
                 if (u.x != (float)x || u.y != (float)y) bad = 1;
             }
-            dp.flags[i] = (unsigned char)f;
         }
+        *flag_ptr(tb, loc) = (unsigned char)f;
     }
     if (bad) atomicAdd(&dp.sc->bad_u, 1u);
     any = __syncthreads_or(any);
@@ -96,10 +116,11 @@ __device__ __forceinline__ void stage_x_tile(const StreamDev& dp, float4 (*T)[TS
         const int x = x0 + lx - 1, y = y0 + ly - 1;
         float4 v = make_float4(0.f, 0.f, 1.f, 0.f);
         if (x >= 0 && x < dp.W && y >= 0 && y < dp.H) {
-            const size_t i = (size_t)y * dp.W + x;
-            if (dp.flags[i] & FLAG_ACTIVE) {
-                const float2 X = dp.X[i];
-                v = make_float4(X.x, X.y, dp.cs[0][i], dp.cs[1][i]);
+            const int tile = (y >> 5) * dp.tx + (x >> 5), loc = ((y & 31) << 5) + (x & 31);
+            float* tb = tile_ptr(dp, tile);
+            if (*flag_ptr(tb, loc) & FLAG_ACTIVE) {
+                const float2 X = dp.X[(size_t)y * dp.W + x];
+                v = make_float4(X.x, X.y, PLN(tb + loc, PL_CS), PLN(tb + loc, PL_CS + 1));
             }
         }
         T[ly][lx] = v;
@@ -118,6 +139,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_init(const StreamDev* __restrict
     __syncthreads();
     const int lx = threadIdx.x & 31, lyb = (threadIdx.x >> 5) * 4;
     const int x = x0 + lx;
+    float* tb = tile_ptr(dp, blockIdx.x);
     float g = 0.0f;
     if (x < W) {
 #pragma unroll
@@ -125,13 +147,13 @@ __global__ void __launch_bounds__(ST_THREADS) k_init(const StreamDev* __restrict
             const int ly = lyb + r, y = y0 + ly;
             if (y >= H) break;
             const size_t i = (size_t)y * W + x;
-            const unsigned f = dp.flags[i];
+            const int loc = ly * ST_TILE + lx;
+            float* px = tb + loc;
+            const unsigned f = *flag_ptr(tb, loc);
             if (!(f & FLAG_ACTIVE)) {
                 // the branch-free PCG kernels rely on zeros here; a previous problem may have left values behind
-                dp.pre[0][i] = 0.f; dp.pre[1][i] = 0.f;
 #pragma unroll
-                for (int k = 0; k < 3; ++k) { dp.r[k][i] = 0.f; dp.p[0][k][i] = 0.f; dp.p[1][k][i] = 0.f; dp.q[k][i] = 0.f; dp.d[k][i] = 0.f; }
-                dp.cs[0][i] = 0.f; dp.cs[1][i] = 0.f;
+                for (int k = 0; k < PL_FLAGS; ++k) PLN(px, k) = 0.f;
                 continue;
             }
             const float4 Ei = T[ly + 1][lx + 1];
@@ -149,34 +171,79 @@ __global__ void __launch_bounds__(ST_THREADS) k_init(const StreamDev* __restrict
             const float pX = guarded_invert(DX), pA = guarded_invert(DA);
             const float r0 = -g0, r1 = -g1, r2 = -ga;
             const float p0 = pX * r0, p1 = pX * r1, p2 = pA * r2;
-            dp.pre[0][i] = pX;
-            dp.pre[1][i] = pA;
-            dp.r[0][i] = r0; dp.r[1][i] = r1; dp.r[2][i] = r2;
-            dp.p[0][0][i] = p0; dp.p[0][1][i] = p1; dp.p[0][2][i] = p2;
-            dp.d[0][i] = 0.f; dp.d[1][i] = 0.f; dp.d[2][i] = 0.f;
+            PLN(px, PL_PRE) = pX;
+            PLN(px, PL_PRE + 1) = pA;
+            PLN(px, PL_R) = r0; PLN(px, PL_R + 1) = r1; PLN(px, PL_R + 2) = r2;
+            PLN(px, PL_P) = p0; PLN(px, PL_P + 1) = p1; PLN(px, PL_P + 2) = p2;
+            PLN(px, PL_D) = 0.f; PLN(px, PL_D + 1) = 0.f; PLN(px, PL_D + 2) = 0.f;
             g = g + dot3(r0, r1, r2, p0, p1, p2);
         }
     }
     publish(dp, bn_set(-1), block_exact_sum(g, red));
 }
 
-// PCGStep3 of the previous iteration fused with PCGStep1 (solverGPUGaussNewton.t:537-550, 421-434)
+// PCGStep3 of the previous iteration fused with PCGStep1 (solverGPUGaussNewton.t:537-550, 421-434).
+// Thread = one vertical quad of the tile (lane = column); threads 0..131 also own one pixel of the 1-pixel ring
+// around the tile, whose NEW direction they recompute (the neighbouring tile is writing it in this very kernel, so p is
+// ping-ponged).  Every global load of the block is issued before the first use; beta is decoded under them.
 template <bool FIRST>
 __global__ void __launch_bounds__(ST_THREADS) k_step_a(const __grid_constant__ StreamPlanes pl,
                                                        const StreamDev* __restrict__ dpp, int it)
 {
-    __shared__ float4 T[TS][TS];
+    __shared__ float4 T[TS][TS]; // (p_x, p_y, sin*p_a, cos*p_a) of tile + ring
     __shared__ double red[64];
     __shared__ float s_beta;
     const bool tile_on = pl.tile_active[blockIdx.x] != 0; // tiles without object pixels have nothing to add
     if (!tile_on && blockIdx.x != 0) return;
-    const float wr2 = dpp->wr2, wf2 = dpp->wf2;
     const int W = pl.W, H = pl.H;
     const int x0 = (blockIdx.x % pl.tx) * ST_TILE, y0 = (blockIdx.x / pl.tx) * ST_TILE;
+    const int lx = threadIdx.x & 31, lyb = (threadIdx.x >> 5) * 4;
+    long long raw = 0;
+    if (!FIRST && threadIdx.x < 32) raw = fetch2(pl, bn_set(it - 1), bn_set(it - 2));
+    const float wr2 = dpp->wr2, wf2 = dpp->wf2;
+    const int src = PL_P + 3 * (FIRST ? 0 : ((it - 1) & 1)), dst = PL_P + 3 * (it & 1);
+    float* const tb = tile_ptr(pl, blockIdx.x);
+    float* const own = tb + lyb * ST_TILE + lx; // plane 0, first row of the quad
+    const float* const ps = own + src * ST_TILE_PX;
+
+    // ---- loads: own quad (pixels outside the image exist in storage and hold zeros) ----
+    float po[4][3], cs[4][2], pre[4][2], rr[4][3];
+    unsigned fl[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const float* px = own + r * ST_TILE;
+        po[r][0] = PLN(ps + r * ST_TILE, 0); po[r][1] = PLN(ps + r * ST_TILE, 1); po[r][2] = PLN(ps + r * ST_TILE, 2);
+        cs[r][0] = PLN(px, PL_CS); cs[r][1] = PLN(px, PL_CS + 1);
+        if (!FIRST) {
+            pre[r][0] = PLN(px, PL_PRE); pre[r][1] = PLN(px, PL_PRE + 1);
+            rr[r][0] = PLN(px, PL_R); rr[r][1] = PLN(px, PL_R + 1); rr[r][2] = PLN(px, PL_R + 2);
+        }
+        fl[r] = *flag_ptr(tb, (lyb + r) * ST_TILE + lx);
+    }
+    // ---- loads: ring pixel of threads 0..131 (top row, bottom row, left column, right column) ----
+    const int t = threadIdx.x;
+    int hlx, hly;
+    if (t < TS) { hlx = t; hly = 0; }
+    else if (t < 2 * TS) { hlx = t - TS; hly = TS - 1; }
+    else if (t < 2 * TS + ST_TILE) { hlx = 0; hly = t - 2 * TS + 1; }
+    else { hlx = TS - 1; hly = t - 2 * TS - ST_TILE + 1; }
+    const int hx = x0 + hlx - 1, hy = y0 + hly - 1;
+    const bool ring = t < 2 * TS + 2 * ST_TILE;
+    const bool hin = ring && hx >= 0 && hx < W && hy >= 0 && hy < H;
+    const float* hpx = hin ? pl.planes + tiled_off(pl, hx, hy) : own;
+    float hp[3], hcs[2], hpre[2], hr[3];
+    hp[0] = PLN(hpx, src); hp[1] = PLN(hpx, src + 1); hp[2] = PLN(hpx, src + 2);
+    hcs[0] = PLN(hpx, PL_CS); hcs[1] = PLN(hpx, PL_CS + 1);
+    if (!FIRST) {
+        hpre[0] = PLN(hpx, PL_PRE); hpre[1] = PLN(hpx, PL_PRE + 1);
+        hr[0] = PLN(hpx, PL_R); hr[1] = PLN(hpx, PL_R + 1); hr[2] = PLN(hpx, PL_R + 2);
+    }
+
+    // ---- beta ----
     float beta = 0.0f;
     if (!FIRST) {
         if (threadIdx.x < 32) {
-            const float v = wide_round(fetch2(pl, bn_set(it - 1), bn_set(it - 2)));
+            const float v = wide_round(raw);
             const float bnum = __shfl_sync(0xffffffffu, v, 0), num = __shfl_sync(0xffffffffu, v, 16);
             if (threadIdx.x == 0) {
                 s_beta = (num > 0.0f) ? bnum / num : 0.0f; // :544-547
@@ -186,59 +253,48 @@ __global__ void __launch_bounds__(ST_THREADS) k_step_a(const __grid_constant__ S
         __syncthreads();
         beta = s_beta;
     }
-    // p is ping-ponged between two buffers: the halo of a tile needs the OLD direction of pixels that
-    // the neighbouring tile is updating in this very kernel.
-    float* const* __restrict__ psrc = pl.p[FIRST ? 0 : ((it - 1) & 1)];
-    float* const* __restrict__ pdst = pl.p[it & 1];
-    // stage (p_x, p_y, sin*p_a, cos*p_a) of tile + halo, p being the NEW direction
-    for (int e = threadIdx.x; tile_on && e < TS * TS; e += ST_THREADS) {
-        const int ly = e / TS, lx = e - ly * TS;
-        const int x = x0 + lx - 1, y = y0 + ly - 1;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (x >= 0 && x < W && y >= 0 && y < H) {
-            // no activity test: every plane of an inactive pixel holds zeros, which flow through as zeros
-            const size_t i = (size_t)y * W + x;
-            float p0 = psrc[0][i], p1 = psrc[1][i], p2 = psrc[2][i];
-            const float c = pl.cs[0][i], sn = pl.cs[1][i];
-            if (!FIRST) {
-                const float pX = pl.pre[0][i], pA = pl.pre[1][i];
-                const float r0 = pl.r[0][i], r1 = pl.r[1][i], r2 = pl.r[2][i];
-                p0 = fmaf(beta, p0, pX * r0);
-                p1 = fmaf(beta, p1, pX * r1);
-                p2 = fmaf(beta, p2, pA * r2);
-                const bool interior = (lx >= 1 && lx <= ST_TILE && ly >= 1 && ly <= ST_TILE);
-                if (interior) { pdst[0][i] = p0; pdst[1][i] = p1; pdst[2][i] = p2; }
-            }
-            v = make_float4(p0, p1, sn * p2, c * p2);
+
+    // ---- new direction: own quad (stored) and ring (kept in the tile only) ----
+    // no activity test: every plane of an inactive pixel holds zeros, which flow through as zeros
+    float* const pd = own + dst * ST_TILE_PX;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        if (!FIRST) {
+            po[r][0] = fmaf(beta, po[r][0], pre[r][0] * rr[r][0]);
+            po[r][1] = fmaf(beta, po[r][1], pre[r][0] * rr[r][1]);
+            po[r][2] = fmaf(beta, po[r][2], pre[r][1] * rr[r][2]);
+            if (tile_on) { PLN(pd + r * ST_TILE, 0) = po[r][0]; PLN(pd + r * ST_TILE, 1) = po[r][1]; PLN(pd + r * ST_TILE, 2) = po[r][2]; }
         }
-        T[ly][lx] = v;
+        T[lyb + r + 1][lx + 1] = make_float4(po[r][0], po[r][1], cs[r][1] * po[r][2], cs[r][0] * po[r][2]);
+    }
+    if (ring) {
+        if (!FIRST) {
+            hp[0] = fmaf(beta, hp[0], hpre[0] * hr[0]);
+            hp[1] = fmaf(beta, hp[1], hpre[0] * hr[1]);
+            hp[2] = fmaf(beta, hp[2], hpre[1] * hr[2]);
+        }
+        T[hly][hlx] = hin ? make_float4(hp[0], hp[1], hcs[1] * hp[2], hcs[0] * hp[2]) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
-    const int lx = threadIdx.x & 31, lyb = (threadIdx.x >> 5) * 4;
-    const int x = x0 + lx;
+
+    // ---- q = J^T J p on the own quad ----
     float g = 0.0f;
-    if (x < W && tile_on) {
+    float* const pq = own + PL_Q * ST_TILE_PX;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int ly = lyb + r, y = y0 + ly;
-            if (y >= H) break;
-            const size_t i = (size_t)y * W + x;
-            const unsigned f = pl.flags[i];
-            if (!(f & FLAG_ACTIVE)) continue;
-            const float4 Pi = T[ly + 1][lx + 1];
-            float pa = psrc[2][i];
-            if (!FIRST) pa = fmaf(beta, pa, pl.pre[1][i] * pl.r[2][i]);
-            JtjAcc a;
-            jtj_zero(a);
-            if (f & 1u) jtj_nb<0>(a, Pi.x, Pi.y, T[ly + 1][lx + 2]);
-            if (f & 2u) jtj_nb<1>(a, Pi.x, Pi.y, T[ly + 1][lx]);
-            if (f & 4u) jtj_nb<2>(a, Pi.x, Pi.y, T[ly + 2][lx + 1]);
-            if (f & 8u) jtj_nb<3>(a, Pi.x, Pi.y, T[ly][lx + 1]);
-            float q0, q1, qa;
-            jtj_finish(a, pl.cs[0][i], pl.cs[1][i], Pi.x, Pi.y, pa, (f & FLAG_FIT) != 0, wr2, wf2, q0, q1, qa);
-            pl.q[0][i] = q0; pl.q[1][i] = q1; pl.q[2][i] = qa;
-            g = g + dot3(Pi.x, Pi.y, pa, q0, q1, qa);
-        }
+    for (int r = 0; r < 4; ++r) {
+        const unsigned f = fl[r];
+        if (!tile_on || !(f & FLAG_ACTIVE)) continue;
+        const int ly = lyb + r;
+        JtjAcc a;
+        jtj_zero(a);
+        jtj_nb_masked<0>(a, po[r][0], po[r][1], T[ly + 1][lx + 2], (f & 1u) ? 1.0f : 0.0f);
+        jtj_nb_masked<1>(a, po[r][0], po[r][1], T[ly + 1][lx], (f & 2u) ? 1.0f : 0.0f);
+        jtj_nb_masked<2>(a, po[r][0], po[r][1], T[ly + 2][lx + 1], (f & 4u) ? 1.0f : 0.0f);
+        jtj_nb_masked<3>(a, po[r][0], po[r][1], T[ly][lx + 1], (f & 8u) ? 1.0f : 0.0f);
+        float q0, q1, qa;
+        jtj_finish(a, cs[r][0], cs[r][1], po[r][0], po[r][1], po[r][2], (f & FLAG_FIT) != 0, wr2, wf2, q0, q1, qa);
+        PLN(pq + r * ST_TILE, 0) = q0; PLN(pq + r * ST_TILE, 1) = q1; PLN(pq + r * ST_TILE, 2) = qa;
+        g = g + dot3(po[r][0], po[r][1], po[r][2], q0, q1, qa);
     }
     publish(pl, ST_ACC_D0 + (it & 1), block_exact_sum(g, red));
 }
@@ -253,28 +309,20 @@ __global__ void __launch_bounds__(ST_THREADS) k_step_b(const __grid_constant__ S
     __shared__ float s_alpha;
     const bool tile_on = pl.tile_active[blockIdx.x] != 0;
     if (!tile_on && blockIdx.x != 0) return;
-    const int W = pl.W, H = pl.H;
-    const int x = (blockIdx.x % pl.tx) * ST_TILE + (threadIdx.x & 31);
-    const int yb = (blockIdx.x / pl.tx) * ST_TILE + (threadIdx.x >> 5) * 4;
     // warp 0: r.z of the previous iteration and this iteration's p.q; fetched before the planes, decoded after
     long long raw = 0;
     if (threadIdx.x < 32) raw = fetch2(pl, bn_set(it - 1), ST_ACC_D0 + (it & 1));
-    const bool on = tile_on && x < W;
-    const float* __restrict__ pk0 = pl.p[it & 1][0];
-    const float* __restrict__ pk1 = pl.p[it & 1][1];
-    const float* __restrict__ pk2 = pl.p[it & 1][2];
+    float* const own = tile_ptr(pl, blockIdx.x) + (threadIdx.x >> 5) * 4 * ST_TILE + (threadIdx.x & 31);
+    const float* const pk = own + (PL_P + 3 * (it & 1)) * ST_TILE_PX;
     float pv[4][3], qv[4][3], rv[4][3], dv[4][3], pre[4][2];
-    if (on) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int y = min(yb + r, H - 1); // rows past the image re-read the last row; they are not stored
-            const size_t i = (size_t)y * W + x;
-            pv[r][0] = pk0[i]; pv[r][1] = pk1[i]; pv[r][2] = pk2[i];
-            qv[r][0] = pl.q[0][i]; qv[r][1] = pl.q[1][i]; qv[r][2] = pl.q[2][i];
-            rv[r][0] = pl.r[0][i]; rv[r][1] = pl.r[1][i]; rv[r][2] = pl.r[2][i];
-            dv[r][0] = pl.d[0][i]; dv[r][1] = pl.d[1][i]; dv[r][2] = pl.d[2][i];
-            pre[r][0] = pl.pre[0][i]; pre[r][1] = pl.pre[1][i];
-        }
+    for (int r = 0; r < 4; ++r) {
+        const float* px = own + r * ST_TILE;
+        pv[r][0] = PLN(pk + r * ST_TILE, 0); pv[r][1] = PLN(pk + r * ST_TILE, 1); pv[r][2] = PLN(pk + r * ST_TILE, 2);
+        qv[r][0] = PLN(px, PL_Q); qv[r][1] = PLN(px, PL_Q + 1); qv[r][2] = PLN(px, PL_Q + 2);
+        rv[r][0] = PLN(px, PL_R); rv[r][1] = PLN(px, PL_R + 1); rv[r][2] = PLN(px, PL_R + 2);
+        dv[r][0] = PLN(px, PL_D); dv[r][1] = PLN(px, PL_D + 1); dv[r][2] = PLN(px, PL_D + 2);
+        pre[r][0] = PLN(px, PL_PRE); pre[r][1] = PLN(px, PL_PRE + 1);
     }
     if (threadIdx.x < 32) {
         const float v = wide_round(raw);
@@ -294,22 +342,20 @@ __global__ void __launch_bounds__(ST_THREADS) k_step_b(const __grid_constant__ S
     __syncthreads();
     const float alpha = s_alpha;
     float g = 0.0f;
-    if (on) {
+    if (tile_on) {
+        // pixels outside the image (edge tiles) hold zeros in every plane and stay zero: 0 + alpha * 0
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            const int y = yb + r;
-            if (y < H) {
-                const size_t i = (size_t)y * W + x;
-                float rr[3], zz[3];
+            float* px = own + r * ST_TILE;
+            float rr[3], zz[3];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    pl.d[k][i] = fmaf(alpha, pv[r][k], dv[r][k]);
-                    rr[k] = fmaf(-alpha, qv[r][k], rv[r][k]);
-                    pl.r[k][i] = rr[k];
-                    zz[k] = ((k < 2) ? pre[r][0] : pre[r][1]) * rr[k];
-                }
-                g = g + dot3(zz[0], zz[1], zz[2], rr[0], rr[1], rr[2]);
+            for (int k = 0; k < 3; ++k) {
+                PLN(px, PL_D + k) = fmaf(alpha, pv[r][k], dv[r][k]);
+                rr[k] = fmaf(-alpha, qv[r][k], rv[r][k]);
+                PLN(px, PL_R + k) = rr[k];
+                zz[k] = ((k < 2) ? pre[r][0] : pre[r][1]) * rr[k];
             }
+            g = g + dot3(zz[0], zz[1], zz[2], rr[0], rr[1], rr[2]);
         }
     }
     publish(pl, bn_set(it), block_exact_sum(g, red));
@@ -320,25 +366,29 @@ __global__ void __launch_bounds__(ST_THREADS) k_update(const StreamDev* __restri
 {
     const StreamDev& dp = *dpp;
     const int W = dp.W, H = dp.H;
-    const int x = (blockIdx.x % dp.tx) * ST_TILE + (threadIdx.x & 31);
-    const int yb = (blockIdx.x / dp.tx) * ST_TILE + (threadIdx.x >> 5) * 4;
+    const int lx = threadIdx.x & 31, lyb = (threadIdx.x >> 5) * 4;
+    const int x = (blockIdx.x % dp.tx) * ST_TILE + lx;
+    const int yb = (blockIdx.x / dp.tx) * ST_TILE + lyb;
     if (x >= W) return;
+    float* tb = tile_ptr(dp, blockIdx.x);
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const int y = yb + r;
         if (y >= H) break;
         const size_t i = (size_t)y * W + x;
-        if (!(dp.flags[i] & FLAG_ACTIVE)) continue;
+        const int loc = (lyb + r) * ST_TILE + lx;
+        if (!(*flag_ptr(tb, loc) & FLAG_ACTIVE)) continue;
+        float* px = tb + loc;
         float2 X = dp.X[i];
-        X.x = X.x + dp.d[0][i];
-        X.y = X.y + dp.d[1][i];
+        X.x = X.x + PLN(px, PL_D);
+        X.y = X.y + PLN(px, PL_D + 1);
         dp.X[i] = X;
-        const float a = dp.A[i] + dp.d[2][i];
+        const float a = dp.A[i] + PLN(px, PL_D + 2);
         dp.A[i] = a;
         float s, c;
         contract_sincos(a, s, c);
-        dp.cs[0][i] = c;
-        dp.cs[1][i] = s;
+        PLN(px, PL_CS) = c;
+        PLN(px, PL_CS + 1) = s;
     }
 }
 
@@ -354,6 +404,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_cost(const StreamDev* __restrict
     __syncthreads();
     const int lx = threadIdx.x & 31, lyb = (threadIdx.x >> 5) * 4;
     const int x = x0 + lx;
+    float* tb = tile_ptr(dp, blockIdx.x);
     float g = 0.0f;
     if (x < W) {
 #pragma unroll
@@ -361,7 +412,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_cost(const StreamDev* __restrict
             const int ly = lyb + r, y = y0 + ly;
             if (y >= H) break;
             const size_t i = (size_t)y * W + x;
-            const unsigned f = dp.flags[i];
+            const unsigned f = *flag_ptr(tb, ly * ST_TILE + lx);
             if (!(f & FLAG_ACTIVE)) continue;
             const float4 Ei = T[ly + 1][lx + 1];
             float acc = 0.0f;
@@ -407,20 +458,9 @@ StreamSolver::StreamSolver(int W, int H)
     h_.tx = (W + ST_TILE - 1) / ST_TILE;
     h_.ty = (H + ST_TILE - 1) / ST_TILE;
     h_.ntiles = h_.tx * h_.ty;
-    const size_t N = (size_t)W * H;
-    const size_t Np = (N + 63) & ~(size_t)63; // keep every plane 256-byte aligned
-    ARAP_CUDA_OR_EXIT(cudaMalloc(&planes_, 19 * Np * sizeof(float)));
-    ARAP_CUDA_OR_EXIT(cudaMemset(planes_, 0, 19 * Np * sizeof(float)));
-    float* b = planes_;
-    for (int k = 0; k < 3; ++k) { h_.r[k] = b; b += Np; }
-    for (int k = 0; k < 3; ++k) { h_.p[0][k] = b; b += Np; }
-    for (int k = 0; k < 3; ++k) { h_.p[1][k] = b; b += Np; }
-    for (int k = 0; k < 3; ++k) { h_.q[k] = b; b += Np; }
-    for (int k = 0; k < 3; ++k) { h_.d[k] = b; b += Np; }
-    for (int k = 0; k < 2; ++k) { h_.cs[k] = b; b += Np; }
-    for (int k = 0; k < 2; ++k) { h_.pre[k] = b; b += Np; }
-    ARAP_CUDA_OR_EXIT(cudaMalloc(&h_.flags, Np));
-    ARAP_CUDA_OR_EXIT(cudaMemset(h_.flags, 0, Np));
+    const size_t bytes = (size_t)h_.ntiles * ST_TILE_FLOATS * sizeof(float);
+    ARAP_CUDA_OR_EXIT(cudaMalloc(&h_.planes, bytes));
+    ARAP_CUDA_OR_EXIT(cudaMemset(h_.planes, 0, bytes));
     ARAP_CUDA_OR_EXIT(cudaMalloc(&h_.tile_active, (size_t)h_.ntiles));
     ARAP_CUDA_OR_EXIT(cudaMemset(h_.tile_active, 1, (size_t)h_.ntiles));
     ARAP_CUDA_OR_EXIT(cudaMalloc(&h_.acc, ACC_BYTES));
@@ -434,12 +474,46 @@ StreamSolver::StreamSolver(int W, int H)
 StreamSolver::~StreamSolver()
 {
     if (graph_) cudaGraphExecDestroy(graph_);
-    cudaFree(planes_);
-    cudaFree(h_.flags);
+    cudaFree(h_.planes);
     cudaFree(h_.tile_active);
     cudaFree(h_.acc);
     cudaFree(h_.sc);
     cudaFree(d_);
+}
+
+// ---- debug access: row-major host image <-> one tile-interleaved plane ----
+static size_t host_tiled_off(const StreamDev& h, int x, int y)
+{
+    return (size_t)((y >> 5) * h.tx + (x >> 5)) * ST_TILE_FLOATS + (size_t)(((y & 31) << 5) + (x & 31));
+}
+
+void StreamSolver::download_plane(int plane, float* dst) const
+{
+    std::vector<float> all((size_t)h_.ntiles * ST_TILE_FLOATS);
+    ARAP_CUDA_OR_EXIT(cudaMemcpy(all.data(), h_.planes, all.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for (int y = 0; y < h_.H; ++y)
+        for (int x = 0; x < h_.W; ++x) dst[(size_t)y * h_.W + x] = all[host_tiled_off(h_, x, y) + (size_t)plane * ST_TILE_PX];
+}
+
+void StreamSolver::upload_plane(int plane, const float* src)
+{
+    std::vector<float> all((size_t)h_.ntiles * ST_TILE_FLOATS);
+    ARAP_CUDA_OR_EXIT(cudaMemcpy(all.data(), h_.planes, all.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for (int y = 0; y < h_.H; ++y)
+        for (int x = 0; x < h_.W; ++x) all[host_tiled_off(h_, x, y) + (size_t)plane * ST_TILE_PX] = src[(size_t)y * h_.W + x];
+    ARAP_CUDA_OR_EXIT(cudaMemcpy(h_.planes, all.data(), all.size() * sizeof(float), cudaMemcpyHostToDevice));
+}
+
+void StreamSolver::download_flags(unsigned char* dst) const
+{
+    std::vector<float> all((size_t)h_.ntiles * ST_TILE_FLOATS);
+    ARAP_CUDA_OR_EXIT(cudaMemcpy(all.data(), h_.planes, all.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for (int y = 0; y < h_.H; ++y)
+        for (int x = 0; x < h_.W; ++x) {
+            const size_t tile0 = (size_t)((y >> 5) * h_.tx + (x >> 5)) * ST_TILE_FLOATS;
+            const unsigned char* fb = reinterpret_cast<const unsigned char*>(all.data() + tile0 + (size_t)PL_FLAGS * ST_TILE_PX);
+            dst[(size_t)y * h_.W + x] = fb[((y & 31) << 5) + (x & 31)];
+        }
 }
 
 void StreamSolver::upload(cudaStream_t stream)

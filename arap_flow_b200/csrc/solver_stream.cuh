@@ -24,18 +24,27 @@ constexpr int ST_ACC_D0 = 3;
 constexpr int ST_ACC_COST = 5;
 constexpr int ST_ACC_SETS = 6;
 
+// Solver-owned state is stored TILE-INTERLEAVED: for every 32 x 32 tile one contiguous block of ST_NPL planes of 1024
+// floats (r, p ping, p pong, q, delta, cos/sin, preconditioner, flags as bytes).  A thread then reaches every value of
+// its pixels as [one base register + compile-time immediate]: no per-load address arithmetic, 4 KB contiguous per plane
+// and tile in DRAM.  Pixels of edge tiles that lie outside the image exist in storage and always hold zeros.
+constexpr int ST_TILE_PX = ST_TILE * ST_TILE;
+constexpr int PL_R = 0;      // 3 planes
+constexpr int PL_P = 3;      // 2 x 3 planes: search direction, ping-ponged per PCG iteration (buffer it & 1)
+constexpr int PL_Q = 9;      // 3
+constexpr int PL_D = 12;     // 3
+constexpr int PL_CS = 15;    // cos, sin of Angle, refreshed per GN step
+constexpr int PL_PRE = 17;   // guarded-inverted diagonal: X part (both comps), angle part
+constexpr int PL_FLAGS = 19; // first 1024 BYTES of this plane
+constexpr int ST_NPL = 20;
+constexpr size_t ST_TILE_FLOATS = (size_t)ST_NPL * ST_TILE_PX;
+
 // What the solver owns, fixed for its lifetime: passed to the kernels BY VALUE (constant bank), so that no block starts
 // with a chain of dependent pointer loads.
 struct StreamPlanes {
     int W, H, tx, ty, ntiles;
-    float* r[3];
-    float* p[2][3];       // search direction, ping-ponged per PCG iteration (buffer it & 1)
-    float* q[3];
-    float* d[3];
-    float* cs[2];         // cos, sin of Angle, refreshed per GN step
-    float* pre[2];        // guarded-inverted diagonal: X part (both comps), angle part
-    unsigned char* flags;
-    unsigned char* tile_active; // per 32x32 tile: any object pixel (set by k_prep)
+    float* planes;              // [ntiles][ST_NPL][32][32]
+    unsigned char* tile_active; // per tile: any object pixel (set by k_prep)
     unsigned long long* acc;    // [ST_ACC_SETS][WA_COPIES][WA_LIMBS]
     StreamScalars* sc;
 };
@@ -74,6 +83,10 @@ public:
     void enqueue_pcg_init(cudaStream_t stream);
     void enqueue_step_a(bool first, int it, cudaStream_t stream); // also decodes p.q into scalars().den
     const StreamDev& host_view() const { return h_; }
+    // debug / parity tests: one plane (PL_*) <-> a row-major host image; blocking
+    void download_plane(int plane, float* dst) const;
+    void upload_plane(int plane, const float* src);
+    void download_flags(unsigned char* dst) const;
     StreamScalars* d_scalars() const { return h_.sc; }
     long long launches() const { return launches_; }
     int W() const { return h_.W; }
@@ -84,7 +97,6 @@ private:
     void launch_gn_body(int nPCG, cudaStream_t stream, bool tracing);
     StreamDev h_{};
     StreamDev* d_ = nullptr;
-    float* planes_ = nullptr;
     cudaGraphExec_t graph_ = nullptr;
     int graph_npcg_ = -1;
     long long graph_nodes_ = 0;
