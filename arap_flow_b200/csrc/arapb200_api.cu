@@ -161,6 +161,17 @@ int arapb200_batch_timing(arapb200_batch* b, float* ms3)
 
 long long arapb200_batch_launches(arapb200_batch* b) { return b ? b->launches : 0; }
 
+int arapb200_batch_set_option(arapb200_batch* b, const char* name, double value)
+{
+    if (!b || !name) return 1;
+    if (strcmp(name, "pcg_rtol") == 0) {
+        if (!(value >= 0.0) || value >= 1.0) return 1;
+        b->pipe->set_pcg_rtol((float)value);
+        return 0;
+    }
+    return 1;
+}
+
 // ------------------------------------------------------------------------------------ debug / parity
 int arapb200_debug_gn_solve(int W, int H, float* X, float* A, const float* U, const float* C, const float* M,
                             float wf, float wr, int nGN, int nPCG, int backend, float* costs, float* scal)

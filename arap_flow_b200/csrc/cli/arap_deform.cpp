@@ -37,6 +37,7 @@ static void usage()
     puts("\n./arap_deform LISTFILE   (one such 6-tuple per line)");
     puts("Environment: ARAP_PLAN = path of the ARAP energy file (default ./arap_plan.t); CUDA_VISIBLE_DEVICES selects the GPU;");
     puts("             ARAP_BATCH = problems solved together (default 8)");
+    puts("             ARAP_PCG_RTOL = opt-in relative PCG tolerance, e.g. 1e-3 (default 0: fixed 400 iterations)");
 }
 
 struct Loaded {
@@ -86,6 +87,8 @@ int main(int argc, const char* argv[])
     const int nCont = 19, nGN = 8, nPCG = 400;
     int batch = getenv("ARAP_BATCH") ? atoi(getenv("ARAP_BATCH")) : 8;
     if (batch < 1) batch = 1;
+    // opt-in, off by default: convergence-aware PCG loops (changes results; include/arapb200.h)
+    const double pcg_rtol = getenv("ARAP_PCG_RTOL") ? atof(getenv("ARAP_PCG_RTOL")) : 0.0;
 
     // Three overlapped stages: the main thread decodes group k+1 and encodes group k-1 while
     // a worker thread runs group k on the GPU.  Output order and the "Saved" lines stay in list order.
@@ -106,6 +109,10 @@ int main(int argc, const char* argv[])
             }
             ctx = arapb200_batch_create(g->W, g->H, batch, nCont, nGN, nPCG, ARAPB200_BACKEND_AUTO);
             if (!ctx) return 1;
+            if (pcg_rtol > 0.0 && arapb200_batch_set_option(ctx, "pcg_rtol", pcg_rtol)) {
+                fprintf(stderr, "ARAP_PCG_RTOL must be in [0, 1)\n");
+                return 1;
+            }
             ctxW = g->W; ctxH = g->H;
         }
         for (size_t k = 0; k < g->items.size(); ++k) {

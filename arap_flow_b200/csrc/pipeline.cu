@@ -181,6 +181,11 @@ void BatchPipeline::solve_streaming(const HostProblem& hp, Dev& d)
     launches_ += solver_->launches() - l0;
 }
 
+void BatchPipeline::set_pcg_rtol(float rtol)
+{
+    if (resident_) resident_->set_pcg_rtol(rtol);
+}
+
 int BatchPipeline::run(const HostProblem* problems, int count)
 {
     if (count <= 0) return 0;

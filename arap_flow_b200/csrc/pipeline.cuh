@@ -49,6 +49,8 @@ public:
     int last_resident_count() const { return n_resident_; }
     int last_group_size() const { return group_size_; }
     int max_problems() const { return (int)dev_.size(); }
+    // opt-in early exit of the PCG loops (resident back-end only; the streaming graph keeps the fixed budget)
+    void set_pcg_rtol(float rtol);
 
 private:
     struct Dev { // device + pinned staging of one problem slot

@@ -45,6 +45,8 @@ bool GnPlan::set_parameter(const char* name, const void* value)
 {
     if (strcmp(name, "nIterations") == 0) { n_iterations_ = *(const int*)value; return true; }
     if (strcmp(name, "lIterations") == 0) { l_iterations_ = *(const int*)value; return true; }
+    // extension: float, relative PCG tolerance; 0 (default) = the reference's fixed budget
+    if (strcmp(name, "pcg_rtol") == 0) { pcg_rtol_ = *(const float*)value; return true; }
     // Levenberg-Marquardt knobs of SolverParameters (:26-39): valid names, unused by gaussNewtonGPU
     static const char* lm[] = {"residual_reset_period", "min_relative_decrease", "min_trust_region_radius",
                                "max_trust_region_radius", "q_tolerance", "function_tolerance",
@@ -75,6 +77,7 @@ void GnPlan::choose_backend(void** pp)
 float GnPlan::run_resident(void** pp, int nGN, float* trace)
 {
     if (nGN + 1 > kMaxCostLog) { fprintf(stderr, "arapb200: nIterations too large\n"); exit(1); }
+    resident_->set_pcg_rtol(pcg_rtol_);
     resident_->enqueue((float2*)pp[0], (float*)pp[1], (const float2*)pp[3], 0, *(const float*)pp[5],
                        *(const float*)pp[6], 1, nGN, l_iterations_, d_costs_, trace, stream_h_);
     float c = 0.f;

@@ -29,6 +29,7 @@ private:
     void check_grid(unsigned bad_u) const;
     int W_, H_, verbosity_, backend_;
     int n_iterations_ = 10, l_iterations_ = 10; // solver_parameter_defaults, :26-39
+    float pcg_rtol_ = 0.0f;                     // extension, 0 = off
     int n_iter_ = 0;
     float prev_cost_ = 0.f;
     cudaStream_t stream_h_ = nullptr;

@@ -55,6 +55,7 @@ struct Ctl {
     int ovf[RS_THREADS_MAX / 32];
     unsigned long long prev[2][4]; // totals last seen in each barrier buffer
     float bc;                      // broadcast result
+    float stop;                    // opt-in early exit: leave the PCG loop once r.z <= stop (-1: never)
     int bc_code;                   // 0 accept, 1 redo with bc_S
     int bc_S;
     int abort;
@@ -646,6 +647,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                     s.own[(k + 1) * TW + lane + 1] = make_float4(p0, p1, ss[k] * pa[k], cc[k] * pa[k]);
                 }
                 if (any_rem) apply_p(s, lane, 0.0f);
+                // N4 (opt-in, never on the parity path): relative tolerance on the preconditioned residual norm
+                if (threadIdx.x == 0) ctl.stop = (P.pcg_rtol2 > 0.0f) ? P.pcg_rtol2 * num : -1.0f;
                 __syncthreads();
             }
 
@@ -746,6 +749,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                 const float beta = (num > 0.0f) ? bnum / num : 0.0f; // :544-547
                 num = bnum;                                          // :1091
                 if (it + 1 == P.nPCG) break; // the direction is not needed after the last iteration
+                if (bnum <= ctl.stop) break; // early exit (every CTA decodes the same bnum: a uniform decision)
 
                 // ---- PCGStep3: p = z + beta p (own pixels, then the remote ring) ----
 #pragma unroll
@@ -1005,6 +1009,7 @@ void ResidentSolver::enqueue_group(int first, int count, int nCont, int nGN, int
     for (int i = 0; i < count; ++i) {
         Slot& sl = slots_[first + i];
         sl.prob.nCont = nCont; sl.prob.nGN = nGN; sl.prob.nPCG = nPCG;
+        sl.prob.pcg_rtol2 = pcg_rtol_ * pcg_rtol_;
         sl.prob.prof = (i == 0) ? d_prof_ : nullptr;
         host[i] = sl.prob;
         gmax = std::max(gmax, sl.G);

@@ -25,7 +25,8 @@ ARAP_SYMBOLS = [
     "arapb200_batch_create", "arapb200_batch_destroy", "arapb200_batch_submit", "arapb200_batch_run",
     "arapb200_batch_timing", "arapb200_batch_launches", "arapb200_debug_gn_solve", "arapb200_debug_eval_jtf",
     "arapb200_debug_apply_jtj", "arapb200_debug_cost", "arapb200_debug_sincos", "arapb200_debug_exact_sum",
-    "arapb200_debug_resident_profile", "arapb200_flatten",
+    "arapb200_debug_resident_profile", "arapb200_flatten", "arapb200_filter_matches", "arapb200_segment_mask",
+    "arapb200_batch_set_option",
 ]
 
 
@@ -170,6 +171,35 @@ def flatten(flows, rgbs, masks, background=None):
     return o_f, o_r, o_m
 
 
+def filter_matches(matches, labels1, labels2):
+    """N3: keep the matches para_gen.valid_cnstr keeps (para_gen.py:216-223, 468-482), in order.
+    Returns (matches int32[k,4], labels uint8[k])."""
+    m = _c(np.asarray(matches, np.int32).reshape(-1, 4), np.int32)
+    l1, l2 = _c(labels1, np.uint8), _c(labels2, np.uint8)
+    n = m.shape[0]
+    out = np.zeros((max(n, 1), 4), np.int32)
+    lab = np.zeros(max(n, 1), np.uint8)
+    cnt = C.c_int(0)
+    L = load()
+    L.arapb200_filter_matches.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                          C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+    _check(L.arapb200_filter_matches(l1.shape[1], l1.shape[0], l1.ctypes.data, l2.shape[1], l2.shape[0], l2.ctypes.data,
+                                     m.ctypes.data, n, out.ctypes.data, lab.ctypes.data, C.byref(cnt)),
+           "arapb200_filter_matches")
+    return out[:cnt.value].copy(), lab[:cnt.value].copy()
+
+
+def segment_mask(labels, segment=0):
+    """N3: the mask image arap_deform expects (0 = solve, 255 = ARAP_BG): one label (--multseg) or all (segment=0)."""
+    l = _c(labels, np.uint8)
+    out = np.zeros(l.shape, np.uint8)
+    L = load()
+    L.arapb200_segment_mask.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    _check(L.arapb200_segment_mask(l.shape[1], l.shape[0], l.ctypes.data, int(segment), out.ctypes.data),
+           "arapb200_segment_mask")
+    return out
+
+
 class Batch:
     """Many independent (image, segment) problems on the current device (arapb200_batch_*)."""
 
@@ -180,6 +210,11 @@ class Batch:
         if not self.h:
             raise RuntimeError("arapb200_batch_create failed")
         self._keep = {}
+
+    def set_option(self, name: str, value: float):
+        """Opt-in behaviour beyond the reference (include/arapb200.h): e.g. set_option("pcg_rtol", 1e-3)."""
+        self.L.arapb200_batch_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        _check(self.L.arapb200_batch_set_option(self.h, name.encode(), float(value)), "arapb200_batch_set_option")
 
     def submit(self, slot, rgb, mask_red, matches):
         H, W = mask_red.shape

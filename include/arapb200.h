@@ -56,6 +56,20 @@ ARAPB200_API int arapb200_flatten(int W, int H, int n_layers, const float* const
                                   const uint8_t* const* masks, const uint8_t* background, float* out_flow,
                                   uint8_t* out_rgb, uint8_t* out_mask);
 
+/* ---- "next" row N3: match ingestion on the device (replaces the Python loops of para_gen.py:216-223 valid_cnstr,
+ * :468-482 filter, :513-537 per-segment masks).
+ * labels1 uint8[W1*H1], labels2 uint8[W2*H2]: the segment-label images of frame 1 and 2 (0 = background).
+ * A raw match (x1 y1 x2 y2) is kept iff both points are inside their images, 0 < |p2 - p1| < 60 px, the label under
+ * p1 is non-zero and equals the label under p2.  Order is preserved (later constraints overwrite earlier ones
+ * downstream, CombinedSolver.h:223-242).  out_matches int32[4*n], out_labels uint8[n] (label under p1 of every kept
+ * match; may be NULL), *n_out = number kept.  Negative coordinates are rejected (the reference would wrap them). */
+ARAPB200_API int arapb200_filter_matches(int W1, int H1, const uint8_t* labels1, int W2, int H2, const uint8_t* labels2,
+                                         const int32_t* matches, int n, int32_t* out_matches, uint8_t* out_labels,
+                                         int* n_out);
+/* The mask image arap_deform expects (red channel 0 = solve here, 255 = ARAP_BG, para_gen.py:30): segment > 0 selects
+ * one label (--multseg, :526-527), segment == 0 selects every non-zero label (:515-516).  out_mask uint8[W*H]. */
+ARAPB200_API int arapb200_segment_mask(int W, int H, const uint8_t* labels, int segment, uint8_t* out_mask);
+
 /* ---- batched, pipelined variant: many independent (image, segment) problems per GPU --------- */
 typedef struct arapb200_batch arapb200_batch;
 /* max_problems problems of at most maxW x maxH in flight on the current device */
@@ -72,6 +86,12 @@ ARAPB200_API int arapb200_batch_run(arapb200_batch* b);
 ARAPB200_API int arapb200_batch_timing(arapb200_batch* b, float* ms3);
 /* number of kernel launches issued by the last run */
 ARAPB200_API long long arapb200_batch_launches(arapb200_batch* b);
+
+/* Options beyond the reference's behaviour; every one defaults to "off" and none is on the parity path.
+ *   "pcg_rtol" (SURVEY.md 8f N4): 0 <= value < 1.  > 0: a PCG loop ends as soon as r.z <= value^2 * (r.z at its start)
+ *   instead of always running lIterations iterations.  Changes results (by design); resident back-end only --
+ *   problems that take the streaming back-end keep the fixed budget.  Returns non-zero for unknown names / bad values. */
+ARAPB200_API int arapb200_batch_set_option(arapb200_batch* b, const char* name, double value);
 
 /* ---- debug / parity entry points (unit-level comparison against the oracle) ----------------- */
 /* one Opt_ProblemSolve on host buffers: X float2[N] and A float[N] in/out; U, C float2[N]; M float[N];

@@ -353,3 +353,67 @@ def test_multiseg_pair_end_to_end_c2_shape(oracle):
     f_o, r_o, m_o = PC.flatten(flows, rgbs, masks)
     assert _eq(f_g, f_o) and _eq(r_g, r_o) and _eq(m_g, m_o)
     b.close()
+
+
+def test_match_filter_and_segment_masks_n3():
+    """N3: device-side valid_cnstr filter + per-segment masks vs para_gen.py's own results (fixture) and the numpy
+    restatement, including order, out-of-range points, zero-length matches and empty inputs."""
+    from oracle import pycomposite as PC
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "para_gen_cases.npz"))
+    mk1, mk2, m = z["vc_mk1"], z["vc_mk2"], z["vc_matches"]
+    km, kl = lib.filter_matches(m, mk1, mk2)
+    assert _eq(km, m[z["vc_keep"]]) and _eq(kl, mk1[km[:, 1], km[:, 0]])
+    # a larger random case against the restatement (> 1024 matches: several compaction rounds)
+    rng = np.random.default_rng(3)
+    H, W = 120, 200
+    l1 = rng.integers(0, 4, (H, W)).astype(np.uint8)
+    l2 = np.roll(l1, (2, -3), axis=(0, 1))
+    n = 5000
+    mm = np.stack([rng.integers(0, W + 3, n), rng.integers(0, H + 3, n), rng.integers(0, W + 3, n), rng.integers(0, H + 3, n)], 1)
+    mm[:, 2] = np.clip(mm[:, 0] + rng.integers(-4, 5, n), 0, None)
+    mm[:, 3] = np.clip(mm[:, 1] + rng.integers(-4, 5, n), 0, None)
+    km, kl = lib.filter_matches(mm, l1, l2)
+    om, ol = PC.filter_matches(mm, l1, l2)
+    assert len(om) > 100 and _eq(km, om) and _eq(kl, ol)
+    km, kl = lib.filter_matches(np.zeros((0, 4), np.int32), l1, l2)
+    assert km.shape == (0, 4) and kl.shape == (0,)
+    for seg in (0, 1, 3):
+        assert _eq(lib.segment_mask(l1, seg), PC.segment_mask(l1, seg))
+    # and the fixture's flatten case through the GPU path
+    f, r, k = lib.flatten(list(z["fl_flows"]), list(z["fl_rgbs"]), list(z["fl_masks"]))
+    assert _eq(f, z["fl_out_flow"]) and _eq(r, z["fl_out_rgb"]) and _eq(k, z["fl_out_mask"])
+    f, r, k = lib.flatten([z["bg_bg"][..., :2].astype(np.float32)], [z["bg_im"]], [z["bg_mk"]], background=z["bg_bg"])
+    assert _eq(r, z["bg_out"])
+
+
+def test_opt_in_pcg_tolerance_n4(oracle):
+    """N4: the convergence-aware schedule is opt-in.  Off (default, or set back to 0) the result is the bit-exact parity
+    result; on, the solve ends earlier with a flow close to the full-budget one, and a tolerance nobody reaches
+    (1e-30) changes nothing."""
+    sp = synth.synth(160, 128, nseg=1, fd=2, seed=5)
+    kw = dict(nCont=3, nGN=3, nPCG=200)
+    b = lib.Batch(sp.W, sp.H, 1, backend=lib.BACKEND_RESIDENT, **kw)
+
+    def run():
+        o = b.submit(0, sp.rgb, sp.masks[0], sp.matches)
+        b.run()
+        return {k: v.copy() for k, v in o.items()}, b.timing_ms()["solve"]
+
+    full, t_full = run()
+    Xo, Ao, co = oracle.solve(sp.masks[0], sp.matches, **kw)
+    assert _eq(full["flow"], oracle.flow(Xo)) and _eq(full["costs"], co)
+    b.set_option("pcg_rtol", 1e-30)
+    same, _ = run()
+    assert _eq(same["flow"], full["flow"]) and _eq(same["costs"], full["costs"])
+    b.set_option("pcg_rtol", 1e-2)
+    fast, t_fast = run()
+    act = sp.masks[0] == 0
+    d = np.linalg.norm(fast["flow"] - full["flow"], axis=-1)[act]
+    assert t_fast < 0.8 * t_full, (t_fast, t_full)
+    assert d.mean() < 0.5 and abs(fast["costs"][-1, -1] - full["costs"][-1, -1]) < 0.2 * abs(full["costs"][-1, -1]) + 1e-3, (d.mean(), fast["costs"][-1], full["costs"][-1])
+    b.set_option("pcg_rtol", 0.0)
+    again, _ = run()
+    assert _eq(again["flow"], full["flow"])
+    with pytest.raises(RuntimeError):
+        b.set_option("no_such_option", 1.0)
+    b.close()

@@ -105,3 +105,18 @@ def test_solve_cat512_full(oracle, gold):
     fl = oracle.flow(X)
     z = np.load(os.path.join(gold, "cat512_oracle_flow.npz"))
     assert np.array_equal(fl, z["flow"])  # the oracle is deterministic
+
+
+def test_composite_restatement_vs_para_gen_itself(gold):
+    """oracle/pycomposite.py against para_gen.py's OWN valid_cnstr / add_bg / flatten, executed on seeded inputs by
+    tools/make_golden.py --para-gen (fixture para_gen_cases.npz)."""
+    from oracle import pycomposite as PC
+    z = np.load(os.path.join(gold, "para_gen_cases.npz"))
+    mk1, mk2, m = z["vc_mk1"], z["vc_mk2"], z["vc_matches"]
+    keep = np.array([PC.valid_cnstr(int(a), int(b), int(c), int(d), mk1, mk2) for a, b, c, d in m])
+    assert np.array_equal(keep, z["vc_keep"]) and 0 < keep.sum() < len(keep)
+    km, kl = PC.filter_matches(m, mk1, mk2)
+    assert np.array_equal(km, m[z["vc_keep"]]) and np.array_equal(kl, mk1[km[:, 1], km[:, 0]])
+    assert np.array_equal(PC.add_bg(z["bg_im"], z["bg_mk"], z["bg_bg"]), z["bg_out"])
+    f, r, k = PC.flatten(list(z["fl_flows"]), list(z["fl_rgbs"]), list(z["fl_masks"]))
+    assert np.array_equal(f, z["fl_out_flow"]) and np.array_equal(r, z["fl_out_rgb"]) and np.array_equal(k, z["fl_out_mask"])

@@ -6,6 +6,7 @@ reference's own warp sources).  Nothing here is needed at test time: the tests r
 
   python tools/make_golden.py            # fixtures: cat512 copies + reference-tool warp outputs
   python tools/make_golden.py --solve    # additionally pin the oracle solve on cat512 (minutes of CPU)
+  python tools/make_golden.py --para-gen # only: para_gen.py's own valid_cnstr / add_bg / flatten run on seeded inputs
 """
 from __future__ import annotations
 
@@ -40,11 +41,92 @@ def ref_warp(rgb, mask, flow, tmp):
     return flowio.read_png_rgb(orr), flowio.read_png_rgb(om)
 
 
+def ref_function(name):
+    """The reference's own top-level function `name` of para_gen.py, compiled from its source text where it lies.
+    (para_gen.py is Python 2 -- print statements -- and cannot be imported; the three functions used here are valid
+    Python 3 as they stand.)"""
+    lines = open("/root/reference/para_gen.py").read().splitlines()
+    start = next(i for i, l in enumerate(lines) if l.startswith("def %s(" % name))
+    end = next((i for i in range(start + 1, len(lines)) if lines[i] and not lines[i][0].isspace() and not lines[i].startswith("#")), len(lines))
+    return "\n".join(lines[start:end])
+
+
+def para_gen_cases():
+    """Run para_gen.valid_cnstr / add_bg / flatten themselves on seeded inputs -> tests/golden/para_gen_cases.npz."""
+    from math import sqrt
+    rng = np.random.default_rng(7)
+    out = {}
+    # --- valid_cnstr over raw matches, two label images of different sizes, points in and out of range
+    H1, W1, H2, W2 = 60, 90, 64, 88
+    yy, xx = np.mgrid[0:H1, 0:W1]
+    mk1 = ((xx // 30) + 1).astype(np.uint8) * (yy > 8)          # labels 1..3, background band on top
+    mk2 = np.zeros((H2, W2), np.uint8)
+    mk2[:H1, :W2] = np.roll(mk1, 3, axis=1)[:, :W2]
+    n = 400
+    m = np.stack([rng.integers(0, W1 + 6, n), rng.integers(0, H1 + 6, n), np.zeros(n, np.int64), np.zeros(n, np.int64)], 1)
+    m[:, 2] = m[:, 0] + rng.integers(-70, 71, n)
+    m[:, 3] = m[:, 1] + rng.integers(-70, 71, n)
+    m[::7, 2:] = m[::7, :2]                                      # zero-length matches are dropped
+    m[:, 2:] = np.abs(m[:, 2:])                                  # the matcher never emits negative coordinates
+    ns = {"sqrt": sqrt}
+    exec(ref_function("valid_cnstr"), ns)
+    keep = np.array([bool(ns["valid_cnstr"](int(a), int(b), int(c), int(d), mk1, mk2)) for a, b, c, d in m])
+    out.update(vc_mk1=mk1, vc_mk2=mk2, vc_matches=m.astype(np.int32), vc_keep=keep)
+    # --- add_bg
+    ns = {"np": np}
+    exec(ref_function("add_bg"), ns)
+    im = rng.integers(0, 256, (40, 56, 3)).astype(np.uint8)
+    mk = (rng.random((40, 56)) < 0.6).astype(np.uint8) * 255
+    bg = rng.integers(0, 256, (40, 56, 3)).astype(np.uint8)
+    out.update(bg_im=im, bg_mk=mk, bg_bg=bg, bg_out=ns["add_bg"](im, mk, bg))
+    # --- flatten: file-based in the reference; run it on an in-memory "file system"
+    fs = {}
+
+    class _Img:
+        def __init__(self, a): self.a = a
+        def save(self, path): fs[path] = np.array(self.a)
+
+    class _Image:
+        @staticmethod
+        def open(path): return fs[path]
+        @staticmethod
+        def fromarray(a): return _Img(a)
+
+    class _Sintel:
+        @staticmethod
+        def flow_read(path): return fs[path][..., 0], fs[path][..., 1]
+        @staticmethod
+        def flow_write(path, a): fs[path] = np.array(a)
+
+    class _Os:
+        @staticmethod
+        def remove(path): fs.pop(path)
+
+    ns = {"np": np, "Image": _Image, "sintel_io": _Sintel, "os": _Os}
+    exec(ref_function("flatten"), ns)
+    L, H, W = 3, 36, 48
+    flows = rng.normal(0, 5, (L, H, W, 2)).astype(np.float32)
+    rgbs = rng.integers(0, 256, (L, H, W, 3)).astype(np.uint8)
+    masks = ((rng.random((L, H, W)) < 0.4) * 255).astype(np.uint8)
+    seg = []
+    for s_ in range(L):
+        fs["f%d" % s_], fs["r%d" % s_], fs["m%d" % s_] = flows[s_], rgbs[s_], masks[s_]
+        seg.append("a b c f%d r%d m%d" % (s_, s_, s_))
+    ns["flatten"]([("a b c F R M", seg)])
+    out.update(fl_flows=flows, fl_rgbs=rgbs, fl_masks=masks, fl_out_flow=fs["F"], fl_out_rgb=fs["R"], fl_out_mask=fs["M"])
+    np.savez_compressed(os.path.join(GOLD, "para_gen_cases.npz"), **out)
+    print("para_gen_cases.npz:", {k: (v.shape, str(v.dtype)) for k, v in out.items()}, "kept", int(keep.sum()), "of", n)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--solve", action="store_true")
+    ap.add_argument("--para-gen", action="store_true")
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
+    if args.para_gen:
+        para_gen_cases()
+        return
     # 1. the reference's own worked-example fixtures (data, not source)
     for src, dst in (
         ("deformation/cat512_iRGB.png", "cat512_iRGB.png"),
