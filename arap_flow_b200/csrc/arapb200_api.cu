@@ -161,6 +161,8 @@ int arapb200_batch_timing(arapb200_batch* b, float* ms3)
 
 long long arapb200_batch_launches(arapb200_batch* b) { return b ? b->launches : 0; }
 
+int arapb200_batch_resident_count(arapb200_batch* b) { return b ? b->pipe->last_resident_count() : 0; }
+
 int arapb200_batch_set_option(arapb200_batch* b, const char* name, double value)
 {
     if (!b || !name) return 1;

@@ -26,7 +26,7 @@ ARAP_SYMBOLS = [
     "arapb200_batch_timing", "arapb200_batch_launches", "arapb200_debug_gn_solve", "arapb200_debug_eval_jtf",
     "arapb200_debug_apply_jtj", "arapb200_debug_cost", "arapb200_debug_sincos", "arapb200_debug_exact_sum",
     "arapb200_debug_resident_profile", "arapb200_flatten", "arapb200_filter_matches", "arapb200_segment_mask",
-    "arapb200_batch_set_option",
+    "arapb200_batch_set_option", "arapb200_batch_resident_count",
 ]
 
 
@@ -239,6 +239,11 @@ class Batch:
 
     def launches(self):
         return int(self.L.arapb200_batch_launches(self.h))
+
+    def resident_count(self):
+        """Problems of the last run() that the resident back-end solved (the others streamed)."""
+        self.L.arapb200_batch_resident_count.argtypes = [C.c_void_p]
+        return int(self.L.arapb200_batch_resident_count(self.h))
 
     def close(self):
         if self.h:

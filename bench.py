@@ -222,6 +222,7 @@ def main():
         dev_ms += tm["solve"] + tm["warp"]
         solve_ms += tm["solve"]
         launches += batch.launches()
+    streamed = batch.resident_count() == 0
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
@@ -246,21 +247,23 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload} {W}x{H} {nseg} segment(s) per pair, synth seeds {WORKLOADS[args.workload][4]}+",
-                       "pairs_per_gpu_per_step": B, "schedule": f"{NCONT}x{NGN}x{NPCG}", "backend": args.backend,
+                       "pairs_per_gpu_per_step": B, "schedule": f"{NCONT}x{NGN}x{NPCG}",
+                       "backend": args.backend + (" (streaming)" if streamed else " (resident)"),
                        "active_px_mean": float(np.mean(active_px)), "parallelism": f"independent pairs x{world}, no collective",
                        "l2_policy": "L2 flushed between steps by writing a 256 MiB buffer; every step also re-uploads its inputs "
                                     "(host->device) and restarts from the reset grid, nothing is reused across steps; within a "
-                                    "solve the PCG state lives in registers/shared memory"},
+                                    "solve the PCG state lives " + ("in HBM/L2 (tile-interleaved planes)" if streamed else
+                                                                    "in registers/shared memory")},
             "e2e": {"value": e2e, "unit": "pairs/s",
                     "h2d_bytes_per_step": int(len(problems) * (4 * N) + nseg * sum(16 * (len(p.matches) + 2 * (W + H)) for p in pairs)),
                     "d2h_bytes_per_step": int(len(problems) * (12 * N + 4 * NCONT * (NGN + 1)))},
             "gpu_launches": int(lt.cpu()[0]),
             "ms_per_gn_solve": solve_ms_max / (B * args.steps * NCONT * NGN),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (measured_traffic() if args.backend != "stream" and B % 4 == 0 and args.workload == "C1" else None),
+                         "traffic": (measured_traffic() if not streamed and B % 4 == 0 and args.workload == "C1" else None),
                          "peak_source": peak_src,
                          "kernel": "k_resident (persistent fused GN/PCG solve; 156 B/active px/PCG iteration algorithmic, "
-                                   "state on chip so a fraction > 1 of the STREAMING roofline is possible)" if args.backend != "stream"
+                                   "state on chip so a fraction > 1 of the STREAMING roofline is possible)" if not streamed
                                    else "k_step_a + k_step_b (streaming PCG iteration; 156 B/active px/iteration algorithmic)"},
             "clocks": clocks,
         }

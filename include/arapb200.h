@@ -87,6 +87,9 @@ ARAPB200_API int arapb200_batch_timing(arapb200_batch* b, float* ms3);
 /* number of kernel launches issued by the last run */
 ARAPB200_API long long arapb200_batch_launches(arapb200_batch* b);
 
+/* how many problems of the last run were solved by the resident (on-chip) back-end; the rest took the streaming one */
+ARAPB200_API int arapb200_batch_resident_count(arapb200_batch* b);
+
 /* Options beyond the reference's behaviour; every one defaults to "off" and none is on the parity path.
  *   "pcg_rtol" (SURVEY.md 8f N4): 0 <= value < 1.  > 0: a PCG loop ends as soon as r.z <= value^2 * (r.z at its start)
  *   instead of always running lIterations iterations.  Changes results (by design); resident back-end only --

@@ -8,7 +8,16 @@ from arap_flow_b200 import lib, synth
 
 cfg = sys.argv[1] if len(sys.argv) > 1 else "C1"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 4
-pairs = [synth.config(cfg, i) for i in range(B)]
+if cfg == "cat512":   # the reference's README example: 9 hand-placed constraints, 101 k active px (chaotic regime)
+    from types import SimpleNamespace
+    from arap_flow_b200 import flowio
+    g = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+    one = SimpleNamespace(W=512, H=512, rgb=flowio.read_png_rgb(os.path.join(g, "cat512_iRGB.png")),
+                          masks=[flowio.read_png_mask_red(os.path.join(g, "cat512_iMsk.png"))],
+                          matches=flowio.read_constraints(os.path.join(g, "cat512_iCstr.txt")))
+    pairs = [one] * B
+else:
+    pairs = [synth.config(cfg, i) for i in range(B)]
 W, H = pairs[0].W, pairs[0].H
 b = lib.Batch(W, H, B, 19, 8, 400, lib.BACKEND_RESIDENT)
 ref = None
