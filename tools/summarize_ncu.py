@@ -65,10 +65,11 @@ def stalls(rep, warps, iters):
     return lines
 
 if __name__ == "__main__":
-    launch_list(os.path.join(G, "r1_launches_bench.csv"), os.path.join(P, "r1_bench_launch_list.csv"),
-                "ncu launch list: python bench.py --steps 1 --warmup 1 --batch 4 --no-cpu-baseline (round 1; 2 steps x 4 pairs)")
+    launch_list(os.path.join(G, "bench_launch_list.csv"), os.path.join(P, "r1_bench_launch_list.csv"),
+                "ncu launch list: python bench.py --steps 1 --warmup 1 --no-cpu-baseline (round 1; 2 steps x 8 pairs, C1)")
     L = full(os.path.join(G, "r1_resident_b4.ncu-rep"), "tools/ncu_target.py resident C1 50 4: 4 co-resident 854x480 problems, 1x1x50 PCG iterations")
     L += stalls(os.path.join(G, "r1_resident_b4.ncu-rep"), 146 * 4 * 4, 58)
-    L += [""] + full(os.path.join(G, "r1_stream_c4.ncu-rep"), "tools/ncu_target.py stream C4 6 1: 1920x1080 (1 378 443 active px) through the streaming back-end")
+    L += [""] + full(os.path.join(G, "r1_stream_c4_v2.ncu-rep"), "tools/ncu_target.py stream C4 8 1: 1920x1080 (1 378 443 active px) through the streaming back-end "
+                     "(capture taken before the tile-interleaved layout; warm-cache per-kernel times of the final kernels: r1_stream_kernel_times.txt)")
     open(os.path.join(P, "r1_ncu_full_summary.txt"), "w").write("\n".join(L) + "\n")
     print("\n".join(L[:40]))
