@@ -439,12 +439,23 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ Ctl ctl;
-    const ResProb& P = probs[blockIdx.y];
-    if ((int)blockIdx.x >= P.G) return;
+    // Two grid shapes (host: enqueue_group).  Equal-sized problems: (G, count), blockIdx.y = problem.  Otherwise a
+    // compact 1-D grid of exactly sum G CTAs, the CTAs of problem k following those of problem k-1.
+    const ResProb* Pp = probs + blockIdx.y;
+    int cta_in_problem = (int)blockIdx.x;
+    if (gridDim.y == 1)
+        while (cta_in_problem >= Pp->G) { cta_in_problem -= Pp->G; ++Pp; }
+    // the problem descriptor is read all through the kernel: keep a copy in shared memory
+    __shared__ ResProb sP;
+    static_assert(sizeof(ResProb) % 4 == 0, "ResProb is copied word by word");
+    for (int w = threadIdx.x; w < (int)(sizeof(ResProb) / 4); w += blockDim.x)
+        reinterpret_cast<int*>(&sP)[w] = reinterpret_cast<const int*>(Pp)[w];
+    __syncthreads();
+    const ResProb& P = sP;
     StripSmem* S = reinterpret_cast<StripSmem*>(smem_raw);
 
     Cta c;
-    c.P = &P; c.ctl = &ctl; c.cta = blockIdx.x; c.G = P.G;
+    c.P = &P; c.ctl = &ctl; c.cta = cta_in_problem; c.G = P.G;
     c.lane = threadIdx.x & 31; c.wid = threadIdx.x >> 5; c.nw = blockDim.x >> 5; c.epoch = 0;
     c.acc[0] = c.acc[1] = c.acc[2] = 0; c.prof = PROF && (P.prof != nullptr);
     unsigned long long ph[4] = {0, 0, 0, 0}; // cycles in PCG phase 1, 2, 3 and everything else (thread 0)
@@ -990,13 +1001,14 @@ void ResidentSolver::set_problem(int slot, float2* X, float* A, const float2* C,
 int ResidentSolver::group_size(int first, int limit) const
 {
     int best = 0;
-    int gmax = 0, nwmax = 0;
+    int nwmax = 0;
+    long long ctas = 0;
     for (int cnt = 1; cnt <= limit && first + cnt <= (int)slots_.size(); ++cnt) {
         const Slot& sl = slots_[first + cnt - 1];
         if (!sl.fits) break;
-        gmax = std::max(gmax, sl.G);
+        ctas += sl.G;
         nwmax = std::max(nwmax, sl.NW);
-        if (pick_variant(nwmax, (long long)gmax * cnt, sm_count_) < 0) break;
+        if (pick_variant(nwmax, ctas, sm_count_) < 0) break;
         best = cnt;
     }
     return best;
@@ -1004,7 +1016,8 @@ int ResidentSolver::group_size(int first, int limit) const
 
 void ResidentSolver::enqueue_group(int first, int count, int nCont, int nGN, int nPCG, cudaStream_t stream)
 {
-    int gmax = 0, nwmax = 0;
+    int nwmax = 0;
+    long long ctas = 0;
     std::vector<ResProb> host(count);
     for (int i = 0; i < count; ++i) {
         Slot& sl = slots_[first + i];
@@ -1012,7 +1025,7 @@ void ResidentSolver::enqueue_group(int first, int count, int nCont, int nGN, int
         sl.prob.pcg_rtol2 = pcg_rtol_ * pcg_rtol_;
         sl.prob.prof = (i == 0) ? d_prof_ : nullptr;
         host[i] = sl.prob;
-        gmax = std::max(gmax, sl.G);
+        ctas += sl.G;
         nwmax = std::max(nwmax, sl.NW);
         // barrier words start at zero; halo tags start at 1, so a zeroed outbox is "nothing published yet"
         ARAP_CUDA_OR_EXIT(cudaMemsetAsync(sl.d_bar, 0, 8 * BAR_STRIDE * sizeof(unsigned long long), stream));
@@ -1020,9 +1033,10 @@ void ResidentSolver::enqueue_group(int first, int count, int nCont, int nGN, int
                                           (size_t)(sl.n_strips > 0 ? sl.n_strips : 1) * RS_OUTBOX_ENTRIES * 3 * sizeof(uint4), stream));
     }
     ARAP_CUDA_OR_EXIT(cudaMemcpyAsync(d_probs_ + first, host.data(), count * sizeof(ResProb), cudaMemcpyHostToDevice, stream));
-    const int v = pick_variant(nwmax, (long long)gmax * count, sm_count_);
+    // the live CTAs of all problems form one 1-D grid; the variant with the most registers that keeps them co-resident
+    const int v = pick_variant(nwmax, ctas, sm_count_);
     if (v < 0) {
-        fprintf(stderr, "arapb200: resident kernel cannot be co-resident (%d x %d CTAs of %d warps)\n", gmax, count, nwmax);
+        fprintf(stderr, "arapb200: resident kernel cannot be co-resident (%lld CTAs of %d warps)\n", ctas, nwmax);
         exit(1);
     }
     last_variant_ = v;
@@ -1031,7 +1045,13 @@ void ResidentSolver::enqueue_group(int first, int count, int nCont, int nGN, int
     const ResProb* dp = d_probs_ + first;
     void* args[] = {(void*)&dp};
     const void* fn = d_prof_ ? (const void*)g_variants[v].fn_prof : (const void*)g_variants[v].fn;
-    ARAP_CUDA_OR_EXIT(cudaLaunchCooperativeKernel(fn, dim3(gmax, count, 1), dim3(threads, 1, 1), args, smem, stream));
+    // equal-sized problems keep the 2-D shape (measured 4 % faster on C1: the hardware's placement of a 2-D grid mixes the
+    // problems better over the SMs); ragged groups (multi-segment pairs) get the compact grid and its better balance
+    const int g0 = slots_[first].G;
+    bool equal = true;
+    for (int i = 1; i < count; ++i) equal = equal && slots_[first + i].G == g0;
+    const dim3 grid = equal ? dim3((unsigned)g0, (unsigned)count, 1) : dim3((unsigned)ctas, 1, 1);
+    ARAP_CUDA_OR_EXIT(cudaLaunchCooperativeKernel(fn, grid, dim3(threads, 1, 1), args, smem, stream));
     launches_ += 1;
 }
 
