@@ -371,9 +371,38 @@ __global__ void k_dbg_exact_sum(size_t n, const float* t, float* out)
         if (threadIdx.x == 0) *out = hl_to_float(run);
     }
 }
+// the streaming back-end's reduction path on its own: every block publishes its exact partial into one wide
+// fixed-point accumulator (common.cuh), a second kernel decodes it
+__global__ void __launch_bounds__(256) k_dbg_wide_publish(size_t n, const float* t, unsigned long long* acc)
+{
+    __shared__ double red[64];
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const HL b = block_exact_sum((i < n) ? t[i] : 0.f, red);
+    if (threadIdx.x == 0) wide_add(acc, blockIdx.x, b.h);
+    if (threadIdx.x == 1) wide_add(acc, blockIdx.x, b.l);
+}
+__global__ void __launch_bounds__(32) k_dbg_wide_decode(const unsigned long long* acc, float* out)
+{
+    const float v = wide_round(wide_fetch(acc, threadIdx.x & 15));
+    if (threadIdx.x == 0) *out = v;
+}
 } // namespace
 
 extern "C" {
+
+int arapb200_debug_wide_sum(size_t n, const float* t, float* sum)
+{
+    if (n == 0 || n > ((size_t)1 << 26)) return 1;
+    DevBuf<float> dt(n), dsum(1);
+    DevBuf<unsigned long long> acc(WA_WORDS);
+    dt.up(t);
+    ARAP_CUDA_OR_RETURN(cudaMemset(acc.p, 0, WA_WORDS * sizeof(unsigned long long)));
+    k_dbg_wide_publish<<<(unsigned)((n + 255) / 256), 256>>>(n, dt.p, acc.p);
+    k_dbg_wide_decode<<<1, 32>>>(acc.p, dsum.p);
+    dsum.down(sum);
+    ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
+    return 0;
+}
 
 int arapb200_debug_sincos(int n, const float* a, float* s, float* c)
 {

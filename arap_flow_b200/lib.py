@@ -26,7 +26,7 @@ ARAP_SYMBOLS = [
     "arapb200_batch_timing", "arapb200_batch_launches", "arapb200_debug_gn_solve", "arapb200_debug_eval_jtf",
     "arapb200_debug_apply_jtj", "arapb200_debug_cost", "arapb200_debug_sincos", "arapb200_debug_exact_sum",
     "arapb200_debug_resident_profile", "arapb200_flatten", "arapb200_filter_matches", "arapb200_segment_mask",
-    "arapb200_batch_set_option", "arapb200_batch_resident_count",
+    "arapb200_batch_set_option", "arapb200_batch_resident_count", "arapb200_debug_wide_sum",
 ]
 
 
@@ -318,6 +318,15 @@ def debug_sincos(a):
     c = np.zeros_like(a)
     _check(load().arapb200_debug_sincos(a.size, a, s, c), "debug_sincos")
     return s, c
+
+
+def debug_wide_sum(t):
+    t = _c(t, np.float32).ravel()
+    out = C.c_float()
+    L = load()
+    L.arapb200_debug_wide_sum.argtypes = [C.c_size_t, _f32p, C.POINTER(C.c_float)]
+    _check(L.arapb200_debug_wide_sum(t.size, t, C.byref(out)), "debug_wide_sum")
+    return np.float32(out.value)
 
 
 def debug_exact_sum(t):

@@ -118,6 +118,8 @@ ARAPB200_API int arapb200_debug_resident_profile(int W, int H, const uint8_t* ma
 /* contract sincos and exact sum on the device */
 ARAPB200_API int arapb200_debug_sincos(int n, const float* a, float* s, float* c);
 ARAPB200_API int arapb200_debug_exact_sum(size_t n, const float* t, float* sum);
+/* the same sum through the streaming back-end's fence-free wide fixed-point accumulators (one block per 256 terms) */
+ARAPB200_API int arapb200_debug_wide_sum(size_t n, const float* t, float* sum);
 
 #ifdef __cplusplus
 }

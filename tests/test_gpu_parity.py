@@ -31,6 +31,46 @@ def test_exact_sum_bit_exact(oracle):
         assert lib.debug_exact_sum(t) == oracle.exact_sum(t)
 
 
+def _exact_f32_sum(t):
+    """Sum of binary32 values, exact in integer arithmetic (units of 2^-149), rounded ONCE to nearest-even binary32."""
+    import math
+    from fractions import Fraction
+    T = sum(int(Fraction(float(x)) * (1 << 149)) for x in t)
+    if T == 0:
+        return np.float32(0.0)
+    a, nb = abs(T), abs(T).bit_length()
+    sh = max(nb - 24, 0)
+    q, rem = a >> sh, a & ((1 << sh) - 1)
+    if sh and (rem > (1 << (sh - 1)) or (rem == (1 << (sh - 1)) and (q & 1))):
+        q += 1
+    return np.float32(math.copysign(math.ldexp(q, sh - 149), T))
+
+
+def test_wide_accumulator_sums_exactly(oracle):
+    """The streaming back-end's fence-free 320-bit accumulators: exact whatever the arrival order, rounded once --
+    wide dynamic range, massive cancellation, negative totals, round-to-even ties, subnormal totals, zeros."""
+    rng = np.random.default_rng(11)
+    cases = []
+    for n in (1, 257, 5000, 100000):
+        cases.append((rng.standard_normal(n) * 10.0 ** rng.uniform(-30, 30, n)).astype(np.float32))
+    x = (rng.standard_normal(20000) * 10.0 ** rng.uniform(-10, 10, 20000)).astype(np.float32)
+    c = np.concatenate([x, -x, np.float32([3e-20, -1e-33])]); rng.shuffle(c); cases.append(c)          # cancellation
+    cases.append(-np.abs(x))                                                                           # negative total
+    cases.append(np.float32([16777216.0, 1.0]))                                                        # tie -> even (down)
+    cases.append(np.float32([16777218.0, 1.0]))                                                        # tie -> even (up)
+    cases.append(np.float32([16777216.0, 1.0, 1e-30]))                                                 # sticky breaks the tie
+    cases.append(np.float32([1e-45] * 700 + [-3e-45] * 100))                                           # subnormal total
+    cases.append(np.float32([3e38, 3e38, -3e38, -2.9e38]))                                             # partials beyond FLT_MAX
+    cases.append(np.zeros(1000, np.float32))
+    for t in cases:
+        want = _exact_f32_sum(t)
+        got = lib.debug_wide_sum(t)
+        assert got == want and np.signbit(got) == np.signbit(want), (len(t), got, want)
+    # and it agrees with the oracle's and the resident path's summation on PCG-like data
+    t = (rng.standard_normal(200000) ** 2 * 10.0 ** rng.uniform(-8, 2, 200000)).astype(np.float32)
+    assert lib.debug_wide_sum(t) == oracle.exact_sum(t) == lib.debug_exact_sum(t)
+
+
 # ------------------------------------------------------------------------------------- single kernels
 @pytest.mark.parametrize("W,H,seed", [(37, 29, 0), (64, 64, 1), (100, 70, 2), (33, 5, 3), (1, 9, 4)])
 def test_kernels_bit_exact(oracle, W, H, seed):
