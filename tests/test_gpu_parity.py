@@ -54,7 +54,13 @@ def test_wide_accumulator_sums_exactly(oracle):
     for n in (1, 257, 5000, 100000):
         cases.append((rng.standard_normal(n) * 10.0 ** rng.uniform(-30, 30, n)).astype(np.float32))
     x = (rng.standard_normal(20000) * 10.0 ** rng.uniform(-10, 10, 20000)).astype(np.float32)
-    c = np.concatenate([x, -x, np.float32([3e-20, -1e-33])]); rng.shuffle(c); cases.append(c)          # cancellation
+    # cancellation ACROSS blocks over 200 binades (inside one 256-term block the (h, l) partial is the contract's
+    # binned sum, exact only up to ~2^-98 of the block's largest term: keep every block on one exponent so that the
+    # partials are exact and the accumulator alone is under test)
+    blocks = [np.ldexp(rng.integers(-255, 256, 256).astype(np.float32), int(e)) for e in rng.integers(-100, 100, 150)]
+    blocks = blocks + [-b for b in blocks] + [np.ldexp(np.float32([3.0] + [0.0] * 255), -120)]
+    order = rng.permutation(len(blocks))
+    cases.append(np.concatenate([blocks[i] for i in order]).astype(np.float32))                        # total = 3 * 2^-120
     cases.append(-np.abs(x))                                                                           # negative total
     cases.append(np.float32([16777216.0, 1.0]))                                                        # tie -> even (down)
     cases.append(np.float32([16777218.0, 1.0]))                                                        # tie -> even (up)
