@@ -7,9 +7,11 @@
 #include "../../../include/arapb200.h"
 #include "image_io.h"
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
+#include <deque>
 #include <future>
 #include <memory>
 #include <sstream>
@@ -89,6 +91,13 @@ int main(int argc, const char* argv[])
     if (batch < 1) batch = 1;
     // opt-in, off by default: convergence-aware PCG loops (changes results; include/arapb200.h)
     const double pcg_rtol = getenv("ARAP_PCG_RTOL") ? atof(getenv("ARAP_PCG_RTOL")) : 0.0;
+    // ARAP_TIMING=1: per-stage wall times on stderr
+    const bool timing = getenv("ARAP_TIMING") != NULL;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [&](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    };
+    double t_decode = 0, t_gpu_wait = 0, t_encode = 0, t_create = 0;
 
     // Three overlapped stages: the main thread decodes group k+1 and encodes group k-1 while
     // a worker thread runs group k on the GPU.  Output order and the "Saved" lines stay in list order.
@@ -107,7 +116,9 @@ int main(int argc, const char* argv[])
                        "same size in the same list.\nStarting to re-build plan...\n");
                 arapb200_batch_destroy(ctx);
             }
+            const auto t0 = std::chrono::steady_clock::now();
             ctx = arapb200_batch_create(g->W, g->H, batch, nCont, nGN, nPCG, ARAPB200_BACKEND_AUTO);
+            t_create += since(t0);
             if (!ctx) return 1;
             if (pcg_rtol > 0.0 && arapb200_batch_set_option(ctx, "pcg_rtol", pcg_rtol)) {
                 fprintf(stderr, "ARAP_PCG_RTOL must be in [0, 1)\n");
@@ -123,64 +134,82 @@ int main(int argc, const char* argv[])
         }
         return arapb200_batch_run(ctx);
     };
+    // decode / encode run one task per list entry (zlib dominates: ~0.1 s of CPU per pair at 854x480)
+    auto save_one = [&](const Group& g, size_t k) -> bool {
+        const Loaded& L = g.items[k];
+        const InputPaths& p = lines[g.first + k];
+        std::vector<uint8_t> m3((size_t)3 * g.W * g.H); // warped mask as an RGB image, 255 = object (README.md:25-32)
+        for (size_t q = 0; q < L.wmask.size(); ++q) m3[3 * q] = m3[3 * q + 1] = m3[3 * q + 2] = L.wmask[q];
+        return save_png_rgb(p.wrgb, g.W, g.H, L.wrgb.data()) && save_png_rgb(p.wmask, g.W, g.H, m3.data()) &&
+               write_flo(p.flo, g.W, g.H, L.flow.data());
+    };
     auto save_stage = [&](const Group& g) -> bool {
-        for (size_t k = 0; k < g.items.size(); ++k) {
-            const Loaded& L = g.items[k];
-            const InputPaths& p = lines[g.first + k];
-            std::vector<uint8_t> m3((size_t)3 * g.W * g.H); // warped mask as an RGB image, 255 = object (README.md:25-32)
-            for (size_t q = 0; q < L.wmask.size(); ++q) m3[3 * q] = m3[3 * q + 1] = m3[3 * q + 2] = L.wmask[q];
-            if (!save_png_rgb(p.wrgb, g.W, g.H, L.wrgb.data()) || !save_png_rgb(p.wmask, g.W, g.H, m3.data()) ||
-                !write_flo(p.flo, g.W, g.H, L.flow.data()))
-                return false;
-            printf("Saved\n");
+        std::vector<std::future<bool>> jobs;
+        for (size_t k = 0; k < g.items.size(); ++k) jobs.push_back(std::async(std::launch::async, save_one, std::cref(g), k));
+        bool ok = true;
+        for (auto& j : jobs) {
+            if (j.get()) printf("Saved\n"); // list order
+            else ok = false;
         }
+        return ok;
+    };
+    auto load_one = [&](size_t idx, Loaded* out) -> bool {
+        Loaded& L = *out;
+        ImageRGB m;
+        if (!read_constraints(lines[idx].cstr, L.cstr) || !load_png_rgb(lines[idx].rgb, L.rgb) || !load_png_rgb(lines[idx].mask, m))
+            return false;
+        if (m.W != L.rgb.W || m.H != L.rgb.H) {
+            fprintf(stderr, "mask %s and image %s differ in size\n", lines[idx].mask.c_str(), lines[idx].rgb.c_str());
+            return false;
+        }
+        const size_t N = (size_t)m.W * m.H;
+        L.mask_red.resize(N);
+        for (size_t q = 0; q < N; ++q) L.mask_red[q] = m.px[3 * q]; // red channel only
+        L.flow.resize(2 * N);
+        L.wrgb.resize(3 * N);
+        L.wmask.resize(N);
         return true;
     };
 
     std::future<int> running;
     std::shared_ptr<Group> in_flight, done;
-    size_t i = 0;
-    Loaded carry; // first entry of the next group when a size change ended the previous one
-    bool have_carry = false;
-    while (i < lines.size() || in_flight) {
-        // ---- decode the next group (up to `batch` consecutive entries of one image size) ----
+    std::deque<Loaded> ready; // decoded, not yet grouped (a size change leaves the tail for the next group)
+    size_t decoded = 0, grouped = 0;
+    while (grouped < lines.size() || in_flight) {
+        // ---- decode ahead: keep up to `batch` entries ready, all of them in parallel ----
         std::shared_ptr<Group> next;
-        if (i < lines.size()) {
+        if (grouped < lines.size()) {
+            const size_t want = std::min(lines.size() - grouped, (size_t)batch);
+            if (ready.size() < want) {
+                const auto t0 = std::chrono::steady_clock::now();
+                const size_t n_new = want - ready.size();
+                std::vector<Loaded> fresh(n_new);
+                std::vector<std::future<bool>> jobs;
+                for (size_t k = 0; k < n_new; ++k) jobs.push_back(std::async(std::launch::async, load_one, decoded + k, &fresh[k]));
+                bool ok = true;
+                for (auto& j : jobs) ok = j.get() && ok;
+                if (!ok) return 1;
+                for (auto& L : fresh) ready.push_back(std::move(L));
+                decoded += n_new;
+                t_decode += since(t0);
+            }
+            // ---- the next group: consecutive entries of one image size ----
             next = std::make_shared<Group>();
-            next->first = i;
-            while (i < lines.size() && (int)next->items.size() < batch) {
-                Loaded L;
-                if (have_carry) {
-                    L = std::move(carry);
-                    have_carry = false;
-                } else {
-                    ImageRGB m;
-                    if (!read_constraints(lines[i].cstr, L.cstr) || !load_png_rgb(lines[i].rgb, L.rgb) || !load_png_rgb(lines[i].mask, m))
-                        return 1;
-                    if (m.W != L.rgb.W || m.H != L.rgb.H) {
-                        fprintf(stderr, "mask %s and image %s differ in size\n", lines[i].mask.c_str(), lines[i].rgb.c_str());
-                        return 1;
-                    }
-                    const size_t N = (size_t)m.W * m.H;
-                    L.mask_red.resize(N);
-                    for (size_t q = 0; q < N; ++q) L.mask_red[q] = m.px[3 * q]; // red channel only
-                    L.flow.resize(2 * N);
-                    L.wrgb.resize(3 * N);
-                    L.wmask.resize(N);
-                }
-                if (next->items.empty()) { next->W = L.rgb.W; next->H = L.rgb.H; }
-                else if (L.rgb.W != next->W || L.rgb.H != next->H) { // belongs to the following group
-                    carry = std::move(L);
-                    have_carry = true;
-                    break;
-                }
-                next->items.push_back(std::move(L));
-                ++i;
+            next->first = grouped;
+            next->W = ready.front().rgb.W;
+            next->H = ready.front().rgb.H;
+            while (!ready.empty() && (int)next->items.size() < batch && ready.front().rgb.W == next->W &&
+                   ready.front().rgb.H == next->H) {
+                next->items.push_back(std::move(ready.front()));
+                ready.pop_front();
+                ++grouped;
             }
         }
         // ---- wait for the group on the GPU, start the next one, then encode the finished one ----
         if (in_flight) {
+            const auto t0 = std::chrono::steady_clock::now();
             const int rc = running.get();
+            t_gpu_wait += since(t0);
             if (rc) {
                 fprintf(stderr, "arap_deform: solver failed (%d)\n", rc);
                 return rc;
@@ -193,10 +222,15 @@ int main(int argc, const char* argv[])
             running = std::async(std::launch::async, gpu_stage, next);
         }
         if (done) {
+            const auto t0 = std::chrono::steady_clock::now();
             if (!save_stage(*done)) return 1;
+            t_encode += since(t0);
             done.reset();
         }
     }
+    if (timing)
+        fprintf(stderr, "arap_deform timing: total %.3f s | decode %.3f | waiting for the GPU %.3f (context + buffers %.3f) | "
+                        "encode %.3f\n", since(t_begin), t_decode, t_gpu_wait, t_create, t_encode);
     if (ctx) arapb200_batch_destroy(ctx);
     return 0;
 }

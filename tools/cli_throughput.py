@@ -17,8 +17,12 @@ for i in range(n):
     items.append(tuple(p))
 lst = os.path.join(d, "list.txt")
 driver.write_list_file(lst, items)
-env = dict(os.environ, ARAP_PLAN=driver.PLAN)
-t0 = time.time()
-subprocess.check_call([driver.ARAP_BIN, lst], env=env, stdout=subprocess.DEVNULL)
-dt = time.time() - t0
-print(f"arap_deform: {n} pairs (PNG in, .flo + PNG out) in {dt:.2f} s = {n / dt:.2f} pairs/s including process start and plan build")
+for rtol in (None, "1e-3"):
+    env = dict(os.environ, ARAP_PLAN=driver.PLAN, ARAP_TIMING="1")
+    if rtol:
+        env["ARAP_PCG_RTOL"] = rtol
+    t0 = time.time()
+    subprocess.check_call([driver.ARAP_BIN, lst], env=env, stdout=subprocess.DEVNULL)
+    dt = time.time() - t0
+    print(f"arap_deform{' ARAP_PCG_RTOL=' + rtol if rtol else ''}: {n} pairs (PNG in, .flo + PNG out) in {dt:.2f} s = "
+          f"{n / dt:.2f} pairs/s including process start and plan build")
