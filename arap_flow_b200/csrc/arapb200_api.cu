@@ -203,6 +203,17 @@ int arapb200_debug_gn_solve(int W, int H, float* X, float* A, const float* U, co
     return 0;
 }
 
+// UrShape == pixel grid on every active pixel?  (what GnPlan::choose_backend checks on the device)
+static bool host_urshape_is_grid(int W, int H, const float* U, const float* M)
+{
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            const size_t i = (size_t)y * W + x;
+            if (M[i] == 0.0f && (U[2 * i] != (float)x || U[2 * i + 1] != (float)y)) return false;
+        }
+    return true;
+}
+
 static int debug_setup(int W, int H, const float* X, const float* A, const float* U, const float* C, const float* M,
                        float wf, float wr, StreamSolver& s, DevBuf<float2>& dX, DevBuf<float2>& dU, DevBuf<float2>& dC,
                        DevBuf<float>& dA, DevBuf<float>& dM)
@@ -216,6 +227,7 @@ static int debug_setup(int W, int H, const float* X, const float* A, const float
     dM.up(M);
     ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
     s.bind(dX.p, dA.p, dU.p, dC.p, dM.p, wf, wr, nullptr);
+    s.set_general(!host_urshape_is_grid(W, H, U, M));
     s.enqueue_prep(nullptr);
     return 0;
 }
@@ -286,6 +298,7 @@ int arapb200_debug_cost(int W, int H, const float* X, const float* A, const floa
     ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
     StreamSolver s(W, H);
     s.bind(dX.p, dA.p, dU.p, dC.p, dM.p, wf, wr, nullptr);
+    s.set_general(!host_urshape_is_grid(W, H, U, M));
     s.enqueue_init(nullptr);
     s.read_back(nullptr, cost, nullptr);
     return 0;

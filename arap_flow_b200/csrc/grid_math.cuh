@@ -207,4 +207,55 @@ __device__ __forceinline__ float cost_fit(float acc, float X0, float X1, float C
     return acc;
 }
 
+// ------------------------------------------------------------------------------------------ general UrShape
+// The same three derived functions for an arbitrary UrShape image: d = u_i - u_j is a runtime vector.  Operation order
+// of oracle/arap_oracle.c (jtf_pixel, jtj_pixel, cost_pixel); with d a signed unit axis vector every expression below
+// reduces bit for bit to the specialised forms above.  Used by the streaming back-end's *_gen kernels only.
+__device__ __forceinline__ void jtj_nb_gen(JtjAcc& a, float px, float py, float pj0, float pj1, float paj, float cj,
+                                           float sj, float dx, float dy)
+{
+    const float dp0 = px - pj0, dp1 = py - pj1;
+    a.sd0 = a.sd0 + dp0;
+    a.sd1 = a.sd1 + dp1;
+    const float Qj0 = (-(sj * dx)) - cj * dy, Qj1 = cj * dx - sj * dy; // R'(a_j) d
+    a.nb0 = a.nb0 + Qj0 * paj;
+    a.nb1 = a.nb1 + Qj1 * paj;
+    a.dd = a.dd + (dx * dp0 + dy * dp1);
+    a.dc = a.dc + (dx * dp1 - dy * dp0);
+    a.Sx = a.Sx + dx;
+    a.Sy = a.Sy + dy;
+    a.nd = a.nd + (dx * dx + dy * dy); // contract C4
+}
+
+__device__ __forceinline__ void jtf_nb_gen(JtfAcc& a, float X0, float X1, float ci, float si, float Xj0, float Xj1,
+                                           float cj, float sj, float dx, float dy)
+{
+    const float dX0 = X0 - Xj0, dX1 = X1 - Xj1;
+    const float Ri0 = ci * dx - si * dy, Ri1 = si * dx + ci * dy;
+    const float Rj0 = cj * dx - sj * dy, Rj1 = sj * dx + cj * dy;
+    const float e0 = dX0 - Ri0, e1 = dX1 - Ri1;
+    float t0 = (dX0 + dX0) - Ri0;
+    t0 = t0 - Rj0;
+    float t1 = (dX1 + dX1) - Ri1;
+    t1 = t1 - Rj1;
+    a.gx0 = a.gx0 + t0;
+    a.gx1 = a.gx1 + t1;
+    const float Q0 = (-(si * dx)) - ci * dy, Q1 = ci * dx - si * dy; // R'(a_i) d
+    a.ga = a.ga + fmaf(Q1, e1, Q0 * e0);
+    a.nd = a.nd + (dx * dx + dy * dy);
+    a.nv = a.nv + 1.0f;
+}
+
+__device__ __forceinline__ float cost_nb_gen(float acc, float X0, float X1, float ci, float si, float Xj0, float Xj1,
+                                             float dx, float dy, float wr)
+{
+    const float dX0 = X0 - Xj0, dX1 = X1 - Xj1;
+    const float Ri0 = ci * dx - si * dy, Ri1 = si * dx + ci * dy;
+    const float e0 = dX0 - Ri0, e1 = dX1 - Ri1;
+    const float w0 = wr * e0, w1 = wr * e1;
+    acc = fmaf(w0, w0, acc);
+    acc = fmaf(w1, w1, acc);
+    return acc;
+}
+
 } // namespace arapb200

@@ -57,11 +57,21 @@ bool GnPlan::set_parameter(const char* name, const void* value)
     return false;
 }
 
-// AUTO: resident when the active part of the image fits on chip, else streaming
+// AUTO: resident when the active part of the image fits on chip, else streaming.  An UrShape image other than the pixel
+// grid (never bound by the ARAP app, CombinedSolver.h:207-221, but legal for an Opt.h caller) takes the streaming
+// back-end's general-d kernels.
 void GnPlan::choose_backend(void** pp)
 {
+    const size_t N = (size_t)W_ * H_;
+    ARAP_CUDA_OR_EXIT(cudaMemsetAsync(d_bad_u_, 0, sizeof(unsigned), stream_h_));
+    k_check_grid<<<(unsigned)((N + 255) / 256), 256, 0, stream_h_>>>(W_, H_, (const float2*)pp[2], (const float*)pp[4],
+                                                                     d_bad_u_);
+    unsigned bad = 0;
+    ARAP_CUDA_OR_EXIT(cudaMemcpyAsync(&bad, d_bad_u_, sizeof(unsigned), cudaMemcpyDeviceToHost, stream_h_));
+    ARAP_CUDA_OR_EXIT(cudaStreamSynchronize(stream_h_));
+    general_ = bad != 0;
     use_resident_ = false;
-    if (backend_ != ARAPB200_BACKEND_STREAM) {
+    if (backend_ != ARAPB200_BACKEND_STREAM && !general_) {
         if (!resident_) resident_.reset(new ResidentSolver(W_, H_));
         use_resident_ = resident_->prepare(W_, H_, (const float*)pp[4], stream_h_);
         if (!use_resident_ && backend_ == ARAPB200_BACKEND_RESIDENT) {
@@ -70,7 +80,10 @@ void GnPlan::choose_backend(void** pp)
             exit(1);
         }
     }
-    if (!use_resident_ && !stream_) stream_.reset(new StreamSolver(W_, H_));
+    if (!use_resident_) {
+        if (!stream_) stream_.reset(new StreamSolver(W_, H_));
+        stream_->set_general(general_);
+    }
 }
 
 // resident launch: cost before and after each of nGN Gauss-Newton steps; returns the last cost
@@ -98,36 +111,17 @@ void GnPlan::bind(void** pp)
                   *(const float*)pp[5], *(const float*)pp[6], stream_h_);
 }
 
-void GnPlan::check_grid(unsigned bad_u) const
-{
-    if (bad_u) {
-        fprintf(stderr,
-                "arapb200: UrShape differs from the pixel grid on %u active pixels; this build only supports "
-                "the grid the ARAP app uploads (CombinedSolver.h:207-221)\n", bad_u);
-        exit(1);
-    }
-}
-
 void GnPlan::init(void** pp)
 {
     choose_backend(pp);
     n_iter_ = 0;
     if (use_resident_) {
-        const size_t N = (size_t)W_ * H_;
-        ARAP_CUDA_OR_EXIT(cudaMemsetAsync(d_bad_u_, 0, sizeof(unsigned), stream_h_));
-        k_check_grid<<<(unsigned)((N + 255) / 256), 256, 0, stream_h_>>>(W_, H_, (const float2*)pp[2],
-                                                                         (const float*)pp[4], d_bad_u_);
-        unsigned bad = 0;
-        ARAP_CUDA_OR_EXIT(cudaMemcpyAsync(&bad, d_bad_u_, sizeof(unsigned), cudaMemcpyDeviceToHost, stream_h_));
         prev_cost_ = run_resident(pp, 0, nullptr);
-        check_grid(bad);
         return;
     }
     bind(pp);
     stream_->enqueue_init(stream_h_);
-    unsigned bad = 0;
-    stream_->read_back(stream_h_, &prev_cost_, &bad);
-    check_grid(bad);
+    stream_->read_back(stream_h_, &prev_cost_, nullptr);
 }
 
 int GnPlan::step(void** pp)
@@ -158,15 +152,8 @@ void GnPlan::solve(void** pp)
     choose_backend(pp);
     n_iter_ = 0;
     if (use_resident_) {
-        const size_t N = (size_t)W_ * H_;
-        ARAP_CUDA_OR_EXIT(cudaMemsetAsync(d_bad_u_, 0, sizeof(unsigned), stream_h_));
-        k_check_grid<<<(unsigned)((N + 255) / 256), 256, 0, stream_h_>>>(W_, H_, (const float2*)pp[2],
-                                                                         (const float*)pp[4], d_bad_u_);
-        unsigned bad = 0;
-        ARAP_CUDA_OR_EXIT(cudaMemcpyAsync(&bad, d_bad_u_, sizeof(unsigned), cudaMemcpyDeviceToHost, stream_h_));
         prev_cost_ = run_resident(pp, n_iterations_, d_trace_); // ONE launch for the whole Opt_ProblemSolve
         n_iter_ = n_iterations_;
-        check_grid(bad);
         return;
     }
     bind(pp);
@@ -175,9 +162,7 @@ void GnPlan::solve(void** pp)
         float* tr = d_trace_ ? d_trace_ + (size_t)3 * l_iterations_ * n_iter_ : nullptr;
         stream_->enqueue_gn_step(l_iterations_, stream_h_, tr);
     }
-    unsigned bad = 0;
-    stream_->read_back(stream_h_, &prev_cost_, &bad);
-    check_grid(bad);
+    stream_->read_back(stream_h_, &prev_cost_, nullptr);
 }
 
 } // namespace arapb200

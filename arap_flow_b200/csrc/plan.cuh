@@ -21,12 +21,12 @@ public:
     double current_cost() const { return (double)prev_cost_; }
     long long launches() const;
     bool using_resident() const { return use_resident_; }
+    bool general_urshape() const { return general_; }
     // parity/debug: device buffer of 3*lIterations floats per GN step, or null
     void set_trace(float* d_trace) { d_trace_ = d_trace; }
 
 private:
     void bind(void** problemparams);
-    void check_grid(unsigned bad_u) const;
     int W_, H_, verbosity_, backend_;
     int n_iterations_ = 10, l_iterations_ = 10; // solver_parameter_defaults, :26-39
     float pcg_rtol_ = 0.0f;                     // extension, 0 = off
@@ -36,6 +36,7 @@ private:
     std::unique_ptr<StreamSolver> stream_;      // created on first use
     std::unique_ptr<ResidentSolver> resident_;  // created on first use
     bool use_resident_ = false;
+    bool general_ = false;                      // UrShape is not the pixel grid
     void** last_params_ = nullptr;
     float* d_costs_ = nullptr;                  // resident: cost log of the current launch
     unsigned* d_bad_u_ = nullptr;

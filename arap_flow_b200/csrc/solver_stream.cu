@@ -430,6 +430,189 @@ __global__ void __launch_bounds__(ST_THREADS) k_cost(const StreamDev* __restrict
     publish(dp, ST_ACC_COST, block_exact_sum(g, red));
 }
 
+// ---------------------------------------------------------------------------------------------
+// General-UrShape variants of the three stencil kernels (Opt.h callers may bind any UrShape image; the ARAP app always
+// binds the pixel grid, which takes the specialised kernels above).  Straightforward: thread = vertical quad, every
+// neighbour value is read from global memory, the neighbour's new direction is recomputed in place.  Same arithmetic
+// contract, bit-exact against the oracle; not tuned.
+struct GenNb {
+    const float* px; // neighbour's plane-0 address
+    float dx, dy;    // u_i - u_j
+    size_t j;        // neighbour's row-major index
+};
+__device__ __forceinline__ GenNb gen_nb(const StreamDev& dp, int x, int y, int n, float2 ui)
+{
+    const int xj = x + (n == 0 ? 1 : n == 1 ? -1 : 0), yj = y + (n == 2 ? 1 : n == 3 ? -1 : 0);
+    GenNb r;
+    r.j = (size_t)yj * dp.W + xj;
+    r.px = dp.planes + tiled_off(dp, xj, yj);
+    const float2 uj = dp.U[r.j];
+    r.dx = ui.x - uj.x;
+    r.dy = ui.y - uj.y;
+    return r;
+}
+
+__global__ void __launch_bounds__(ST_THREADS) k_init_gen(const StreamDev* __restrict__ dpp)
+{
+    __shared__ double red[64];
+    const StreamDev& dp = *dpp;
+    const int W = dp.W, H = dp.H;
+    const int lx = threadIdx.x & 31, lyb = (threadIdx.x >> 5) * 4;
+    const int x = (blockIdx.x % dp.tx) * ST_TILE + lx, y0 = (blockIdx.x / dp.tx) * ST_TILE;
+    float* tb = tile_ptr(dp, blockIdx.x);
+    float g = 0.0f;
+    if (x < W) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int ly = lyb + r, y = y0 + ly;
+            if (y >= H) break;
+            const size_t i = (size_t)y * W + x;
+            const int loc = ly * ST_TILE + lx;
+            float* px = tb + loc;
+            const unsigned f = *flag_ptr(tb, loc);
+            if (!(f & FLAG_ACTIVE)) {
+#pragma unroll
+                for (int k = 0; k < PL_FLAGS; ++k) PLN(px, k) = 0.f;
+                continue;
+            }
+            const float2 Xi = dp.X[i], ui = dp.U[i];
+            const float ci = PLN(px, PL_CS), si = PLN(px, PL_CS + 1);
+            JtfAcc a;
+            jtf_zero(a);
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                if (!(f & (1u << n))) continue;
+                const GenNb nb = gen_nb(dp, x, y, n, ui);
+                const float2 Xj = dp.X[nb.j];
+                jtf_nb_gen(a, Xi.x, Xi.y, ci, si, Xj.x, Xj.y, PLN(nb.px, PL_CS), PLN(nb.px, PL_CS + 1), nb.dx, nb.dy);
+            }
+            const bool fit = (f & FLAG_FIT) != 0;
+            float2 c = make_float2(0.f, 0.f);
+            if (fit) c = dp.C[i];
+            float g0, g1, ga, DX, DA;
+            jtf_finish(a, Xi.x, Xi.y, fit, c.x, c.y, dp.wr2, dp.wf2, g0, g1, ga, DX, DA);
+            const float pX = guarded_invert(DX), pA = guarded_invert(DA);
+            const float r0 = -g0, r1 = -g1, r2 = -ga;
+            const float p0 = pX * r0, p1 = pX * r1, p2 = pA * r2;
+            PLN(px, PL_PRE) = pX;
+            PLN(px, PL_PRE + 1) = pA;
+            PLN(px, PL_R) = r0; PLN(px, PL_R + 1) = r1; PLN(px, PL_R + 2) = r2;
+            PLN(px, PL_P) = p0; PLN(px, PL_P + 1) = p1; PLN(px, PL_P + 2) = p2;
+            PLN(px, PL_D) = 0.f; PLN(px, PL_D + 1) = 0.f; PLN(px, PL_D + 2) = 0.f;
+            g = g + dot3(r0, r1, r2, p0, p1, p2);
+        }
+    }
+    publish(dp, bn_set(-1), block_exact_sum(g, red));
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(ST_THREADS) k_step_a_gen(const __grid_constant__ StreamPlanes pl,
+                                                           const StreamDev* __restrict__ dpp, int it)
+{
+    __shared__ double red[64];
+    __shared__ float s_beta;
+    const StreamDev& dp = *dpp;
+    const bool tile_on = pl.tile_active[blockIdx.x] != 0;
+    if (!tile_on && blockIdx.x != 0) return;
+    float beta = 0.0f;
+    if (!FIRST) {
+        if (threadIdx.x < 32) {
+            const float v = wide_round(fetch2(pl, bn_set(it - 1), bn_set(it - 2)));
+            const float bnum = __shfl_sync(0xffffffffu, v, 0), num = __shfl_sync(0xffffffffu, v, 16);
+            if (threadIdx.x == 0) {
+                s_beta = (num > 0.0f) ? bnum / num : 0.0f;
+                if (blockIdx.x == 0 && dp.trace) dp.trace[3 * (it - 1) + 2] = bnum;
+            }
+        }
+        __syncthreads();
+        beta = s_beta;
+    }
+    const int W = pl.W, H = pl.H;
+    const int src = PL_P + 3 * (FIRST ? 0 : ((it - 1) & 1)), dst = PL_P + 3 * (it & 1);
+    const int lx = threadIdx.x & 31, lyb = (threadIdx.x >> 5) * 4;
+    const int x = (blockIdx.x % pl.tx) * ST_TILE + lx, y0 = (blockIdx.x / pl.tx) * ST_TILE;
+    float* tb = tile_ptr(pl, blockIdx.x);
+    // the new direction of pixel at plane-0 address q (ping-pong: neighbours are recomputed, never read from dst)
+    auto new_p = [&](const float* q, float& p0, float& p1, float& pa) {
+        p0 = PLN(q, src); p1 = PLN(q, src + 1); pa = PLN(q, src + 2);
+        if (!FIRST) {
+            const float pX = PLN(q, PL_PRE), pA = PLN(q, PL_PRE + 1);
+            p0 = fmaf(beta, p0, pX * PLN(q, PL_R));
+            p1 = fmaf(beta, p1, pX * PLN(q, PL_R + 1));
+            pa = fmaf(beta, pa, pA * PLN(q, PL_R + 2));
+        }
+    };
+    float g = 0.0f;
+    if (x < W && tile_on) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int ly = lyb + r, y = y0 + ly;
+            if (y >= H) break;
+            const int loc = ly * ST_TILE + lx;
+            float* px = tb + loc;
+            float p0, p1, pa;
+            new_p(px, p0, p1, pa);
+            if (!FIRST) { PLN(px, dst) = p0; PLN(px, dst + 1) = p1; PLN(px, dst + 2) = pa; }
+            const unsigned f = *flag_ptr(tb, loc);
+            if (!(f & FLAG_ACTIVE)) continue;
+            const float2 ui = dp.U[(size_t)y * W + x];
+            JtjAcc a;
+            jtj_zero(a);
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                if (!(f & (1u << n))) continue;
+                const GenNb nb = gen_nb(dp, x, y, n, ui);
+                float q0, q1, qa;
+                new_p(nb.px, q0, q1, qa);
+                jtj_nb_gen(a, p0, p1, q0, q1, qa, PLN(nb.px, PL_CS), PLN(nb.px, PL_CS + 1), nb.dx, nb.dy);
+            }
+            float q0, q1, qa;
+            jtj_finish(a, PLN(px, PL_CS), PLN(px, PL_CS + 1), p0, p1, pa, (f & FLAG_FIT) != 0, dp.wr2, dp.wf2, q0, q1, qa);
+            PLN(px, PL_Q) = q0; PLN(px, PL_Q + 1) = q1; PLN(px, PL_Q + 2) = qa;
+            g = g + dot3(p0, p1, pa, q0, q1, qa);
+        }
+    }
+    publish(pl, ST_ACC_D0 + (it & 1), block_exact_sum(g, red));
+}
+
+__global__ void __launch_bounds__(ST_THREADS) k_cost_gen(const StreamDev* __restrict__ dpp)
+{
+    __shared__ double red[64];
+    const StreamDev& dp = *dpp;
+    const int W = dp.W, H = dp.H;
+    const int lx = threadIdx.x & 31, lyb = (threadIdx.x >> 5) * 4;
+    const int x = (blockIdx.x % dp.tx) * ST_TILE + lx, y0 = (blockIdx.x / dp.tx) * ST_TILE;
+    float* tb = tile_ptr(dp, blockIdx.x);
+    float g = 0.0f;
+    if (x < W) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int ly = lyb + r, y = y0 + ly;
+            if (y >= H) break;
+            const size_t i = (size_t)y * W + x;
+            const int loc = ly * ST_TILE + lx;
+            const unsigned f = *flag_ptr(tb, loc);
+            if (!(f & FLAG_ACTIVE)) continue;
+            const float2 Xi = dp.X[i], ui = dp.U[i];
+            const float ci = PLN(tb + loc, PL_CS), si = PLN(tb + loc, PL_CS + 1);
+            float acc = 0.0f;
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                if (!(f & (1u << n))) continue;
+                const GenNb nb = gen_nb(dp, x, y, n, ui);
+                const float2 Xj = dp.X[nb.j];
+                acc = cost_nb_gen(acc, Xi.x, Xi.y, ci, si, Xj.x, Xj.y, nb.dx, nb.dy, dp.wr);
+            }
+            if (f & FLAG_FIT) {
+                const float2 c = dp.C[i];
+                acc = cost_fit(acc, Xi.x, Xi.y, c.x, c.y, dp.wf);
+            }
+            g = g + acc;
+        }
+    }
+    publish(dp, ST_ACC_COST, block_exact_sum(g, red));
+}
+
 // Cost accumulator -> scalars; with tracing, also the last iteration's r.z
 __global__ void __launch_bounds__(32) k_finish(const __grid_constant__ StreamPlanes pl, const StreamDev* __restrict__ dpp,
                                                int last_it)
@@ -539,15 +722,34 @@ void StreamSolver::enqueue_prep(cudaStream_t stream)
 
 void StreamSolver::enqueue_pcg_init(cudaStream_t stream)
 {
-    k_init<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
+    if (general_) k_init_gen<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
+    else k_init<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
     ++launches_;
+}
+
+void StreamSolver::launch_step_a(bool first, int it, cudaStream_t stream)
+{
+    const StreamPlanes& pl = h_;
+    if (general_) {
+        if (first) k_step_a_gen<true><<<h_.ntiles, ST_THREADS, 0, stream>>>(pl, d_, it);
+        else k_step_a_gen<false><<<h_.ntiles, ST_THREADS, 0, stream>>>(pl, d_, it);
+    } else {
+        if (first) k_step_a<true><<<h_.ntiles, ST_THREADS, 0, stream>>>(pl, d_, it);
+        else k_step_a<false><<<h_.ntiles, ST_THREADS, 0, stream>>>(pl, d_, it);
+    }
+}
+
+void StreamSolver::set_general(bool general)
+{
+    if (general == general_) return;
+    general_ = general;
+    if (graph_) { cudaGraphExecDestroy(graph_); graph_ = nullptr; graph_npcg_ = -1; } // other kernels: re-capture
 }
 
 void StreamSolver::enqueue_step_a(bool first, int it, cudaStream_t stream)
 {
     const StreamPlanes& pl = h_;
-    if (first) k_step_a<true><<<h_.ntiles, ST_THREADS, 0, stream>>>(pl, d_, it);
-    else k_step_a<false><<<h_.ntiles, ST_THREADS, 0, stream>>>(pl, d_, it);
+    launch_step_a(first, it, stream);
     k_decode<<<1, 32, 0, stream>>>(pl, ST_ACC_D0 + (it & 1), &h_.sc->den);
     launches_ += 2;
 }
@@ -557,7 +759,8 @@ void StreamSolver::enqueue_init(cudaStream_t stream)
     const StreamPlanes& pl = h_;
     ARAP_CUDA_OR_EXIT(cudaMemsetAsync(&h_.sc->bad_u, 0, sizeof(unsigned), stream));
     enqueue_prep(stream);
-    k_cost<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
+    if (general_) k_cost_gen<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
+    else k_cost<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
     k_finish<<<1, 32, 0, stream>>>(pl, d_, -1);
     launches_ += 2;
     ARAP_CUDA_OR_EXIT(cudaGetLastError());
@@ -569,14 +772,15 @@ void StreamSolver::launch_gn_body(int nPCG, cudaStream_t stream, bool tracing)
     ARAP_CUDA_OR_EXIT(cudaMemsetAsync(h_.acc, 0, ACC_BYTES, stream));
     // the caller may have changed the constraint image / mask between steps (Opt.h:58-60): refresh flags
     k_prep<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
-    k_init<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
+    if (general_) k_init_gen<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
+    else k_init<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
     for (int it = 0; it < nPCG; ++it) {
-        if (it == 0) k_step_a<true><<<h_.ntiles, ST_THREADS, 0, stream>>>(pl, d_, it);
-        else k_step_a<false><<<h_.ntiles, ST_THREADS, 0, stream>>>(pl, d_, it);
+        launch_step_a(it == 0, it, stream);
         k_step_b<<<h_.ntiles, ST_THREADS, 0, stream>>>(pl, d_, it);
     }
     k_update<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
-    k_cost<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
+    if (general_) k_cost_gen<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
+    else k_cost<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
     k_finish<<<1, 32, 0, stream>>>(pl, d_, nPCG - 1);
     (void)tracing;
 }

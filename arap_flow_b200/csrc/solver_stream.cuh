@@ -82,6 +82,9 @@ public:
     void enqueue_prep(cudaStream_t stream);
     void enqueue_pcg_init(cudaStream_t stream);
     void enqueue_step_a(bool first, int it, cudaStream_t stream); // also decodes p.q into scalars().den
+    // UrShape is not the pixel grid: use the general-d kernels (slower; same arithmetic contract)
+    void set_general(bool general);
+    bool general() const { return general_; }
     const StreamDev& host_view() const { return h_; }
     // debug / parity tests: one plane (PL_*) <-> a row-major host image; blocking
     void download_plane(int plane, float* dst) const;
@@ -95,6 +98,8 @@ public:
 private:
     void upload(cudaStream_t stream);
     void launch_gn_body(int nPCG, cudaStream_t stream, bool tracing);
+    void launch_step_a(bool first, int it, cudaStream_t stream);
+    bool general_ = false;
     StreamDev h_{};
     StreamDev* d_ = nullptr;
     cudaGraphExec_t graph_ = nullptr;
