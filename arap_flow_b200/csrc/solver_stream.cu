@@ -257,6 +257,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_step_a(const __grid_constant__ S
     // ---- new direction: own quad (stored) and ring (kept in the tile only) ----
     // no activity test: every plane of an inactive pixel holds zeros, which flow through as zeros
     float* const pd = own + dst * ST_TILE_PX;
+    float4 ent[4]; // the quad's own tile entries: vertical neighbours inside the quad come from registers
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         if (!FIRST) {
@@ -265,7 +266,8 @@ __global__ void __launch_bounds__(ST_THREADS) k_step_a(const __grid_constant__ S
             po[r][2] = fmaf(beta, po[r][2], pre[r][1] * rr[r][2]);
             if (tile_on) { PLN(pd + r * ST_TILE, 0) = po[r][0]; PLN(pd + r * ST_TILE, 1) = po[r][1]; PLN(pd + r * ST_TILE, 2) = po[r][2]; }
         }
-        T[lyb + r + 1][lx + 1] = make_float4(po[r][0], po[r][1], cs[r][1] * po[r][2], cs[r][0] * po[r][2]);
+        ent[r] = make_float4(po[r][0], po[r][1], cs[r][1] * po[r][2], cs[r][0] * po[r][2]);
+        T[lyb + r + 1][lx + 1] = ent[r];
     }
     if (ring) {
         if (!FIRST) {
@@ -289,8 +291,8 @@ __global__ void __launch_bounds__(ST_THREADS) k_step_a(const __grid_constant__ S
         jtj_zero(a);
         jtj_nb_masked<0>(a, po[r][0], po[r][1], T[ly + 1][lx + 2], (f & 1u) ? 1.0f : 0.0f);
         jtj_nb_masked<1>(a, po[r][0], po[r][1], T[ly + 1][lx], (f & 2u) ? 1.0f : 0.0f);
-        jtj_nb_masked<2>(a, po[r][0], po[r][1], T[ly + 2][lx + 1], (f & 4u) ? 1.0f : 0.0f);
-        jtj_nb_masked<3>(a, po[r][0], po[r][1], T[ly][lx + 1], (f & 8u) ? 1.0f : 0.0f);
+        jtj_nb_masked<2>(a, po[r][0], po[r][1], r < 3 ? ent[r < 3 ? r + 1 : 3] : T[ly + 2][lx + 1], (f & 4u) ? 1.0f : 0.0f);
+        jtj_nb_masked<3>(a, po[r][0], po[r][1], r > 0 ? ent[r > 0 ? r - 1 : 0] : T[ly][lx + 1], (f & 8u) ? 1.0f : 0.0f);
         float q0, q1, qa;
         jtj_finish(a, cs[r][0], cs[r][1], po[r][0], po[r][1], po[r][2], (f & FLAG_FIT) != 0, wr2, wf2, q0, q1, qa);
         PLN(pq + r * ST_TILE, 0) = q0; PLN(pq + r * ST_TILE, 1) = q1; PLN(pq + r * ST_TILE, 2) = qa;
