@@ -49,7 +49,8 @@ def full(rep, notes):
 def stalls(rep, warps, iters):
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    hdr, data = rows[1], rows[2:]
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
+    hdr, data = rows[starts[-2] + 1], rows[starts[-2] + 2:starts[-1]]   # the last captured launch
     cols = [(i, h) for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
     tot = collections.Counter()
     for r in data:
@@ -67,9 +68,9 @@ def stalls(rep, warps, iters):
 if __name__ == "__main__":
     launch_list(os.path.join(G, "bench_launch_list.csv"), os.path.join(P, "r1_bench_launch_list.csv"),
                 "ncu launch list: python bench.py --steps 1 --warmup 1 --no-cpu-baseline (round 1; 2 steps x 8 pairs, C1)")
-    L = full(os.path.join(G, "r1_resident_b4.ncu-rep"), "tools/ncu_target.py resident C1 50 4: 4 co-resident 854x480 problems, 1x1x50 PCG iterations")
-    L += stalls(os.path.join(G, "r1_resident_b4.ncu-rep"), 146 * 4 * 4, 58)
-    L += [""] + full(os.path.join(G, "r1_stream_c4_v2.ncu-rep"), "tools/ncu_target.py stream C4 8 1: 1920x1080 (1 378 443 active px) through the streaming back-end "
-                     "(capture taken before the tile-interleaved layout; warm-cache per-kernel times of the final kernels: r1_stream_kernel_times.txt)")
+    L = full(os.path.join(G, "r1_resident_b4_final.ncu-rep"), "tools/ncu_target.py resident C1 50 4: 4 co-resident 854x480 problems, 1x1x50 PCG iterations")
+    L += stalls(os.path.join(G, "r1_resident_b4_final.ncu-rep"), 555 * 4, 52)
+    L += [""] + full(os.path.join(G, "r1_stream_c4_v3.ncu-rep"), "tools/ncu_target.py stream C4 8 1: 1920x1080 (1 378 443 active px) through the streaming back-end "
+                     "(tile-interleaved layout; warm-cache per-kernel times of the final kernels: r1_stream_kernel_times.txt)")
     open(os.path.join(P, "r1_ncu_full_summary.txt"), "w").write("\n".join(L) + "\n")
     print("\n".join(L[:40]))
