@@ -174,6 +174,10 @@ def main():
     if world > 1:
         # stdout carries exactly one JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION|INFO) goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":   # that banner is printf'ed to stdout regardless
+            os.environ["NCCL_DEBUG"] = "WARN"
+            if rank == 0:
+                print("NCCL version %s" % ".".join(str(v) for v in torch.cuda.nccl.version()), file=sys.stderr)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from arap_flow_b200 import lib
     lib.load()
