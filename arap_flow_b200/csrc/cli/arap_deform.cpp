@@ -40,6 +40,7 @@ static void usage()
     puts("Environment: ARAP_PLAN = path of the ARAP energy file (default ./arap_plan.t); CUDA_VISIBLE_DEVICES selects the GPU;");
     puts("             ARAP_BATCH = problems solved together (default 8)");
     puts("             ARAP_PCG_RTOL = opt-in relative PCG tolerance, e.g. 1e-3 (default 0: fixed 400 iterations)");
+    puts("             ARAP_GN_RTOL = opt-in relative cost-decrease tolerance of the Gauss-Newton steps (default 0: fixed 8 steps)");
 }
 
 struct Loaded {
@@ -91,6 +92,7 @@ int main(int argc, const char* argv[])
     if (batch < 1) batch = 1;
     // opt-in, off by default: convergence-aware PCG loops (changes results; include/arapb200.h)
     const double pcg_rtol = getenv("ARAP_PCG_RTOL") ? atof(getenv("ARAP_PCG_RTOL")) : 0.0;
+    const double gn_rtol = getenv("ARAP_GN_RTOL") ? atof(getenv("ARAP_GN_RTOL")) : 0.0;
     // ARAP_TIMING=1: per-stage wall times on stderr
     const bool timing = getenv("ARAP_TIMING") != NULL;
     const auto t_begin = std::chrono::steady_clock::now();
@@ -122,6 +124,10 @@ int main(int argc, const char* argv[])
             if (!ctx) return 1;
             if (pcg_rtol > 0.0 && arapb200_batch_set_option(ctx, "pcg_rtol", pcg_rtol)) {
                 fprintf(stderr, "ARAP_PCG_RTOL must be in [0, 1)\n");
+                return 1;
+            }
+            if (gn_rtol > 0.0 && arapb200_batch_set_option(ctx, "gn_rtol", gn_rtol)) {
+                fprintf(stderr, "ARAP_GN_RTOL must be in [0, 1)\n");
                 return 1;
             }
             ctxW = g->W; ctxH = g->H;

@@ -186,6 +186,11 @@ void BatchPipeline::set_pcg_rtol(float rtol)
     if (resident_) resident_->set_pcg_rtol(rtol);
 }
 
+void BatchPipeline::set_gn_rtol(float rtol)
+{
+    if (resident_) resident_->set_gn_rtol(rtol);
+}
+
 int BatchPipeline::run(const HostProblem* problems, int count)
 {
     if (count <= 0) return 0;

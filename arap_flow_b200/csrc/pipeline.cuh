@@ -51,6 +51,7 @@ public:
     int max_problems() const { return (int)dev_.size(); }
     // opt-in early exit of the PCG loops (resident back-end only; the streaming graph keeps the fixed budget)
     void set_pcg_rtol(float rtol);
+    void set_gn_rtol(float rtol);
 
 private:
     struct Dev { // device + pinned staging of one problem slot

@@ -56,6 +56,7 @@ struct Ctl {
     unsigned long long prev[2][4]; // totals last seen in each barrier buffer
     float bc;                      // broadcast result
     float stop;                    // opt-in early exit: leave the PCG loop once r.z <= stop (-1: never)
+    float prev_cost;               // opt-in early exit of the Gauss-Newton loop: cost before the last step
     int bc_code;                   // 0 accept, 1 redo with bc_S
     int bc_S;
     int abort;
@@ -589,6 +590,18 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                 const float tot = grid_sum(c, gs0, gs1, S_cost, ok);
                 if (!ok) break;
                 if (c.cta == 0 && threadIdx.x == 0) P.costs[(size_t)t * (P.nGN + 1) + g] = 0.5f * tot;
+                if (P.gn_rtol > 0.0f) {
+                    // N4 (opt-in, never on the parity path): stop the Gauss-Newton steps of this continuation step once
+                    // a step improves the cost by less than gn_rtol (relative); every CTA holds the same `tot`
+                    const float prevc = ctl.prev_cost;
+                    __syncthreads();
+                    if (threadIdx.x == 0) ctl.prev_cost = tot;
+                    if (g > 0 && g < P.nGN && !((prevc - tot) > P.gn_rtol * prevc)) {
+                        if (c.cta == 0 && threadIdx.x == 0)
+                            for (int gg = g + 1; gg <= P.nGN; ++gg) P.costs[(size_t)t * (P.nGN + 1) + gg] = 0.5f * tot;
+                        break;
+                    }
+                }
             }
             if (g == P.nGN) break; // the trailing prologue only produced the final cost
 
@@ -1023,6 +1036,7 @@ void ResidentSolver::enqueue_group(int first, int count, int nCont, int nGN, int
         Slot& sl = slots_[first + i];
         sl.prob.nCont = nCont; sl.prob.nGN = nGN; sl.prob.nPCG = nPCG;
         sl.prob.pcg_rtol2 = pcg_rtol_ * pcg_rtol_;
+        sl.prob.gn_rtol = gn_rtol_;
         sl.prob.prof = (i == 0) ? d_prof_ : nullptr;
         host[i] = sl.prob;
         ctas += sl.G;

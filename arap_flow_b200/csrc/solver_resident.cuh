@@ -37,6 +37,7 @@ struct ResProb {
     float* trace;              // optional [nCont*nGN][nPCG][3]
     int* status;               // [0] abort flag, [1] error code
     int nCont, nGN, nPCG;
+    float gn_rtol;             // 0 = every GN step runs; > 0: a continuation step ends once a GN step gains less than this (relative)
     float pcg_rtol2;           // 0 = fixed budget (reference behaviour); > 0: leave a PCG loop once r.z <= rtol^2 * r0.z0
     unsigned long long* prof;  // optional [G][8] cycle counters (debug)
 };
@@ -79,6 +80,7 @@ public:
     void set_profile(unsigned long long* d_prof) { d_prof_ = d_prof; }
     // opt-in convergence-aware schedule; 0 restores the reference's fixed iteration budget
     void set_pcg_rtol(float rtol) { pcg_rtol_ = rtol > 0.0f ? rtol : 0.0f; }
+    void set_gn_rtol(float rtol) { gn_rtol_ = rtol > 0.0f ? rtol : 0.0f; }
 
 private:
     struct Slot {
@@ -102,7 +104,7 @@ private:
     long long launches_ = 0;
     unsigned long long* d_prof_ = nullptr;
     int last_variant_ = -1;
-    float pcg_rtol_ = 0.0f;
+    float pcg_rtol_ = 0.0f, gn_rtol_ = 0.0f;
 };
 
 } // namespace arapb200

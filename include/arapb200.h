@@ -93,7 +93,11 @@ ARAPB200_API int arapb200_batch_resident_count(arapb200_batch* b);
 /* Options beyond the reference's behaviour; every one defaults to "off" and none is on the parity path.
  *   "pcg_rtol" (SURVEY.md 8f N4): 0 <= value < 1.  > 0: a PCG loop ends as soon as r.z <= value^2 * (r.z at its start)
  *   instead of always running lIterations iterations.  Changes results (by design); resident back-end only --
- *   problems that take the streaming back-end keep the fixed budget.  Returns non-zero for unknown names / bad values. */
+ *   problems that take the streaming back-end keep the fixed budget.
+ *   "gn_rtol": 0 <= value < 1.  > 0: the Gauss-Newton steps of a continuation step end as soon as one of them lowers
+ *   the cost by less than value (relative) instead of always running nIterations steps; the skipped entries of
+ *   out_costs repeat the last cost.  Same scope and caveats as "pcg_rtol".
+ * Returns non-zero for unknown names / bad values. */
 ARAPB200_API int arapb200_batch_set_option(arapb200_batch* b, const char* name, double value);
 
 /* ---- debug / parity entry points (unit-level comparison against the oracle) ----------------- */

@@ -457,7 +457,13 @@ def test_opt_in_pcg_tolerance_n4(oracle):
     d = np.linalg.norm(fast["flow"] - full["flow"], axis=-1)[act]
     assert t_fast < 0.8 * t_full, (t_fast, t_full)
     assert d.mean() < 0.5 and abs(fast["costs"][-1, -1] - full["costs"][-1, -1]) < 0.2 * abs(full["costs"][-1, -1]) + 1e-3, (d.mean(), fast["costs"][-1], full["costs"][-1])
+    b.set_option("gn_rtol", 1e-2)
+    faster, t_faster = run()
+    d2 = np.linalg.norm(faster["flow"] - full["flow"], axis=-1)[act]
+    assert t_faster <= t_fast * 1.05 and d2.mean() < 0.5, (t_faster, t_fast, d2.mean())
+    assert np.all(np.diff(faster["costs"], axis=1) <= 1e-6 * np.abs(faster["costs"][:, :-1]) + 1e-9)  # skipped steps repeat the cost
     b.set_option("pcg_rtol", 0.0)
+    b.set_option("gn_rtol", 0.0)
     again, _ = run()
     assert _eq(again["flow"], full["flow"])
     with pytest.raises(RuntimeError):

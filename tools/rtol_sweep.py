@@ -22,8 +22,10 @@ W, H = pairs[0].W, pairs[0].H
 b = lib.Batch(W, H, B, 19, 8, 400, lib.BACKEND_RESIDENT)
 ref = None
 rows = []
-for rtol in (0.0, 1e-5, 1e-4, 1e-3, 1e-2, 1e-1):
+for rtol, gtol in ((0.0, 0.0), (1e-5, 0.0), (1e-4, 0.0), (1e-3, 0.0), (1e-2, 0.0), (1e-1, 0.0),
+                   (1e-3, 1e-4), (1e-3, 1e-3), (1e-3, 1e-2), (1e-2, 1e-2)):
     b.set_option("pcg_rtol", rtol)
+    b.set_option("gn_rtol", gtol)
     for _ in range(2):
         outs = [b.submit(i, p.rgb, p.masks[0], p.matches) for i, p in enumerate(pairs)]
         b.run()
@@ -34,7 +36,7 @@ for rtol in (0.0, 1e-5, 1e-4, 1e-3, 1e-2, 1e-1):
         ref = flows
     epe = [float(np.linalg.norm(f - r, axis=-1)[p.masks[0] == 0].mean()) for f, r, p in zip(flows, ref, pairs)]
     mag = [float(np.linalg.norm(r, axis=-1)[p.masks[0] == 0].mean()) for r, p in zip(ref, pairs)]
-    rows.append(dict(pcg_rtol=rtol, solve_ms_per_pair=ms / B, pairs_per_s=1000.0 * B / ms, mean_epe_vs_full_px=float(np.mean(epe)),
+    rows.append(dict(pcg_rtol=rtol, gn_rtol=gtol, solve_ms_per_pair=ms / B, pairs_per_s=1000.0 * B / ms, mean_epe_vs_full_px=float(np.mean(epe)),
                      max_pair_epe_px=float(np.max(epe)), mean_flow_px=float(np.mean(mag)), final_cost_mean=float(np.mean(costs))))
     print(json.dumps(rows[-1]), flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
