@@ -43,12 +43,6 @@ __device__ __forceinline__ long long fetch2(const StreamPlanes& pl, int set_lo, 
     const int lane = threadIdx.x & 31;
     return wide_fetch(acc_set(pl, lane < 16 ? set_lo : set_hi), lane & 15);
 }
-__device__ __forceinline__ void zero_set(const StreamPlanes& pl, int set, int first_thread)
-{
-    const int t = (int)threadIdx.x - first_thread;
-    if (t >= 0 && t < WA_WORDS) acc_set(pl, set)[t] = 0ULL;
-}
-
 // ---- tile-interleaved addressing ----
 __device__ __forceinline__ float* tile_ptr(const StreamPlanes& pl, int tile)
 {
@@ -186,24 +180,28 @@ __global__ void __launch_bounds__(ST_THREADS) k_init(const StreamDev* __restrict
 // Thread = one vertical quad of the tile (lane = column); threads 0..131 also own one pixel of the 1-pixel ring
 // around the tile, whose NEW direction they recompute (the neighbouring tile is writing it in this very kernel, so p is
 // ping-ponged).  Every global load of the block is issued before the first use; beta is decoded under them.
-template <bool FIRST>
-__global__ void __launch_bounds__(ST_THREADS) k_step_a(const __grid_constant__ StreamPlanes pl,
-                                                       const StreamDev* __restrict__ dpp, int it)
+// SUB = rows per block (32: one block per tile, 256 threads; 16: two blocks per tile, 128 threads -- shorter blocks leave
+// less idle time at the end of the grid).
+template <bool FIRST, int SUB>
+__global__ void __launch_bounds__(SUB * 8) k_step_a(const __grid_constant__ StreamPlanes pl,
+                                                    const StreamDev* __restrict__ dpp, int it)
 {
-    __shared__ float4 T[TS][TS]; // (p_x, p_y, sin*p_a, cos*p_a) of tile + ring
+    constexpr int NSUB = ST_TILE / SUB, TSY = SUB + 2;
+    __shared__ float4 T[TSY][TS]; // (p_x, p_y, sin*p_a, cos*p_a) of the block's rows + ring
     __shared__ double red[64];
     __shared__ float s_beta;
-    const bool tile_on = pl.tile_active[blockIdx.x] != 0; // tiles without object pixels have nothing to add
+    const int tile = blockIdx.x / NSUB, sub = blockIdx.x % NSUB;
+    const bool tile_on = pl.tile_active[tile] != 0; // tiles without object pixels have nothing to add
     if (!tile_on && blockIdx.x != 0) return;
     const int W = pl.W, H = pl.H;
-    const int x0 = (blockIdx.x % pl.tx) * ST_TILE, y0 = (blockIdx.x / pl.tx) * ST_TILE;
-    const int lx = threadIdx.x & 31, lyb = (threadIdx.x >> 5) * 4;
+    const int x0 = (tile % pl.tx) * ST_TILE, y0 = (tile / pl.tx) * ST_TILE + sub * SUB;
+    const int lx = threadIdx.x & 31, lyb = (threadIdx.x >> 5) * 4; // row inside the block
     long long raw = 0;
     if (!FIRST && threadIdx.x < 32) raw = fetch2(pl, bn_set(it - 1), bn_set(it - 2));
     const float wr2 = dpp->wr2, wf2 = dpp->wf2;
     const int src = PL_P + 3 * (FIRST ? 0 : ((it - 1) & 1)), dst = PL_P + 3 * (it & 1);
-    float* const tb = tile_ptr(pl, blockIdx.x);
-    float* const own = tb + lyb * ST_TILE + lx; // plane 0, first row of the quad
+    float* const tb = tile_ptr(pl, tile);
+    float* const own = tb + (sub * SUB + lyb) * ST_TILE + lx; // plane 0, first row of the quad
     const float* const ps = own + src * ST_TILE_PX;
 
     // ---- loads: own quad (pixels outside the image exist in storage and hold zeros) ----
@@ -218,17 +216,17 @@ __global__ void __launch_bounds__(ST_THREADS) k_step_a(const __grid_constant__ S
             pre[r][0] = PLN(px, PL_PRE); pre[r][1] = PLN(px, PL_PRE + 1);
             rr[r][0] = PLN(px, PL_R); rr[r][1] = PLN(px, PL_R + 1); rr[r][2] = PLN(px, PL_R + 2);
         }
-        fl[r] = *flag_ptr(tb, (lyb + r) * ST_TILE + lx);
+        fl[r] = *flag_ptr(tb, (sub * SUB + lyb + r) * ST_TILE + lx);
     }
     // ---- loads: ring pixel of threads 0..131 (top row, bottom row, left column, right column) ----
     const int t = threadIdx.x;
     int hlx, hly;
     if (t < TS) { hlx = t; hly = 0; }
-    else if (t < 2 * TS) { hlx = t - TS; hly = TS - 1; }
-    else if (t < 2 * TS + ST_TILE) { hlx = 0; hly = t - 2 * TS + 1; }
-    else { hlx = TS - 1; hly = t - 2 * TS - ST_TILE + 1; }
+    else if (t < 2 * TS) { hlx = t - TS; hly = TSY - 1; }
+    else if (t < 2 * TS + SUB) { hlx = 0; hly = t - 2 * TS + 1; }
+    else { hlx = TS - 1; hly = t - 2 * TS - SUB + 1; }
     const int hx = x0 + hlx - 1, hy = y0 + hly - 1;
-    const bool ring = t < 2 * TS + 2 * ST_TILE;
+    const bool ring = t < 2 * TS + 2 * SUB;
     const bool hin = ring && hx >= 0 && hx < W && hy >= 0 && hy < H;
     const float* hpx = hin ? pl.planes + tiled_off(pl, hx, hy) : own;
     float hp[3], hcs[2], hpre[2], hr[3];
@@ -304,17 +302,20 @@ __global__ void __launch_bounds__(ST_THREADS) k_step_a(const __grid_constant__ S
 // PCGStep2 (solverGPUGaussNewton.t:446-489).  Branch-free: the planes of inactive pixels hold zeros (they are
 // zero-initialised and never written), so they flow through as exact zeros and add +0 to the group term;
 // every load of the four rows is issued before the first use.
-__global__ void __launch_bounds__(ST_THREADS) k_step_b(const __grid_constant__ StreamPlanes pl,
-                                                       const StreamDev* __restrict__ dpp, int it)
+template <int SUB>
+__global__ void __launch_bounds__(SUB * 8) k_step_b(const __grid_constant__ StreamPlanes pl,
+                                                    const StreamDev* __restrict__ dpp, int it)
 {
+    constexpr int NSUB = ST_TILE / SUB;
     __shared__ double red[64];
     __shared__ float s_alpha;
-    const bool tile_on = pl.tile_active[blockIdx.x] != 0;
+    const int tile = blockIdx.x / NSUB, sub = blockIdx.x % NSUB;
+    const bool tile_on = pl.tile_active[tile] != 0;
     if (!tile_on && blockIdx.x != 0) return;
     // warp 0: r.z of the previous iteration and this iteration's p.q; fetched before the planes, decoded after
     long long raw = 0;
     if (threadIdx.x < 32) raw = fetch2(pl, bn_set(it - 1), ST_ACC_D0 + (it & 1));
-    float* const own = tile_ptr(pl, blockIdx.x) + (threadIdx.x >> 5) * 4 * ST_TILE + (threadIdx.x & 31);
+    float* const own = tile_ptr(pl, tile) + (sub * SUB + (threadIdx.x >> 5) * 4) * ST_TILE + (threadIdx.x & 31);
     const float* const pk = own + (PL_P + 3 * (it & 1)) * ST_TILE_PX;
     float pv[4][3], qv[4][3], rv[4][3], dv[4][3], pre[4][2];
 #pragma unroll
@@ -338,8 +339,10 @@ __global__ void __launch_bounds__(ST_THREADS) k_step_b(const __grid_constant__ S
         }
     }
     if (blockIdx.x == 0) { // recycle the accumulators nobody reads any more (their next writers are later kernels)
-        zero_set(pl, bn_set(it - 2), 64);
-        zero_set(pl, ST_ACC_D0 + ((it + 1) & 1), 160);
+        for (int w = threadIdx.x; w < WA_WORDS; w += blockDim.x) {
+            acc_set(pl, bn_set(it - 2))[w] = 0ULL;
+            acc_set(pl, ST_ACC_D0 + ((it + 1) & 1))[w] = 0ULL;
+        }
     }
     __syncthreads();
     const float alpha = s_alpha;
@@ -654,6 +657,8 @@ StreamSolver::StreamSolver(int W, int H)
     ARAP_CUDA_OR_EXIT(cudaMemset(h_.sc, 0, sizeof(StreamScalars)));
     ARAP_CUDA_OR_EXIT(cudaMalloc(&d_, sizeof(StreamDev)));
     h_.trace = nullptr;
+    const char* e = getenv("ARAP_STREAM_SUB");
+    sub16_ = !(e && atoi(e) == 32);
 }
 
 StreamSolver::~StreamSolver()
@@ -736,9 +741,21 @@ void StreamSolver::launch_step_a(bool first, int it, cudaStream_t stream)
         if (first) k_step_a_gen<true><<<h_.ntiles, ST_THREADS, 0, stream>>>(pl, d_, it);
         else k_step_a_gen<false><<<h_.ntiles, ST_THREADS, 0, stream>>>(pl, d_, it);
     } else {
-        if (first) k_step_a<true><<<h_.ntiles, ST_THREADS, 0, stream>>>(pl, d_, it);
-        else k_step_a<false><<<h_.ntiles, ST_THREADS, 0, stream>>>(pl, d_, it);
+        if (sub16_) {
+            if (first) k_step_a<true, 16><<<2 * h_.ntiles, 128, 0, stream>>>(pl, d_, it);
+            else k_step_a<false, 16><<<2 * h_.ntiles, 128, 0, stream>>>(pl, d_, it);
+        } else {
+            if (first) k_step_a<true, 32><<<h_.ntiles, 256, 0, stream>>>(pl, d_, it);
+            else k_step_a<false, 32><<<h_.ntiles, 256, 0, stream>>>(pl, d_, it);
+        }
     }
+}
+
+void StreamSolver::launch_step_b(int it, cudaStream_t stream)
+{
+    const StreamPlanes& pl = h_;
+    if (sub16_) k_step_b<16><<<2 * h_.ntiles, 128, 0, stream>>>(pl, d_, it);
+    else k_step_b<32><<<h_.ntiles, 256, 0, stream>>>(pl, d_, it);
 }
 
 void StreamSolver::set_general(bool general)
@@ -778,7 +795,7 @@ void StreamSolver::launch_gn_body(int nPCG, cudaStream_t stream, bool tracing)
     else k_init<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
     for (int it = 0; it < nPCG; ++it) {
         launch_step_a(it == 0, it, stream);
-        k_step_b<<<h_.ntiles, ST_THREADS, 0, stream>>>(pl, d_, it);
+        launch_step_b(it, stream);
     }
     k_update<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
     if (general_) k_cost_gen<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);

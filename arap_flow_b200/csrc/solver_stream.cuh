@@ -99,7 +99,9 @@ private:
     void upload(cudaStream_t stream);
     void launch_gn_body(int nPCG, cudaStream_t stream, bool tracing);
     void launch_step_a(bool first, int it, cudaStream_t stream);
+    void launch_step_b(int it, cudaStream_t stream);
     bool general_ = false;
+    bool sub16_ = true; // two 128-thread blocks per tile in the PCG kernels (ARAP_STREAM_SUB=32: one 256-thread block)
     StreamDev h_{};
     StreamDev* d_ = nullptr;
     cudaGraphExec_t graph_ = nullptr;
