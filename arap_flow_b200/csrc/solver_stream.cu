@@ -59,6 +59,17 @@ __device__ __forceinline__ unsigned char* flag_ptr(float* tb, int local)
     return reinterpret_cast<unsigned char*>(tb + PL_FLAGS * ST_TILE_PX) + local;
 }
 #define PLN(base, k) ((base)[(k) * ST_TILE_PX])
+// edge mirrors (PL_EDGE): slot of a halo-relevant plane (r 0-2, p 3-8, cos/sin 15-16, pre 17-18)
+__device__ __forceinline__ int edge_slot(int plane)
+{
+    return plane < 9 ? plane : plane - 6;
+}
+// to be called with every store to such a plane: pixels in column 0 / 31 also update their mirror
+__device__ __forceinline__ void edge_put(float* tb, int plane, int lx, int row, float v)
+{
+    if (lx == 0 || lx == ST_TILE - 1)
+        tb[PL_EDGE * ST_TILE_PX + (edge_slot(plane) * 2 + (lx != 0 ? 1 : 0)) * ST_TILE + row] = v;
+}
 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ST_THREADS) k_prep(const StreamDev* __restrict__ dpp)
@@ -91,6 +102,8 @@ __global__ void __launch_bounds__(ST_THREADS) k_prep(const StreamDev* __restrict
                 contract_sincos(dp.A[i], s, co);
                 PLN(tb + loc, PL_CS) = co;
                 PLN(tb + loc, PL_CS + 1) = s;
+                edge_put(tb, PL_CS, lx, lyb + r, co);
+                edge_put(tb, PL_CS + 1, lx, lyb + r, s);
                 const float2 u = dp.U[i];
                 if (u.x != (float)x || u.y != (float)y) bad = 1;
             }
@@ -148,6 +161,9 @@ __global__ void __launch_bounds__(ST_THREADS) k_init(const StreamDev* __restrict
                 // the branch-free PCG kernels rely on zeros here; a previous problem may have left values behind
 #pragma unroll
                 for (int k = 0; k < PL_FLAGS; ++k) PLN(px, k) = 0.f;
+#pragma unroll
+                for (int k = 0; k < PL_FLAGS; ++k)
+                    if (k < PL_Q || k >= PL_CS) edge_put(tb, k, lx, ly, 0.f);
                 continue;
             }
             const float4 Ei = T[ly + 1][lx + 1];
@@ -169,6 +185,9 @@ __global__ void __launch_bounds__(ST_THREADS) k_init(const StreamDev* __restrict
             PLN(px, PL_PRE + 1) = pA;
             PLN(px, PL_R) = r0; PLN(px, PL_R + 1) = r1; PLN(px, PL_R + 2) = r2;
             PLN(px, PL_P) = p0; PLN(px, PL_P + 1) = p1; PLN(px, PL_P + 2) = p2;
+            edge_put(tb, PL_PRE, lx, ly, pX); edge_put(tb, PL_PRE + 1, lx, ly, pA);
+            edge_put(tb, PL_R, lx, ly, r0); edge_put(tb, PL_R + 1, lx, ly, r1); edge_put(tb, PL_R + 2, lx, ly, r2);
+            edge_put(tb, PL_P, lx, ly, p0); edge_put(tb, PL_P + 1, lx, ly, p1); edge_put(tb, PL_P + 2, lx, ly, p2);
             PLN(px, PL_D) = 0.f; PLN(px, PL_D + 1) = 0.f; PLN(px, PL_D + 2) = 0.f;
             g = g + dot3(r0, r1, r2, p0, p1, p2);
         }
@@ -228,13 +247,21 @@ __global__ void __launch_bounds__(SUB * 8) k_step_a(const __grid_constant__ Stre
     const int hx = x0 + hlx - 1, hy = y0 + hly - 1;
     const bool ring = t < 2 * TS + 2 * SUB;
     const bool hin = ring && hx >= 0 && hx < W && hy >= 0 && hy < H;
-    const float* hpx = hin ? pl.planes + tiled_off(pl, hx, hy) : own;
+    // top / bottom ring pixels are read from the neighbour's planes (contiguous in x); left / right ring pixels from the
+    // neighbour's edge mirrors (contiguous in y)
+    const bool hedge = hin && (hlx == 0 || hlx == TS - 1);
+    const float* hpx = own;
+    if (hin) {
+        hpx = hedge ? tile_ptr(pl, (hy >> 5) * pl.tx + (hx >> 5)) + PL_EDGE * ST_TILE_PX + ((hx & 31) != 0 ? ST_TILE : 0) + (hy & 31)
+                    : pl.planes + tiled_off(pl, hx, hy);
+    }
+    auto hval = [&](int plane) { return hpx[hedge ? edge_slot(plane) * 2 * ST_TILE : plane * ST_TILE_PX]; };
     float hp[3], hcs[2], hpre[2], hr[3];
-    hp[0] = PLN(hpx, src); hp[1] = PLN(hpx, src + 1); hp[2] = PLN(hpx, src + 2);
-    hcs[0] = PLN(hpx, PL_CS); hcs[1] = PLN(hpx, PL_CS + 1);
+    hp[0] = hval(src); hp[1] = hval(src + 1); hp[2] = hval(src + 2);
+    hcs[0] = hval(PL_CS); hcs[1] = hval(PL_CS + 1);
     if (!FIRST) {
-        hpre[0] = PLN(hpx, PL_PRE); hpre[1] = PLN(hpx, PL_PRE + 1);
-        hr[0] = PLN(hpx, PL_R); hr[1] = PLN(hpx, PL_R + 1); hr[2] = PLN(hpx, PL_R + 2);
+        hpre[0] = hval(PL_PRE); hpre[1] = hval(PL_PRE + 1);
+        hr[0] = hval(PL_R); hr[1] = hval(PL_R + 1); hr[2] = hval(PL_R + 2);
     }
 
     // ---- beta ----
@@ -262,7 +289,12 @@ __global__ void __launch_bounds__(SUB * 8) k_step_a(const __grid_constant__ Stre
             po[r][0] = fmaf(beta, po[r][0], pre[r][0] * rr[r][0]);
             po[r][1] = fmaf(beta, po[r][1], pre[r][0] * rr[r][1]);
             po[r][2] = fmaf(beta, po[r][2], pre[r][1] * rr[r][2]);
-            if (tile_on) { PLN(pd + r * ST_TILE, 0) = po[r][0]; PLN(pd + r * ST_TILE, 1) = po[r][1]; PLN(pd + r * ST_TILE, 2) = po[r][2]; }
+            if (tile_on) {
+                PLN(pd + r * ST_TILE, 0) = po[r][0]; PLN(pd + r * ST_TILE, 1) = po[r][1]; PLN(pd + r * ST_TILE, 2) = po[r][2];
+                edge_put(tb, dst, lx, sub * SUB + lyb + r, po[r][0]);
+                edge_put(tb, dst + 1, lx, sub * SUB + lyb + r, po[r][1]);
+                edge_put(tb, dst + 2, lx, sub * SUB + lyb + r, po[r][2]);
+            }
         }
         ent[r] = make_float4(po[r][0], po[r][1], cs[r][1] * po[r][2], cs[r][0] * po[r][2]);
         T[lyb + r + 1][lx + 1] = ent[r];
@@ -315,16 +347,18 @@ __global__ void __launch_bounds__(SUB * 8) k_step_b(const __grid_constant__ Stre
     // warp 0: r.z of the previous iteration and this iteration's p.q; fetched before the planes, decoded after
     long long raw = 0;
     if (threadIdx.x < 32) raw = fetch2(pl, bn_set(it - 1), ST_ACC_D0 + (it & 1));
-    float* const own = tile_ptr(pl, tile) + (sub * SUB + (threadIdx.x >> 5) * 4) * ST_TILE + (threadIdx.x & 31);
+    float* const tbb = tile_ptr(pl, tile);
+    float* const own = tbb + (sub * SUB + (threadIdx.x >> 5) * 4) * ST_TILE + (threadIdx.x & 31);
     const float* const pk = own + (PL_P + 3 * (it & 1)) * ST_TILE_PX;
     float pv[4][3], qv[4][3], rv[4][3], dv[4][3], pre[4][2];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const float* px = own + r * ST_TILE;
         pv[r][0] = PLN(pk + r * ST_TILE, 0); pv[r][1] = PLN(pk + r * ST_TILE, 1); pv[r][2] = PLN(pk + r * ST_TILE, 2);
-        qv[r][0] = PLN(px, PL_Q); qv[r][1] = PLN(px, PL_Q + 1); qv[r][2] = PLN(px, PL_Q + 2);
+        // q is dead after this read and delta is touched once per iteration: streaming hints keep L2 for r, p, pre
+        qv[r][0] = __ldcs(&PLN(px, PL_Q)); qv[r][1] = __ldcs(&PLN(px, PL_Q + 1)); qv[r][2] = __ldcs(&PLN(px, PL_Q + 2));
         rv[r][0] = PLN(px, PL_R); rv[r][1] = PLN(px, PL_R + 1); rv[r][2] = PLN(px, PL_R + 2);
-        dv[r][0] = PLN(px, PL_D); dv[r][1] = PLN(px, PL_D + 1); dv[r][2] = PLN(px, PL_D + 2);
+        dv[r][0] = __ldcs(&PLN(px, PL_D)); dv[r][1] = __ldcs(&PLN(px, PL_D + 1)); dv[r][2] = __ldcs(&PLN(px, PL_D + 2));
         pre[r][0] = PLN(px, PL_PRE); pre[r][1] = PLN(px, PL_PRE + 1);
     }
     if (threadIdx.x < 32) {
@@ -355,9 +389,10 @@ __global__ void __launch_bounds__(SUB * 8) k_step_b(const __grid_constant__ Stre
             float rr[3], zz[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                PLN(px, PL_D + k) = fmaf(alpha, pv[r][k], dv[r][k]);
+                __stcs(&PLN(px, PL_D + k), fmaf(alpha, pv[r][k], dv[r][k]));
                 rr[k] = fmaf(-alpha, qv[r][k], rv[r][k]);
                 PLN(px, PL_R + k) = rr[k];
+                edge_put(tbb, PL_R + k, threadIdx.x & 31, sub * SUB + (threadIdx.x >> 5) * 4 + r, rr[k]);
                 zz[k] = ((k < 2) ? pre[r][0] : pre[r][1]) * rr[k];
             }
             g = g + dot3(zz[0], zz[1], zz[2], rr[0], rr[1], rr[2]);
@@ -394,6 +429,8 @@ __global__ void __launch_bounds__(ST_THREADS) k_update(const StreamDev* __restri
         contract_sincos(a, s, c);
         PLN(px, PL_CS) = c;
         PLN(px, PL_CS + 1) = s;
+        edge_put(tb, PL_CS, lx, lyb + r, c);
+        edge_put(tb, PL_CS + 1, lx, lyb + r, s);
     }
 }
 
@@ -478,6 +515,9 @@ __global__ void __launch_bounds__(ST_THREADS) k_init_gen(const StreamDev* __rest
             if (!(f & FLAG_ACTIVE)) {
 #pragma unroll
                 for (int k = 0; k < PL_FLAGS; ++k) PLN(px, k) = 0.f;
+#pragma unroll
+                for (int k = 0; k < PL_FLAGS; ++k)
+                    if (k < PL_Q || k >= PL_CS) edge_put(tb, k, lx, ly, 0.f);
                 continue;
             }
             const float2 Xi = dp.X[i], ui = dp.U[i];
@@ -503,6 +543,9 @@ __global__ void __launch_bounds__(ST_THREADS) k_init_gen(const StreamDev* __rest
             PLN(px, PL_PRE + 1) = pA;
             PLN(px, PL_R) = r0; PLN(px, PL_R + 1) = r1; PLN(px, PL_R + 2) = r2;
             PLN(px, PL_P) = p0; PLN(px, PL_P + 1) = p1; PLN(px, PL_P + 2) = p2;
+            edge_put(tb, PL_PRE, lx, ly, pX); edge_put(tb, PL_PRE + 1, lx, ly, pA);
+            edge_put(tb, PL_R, lx, ly, r0); edge_put(tb, PL_R + 1, lx, ly, r1); edge_put(tb, PL_R + 2, lx, ly, r2);
+            edge_put(tb, PL_P, lx, ly, p0); edge_put(tb, PL_P + 1, lx, ly, p1); edge_put(tb, PL_P + 2, lx, ly, p2);
             PLN(px, PL_D) = 0.f; PLN(px, PL_D + 1) = 0.f; PLN(px, PL_D + 2) = 0.f;
             g = g + dot3(r0, r1, r2, p0, p1, p2);
         }
@@ -557,7 +600,10 @@ __global__ void __launch_bounds__(ST_THREADS) k_step_a_gen(const __grid_constant
             float* px = tb + loc;
             float p0, p1, pa;
             new_p(px, p0, p1, pa);
-            if (!FIRST) { PLN(px, dst) = p0; PLN(px, dst + 1) = p1; PLN(px, dst + 2) = pa; }
+            if (!FIRST) {
+                PLN(px, dst) = p0; PLN(px, dst + 1) = p1; PLN(px, dst + 2) = pa;
+                edge_put(tb, dst, lx, ly, p0); edge_put(tb, dst + 1, lx, ly, p1); edge_put(tb, dst + 2, lx, ly, pa);
+            }
             const unsigned f = *flag_ptr(tb, loc);
             if (!(f & FLAG_ACTIVE)) continue;
             const float2 ui = dp.U[(size_t)y * W + x];
@@ -690,7 +736,16 @@ void StreamSolver::upload_plane(int plane, const float* src)
     std::vector<float> all((size_t)h_.ntiles * ST_TILE_FLOATS);
     ARAP_CUDA_OR_EXIT(cudaMemcpy(all.data(), h_.planes, all.size() * sizeof(float), cudaMemcpyDeviceToHost));
     for (int y = 0; y < h_.H; ++y)
-        for (int x = 0; x < h_.W; ++x) all[host_tiled_off(h_, x, y) + (size_t)plane * ST_TILE_PX] = src[(size_t)y * h_.W + x];
+        for (int x = 0; x < h_.W; ++x) {
+            const float v = src[(size_t)y * h_.W + x];
+            all[host_tiled_off(h_, x, y) + (size_t)plane * ST_TILE_PX] = v;
+            const bool halo_plane = plane < PL_Q || (plane >= PL_CS && plane < PL_FLAGS);
+            if (halo_plane && ((x & 31) == 0 || (x & 31) == 31)) { // keep the edge mirror in step (PL_EDGE)
+                const size_t tile0 = (size_t)((y >> 5) * h_.tx + (x >> 5)) * ST_TILE_FLOATS;
+                const int slot = plane < 9 ? plane : plane - 6;
+                all[tile0 + (size_t)PL_EDGE * ST_TILE_PX + (size_t)(slot * 2 + ((x & 31) ? 1 : 0)) * ST_TILE + (y & 31)] = v;
+            }
+        }
     ARAP_CUDA_OR_EXIT(cudaMemcpy(h_.planes, all.data(), all.size() * sizeof(float), cudaMemcpyHostToDevice));
 }
 

@@ -36,7 +36,10 @@ constexpr int PL_D = 12;     // 3
 constexpr int PL_CS = 15;    // cos, sin of Angle, refreshed per GN step
 constexpr int PL_PRE = 17;   // guarded-inverted diagonal: X part (both comps), angle part
 constexpr int PL_FLAGS = 19; // first 1024 BYTES of this plane
-constexpr int ST_NPL = 20;
+constexpr int PL_EDGE = 20;  // [13 halo-relevant planes][column 0, column 31][32 rows]: mirrors of the tile's outer
+                             // columns, so that a neighbour reads its ring column as ONE contiguous 128-byte run
+                             // instead of 32 strided sectors
+constexpr int ST_NPL = 21;
 constexpr size_t ST_TILE_FLOATS = (size_t)ST_NPL * ST_TILE_PX;
 
 // What the solver owns, fixed for its lifetime: passed to the kernels BY VALUE (constant bank), so that no block starts
