@@ -59,6 +59,14 @@ __device__ __forceinline__ unsigned char* flag_ptr(float* tb, int local)
     return reinterpret_cast<unsigned char*>(tb + PL_FLAGS * ST_TILE_PX) + local;
 }
 #define PLN(base, k) ((base)[(k) * ST_TILE_PX])
+// read-only planes that every PCG kernel re-reads (cos/sin, preconditioner): ask L2 to keep them
+__device__ __forceinline__ float ld_keep(const float* p)
+{
+    float v;
+    asm volatile("{\n\t.reg .b64 pol;\n\tcreatepolicy.fractional.L2::evict_last.b64 pol, 1.0;\n\t"
+                 "ld.global.L2::cache_hint.f32 %0, [%1], pol;\n\t}" : "=f"(v) : "l"(p));
+    return v;
+}
 // edge mirrors (PL_EDGE): slot of a halo-relevant plane (r 0-2, p 3-8, cos/sin 15-16, pre 17-18)
 __device__ __forceinline__ int edge_slot(int plane)
 {
@@ -229,10 +237,14 @@ __global__ void __launch_bounds__(SUB * 8) k_step_a(const __grid_constant__ Stre
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const float* px = own + r * ST_TILE;
-        po[r][0] = PLN(ps + r * ST_TILE, 0); po[r][1] = PLN(ps + r * ST_TILE, 1); po[r][2] = PLN(ps + r * ST_TILE, 2);
-        cs[r][0] = PLN(px, PL_CS); cs[r][1] = PLN(px, PL_CS + 1);
+        if (FIRST) {
+            po[r][0] = PLN(ps + r * ST_TILE, 0); po[r][1] = PLN(ps + r * ST_TILE, 1); po[r][2] = PLN(ps + r * ST_TILE, 2);
+        } else { // the old direction is dead after this kernel
+            po[r][0] = __ldcs(&PLN(ps + r * ST_TILE, 0)); po[r][1] = __ldcs(&PLN(ps + r * ST_TILE, 1)); po[r][2] = __ldcs(&PLN(ps + r * ST_TILE, 2));
+        }
+        cs[r][0] = ld_keep(&PLN(px, PL_CS)); cs[r][1] = ld_keep(&PLN(px, PL_CS + 1));
         if (!FIRST) {
-            pre[r][0] = PLN(px, PL_PRE); pre[r][1] = PLN(px, PL_PRE + 1);
+            pre[r][0] = ld_keep(&PLN(px, PL_PRE)); pre[r][1] = ld_keep(&PLN(px, PL_PRE + 1));
             rr[r][0] = PLN(px, PL_R); rr[r][1] = PLN(px, PL_R + 1); rr[r][2] = PLN(px, PL_R + 2);
         }
         fl[r] = *flag_ptr(tb, (sub * SUB + lyb + r) * ST_TILE + lx);
@@ -359,7 +371,7 @@ __global__ void __launch_bounds__(SUB * 8) k_step_b(const __grid_constant__ Stre
         qv[r][0] = __ldcs(&PLN(px, PL_Q)); qv[r][1] = __ldcs(&PLN(px, PL_Q + 1)); qv[r][2] = __ldcs(&PLN(px, PL_Q + 2));
         rv[r][0] = PLN(px, PL_R); rv[r][1] = PLN(px, PL_R + 1); rv[r][2] = PLN(px, PL_R + 2);
         dv[r][0] = __ldcs(&PLN(px, PL_D)); dv[r][1] = __ldcs(&PLN(px, PL_D + 1)); dv[r][2] = __ldcs(&PLN(px, PL_D + 2));
-        pre[r][0] = PLN(px, PL_PRE); pre[r][1] = PLN(px, PL_PRE + 1);
+        pre[r][0] = ld_keep(&PLN(px, PL_PRE)); pre[r][1] = ld_keep(&PLN(px, PL_PRE + 1));
     }
     if (threadIdx.x < 32) {
         const float v = wide_round(raw);
