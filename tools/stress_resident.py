@@ -7,14 +7,17 @@ from arap_flow_b200 import lib, synth
 
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 cases = [("C1", 4, dict(nCont=1, nGN=2, nPCG=200)), ("C3", 3, dict(nCont=1, nGN=2, nPCG=200)), ("C0", 8, dict(nCont=2, nGN=2, nPCG=100))]
+cases += [("C2", 2, dict(nCont=1, nGN=2, nPCG=200)),          # ragged group: compact 1-D cooperative grid
+          ("C4", 1, dict(nCont=1, nGN=1, nPCG=60))]           # streaming back-end (fence-free wide accumulators)
 for cfg, B, kw in cases:
     pairs = [synth.config(cfg, i) for i in range(B)]
     W, H = pairs[0].W, pairs[0].H
-    b = lib.Batch(W, H, B, kw["nCont"], kw["nGN"], kw["nPCG"], lib.BACKEND_RESIDENT)
+    problems = [(p, m) for p in pairs for m in p.masks]
+    b = lib.Batch(W, H, len(problems), kw["nCont"], kw["nGN"], kw["nPCG"], lib.BACKEND_AUTO if cfg == "C4" else lib.BACKEND_RESIDENT)
     ref = None
     t0 = time.time()
     for r in range(reps):
-        outs = [b.submit(i, p.rgb, p.masks[0], p.matches) for i, p in enumerate(pairs)]
+        outs = [b.submit(i, p.rgb, m, p.matches) for i, (p, m) in enumerate(problems)]
         b.run()
         cur = [(o["flow"].copy(), o["costs"].copy()) for o in outs]
         if ref is None:
