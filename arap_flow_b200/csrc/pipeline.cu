@@ -1,5 +1,6 @@
 // pipeline.cu -- see pipeline.cuh
 #include "pipeline.cuh"
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <unordered_map>
@@ -259,7 +260,11 @@ int BatchPipeline::run(const HostProblem* problems, int count)
         }
         int run_len = 0; // consecutive resident problems
         while (i + run_len < count && dev_[i + run_len].resident) ++run_len;
-        const int gsz = resident_->group_size(i, run_len);
+        int gsz = resident_->group_size(i, run_len);
+        if (gsz < run_len) { // several launches: split the run evenly instead of one full launch and a small remainder
+            const int ngroups = (run_len + gsz - 1) / gsz;
+            gsz = std::min(gsz, (run_len + ngroups - 1) / ngroups);
+        }
         for (int j = 0; j < gsz; ++j) {
             Dev& dj = dev_[i + j];
             const HostProblem& hp = problems[i + j];
