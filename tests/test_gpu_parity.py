@@ -496,3 +496,15 @@ def test_general_urshape_bit_exact(oracle, W, H, seed):
     Xo, Ao, co, _ = oracle.gn_solve(pr["X"], pr["A"], pr["U"], pr["C"], pr["M"], 1, 20)
     Xg, Ag, cg, _ = lib.debug_gn_solve(pr["X"], pr["A"], pr["U"], pr["C"], pr["M"], 1, 20, oracle.WF, oracle.WR, backend=lib.BACKEND_STREAM)
     assert _eq(Xg, Xo) and _eq(Ag, Ao) and _eq(cg, co)
+
+
+@pytest.mark.parametrize("backend", [lib.BACKEND_STREAM, lib.BACKEND_RESIDENT])
+@pytest.mark.parametrize("kw", [dict(nCont=1, nGN=1, nPCG=0), dict(nCont=1, nGN=0, nPCG=5), dict(nCont=2, nGN=1, nPCG=1),
+                                dict(nCont=1, nGN=2, nPCG=1)])
+def test_degenerate_schedules(oracle, backend, kw):
+    """Zero PCG iterations, zero Gauss-Newton steps, single iterations: the loops' boundary cases (Opt accepts any
+    nIterations / lIterations, solverGPUGaussNewton.t:1016-1103)."""
+    sp = synth.synth(48, 40, nseg=1, fd=2, seed=3)
+    fl, rgb, msk, costs = lib.deform(sp.rgb, sp.masks[0], sp.matches, backend=backend, **kw)
+    Xo, Ao, co = oracle.solve(sp.masks[0], sp.matches, **kw)
+    assert _eq(fl, oracle.flow(Xo)) and _eq(costs, co)
