@@ -3,6 +3,8 @@ import ctypes
 import os
 import re
 
+import pytest
+
 from arap_flow_b200 import lib
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -44,3 +46,41 @@ def test_problem_define_refuses_foreign_plans(tmp_path):
     p = L.Opt_ProblemDefine(st, good.encode(), b"gaussNewtonGPU")
     assert p
     L.Opt_ProblemDelete(st, p)
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under arap_flow_b200/ (Python or native sources) may import, link or
+    execute it, and the shared library must not depend on liboracle."""
+    import re
+    import subprocess
+    pkg = os.path.join(ROOT, "arap_flow_b200")
+    offenders = []
+    for dp, dn, fn in os.walk(pkg):
+        if os.path.basename(dp) in ("build", "bin", "__pycache__"):
+            continue
+        for f in fn:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) or f == "Makefile":
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b|liboracle|pyoracle|oracle/_ref", txt, re.M):
+                    offenders.append(os.path.join(dp, f))
+    assert not offenders, offenders
+    needed = subprocess.run(["readelf", "-d", lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in needed
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    """Without a CUDA device every compute entry point fails loudly (non-zero code / exit), it never computes on the host."""
+    import subprocess
+    import sys
+    probe = subprocess.run([sys.executable, "-c", "import torch,sys; sys.exit(0 if torch.cuda.is_available() else 3)"],
+                           capture_output=True)
+    if probe.returncode == 0:
+        pytest.skip("a GPU is present")
+    code = ("import numpy as np\n"
+            "from arap_flow_b200 import lib, synth\n"
+            "sp = synth.synth(32, 32, 1, 1, 0)\n"
+            "lib.deform(sp.rgb, sp.masks[0], sp.matches, nCont=1, nGN=1, nPCG=1)\n"
+            "print('COMPUTED')\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
+    assert r.returncode != 0 and "COMPUTED" not in r.stdout
+    assert "CUDA" in (r.stderr + r.stdout) or "failed" in (r.stderr + r.stdout)
