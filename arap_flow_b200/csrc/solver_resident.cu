@@ -136,6 +136,7 @@ struct StripCtx {
     float2* pre;            // &pre[0][lane]
     int rem[4];             // remote neighbour strip id per side (0 up, 1 down, 2 left, 3 right) or -1
     uint4* outbox;          // own outbox: [RS_OUTBOX_ENTRIES][3]
+    uint4* side_out;        // lane 0 / lane 31: where the left / right column entries of row 0 go (null: nothing to publish)
 };
 
 struct Cta {
@@ -319,8 +320,7 @@ __device__ __forceinline__ void publish_rowcol(const StripCtx& s, int lane, int 
 {
     if (s.rem[0] >= 0 && k == 0) put_entry(s.outbox + 3 * lane, tag, a, b, c2, d, e2, f, three);
     if (s.rem[1] >= 0 && k == RS_STRIP_H - 1) put_entry(s.outbox + 3 * (32 + lane), tag, a, b, c2, d, e2, f, three);
-    if (s.rem[2] >= 0 && lane == 0) put_entry(s.outbox + 3 * (OB_LEFT + k), tag, a, b, c2, d, e2, f, three);
-    if (s.rem[3] >= 0 && lane == 31) put_entry(s.outbox + 3 * (OB_RIGHT + k), tag, a, b, c2, d, e2, f, three);
+    if (s.side_out) put_entry(s.side_out + 3 * k, tag, a, b, c2, d, e2, f, three); // both columns in one predicated store
 }
 
 // What a lane receives: the pixel above / below its column (all lanes) and, for lanes 0..H-1 (left column)
@@ -501,6 +501,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
         if (nl >= 0) { if (nl >= s_begin && nl < s_end) { if (lane == 0) s.lptr = &S[nl - s_begin].T[1][TW - 2]; } else s.rem[2] = nl; }
         if (nr >= 0) { if (nr >= s_begin && nr < s_end) { if (lane == 31) s.rptr = &S[nr - s_begin].T[1][1]; } else s.rem[3] = nr; }
     }
+    s.side_out = nullptr;
+    if (s.has && lane == 0 && s.rem[2] >= 0) s.side_out = s.outbox + 3 * OB_LEFT;
+    if (s.has && lane == 31 && s.rem[3] >= 0) s.side_out = s.outbox + 3 * OB_RIGHT;
     s.x = sx * RS_STRIP_W + lane;
     s.y0 = sy * RS_STRIP_H;
     const bool any_rem = s.has && (s.rem[0] >= 0 || s.rem[1] >= 0 || s.rem[2] >= 0 || s.rem[3] >= 0); // warp-uniform
