@@ -410,10 +410,13 @@ __device__ __forceinline__ void apply_p(const StripCtx& s, int lane, float beta)
 {
     if (s.rem[0] >= 0) s.own[0 * TW + lane + 1] = p_entry_from(s.stage + 6 * lane, beta, s.rcs[lane]);
     if (s.rem[1] >= 0) s.own[(TH - 1) * TW + lane + 1] = p_entry_from(s.stage + 6 * (32 + lane), beta, s.rcs[32 + lane]);
-    if (s.rem[2] >= 0 && lane < RS_STRIP_H)
-        s.own[(lane + 1) * TW + 0] = p_entry_from(s.stage + 6 * (OB_LEFT + lane), beta, s.rcs[OB_LEFT + lane]);
-    if (s.rem[3] >= 0 && lane >= 8 && lane < 8 + RS_STRIP_H)
-        s.own[(lane - 8 + 1) * TW + TW - 1] = p_entry_from(s.stage + 6 * (OB_RIGHT + lane - 8), beta, s.rcs[OB_RIGHT + lane - 8]);
+    // left column (lanes 0..H-1) and right column (lanes 8..8+H-1) in one predicated block
+    const bool lft = lane < RS_STRIP_H;
+    const int row = lft ? lane : lane - 8;
+    if ((lft && s.rem[2] >= 0) || (!lft && lane >= 8 && lane < 8 + RS_STRIP_H && s.rem[3] >= 0)) {
+        const int slot = (lft ? OB_LEFT : OB_RIGHT) + row;
+        s.own[(row + 1) * TW + (lft ? 0 : TW - 1)] = p_entry_from(s.stage + 6 * slot, beta, s.rcs[slot]);
+    }
 }
 
 // constraint of a pixel for the current continuation weight (CombinedSolver.h:236-239)
