@@ -46,7 +46,7 @@ struct __align__(16) StripSmem {
     float4 T[TH][TW];              // tile + ring: (p_x, p_y, sin*p_a, cos*p_a) or (X_x, X_y, cos, sin)
     float D[3][RS_STRIP_H][32];    // delta
     float2 rcs[RS_OUTBOX_ENTRIES]; // cos/sin of the ring pixels (remote sides only)
-    float stage[RS_OUTBOX_ENTRIES][6]; // fetched (z, p_old) of the remote ring pixels, parked until beta is known
+    float stage[RS_OUTBOX_ENTRIES][4]; // remote ring pixels: [0..2] fetched z (parked until beta is known), [3] their p_a
     float2 pre[RS_STRIP_H][32];        // (1/(1+sqrt(D_X))^2, 1/(1+sqrt(D_a))^2) per pixel, constant during a GN step
 };
 
@@ -305,61 +305,61 @@ __device__ __forceinline__ float grid_sum(Cta& c, float g0, float g1, int& S, bo
 }
 
 // ---- halo publication / reception ----------------------------------------------------------------
-// An outbox entry is 3 x uint4 = six (float, tag) words: (z0, z1 | z2, p0 | p1, pa) or (X0, X1 | c, s | -, -).
-__device__ __forceinline__ void put_entry(uint4* e, unsigned tag, float a, float b, float c2, float d, float e2, float f,
-                                          bool three)
+// An outbox entry is 2 x uint4 = four (float, tag) words: (z0, z1 | z2, -) or (X0, X1 | c, s).  Only z travels during the
+// PCG iterations: the receiver already holds the neighbour's previous direction (it computed it one iteration ago).
+__device__ __forceinline__ void put_entry(uint4* e, unsigned tag, float a, float b, float c2, float d)
 {
     st_u4(e, make_uint4(__float_as_uint(a), tag, __float_as_uint(b), tag));
     st_u4(e + 1, make_uint4(__float_as_uint(c2), tag, __float_as_uint(d), tag));
-    if (three) st_u4(e + 2, make_uint4(__float_as_uint(e2), tag, __float_as_uint(f), tag));
 }
 
 // called once per row k (fully unrolled) with the entry of pixel (lane, k)
 __device__ __forceinline__ void publish_rowcol(const StripCtx& s, int lane, int k, unsigned tag, float a, float b, float c2,
-                                               float d, float e2, float f, bool three)
+                                               float d)
 {
-    if (s.rem[0] >= 0 && k == 0) put_entry(s.outbox + 3 * lane, tag, a, b, c2, d, e2, f, three);
-    if (s.rem[1] >= 0 && k == RS_STRIP_H - 1) put_entry(s.outbox + 3 * (32 + lane), tag, a, b, c2, d, e2, f, three);
-    if (s.side_out) put_entry(s.side_out + 3 * k, tag, a, b, c2, d, e2, f, three); // both columns in one predicated store
+    if (s.rem[0] >= 0 && k == 0) put_entry(s.outbox + 2 * lane, tag, a, b, c2, d);
+    if (s.rem[1] >= 0 && k == RS_STRIP_H - 1) put_entry(s.outbox + 2 * (32 + lane), tag, a, b, c2, d);
+    if (s.side_out) put_entry(s.side_out + 2 * k, tag, a, b, c2, d); // both columns in one predicated store
 }
 
 // What a lane receives: the pixel above / below its column (all lanes) and, for lanes 0..H-1 (left column)
 // or 8..8+H-1 (right column), one pixel beside the strip.  Fetched values are parked in shared memory
 // (stage[ring slot][6]) so that they do not occupy registers across the barrier.
-__device__ __forceinline__ bool entry_ok(const uint4 w0, const uint4 w1, const uint4 w2, unsigned tag)
+__device__ __forceinline__ bool entry_ok(const uint4 w0, const uint4 w1, unsigned tag)
 {
-    return w0.y == tag && w0.w == tag && w1.y == tag && w1.w == tag && w2.y == tag && w2.w == tag;
+    return w0.y == tag && w0.w == tag && w1.y == tag && w1.w == tag;
 }
-__device__ __forceinline__ void entry_park(float* st, const uint4 w0, const uint4 w1, const uint4 w2)
+// four = false: only [0..2] are written -- [3] keeps the ring pixel's p_a between iterations
+__device__ __forceinline__ void entry_park(float* st, const uint4 w0, const uint4 w1, bool four)
 {
     *reinterpret_cast<float2*>(st) = make_float2(__uint_as_float(w0.x), __uint_as_float(w0.z));
-    *reinterpret_cast<float2*>(st + 2) = make_float2(__uint_as_float(w1.x), __uint_as_float(w1.z));
-    *reinterpret_cast<float2*>(st + 4) = make_float2(__uint_as_float(w2.x), __uint_as_float(w2.z));
+    st[2] = __uint_as_float(w1.x);
+    if (four) st[3] = __uint_as_float(w1.z);
 }
 
 // Spin until every remote entry this lane needs carries `tag`.  All loads of a round are in flight together;
 // normally the first round succeeds because the neighbours published before they went into the barrier that
 // this warp has just arrived at (the call sits between arrival and completion, so its latency hides there).
-__device__ __forceinline__ void fetch_halo(const ResProb& P, Ctl* ctl, const StripCtx& s, int lane, unsigned tag, bool three)
+__device__ __forceinline__ void fetch_halo(const ResProb& P, Ctl* ctl, const StripCtx& s, int lane, unsigned tag, bool four)
 {
     const bool left = s.rem[2] >= 0 && lane < RS_STRIP_H;
     const bool right = s.rem[3] >= 0 && lane >= 8 && lane < 8 + RS_STRIP_H;
-    const uint4* pu = (s.rem[0] >= 0) ? P.outbox + ((size_t)s.rem[0] * RS_OUTBOX_ENTRIES + 32 + lane) * 3 : nullptr;
-    const uint4* pd = (s.rem[1] >= 0) ? P.outbox + ((size_t)s.rem[1] * RS_OUTBOX_ENTRIES + lane) * 3 : nullptr;
-    const uint4* ps = left ? P.outbox + ((size_t)s.rem[2] * RS_OUTBOX_ENTRIES + OB_RIGHT + lane) * 3
-                           : (right ? P.outbox + ((size_t)s.rem[3] * RS_OUTBOX_ENTRIES + OB_LEFT + lane - 8) * 3 : nullptr);
+    const uint4* pu = (s.rem[0] >= 0) ? P.outbox + ((size_t)s.rem[0] * RS_OUTBOX_ENTRIES + 32 + lane) * 2 : nullptr;
+    const uint4* pd = (s.rem[1] >= 0) ? P.outbox + ((size_t)s.rem[1] * RS_OUTBOX_ENTRIES + lane) * 2 : nullptr;
+    const uint4* ps = left ? P.outbox + ((size_t)s.rem[2] * RS_OUTBOX_ENTRIES + OB_RIGHT + lane) * 2
+                           : (right ? P.outbox + ((size_t)s.rem[3] * RS_OUTBOX_ENTRIES + OB_LEFT + lane - 8) * 2 : nullptr);
     const int side_slot = left ? OB_LEFT + lane : OB_RIGHT + lane - 8;
     const uint4 fake = make_uint4(0u, tag, 0u, tag);
     unsigned spins = 0;
     for (;;) {
-        uint4 u0 = fake, u1 = fake, u2 = fake, d0 = fake, d1 = fake, d2 = fake, s0 = fake, s1 = fake, s2 = fake;
-        if (pu) { u0 = ld_u4_volatile(pu); u1 = ld_u4_volatile(pu + 1); if (three) u2 = ld_u4_volatile(pu + 2); }
-        if (pd) { d0 = ld_u4_volatile(pd); d1 = ld_u4_volatile(pd + 1); if (three) d2 = ld_u4_volatile(pd + 2); }
-        if (ps) { s0 = ld_u4_volatile(ps); s1 = ld_u4_volatile(ps + 1); if (three) s2 = ld_u4_volatile(ps + 2); }
-        if (entry_ok(u0, u1, u2, tag) && entry_ok(d0, d1, d2, tag) && entry_ok(s0, s1, s2, tag)) {
-            if (pu) entry_park(s.stage + 6 * lane, u0, u1, u2);
-            if (pd) entry_park(s.stage + 6 * (32 + lane), d0, d1, d2);
-            if (ps) entry_park(s.stage + 6 * side_slot, s0, s1, s2);
+        uint4 u0 = fake, u1 = fake, d0 = fake, d1 = fake, s0 = fake, s1 = fake;
+        if (pu) { u0 = ld_u4_volatile(pu); u1 = ld_u4_volatile(pu + 1); }
+        if (pd) { d0 = ld_u4_volatile(pd); d1 = ld_u4_volatile(pd + 1); }
+        if (ps) { s0 = ld_u4_volatile(ps); s1 = ld_u4_volatile(ps + 1); }
+        if (entry_ok(u0, u1, tag) && entry_ok(d0, d1, tag) && entry_ok(s0, s1, tag)) {
+            if (pu) entry_park(s.stage + 4 * lane, u0, u1, four);
+            if (pd) entry_park(s.stage + 4 * (32 + lane), d0, d1, four);
+            if (ps) entry_park(s.stage + 4 * side_slot, s0, s1, four);
             return;
         }
         if ((++spins & 0xffu) == 0 && (*(volatile int*)P.status || spins > (1u << 22))) {
@@ -375,47 +375,55 @@ __device__ __forceinline__ void fetch_halo(const ResProb& P, Ctl* ctl, const Str
 __device__ __forceinline__ void apply_x(const StripCtx& s, int lane)
 {
     if (s.rem[0] >= 0) {
-        const float* v = s.stage + 6 * lane;
+        const float* v = s.stage + 4 * lane;
         s.own[0 * TW + lane + 1] = make_float4(v[0], v[1], v[2], v[3]);
         s.rcs[lane] = make_float2(v[2], v[3]);
     }
     if (s.rem[1] >= 0) {
-        const float* v = s.stage + 6 * (32 + lane);
+        const float* v = s.stage + 4 * (32 + lane);
         s.own[(TH - 1) * TW + lane + 1] = make_float4(v[0], v[1], v[2], v[3]);
         s.rcs[32 + lane] = make_float2(v[2], v[3]);
     }
     if (s.rem[2] >= 0 && lane < RS_STRIP_H) {
-        const float* v = s.stage + 6 * (OB_LEFT + lane);
+        const float* v = s.stage + 4 * (OB_LEFT + lane);
         s.own[(lane + 1) * TW + 0] = make_float4(v[0], v[1], v[2], v[3]);
         s.rcs[OB_LEFT + lane] = make_float2(v[2], v[3]);
     }
     if (s.rem[3] >= 0 && lane >= 8 && lane < 8 + RS_STRIP_H) {
-        const float* v = s.stage + 6 * (OB_RIGHT + lane - 8);
+        const float* v = s.stage + 4 * (OB_RIGHT + lane - 8);
         s.own[(lane - 8 + 1) * TW + TW - 1] = make_float4(v[0], v[1], v[2], v[3]);
         s.rcs[OB_RIGHT + lane - 8] = make_float2(v[2], v[3]);
     }
 }
 
-__device__ __forceinline__ float4 p_entry_from(const float* v, float beta, float2 cs)
+// One ring pixel's new direction p = z + beta * p_old from the neighbour's published z; p_old is what this warp computed
+// for that pixel one iteration ago (p_x, p_y in the ring cell, p_a in st[3]).  FIRST: p_0 = z_0 (PCGInit1).
+template <bool FIRST>
+__device__ __forceinline__ void ring_update(float4* cell, float* st, float beta, float2 cs)
 {
-    // v = (z0, z1, z2, p0_old, p1_old, pa_old); cs = (cos, sin)
-    const float p0 = fmaf(beta, v[3], v[0]);
-    const float p1 = fmaf(beta, v[4], v[1]);
-    const float pa = fmaf(beta, v[5], v[2]);
-    return make_float4(p0, p1, cs.y * pa, cs.x * pa);
+    float p0 = st[0], p1 = st[1], pa = st[2];
+    if (!FIRST) {
+        const float4 old = *cell;
+        p0 = fmaf(beta, old.x, p0);
+        p1 = fmaf(beta, old.y, p1);
+        pa = fmaf(beta, st[3], pa);
+    }
+    st[3] = pa;
+    *cell = make_float4(p0, p1, cs.y * pa, cs.x * pa);
 }
 
-// ring <- neighbours' new direction, computed from their published (z, p_old)
+// ring <- neighbours' new direction
+template <bool FIRST>
 __device__ __forceinline__ void apply_p(const StripCtx& s, int lane, float beta)
 {
-    if (s.rem[0] >= 0) s.own[0 * TW + lane + 1] = p_entry_from(s.stage + 6 * lane, beta, s.rcs[lane]);
-    if (s.rem[1] >= 0) s.own[(TH - 1) * TW + lane + 1] = p_entry_from(s.stage + 6 * (32 + lane), beta, s.rcs[32 + lane]);
+    if (s.rem[0] >= 0) ring_update<FIRST>(&s.own[0 * TW + lane + 1], s.stage + 4 * lane, beta, s.rcs[lane]);
+    if (s.rem[1] >= 0) ring_update<FIRST>(&s.own[(TH - 1) * TW + lane + 1], s.stage + 4 * (32 + lane), beta, s.rcs[32 + lane]);
     // left column (lanes 0..H-1) and right column (lanes 8..8+H-1) in one predicated block
     const bool lft = lane < RS_STRIP_H;
     const int row = lft ? lane : lane - 8;
     if ((lft && s.rem[2] >= 0) || (!lft && lane >= 8 && lane < 8 + RS_STRIP_H && s.rem[3] >= 0)) {
         const int slot = (lft ? OB_LEFT : OB_RIGHT) + row;
-        s.own[(row + 1) * TW + (lft ? 0 : TW - 1)] = p_entry_from(s.stage + 6 * slot, beta, s.rcs[slot]);
+        ring_update<FIRST>(&s.own[(row + 1) * TW + (lft ? 0 : TW - 1)], s.stage + 4 * slot, beta, s.rcs[slot]);
     }
 }
 
@@ -494,7 +502,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
     if (s.has) {
         const int2 xy = P.strip_xy[slot];
         sx = xy.x; sy = xy.y;
-        s.outbox = P.outbox + (size_t)slot * RS_OUTBOX_ENTRIES * 3;
+        s.outbox = P.outbox + (size_t)slot * RS_OUTBOX_ENTRIES * 2;
         const int nu = (sy > 0) ? P.slot_of_strip[(sy - 1) * P.SX + sx] : -1;
         const int nd = (sy + 1 < P.SY) ? P.slot_of_strip[(sy + 1) * P.SX + sx] : -1;
         const int nl = (sx > 0) ? P.slot_of_strip[sy * P.SX + sx - 1] : -1;
@@ -505,8 +513,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
         if (nr >= 0) { if (nr >= s_begin && nr < s_end) { if (lane == 31) s.rptr = &S[nr - s_begin].T[1][1]; } else s.rem[3] = nr; }
     }
     s.side_out = nullptr;
-    if (s.has && lane == 0 && s.rem[2] >= 0) s.side_out = s.outbox + 3 * OB_LEFT;
-    if (s.has && lane == 31 && s.rem[3] >= 0) s.side_out = s.outbox + 3 * OB_RIGHT;
+    if (s.has && lane == 0 && s.rem[2] >= 0) s.side_out = s.outbox + 2 * OB_LEFT;
+    if (s.has && lane == 31 && s.rem[3] >= 0) s.side_out = s.outbox + 2 * OB_RIGHT;
     s.x = sx * RS_STRIP_W + lane;
     s.y0 = sy * RS_STRIP_H;
     const bool any_rem = s.has && (s.rem[0] >= 0 || s.rem[1] >= 0 || s.rem[2] >= 0 || s.rem[3] >= 0); // warp-uniform
@@ -564,10 +572,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                     e = make_float4(X.x, X.y, cs, sn);
                 }
                 s.own[(k + 1) * TW + lane + 1] = e;
-                if (any_rem) publish_rowcol(s, lane, k, seq, e.x, e.y, e.z, e.w, 0.f, 0.f, false);
+                if (any_rem) publish_rowcol(s, lane, k, seq, e.x, e.y, e.z, e.w);
             }
             if (any_rem) {
-                fetch_halo(P, &ctl, s, lane, seq, false);
+                fetch_halo(P, &ctl, s, lane, seq, true);
                 apply_x(s, lane);
             }
             __syncthreads();
@@ -659,12 +667,12 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                 for (int k = 0; k < RS_STRIP_H; ++k) {
                     if (any_rem) {
                         const float2 pre = s.pre[k * 32];
-                        publish_rowcol(s, lane, k, seq, pre.x * r0[k], pre.x * r1[k], pre.y * r2[k], 0.f, 0.f, 0.f, true);
+                        publish_rowcol(s, lane, k, seq, pre.x * r0[k], pre.x * r1[k], pre.y * r2[k], 0.f);
                     }
                 }
                 long long ta0 = 0, ta1 = 0;
                 grid_arrive(c, gs0, gs1, S_num, ta0, ta1);
-                if (any_rem) fetch_halo(P, &ctl, s, lane, seq, true); // overlaps the barrier latency
+                if (any_rem) fetch_halo(P, &ctl, s, lane, seq, false); // overlaps the barrier latency
                 num = grid_finish(c, gs0, gs1, S_num, ok, ta0, ta1); // solverGPUGaussNewton.t:395 scanAlphaNumerator
                 if (!ok) break;
                 // p_0 = z_0 into the tile (all warps are past their J^T F reads: grid_sum synchronised)
@@ -676,7 +684,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                     pa[k] = pA * r2[k];
                     s.own[(k + 1) * TW + lane + 1] = make_float4(p0, p1, ss[k] * pa[k], cc[k] * pa[k]);
                 }
-                if (any_rem) apply_p(s, lane, 0.0f);
+                if (any_rem) apply_p<true>(s, lane, 0.0f);
                 // N4 (opt-in, never on the parity path): relative tolerance on the preconditioned residual norm
                 if (threadIdx.x == 0) ctl.stop = (P.pcg_rtol2 > 0.0f) ? P.pcg_rtol2 * num : -1.0f;
                 __syncthreads();
@@ -763,12 +771,12 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                     const float z0 = pX * r0[k], z1 = pX * r1[k], z2 = pA * r2[k];
                     const float term = dot3(z0, z1, z2, r0[k], r1[k], r2[k]);
                     if (k < 4) gs0 = gs0 + term; else gs1 = gs1 + term;
-                    if (pub) publish_rowcol(s, lane, k, seq, z0, z1, z2, e.x, e.y, pa[k], true);
+                    if (pub) publish_rowcol(s, lane, k, seq, z0, z1, z2, 0.f);
                 }
                 RS_TICK(1);
                 long long tb0 = 0, tb1 = 0;
                 grid_arrive(c, gs0, gs1, S_bnum, tb0, tb1);
-                if (pub) fetch_halo(P, &ctl, s, lane, seq, true); // overlaps the barrier latency
+                if (pub) fetch_halo(P, &ctl, s, lane, seq, false); // overlaps the barrier latency
                 const float bnum = grid_finish(c, gs0, gs1, S_bnum, ok, tb0, tb1);
                 RS_TOCK();
                 if (!ok) break;
@@ -792,7 +800,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                     pa[k] = fmaf(beta, pa[k], pA * r2[k]);
                     s.own[(k + 1) * TW + lane + 1] = make_float4(p0, p1, ss[k] * pa[k], cc[k] * pa[k]);
                 }
-                if (any_rem) apply_p(s, lane, beta);
+                if (any_rem) apply_p<false>(s, lane, beta);
                 __syncthreads();
                 RS_TICK(2);
             }
@@ -937,7 +945,7 @@ ResidentSolver::ResidentSolver(int maxW, int maxH, int max_slots) : maxW_(maxW),
         ARAP_CUDA_OR_EXIT(cudaMalloc(&sl.d_count, sizeof(int)));
         // the outbox only has to hold what can be resident: at most sm_count * max warps strips
         const size_t ob = std::min(strip_cap_, (size_t)sm_count_ * (RS_THREADS_MAX / 32));
-        ARAP_CUDA_OR_EXIT(cudaMalloc(&sl.d_outbox, ob * RS_OUTBOX_ENTRIES * 3 * sizeof(uint4)));
+        ARAP_CUDA_OR_EXIT(cudaMalloc(&sl.d_outbox, ob * RS_OUTBOX_ENTRIES * 2 * sizeof(uint4)));
         ARAP_CUDA_OR_EXIT(cudaMalloc(&sl.d_bar, 8 * BAR_STRIDE * sizeof(unsigned long long)));
     }
     ARAP_CUDA_OR_EXIT(cudaMallocHost(&h_counts_, slots_.size() * sizeof(int)));
@@ -1050,7 +1058,7 @@ void ResidentSolver::enqueue_group(int first, int count, int nCont, int nGN, int
         // barrier words start at zero; halo tags start at 1, so a zeroed outbox is "nothing published yet"
         ARAP_CUDA_OR_EXIT(cudaMemsetAsync(sl.d_bar, 0, 8 * BAR_STRIDE * sizeof(unsigned long long), stream));
         ARAP_CUDA_OR_EXIT(cudaMemsetAsync(sl.d_outbox, 0,
-                                          (size_t)(sl.n_strips > 0 ? sl.n_strips : 1) * RS_OUTBOX_ENTRIES * 3 * sizeof(uint4), stream));
+                                          (size_t)(sl.n_strips > 0 ? sl.n_strips : 1) * RS_OUTBOX_ENTRIES * 2 * sizeof(uint4), stream));
     }
     ARAP_CUDA_OR_EXIT(cudaMemcpyAsync(d_probs_ + first, host.data(), count * sizeof(ResProb), cudaMemcpyHostToDevice, stream));
     // the live CTAs of all problems form one 1-D grid; the variant with the most registers that keeps them co-resident

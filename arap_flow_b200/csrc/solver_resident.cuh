@@ -16,7 +16,7 @@ constexpr int RS_STRIP_W = 32;   // a strip is 32 x RS_STRIP_H pixels: one warp,
 constexpr int RS_STRIP_H = ARAP_RS_STRIP_H; // 4 (one contract-C3 group per lane) or 8 (two)
 constexpr int RS_MAX_WARPS = 16; // strips per CTA
 constexpr int RS_MAX_CTAS = 160; // CTAs per problem (8-bit arrival count per barrier word)
-constexpr int RS_OUTBOX_ENTRIES = 64 + 2 * RS_STRIP_H; // top row, bottom row, left column, right column; 48 bytes each
+constexpr int RS_OUTBOX_ENTRIES = 64 + 2 * RS_STRIP_H; // top row, bottom row, left column, right column; 32 bytes each
 
 // One problem as the kernel sees it (device memory, one per blockIdx.y)
 struct ResProb {
@@ -31,7 +31,7 @@ struct ResProb {
     float wf, wr, wf2, wr2;
     const int2* strip_xy;      // [n_strips] strip coordinates (sx, sy), column-major order
     const int* slot_of_strip;  // [SY*SX] -> slot or -1
-    uint4* outbox;             // [n_strips][RS_OUTBOX_ENTRIES][3]: six (float, tag) words per boundary pixel
+    uint4* outbox;             // [n_strips][RS_OUTBOX_ENTRIES][2]: four (float, tag) words per boundary pixel
     unsigned long long* bar;   // [2][4] barrier words: 16-bit arrival count | 48-bit fixed-point limb sum
     float* costs;              // [nCont][nGN+1]
     float* trace;              // optional [nCont*nGN][nPCG][3]
