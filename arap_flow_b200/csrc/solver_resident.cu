@@ -538,10 +538,6 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
         if (k < 4) flo |= f << (8 * k); else fhi |= f << (8 * (k - 4));
     }
 
-    // warp-uniform: every pixel of the strip is active with four valid neighbours -> mask-free fast paths
-    const bool interior = __all_sync(0xffffffffu, (flo & 0x2f2f2f2fu) == 0x2f2f2f2fu &&
-                                                      (RS_STRIP_H == 4 || (fhi & 0x2f2f2f2fu) == 0x2f2f2f2fu));
-
     // registers that live across the PCG loop
     float r0[RS_STRIP_H], r1[RS_STRIP_H], r2[RS_STRIP_H];
     float pa[RS_STRIP_H], cc[RS_STRIP_H], ss[RS_STRIP_H];
@@ -693,58 +689,31 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
             // ======== PCG iterations ========
             RS_TICK(3);
             for (int it = 0; it < P.nPCG; ++it) {
-                // ---- PCGStep1: q = J^T J p, den = sum p.q.  Branch-free: an invalid neighbour is replaced by
-                // (own p_x, own p_y, 0, 0), which contributes exact zeros; inactive pixels hold zeros throughout.
+                // ---- PCGStep1: q = J^T J p, den = sum p.q.  Inactive pixels hold zeros throughout.
                 float gs0 = 0.f, gs1 = 0.f;
-                if (interior) {
-                    // all neighbours valid: S = sum d = 0 (no own-angle term), |d|^2 sum = 4, no selects
-                    float4 up = s.up_row[lane], cur = s.own[1 * TW + lane + 1];
+                // One code path for every strip: 0/1-masked FMAs (bit-identical to skipping invalid neighbours).  A
+                // second, mask-free path for all-interior strips made the kernel SLOWER (7.51 vs 7.88 pairs/s on C1):
+                // warps of one CTA then finish phase 1 at different times and the loop body doubles in size.
+                float4 up = s.up_row[lane], cur = s.own[1 * TW + lane + 1];
 #pragma unroll
-                    for (int k = 0; k < RS_STRIP_H; ++k) {
-                        const float4 dn = (k < RS_STRIP_H - 1) ? s.own[(k + 2) * TW + lane + 1] : s.down_row[lane];
-                        const float4 lf = s.lptr[k * TW], rt = s.rptr[k * TW];
-                        JtjAcc a;
-                        jtj_zero(a);
-                        jtj_nb<0>(a, cur.x, cur.y, rt);
-                        jtj_nb<1>(a, cur.x, cur.y, lf);
-                        jtj_nb<2>(a, cur.x, cur.y, dn);
-                        jtj_nb<3>(a, cur.x, cur.y, up);
-                        const float t0 = (a.sd0 + a.sd0) - a.nb0, t1 = (a.sd1 + a.sd1) - a.nb1;
-                        float qq0 = wr2 * t0, qq1 = wr2 * t1;
-                        const float rdp = fmaf(cc[k], a.dc, -(ss[k] * a.dd));
-                        qa[k] = wr2 * fmaf(4.0f, pa[k], -rdp);
-                        if (flag_of(flo, fhi, k) & FLAG_FIT) {
-                            qq0 = fmaf(wf2, cur.x, qq0);
-                            qq1 = fmaf(wf2, cur.y, qq1);
-                        }
-                        q0[k] = qq0; q1[k] = qq1;
-                        const float term = dot3(cur.x, cur.y, pa[k], qq0, qq1, qa[k]);
-                        if (k < 4) gs0 = gs0 + term; else gs1 = gs1 + term;
-                        up = cur;
-                        cur = dn;
-                    }
-                } else {
-                    float4 up = s.up_row[lane], cur = s.own[1 * TW + lane + 1];
-#pragma unroll
-                    for (int k = 0; k < RS_STRIP_H; ++k) {
-                        const float4 dn = (k < RS_STRIP_H - 1) ? s.own[(k + 2) * TW + lane + 1] : s.down_row[lane];
-                        const float4 lf = s.lptr[k * TW], rt = s.rptr[k * TW];
-                        const unsigned f = flag_of(flo, fhi, k);
-                        // validity as 0/1 multipliers (every tile cell holds finite data: tiles are zeroed at start)
-                        const float m0 = (f & 1u) ? 1.0f : 0.0f, m1 = (f & 2u) ? 1.0f : 0.0f;
-                        const float m2 = (f & 4u) ? 1.0f : 0.0f, m3 = (f & 8u) ? 1.0f : 0.0f;
-                        JtjAcc a;
-                        jtj_zero(a);
-                        jtj_nb_masked<0>(a, cur.x, cur.y, rt, m0);
-                        jtj_nb_masked<1>(a, cur.x, cur.y, lf, m1);
-                        jtj_nb_masked<2>(a, cur.x, cur.y, dn, m2);
-                        jtj_nb_masked<3>(a, cur.x, cur.y, up, m3);
-                        jtj_finish(a, cc[k], ss[k], cur.x, cur.y, pa[k], (f & FLAG_FIT) != 0, wr2, wf2, q0[k], q1[k], qa[k]);
-                        const float term = dot3(cur.x, cur.y, pa[k], q0[k], q1[k], qa[k]);
-                        if (k < 4) gs0 = gs0 + term; else gs1 = gs1 + term;
-                        up = cur;
-                        cur = dn;
-                    }
+                for (int k = 0; k < RS_STRIP_H; ++k) {
+                    const float4 dn = (k < RS_STRIP_H - 1) ? s.own[(k + 2) * TW + lane + 1] : s.down_row[lane];
+                    const float4 lf = s.lptr[k * TW], rt = s.rptr[k * TW];
+                    const unsigned f = flag_of(flo, fhi, k);
+                    // validity as 0/1 multipliers (every tile cell holds finite data: tiles are zeroed at start)
+                    const float m0 = (f & 1u) ? 1.0f : 0.0f, m1 = (f & 2u) ? 1.0f : 0.0f;
+                    const float m2 = (f & 4u) ? 1.0f : 0.0f, m3 = (f & 8u) ? 1.0f : 0.0f;
+                    JtjAcc a;
+                    jtj_zero(a);
+                    jtj_nb_masked<0>(a, cur.x, cur.y, rt, m0);
+                    jtj_nb_masked<1>(a, cur.x, cur.y, lf, m1);
+                    jtj_nb_masked<2>(a, cur.x, cur.y, dn, m2);
+                    jtj_nb_masked<3>(a, cur.x, cur.y, up, m3);
+                    jtj_finish(a, cc[k], ss[k], cur.x, cur.y, pa[k], (f & FLAG_FIT) != 0, wr2, wf2, q0[k], q1[k], qa[k]);
+                    const float term = dot3(cur.x, cur.y, pa[k], q0[k], q1[k], qa[k]);
+                    if (k < 4) gs0 = gs0 + term; else gs1 = gs1 + term;
+                    up = cur;
+                    cur = dn;
                 }
                 RS_TICK(0);
                 const float den = grid_sum(c, gs0, gs1, S_den, ok);
