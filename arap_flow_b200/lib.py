@@ -216,13 +216,16 @@ class Batch:
         self.L.arapb200_batch_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
         _check(self.L.arapb200_batch_set_option(self.h, name.encode(), float(value)), "arapb200_batch_set_option")
 
-    def submit(self, slot, rgb, mask_red, matches):
+    def submit(self, slot, rgb, mask_red, matches, out=None):
+        """Queue one problem.  `out` may be the dict a previous submit() of the same image size returned: its arrays are
+        then written in place instead of allocating fresh ones (what a caller looping over many pairs does)."""
         H, W = mask_red.shape
         rgb = _c(rgb, np.uint8)
         mask_red = _c(mask_red, np.uint8)
         m = _c(matches, np.int32).reshape(-1, 4)
-        out = dict(flow=np.zeros((H, W, 2), np.float32), rgb=np.zeros((H, W, 3), np.uint8),
-                   mask=np.zeros((H, W), np.uint8), costs=np.zeros((self.nCont, self.nGN + 1), np.float32))
+        if out is None or out["flow"].shape != (H, W, 2):
+            out = dict(flow=np.zeros((H, W, 2), np.float32), rgb=np.zeros((H, W, 3), np.uint8),
+                       mask=np.zeros((H, W), np.uint8), costs=np.zeros((self.nCont, self.nGN + 1), np.float32))
         self._keep[slot] = (rgb, mask_red, m, out)
         _check(self.L.arapb200_batch_submit(self.h, slot, W, H, rgb.ctypes.data, mask_red.ctypes.data, m.ctypes.data,
                                             len(m), out["flow"].ctypes.data, out["rgb"].ctypes.data,

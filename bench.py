@@ -199,8 +199,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    out_bufs = [None] * len(problems)   # output arrays are allocated once and reused, as a caller looping over pairs would
+
     def one_step():
-        outs = [batch.submit(i, p.rgb, m, p.matches) for i, (p, m) in enumerate(problems)]
+        outs = [batch.submit(i, p.rgb, m, p.matches, out=out_bufs[i]) for i, (p, m) in enumerate(problems)]
+        out_bufs[:] = outs
         batch.run()
         if nseg > 1:  # layer flatten of every pair (para_gen.py:136-175) belongs to the pair's end-to-end time
             for k in range(len(pairs)):
