@@ -38,7 +38,7 @@ static void usage()
     puts("warped_Mask \t [output] path to output warped mask (.png), all intermediate directories must exist");
     puts("\n./arap_deform LISTFILE   (one such 6-tuple per line)");
     puts("Environment: ARAP_PLAN = path of the ARAP energy file (default ./arap_plan.t); CUDA_VISIBLE_DEVICES selects the GPU;");
-    puts("             ARAP_BATCH = problems solved together (default 8)");
+    puts("             ARAP_BATCH = problems solved together (default 9: three cooperative launches of three)");
     puts("             ARAP_PCG_RTOL = opt-in relative PCG tolerance, e.g. 1e-3 (default 0: fixed 400 iterations)");
     puts("             ARAP_GN_RTOL = opt-in relative cost-decrease tolerance of the Gauss-Newton steps (default 0: fixed 8 steps)");
 }
@@ -88,7 +88,7 @@ int main(int argc, const char* argv[])
     }
     // the solver budget is a compile-time constant of the reference: main.cpp:215-221
     const int nCont = 19, nGN = 8, nPCG = 400;
-    int batch = getenv("ARAP_BATCH") ? atoi(getenv("ARAP_BATCH")) : 8;
+    int batch = getenv("ARAP_BATCH") ? atoi(getenv("ARAP_BATCH")) : 9;
     if (batch < 1) batch = 1;
     // opt-in, off by default: convergence-aware PCG loops (changes results; include/arapb200.h)
     const double pcg_rtol = getenv("ARAP_PCG_RTOL") ? atof(getenv("ARAP_PCG_RTOL")) : 0.0;

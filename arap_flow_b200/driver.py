@@ -47,7 +47,7 @@ def shard(items: Sequence[Item], rank: int, world: int) -> List[Item]:
     return [it for i, it in enumerate(items) if i % world == rank]
 
 
-def do_arap(items: Sequence[Item], gpu: int, tmp_dir: str, arap_bin: str = ARAP_BIN, plan: str = PLAN, batch: int = 8):
+def do_arap(items: Sequence[Item], gpu: int, tmp_dir: str, arap_bin: str = ARAP_BIN, plan: str = PLAN, batch: int = 9):
     """para_gen.do_arap (para_gen.py:178-200): write a temporary list file, run the solver binary on one GPU, assert
     a zero exit code, always remove the list file.  Returns the elapsed seconds."""
     os.makedirs(tmp_dir, exist_ok=True)

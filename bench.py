@@ -39,11 +39,13 @@ def make_pairs(workload: str, count: int, first: int):
     return [synth.synth(W, H, nseg, fd, seed0 + first + i, axes=axes) for i in range(count)]
 
 
-def measured_traffic():
-    """DRAM bytes per k_resident launch from the committed ncu capture (profiles/r1_traffic.json), or None."""
+def measured_traffic(problems_per_launch: int):
+    """DRAM bytes of one k_resident launch of that many co-resident problems, from the committed ncu captures
+    (profiles/r1_traffic.json), or None."""
     p = os.path.join(ROOT, "profiles", "r1_traffic.json")
     try:
-        return int(json.load(open(p))["dram_bytes_per_launch"])
+        with open(p) as f:
+            return int(json.load(f)["launches"][str(problems_per_launch)]["dram_bytes_per_launch"])
     except Exception:
         return None
 
@@ -183,9 +185,10 @@ def main():
     lib.load()
     backend = {"auto": lib.BACKEND_AUTO, "stream": lib.BACKEND_STREAM, "resident": lib.BACKEND_RESIDENT}[args.backend]
     W, H = WORKLOADS[args.workload][:2]
-    # resident back-end: 4 problems share one cooperative launch (one CTA of each per SM); 8 = two such launches
+    # resident back-end: 3 (168 registers) or 4 (128 registers) problems share one cooperative launch; 9 = three launches of
+    # three, measured 2 % faster than two launches of four (profiles/r1_batch_choice.txt)
     B = args.batch if args.batch > 0 else (1 if (args.backend == "stream" or args.workload == "C4") else
-                                           (2 if args.workload == "C2" else 8))
+                                           (2 if args.workload == "C2" else 9))
     pairs = make_pairs(args.workload, B, first=rank * B)
     nseg = WORKLOADS[args.workload][2]
     # --multseg (C2): one independent problem per segment, all of them sharing the pair's constraint list
@@ -269,7 +272,7 @@ def main():
             "gpu_launches": int(lt.cpu()[0]),
             "ms_per_gn_solve": solve_ms_max / (B * args.steps * NCONT * NGN),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (measured_traffic() if not streamed and B % 4 == 0 and args.workload == "C1" else None),
+                         "traffic": (measured_traffic(3 if B % 3 == 0 else 4) if not streamed and (B % 3 == 0 or B % 4 == 0) and args.workload == "C1" else None),
                          "peak_source": peak_src,
                          "kernel": "k_resident (persistent fused GN/PCG solve; 156 B/active px/PCG iteration algorithmic, "
                                    "state on chip so a fraction > 1 of the STREAMING roofline is possible)" if not streamed

@@ -14,5 +14,6 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 tools/kernel_times.sh stream C4 8 1 > gpurun_out/stream_kernel_times.txt 2>&1; grep -E "k_step|k_init" gpurun_out/stream_kernel_times.txt
 # DRAM traffic of one full-schedule resident launch (4 co-resident C1 problems)
 timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:k_resident --launch-skip 1 --launch-count 1 --csv --log-file gpurun_out/traffic_resident.csv python bench.py --steps 1 --warmup 1 --batch 4 --no-cpu-baseline > gpurun_out/ncu_traffic.log 2>&1 || echo "traffic capture failed"
-tail -4 gpurun_out/traffic_resident.csv
+timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:k_resident --launch-skip 1 --launch-count 1 --csv --log-file gpurun_out/traffic_resident3.csv python bench.py --steps 1 --warmup 1 --batch 3 --no-cpu-baseline > gpurun_out/ncu_traffic3.log 2>&1 || echo "traffic capture (3) failed"
+tail -2 gpurun_out/traffic_resident.csv; tail -2 gpurun_out/traffic_resident3.csv   # then: python tools/update_traffic.py
 timeout 300 python tools/cli_throughput.py 64 > gpurun_out/cli_throughput.txt 2>&1; cat gpurun_out/cli_throughput.txt
