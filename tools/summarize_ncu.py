@@ -68,8 +68,10 @@ def stalls(rep, warps, iters):
 if __name__ == "__main__":
     launch_list(os.path.join(G, "bench_launch_list.csv"), os.path.join(P, "r1_bench_launch_list.csv"),
                 "ncu launch list: python bench.py --steps 1 --warmup 1 --no-cpu-baseline (round 1; 2 steps x 9 pairs, C1)")
-    L = full(os.path.join(G, "r1_resident_b4_final.ncu-rep"), "tools/ncu_target.py resident C1 50 4: 4 co-resident 854x480 problems, 1x1x50 PCG iterations")
-    L += stalls(os.path.join(G, "r1_resident_b4_final.ncu-rep"), 555 * 4, 52)
+    L = full(os.path.join(G, "r1_resident_b3_final.ncu-rep"), "tools/ncu_target.py resident C1 50 3: 3 co-resident 854x480 problems (the default bench's launch shape, 168-register variant), 1x1x50 PCG iterations")
+    L += stalls(os.path.join(G, "r1_resident_b3_final.ncu-rep"), 584 * 3, 52)
+    L += [""] + full(os.path.join(G, "r1_resident_b4_final.ncu-rep"), "tools/ncu_target.py resident C1 50 4: 4 co-resident problems (128-register variant)")
+    L += stalls(os.path.join(G, "r1_resident_b4_final.ncu-rep"), 584 * 4, 52)
     L += [""] + full(os.path.join(G, "r1_stream_c4_final.ncu-rep"), "tools/ncu_target.py stream C4 8 1: 1920x1080 (1 378 443 active px) through the streaming back-end "
                      "(tile-interleaved layout; warm-cache per-kernel times of the final kernels: r1_stream_kernel_times.txt)")
     open(os.path.join(P, "r1_ncu_full_summary.txt"), "w").write("\n".join(L) + "\n")
