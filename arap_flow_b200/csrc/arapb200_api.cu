@@ -15,17 +15,17 @@ template <class T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
-    explicit DevBuf(size_t count) : n(count) { ARAP_CUDA_OR_EXIT(cudaMalloc(&p, (count ? count : 1) * sizeof(T))); }
+    explicit DevBuf(size_t count) : n(count) { ARAP_CUDA_CHECK(cudaMalloc(&p, (count ? count : 1) * sizeof(T))); }
     ~DevBuf() { cudaFree(p); }
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     void up(const T* h, cudaStream_t s = nullptr)
     {
-        ARAP_CUDA_OR_EXIT(cudaMemcpyAsync(p, h, n * sizeof(T), cudaMemcpyHostToDevice, s));
+        ARAP_CUDA_CHECK(cudaMemcpyAsync(p, h, n * sizeof(T), cudaMemcpyHostToDevice, s));
     }
     void down(T* h, cudaStream_t s = nullptr)
     {
-        ARAP_CUDA_OR_EXIT(cudaMemcpyAsync(h, p, n * sizeof(T), cudaMemcpyDeviceToHost, s));
+        ARAP_CUDA_CHECK(cudaMemcpyAsync(h, p, n * sizeof(T), cudaMemcpyDeviceToHost, s));
     }
 };
 
@@ -53,6 +53,23 @@ int warp_common(int W, int H, const float* pos_or_flow, bool is_flow, const uint
     return 0;
 }
 
+// every extern "C" entry point runs its body through this: an ArapError (CUDA failure, watchdog, capacity) becomes the
+// function's non-zero return code instead of taking the host process down
+template <class F>
+int guarded(F&& f)
+{
+    try {
+        return f();
+    } catch (const ArapError& e) {
+        return e.code;
+    } catch (const std::exception& e) {
+        fprintf(stderr, "arapb200: %s\n", e.what());
+        return 2;
+    } catch (...) {
+        return 2;
+    }
+}
+
 } // namespace
 
 struct arapb200_batch {
@@ -71,50 +88,64 @@ const char* arapb200_version(void) { return "arapb200 0.1.0 (sm_100a)"; }
 
 int arapb200_device_info(int* sm_count, size_t* l2_bytes, int* cc_major, int* cc_minor)
 {
-    int dev = 0;
-    ARAP_CUDA_OR_RETURN(cudaGetDevice(&dev));
-    cudaDeviceProp p;
-    ARAP_CUDA_OR_RETURN(cudaGetDeviceProperties(&p, dev));
-    if (sm_count) *sm_count = p.multiProcessorCount;
-    if (l2_bytes) *l2_bytes = (size_t)p.l2CacheSize;
-    if (cc_major) *cc_major = p.major;
-    if (cc_minor) *cc_minor = p.minor;
-    return 0;
+    return guarded([&]() -> int {
+        int dev = 0;
+        ARAP_CUDA_OR_RETURN(cudaGetDevice(&dev));
+        cudaDeviceProp p;
+        ARAP_CUDA_OR_RETURN(cudaGetDeviceProperties(&p, dev));
+        if (sm_count) *sm_count = p.multiProcessorCount;
+        if (l2_bytes) *l2_bytes = (size_t)p.l2CacheSize;
+        if (cc_major) *cc_major = p.major;
+        if (cc_minor) *cc_minor = p.minor;
+        return 0;
+    });
 }
 
 int arapb200_warp(int W, int H, const float* pos, const uint8_t* rgb, const uint8_t* mask_red, uint8_t* out_rgb,
                   uint8_t* out_mask, uint32_t* out_splat)
 {
-    return warp_common(W, H, pos, false, rgb, mask_red, out_rgb, out_mask, out_splat);
+    return guarded([&]() -> int {
+        return warp_common(W, H, pos, false, rgb, mask_red, out_rgb, out_mask, out_splat);
+    });
 }
 
 int arapb200_warp_flow(int W, int H, const float* flow, const uint8_t* rgb, const uint8_t* mask_red,
                        uint8_t* out_rgb, uint8_t* out_mask, uint32_t* out_splat)
 {
-    return warp_common(W, H, flow, true, rgb, mask_red, out_rgb, out_mask, out_splat);
+    return guarded([&]() -> int {
+        return warp_common(W, H, flow, true, rgb, mask_red, out_rgb, out_mask, out_splat);
+    });
 }
 
 int arapb200_deform(int W, int H, const uint8_t* rgb, const uint8_t* mask_red, const int32_t* matches, int n_matches,
                     int nCont, int nGN, int nPCG, int backend, float* out_flow, uint8_t* out_rgb, uint8_t* out_mask,
                     float* out_costs)
 {
-    if (W <= 0 || H <= 0 || !rgb || !mask_red || (n_matches > 0 && !matches)) return 1;
-    BatchPipeline pipe(W, H, 1, nCont, nGN, nPCG, backend);
-    HostProblem hp;
-    hp.W = W; hp.H = H; hp.rgb = rgb; hp.mask_red = mask_red; hp.matches = matches; hp.n_matches = n_matches;
-    hp.out_flow = out_flow; hp.out_rgb = out_rgb; hp.out_mask = out_mask; hp.out_costs = out_costs;
-    return pipe.run(&hp, 1);
+    return guarded([&]() -> int {
+        if (W <= 0 || H <= 0 || !rgb || !mask_red || (n_matches > 0 && !matches)) return 1;
+        BatchPipeline pipe(W, H, 1, nCont, nGN, nPCG, backend);
+        HostProblem hp;
+        hp.W = W; hp.H = H; hp.rgb = rgb; hp.mask_red = mask_red; hp.matches = matches; hp.n_matches = n_matches;
+        hp.out_flow = out_flow; hp.out_rgb = out_rgb; hp.out_mask = out_mask; hp.out_costs = out_costs;
+        return pipe.run(&hp, 1);
+    });
 }
 
 arapb200_batch* arapb200_batch_create(int maxW, int maxH, int max_problems, int nCont, int nGN, int nPCG, int backend)
 {
     if (maxW <= 0 || maxH <= 0 || max_problems <= 0) return nullptr;
-    arapb200_batch* b = new arapb200_batch;
-    b->maxW = maxW; b->maxH = maxH; b->max_problems = max_problems;
-    b->nCont = nCont; b->nGN = nGN; b->nPCG = nPCG; b->backend = backend;
-    b->pipe.reset(new BatchPipeline(maxW, maxH, max_problems, nCont, nGN, nPCG, backend));
-    b->slots.resize(max_problems);
-    b->pending.assign(max_problems, 0);
+    if (nCont < 0 || nGN < 0 || nPCG < 0 || backend < ARAPB200_BACKEND_AUTO || backend > ARAPB200_BACKEND_RESIDENT) return nullptr;
+    arapb200_batch* b = nullptr;
+    const int rc = guarded([&]() -> int {
+        b = new arapb200_batch;
+        b->maxW = maxW; b->maxH = maxH; b->max_problems = max_problems;
+        b->nCont = nCont; b->nGN = nGN; b->nPCG = nPCG; b->backend = backend;
+        b->pipe.reset(new BatchPipeline(maxW, maxH, max_problems, nCont, nGN, nPCG, backend));
+        b->slots.resize(max_problems);
+        b->pending.assign(max_problems, 0);
+        return 0;
+    });
+    if (rc) { delete b; return nullptr; }
     return b;
 }
 
@@ -124,88 +155,112 @@ int arapb200_batch_submit(arapb200_batch* b, int slot, int W, int H, const uint8
                           const int32_t* matches, int n_matches, float* out_flow, uint8_t* out_rgb,
                           uint8_t* out_mask, float* out_costs)
 {
-    if (!b || slot < 0 || slot >= b->max_problems) return 1;
-    HostProblem& hp = b->slots[slot];
-    hp.W = W; hp.H = H; hp.rgb = rgb; hp.mask_red = mask_red; hp.matches = matches; hp.n_matches = n_matches;
-    hp.out_flow = out_flow; hp.out_rgb = out_rgb; hp.out_mask = out_mask; hp.out_costs = out_costs;
-    b->pending[slot] = 1;
-    return 0;
+    return guarded([&]() -> int {
+        if (!b || slot < 0 || slot >= b->max_problems) return 1;
+        // everything run() will dereference is checked here, while the caller can still be told
+        if (W <= 0 || H <= 0 || (size_t)W * H > (size_t)b->maxW * b->maxH || !rgb || !mask_red || n_matches < 0 ||
+            (n_matches > 0 && !matches)) {
+            fprintf(stderr, "arapb200: batch_submit: bad problem (%dx%d in a %dx%d batch, %d matches, null input?)\n", W, H,
+                    b->maxW, b->maxH, n_matches);
+            return 1;
+        }
+        HostProblem& hp = b->slots[slot];
+        hp.W = W; hp.H = H; hp.rgb = rgb; hp.mask_red = mask_red; hp.matches = matches; hp.n_matches = n_matches;
+        hp.out_flow = out_flow; hp.out_rgb = out_rgb; hp.out_mask = out_mask; hp.out_costs = out_costs;
+        b->pending[slot] = 1;
+        return 0;
+    });
 }
 
 int arapb200_batch_run(arapb200_batch* b)
 {
-    if (!b) return 1;
-    b->ms[0] = b->ms[1] = b->ms[2] = 0.f;
-    const long long l0 = b->pipe->launches();
-    b->todo.clear();
-    for (int s = 0; s < b->max_problems; ++s)
-        if (b->pending[s]) {
-            b->todo.push_back(b->slots[s]);
-            b->pending[s] = 0;
-        }
-    const int rc = b->pipe->run(b->todo.data(), (int)b->todo.size());
-    if (rc) return rc;
-    b->ms[0] = b->pipe->last_ms_total();
-    b->ms[1] = b->pipe->last_ms_solve();
-    b->ms[2] = b->pipe->last_ms_warp();
-    b->launches = b->pipe->launches() - l0;
-    return 0;
+    return guarded([&]() -> int {
+        if (!b) return 1;
+        b->ms[0] = b->ms[1] = b->ms[2] = 0.f;
+        const long long l0 = b->pipe->launches();
+        b->todo.clear();
+        for (int s = 0; s < b->max_problems; ++s)
+            if (b->pending[s]) {
+                b->todo.push_back(b->slots[s]);
+                b->pending[s] = 0;
+            }
+        const int rc = b->pipe->run(b->todo.data(), (int)b->todo.size());
+        if (rc) return rc;
+        b->ms[0] = b->pipe->last_ms_total();
+        b->ms[1] = b->pipe->last_ms_solve();
+        b->ms[2] = b->pipe->last_ms_warp();
+        b->launches = b->pipe->launches() - l0;
+        return 0;
+    });
 }
 
 int arapb200_batch_timing(arapb200_batch* b, float* ms3)
 {
-    if (!b || !ms3) return 1;
-    ms3[0] = b->ms[0]; ms3[1] = b->ms[1]; ms3[2] = b->ms[2];
-    return 0;
+    return guarded([&]() -> int {
+        if (!b || !ms3) return 1;
+        ms3[0] = b->ms[0]; ms3[1] = b->ms[1]; ms3[2] = b->ms[2];
+        return 0;
+    });
 }
 
 long long arapb200_batch_launches(arapb200_batch* b) { return b ? b->launches : 0; }
 
 int arapb200_batch_resident_count(arapb200_batch* b) { return b ? b->pipe->last_resident_count() : 0; }
 
+int arapb200_batch_launch_info(arapb200_batch* b, int* info6)
+{
+    if (!b || !info6) return 1;
+    b->pipe->last_launch_info(info6);
+    return 0;
+}
+
 int arapb200_batch_set_option(arapb200_batch* b, const char* name, double value)
 {
-    if (!b || !name) return 1;
-    if (strcmp(name, "pcg_rtol") == 0) {
-        if (!(value >= 0.0) || value >= 1.0) return 1;
-        b->pipe->set_pcg_rtol((float)value);
-        return 0;
-    }
-    if (strcmp(name, "gn_rtol") == 0) {
-        if (!(value >= 0.0) || value >= 1.0) return 1;
-        b->pipe->set_gn_rtol((float)value);
-        return 0;
-    }
-    return 1;
+    return guarded([&]() -> int {
+        if (!b || !name) return 1;
+        if (strcmp(name, "pcg_rtol") == 0) {
+            if (!(value >= 0.0) || value >= 1.0) return 1;
+            b->pipe->set_pcg_rtol((float)value);
+            return 0;
+        }
+        if (strcmp(name, "gn_rtol") == 0) {
+            if (!(value >= 0.0) || value >= 1.0) return 1;
+            b->pipe->set_gn_rtol((float)value);
+            return 0;
+        }
+        return 1;
+    });
 }
 
 // ------------------------------------------------------------------------------------ debug / parity
 int arapb200_debug_gn_solve(int W, int H, float* X, float* A, const float* U, const float* C, const float* M,
                             float wf, float wr, int nGN, int nPCG, int backend, float* costs, float* scal)
 {
-    const size_t N = (size_t)W * H;
-    DevBuf<float2> dX(N), dU(N), dC(N);
-    DevBuf<float> dA(N), dM(N);
-    DevBuf<float> dtr(scal ? (size_t)3 * nGN * nPCG : 0);
-    dX.up((const float2*)X); dU.up((const float2*)U); dC.up((const float2*)C); dA.up(A); dM.up(M);
-    ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
-    GnPlan plan(W, H, 0, backend);
-    plan.set_parameter("nIterations", &nGN);
-    plan.set_parameter("lIterations", &nPCG);
-    if (scal) plan.set_trace(dtr.p);
-    void* pp[7] = {dX.p, dA.p, dU.p, dC.p, dM.p, &wf, &wr};
-    plan.init(pp);
-    if (costs) costs[0] = (float)plan.current_cost();
-    int g = 0;
-    while (plan.step(pp)) {
-        ++g;
-        if (costs) costs[g] = (float)plan.current_cost();
-    }
-    dX.down((float2*)X);
-    dA.down(A);
-    if (scal) dtr.down(scal);
-    ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
-    return 0;
+    return guarded([&]() -> int {
+        const size_t N = (size_t)W * H;
+        DevBuf<float2> dX(N), dU(N), dC(N);
+        DevBuf<float> dA(N), dM(N);
+        DevBuf<float> dtr(scal ? (size_t)3 * nGN * nPCG : 0);
+        dX.up((const float2*)X); dU.up((const float2*)U); dC.up((const float2*)C); dA.up(A); dM.up(M);
+        ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
+        GnPlan plan(W, H, 0, backend);
+        plan.set_parameter("nIterations", &nGN);
+        plan.set_parameter("lIterations", &nPCG);
+        if (scal) plan.set_trace(dtr.p);
+        void* pp[7] = {dX.p, dA.p, dU.p, dC.p, dM.p, &wf, &wr};
+        plan.init(pp);
+        if (costs) costs[0] = (float)plan.current_cost();
+        int g = 0;
+        while (plan.step(pp)) {
+            ++g;
+            if (costs) costs[g] = (float)plan.current_cost();
+        }
+        dX.down((float2*)X);
+        dA.down(A);
+        if (scal) dtr.down(scal);
+        ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
+        return 0;
+    });
 }
 
 // UrShape == pixel grid on every active pixel?  (what GnPlan::choose_backend checks on the device)
@@ -250,63 +305,69 @@ static void gather3(const StreamSolver& s, const int planes[3], size_t N, float*
 int arapb200_debug_eval_jtf(int W, int H, const float* X, const float* A, const float* U, const float* C,
                             const float* M, float wf, float wr, float* r3, float* pre3)
 {
-    const size_t N = (size_t)W * H;
-    DevBuf<float2> dX(N), dU(N), dC(N);
-    DevBuf<float> dA(N), dM(N);
-    StreamSolver s(W, H);
-    if (int rc = debug_setup(W, H, X, A, U, C, M, wf, wr, s, dX, dU, dC, dA, dM)) return rc;
-    s.enqueue_pcg_init(nullptr);
-    ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
-    std::vector<unsigned char> flags(N);
-    s.download_flags(flags.data());
-    const int r_planes[3] = {PL_R, PL_R + 1, PL_R + 2};
-    gather3(s, r_planes, N, r3, flags);
-    const int pre_planes[3] = {PL_PRE, PL_PRE, PL_PRE + 1};
-    gather3(s, pre_planes, N, pre3, flags);
-    return 0;
+    return guarded([&]() -> int {
+        const size_t N = (size_t)W * H;
+        DevBuf<float2> dX(N), dU(N), dC(N);
+        DevBuf<float> dA(N), dM(N);
+        StreamSolver s(W, H);
+        if (int rc = debug_setup(W, H, X, A, U, C, M, wf, wr, s, dX, dU, dC, dA, dM)) return rc;
+        s.enqueue_pcg_init(nullptr);
+        ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
+        std::vector<unsigned char> flags(N);
+        s.download_flags(flags.data());
+        const int r_planes[3] = {PL_R, PL_R + 1, PL_R + 2};
+        gather3(s, r_planes, N, r3, flags);
+        const int pre_planes[3] = {PL_PRE, PL_PRE, PL_PRE + 1};
+        gather3(s, pre_planes, N, pre3, flags);
+        return 0;
+    });
 }
 
 int arapb200_debug_apply_jtj(int W, int H, const float* A, const float* U, const float* C, const float* M, float wf,
                              float wr, const float* p3, float* q3, float* dot)
 {
-    const size_t N = (size_t)W * H;
-    DevBuf<float2> dX(N), dU(N), dC(N);
-    DevBuf<float> dA(N), dM(N);
-    StreamSolver s(W, H);
-    if (int rc = debug_setup(W, H, nullptr, A, U, C, M, wf, wr, s, dX, dU, dC, dA, dM)) return rc;
-    const StreamDev& v = s.host_view();
-    ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
-    std::vector<float> tmp(N);
-    for (int k = 0; k < 3; ++k) {
-        for (size_t i = 0; i < N; ++i) tmp[i] = p3[3 * i + k];
-        s.upload_plane(PL_P + k, tmp.data());
-    }
-    s.enqueue_step_a(true, 0, nullptr);
-    ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
-    std::vector<unsigned char> flags(N);
-    s.download_flags(flags.data());
-    const int q_planes[3] = {PL_Q, PL_Q + 1, PL_Q + 2};
-    gather3(s, q_planes, N, q3, flags);
-    StreamScalars sc;
-    ARAP_CUDA_OR_RETURN(cudaMemcpy(&sc, v.sc, sizeof(sc), cudaMemcpyDeviceToHost));
-    if (dot) *dot = sc.den;
-    return 0;
+    return guarded([&]() -> int {
+        const size_t N = (size_t)W * H;
+        DevBuf<float2> dX(N), dU(N), dC(N);
+        DevBuf<float> dA(N), dM(N);
+        StreamSolver s(W, H);
+        if (int rc = debug_setup(W, H, nullptr, A, U, C, M, wf, wr, s, dX, dU, dC, dA, dM)) return rc;
+        const StreamDev& v = s.host_view();
+        ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
+        std::vector<float> tmp(N);
+        for (int k = 0; k < 3; ++k) {
+            for (size_t i = 0; i < N; ++i) tmp[i] = p3[3 * i + k];
+            s.upload_plane(PL_P + k, tmp.data());
+        }
+        s.enqueue_step_a(true, 0, nullptr);
+        ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
+        std::vector<unsigned char> flags(N);
+        s.download_flags(flags.data());
+        const int q_planes[3] = {PL_Q, PL_Q + 1, PL_Q + 2};
+        gather3(s, q_planes, N, q3, flags);
+        StreamScalars sc;
+        ARAP_CUDA_OR_RETURN(cudaMemcpy(&sc, v.sc, sizeof(sc), cudaMemcpyDeviceToHost));
+        if (dot) *dot = sc.den;
+        return 0;
+    });
 }
 
 int arapb200_debug_cost(int W, int H, const float* X, const float* A, const float* U, const float* C, const float* M,
                         float wf, float wr, float* cost)
 {
-    const size_t N = (size_t)W * H;
-    DevBuf<float2> dX(N), dU(N), dC(N);
-    DevBuf<float> dA(N), dM(N);
-    dX.up((const float2*)X); dU.up((const float2*)U); dC.up((const float2*)C); dA.up(A); dM.up(M);
-    ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
-    StreamSolver s(W, H);
-    s.bind(dX.p, dA.p, dU.p, dC.p, dM.p, wf, wr, nullptr);
-    s.set_general(!host_urshape_is_grid(W, H, U, M));
-    s.enqueue_init(nullptr);
-    s.read_back(nullptr, cost, nullptr);
-    return 0;
+    return guarded([&]() -> int {
+        const size_t N = (size_t)W * H;
+        DevBuf<float2> dX(N), dU(N), dC(N);
+        DevBuf<float> dA(N), dM(N);
+        dX.up((const float2*)X); dU.up((const float2*)U); dC.up((const float2*)C); dA.up(A); dM.up(M);
+        ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
+        StreamSolver s(W, H);
+        s.bind(dX.p, dA.p, dU.p, dC.p, dM.p, wf, wr, nullptr);
+        s.set_general(!host_urshape_is_grid(W, H, U, M));
+        s.enqueue_init(nullptr);
+        s.read_back(nullptr, cost, nullptr);
+        return 0;
+    });
 }
 
 // Cycle accounting of the resident kernel on one problem (see solver_resident.cu, RS_TICK):
@@ -315,38 +376,40 @@ int arapb200_debug_cost(int W, int H, const float* X, const float* A, const floa
 int arapb200_debug_resident_profile(int W, int H, const uint8_t* mask_red, const int32_t* matches, int n_matches,
                                     int nCont, int nGN, int nPCG, unsigned long long* prof, int* info, float* ms)
 {
-    const size_t N = (size_t)W * H;
-    std::vector<MatchRec> recs;
-    build_match_records(W, H, mask_red, matches, n_matches, recs);
-    DevBuf<unsigned char> dmask(N);
-    DevBuf<float2> dX(N), dU(N), dC(N);
-    DevBuf<float> dA(N), dM(N), dcost((size_t)nCont * (nGN + 1));
-    DevBuf<MatchRec> dm(recs.size());
-    DevBuf<unsigned long long> dprof(RS_MAX_CTAS * 8);
-    dmask.up(mask_red);
-    if (!recs.empty()) dm.up(recs.data());
-    ARAP_CUDA_OR_RETURN(cudaMemset(dprof.p, 0, RS_MAX_CTAS * 8 * sizeof(unsigned long long)));
-    enqueue_reset_state(W, H, dmask.p, dX.p, dU.p, dA.p, dM.p, nullptr);
-    enqueue_target_image(W, H, dm.p, (int)recs.size(), dC.p, nullptr);
-    ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
-    ResidentSolver rs(W, H);
-    if (!rs.prepare(W, H, dM.p, nullptr)) return 3;
-    rs.set_profile(dprof.p);
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0);
-    cudaEventCreate(&e1);
-    cudaEventRecord(e0, nullptr);
-    rs.enqueue(dX.p, dA.p, dC.p, 1, sqrtf(100.f), sqrtf(0.01f), nCont, nGN, nPCG, dcost.p, nullptr, nullptr);
-    cudaEventRecord(e1, nullptr);
-    ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
-    if (ms) cudaEventElapsedTime(ms, e0, e1);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    if (int st = rs.status(nullptr)) return 100 + st;
-    dprof.down(prof);
-    ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
-    if (info) { info[0] = rs.n_strips(); info[1] = rs.ctas(); info[2] = rs.warps(); }
-    return 0;
+    return guarded([&]() -> int {
+        const size_t N = (size_t)W * H;
+        std::vector<MatchRec> recs;
+        build_match_records(W, H, mask_red, matches, n_matches, recs);
+        DevBuf<unsigned char> dmask(N);
+        DevBuf<float2> dX(N), dU(N), dC(N);
+        DevBuf<float> dA(N), dM(N), dcost((size_t)nCont * (nGN + 1));
+        DevBuf<MatchRec> dm(recs.size());
+        DevBuf<unsigned long long> dprof(RS_MAX_CTAS * 8);
+        dmask.up(mask_red);
+        if (!recs.empty()) dm.up(recs.data());
+        ARAP_CUDA_OR_RETURN(cudaMemset(dprof.p, 0, RS_MAX_CTAS * 8 * sizeof(unsigned long long)));
+        enqueue_reset_state(W, H, dmask.p, dX.p, dU.p, dA.p, dM.p, nullptr);
+        enqueue_target_image(W, H, dm.p, (int)recs.size(), dC.p, nullptr);
+        ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
+        ResidentSolver rs(W, H);
+        if (!rs.prepare(W, H, dM.p, nullptr)) return 3;
+        rs.set_profile(dprof.p);
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, nullptr);
+        rs.enqueue(dX.p, dA.p, dC.p, 1, sqrtf(100.f), sqrtf(0.01f), nCont, nGN, nPCG, dcost.p, nullptr, nullptr);
+        cudaEventRecord(e1, nullptr);
+        ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
+        if (ms) cudaEventElapsedTime(ms, e0, e1);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        if (int st = rs.status(nullptr)) return 100 + st;
+        dprof.down(prof);
+        ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
+        if (info) { info[0] = rs.n_strips(); info[1] = rs.ctas(); info[2] = rs.warps(); }
+        return 0;
+    });
 }
 
 } // extern "C"
@@ -410,39 +473,45 @@ extern "C" {
 
 int arapb200_debug_wide_sum(size_t n, const float* t, float* sum)
 {
-    if (n == 0 || n > ((size_t)1 << 26)) return 1;
-    DevBuf<float> dt(n), dsum(1);
-    DevBuf<unsigned long long> acc(WA_WORDS);
-    dt.up(t);
-    ARAP_CUDA_OR_RETURN(cudaMemset(acc.p, 0, WA_WORDS * sizeof(unsigned long long)));
-    k_dbg_wide_publish<<<(unsigned)((n + 255) / 256), 256>>>(n, dt.p, acc.p);
-    k_dbg_wide_decode<<<1, 32>>>(acc.p, dsum.p);
-    dsum.down(sum);
-    ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
-    return 0;
+    return guarded([&]() -> int {
+        if (n == 0 || n > ((size_t)1 << 26)) return 1;
+        DevBuf<float> dt(n), dsum(1);
+        DevBuf<unsigned long long> acc(WA_WORDS);
+        dt.up(t);
+        ARAP_CUDA_OR_RETURN(cudaMemset(acc.p, 0, WA_WORDS * sizeof(unsigned long long)));
+        k_dbg_wide_publish<<<(unsigned)((n + 255) / 256), 256>>>(n, dt.p, acc.p);
+        k_dbg_wide_decode<<<1, 32>>>(acc.p, dsum.p);
+        dsum.down(sum);
+        ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
+        return 0;
+    });
 }
 
 int arapb200_debug_sincos(int n, const float* a, float* s, float* c)
 {
-    DevBuf<float> da(n), ds(n), dc(n);
-    da.up(a);
-    k_dbg_sincos<<<(n + 255) / 256, 256>>>(n, da.p, ds.p, dc.p);
-    ds.down(s);
-    dc.down(c);
-    ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
-    return 0;
+    return guarded([&]() -> int {
+        DevBuf<float> da(n), ds(n), dc(n);
+        da.up(a);
+        k_dbg_sincos<<<(n + 255) / 256, 256>>>(n, da.p, ds.p, dc.p);
+        ds.down(s);
+        dc.down(c);
+        ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
+        return 0;
+    });
 }
 
 int arapb200_debug_exact_sum(size_t n, const float* t, float* sum)
 {
-    if (n > (size_t)256 * 2048) return 1;
-    DevBuf<float> dt(n), dsum(1);
-    dt.up(t);
-    const size_t nchunks = (n + 255) / 256;
-    k_dbg_exact_sum<<<1, 256, 2 * nchunks * sizeof(double)>>>(n, dt.p, dsum.p);
-    dsum.down(sum);
-    ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
-    return 0;
+    return guarded([&]() -> int {
+        if (n > (size_t)256 * 2048) return 1;
+        DevBuf<float> dt(n), dsum(1);
+        dt.up(t);
+        const size_t nchunks = (n + 255) / 256;
+        k_dbg_exact_sum<<<1, 256, 2 * nchunks * sizeof(double)>>>(n, dt.p, dsum.p);
+        dsum.down(sum);
+        ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
+        return 0;
+    });
 }
 
 } // extern "C"

@@ -3,14 +3,34 @@
 //   arap_deform RGB MASK CSTR FLO_out WRGB_out WMASK_out      or      arap_deform LISTFILE
 // Differences from the reference are on the inside only: consecutive list entries of one image size are
 // solved together (several problems per cooperative launch), nothing is interpreted from $ARAP_PLAN.
+//
+// Resident worker (second half).  para_gen.py spawns one solver process per dispatch
+// (para_gen.py:178-200), and every process pays CUDA context creation + buffer allocation (0.6-4 s) before
+// its first pair -- more than the GPU work of a handful of pairs.  Two extra invocations remove that cost
+// without touching the driver's calling convention:
+//   arap_deform --serve SPOOLDIR     one long-lived process per GPU: keeps the context, the plan and the
+//                                    device buffers, and runs every list file dropped into SPOOLDIR
+//   ARAP_SERVER=SPOOLDIR arap_deform LISTFILE | RGB MASK CSTR FLO WRGB WMASK
+//                                    thin client: same argv contract, same "Saved" lines, same exit code;
+//                                    the work is done by the server that watches SPOOLDIR
+// Protocol: the client writes SPOOLDIR/<id>.job.tmp (the 6-tuples, one per line), renames it to <id>.job and
+// waits for <id>.done (first line = exit code); the server renames <id>.job to <id>.run while it works.
+// SPOOLDIR/stop makes the server exit.
 #include "../../../include/Opt.h"
 #include "../../../include/arapb200.h"
 #include "image_io.h"
 
 #include <chrono>
+#include <csignal>
 #include <cstdio>
+#include <cstring>
+#include <dirent.h>
+#include <sys/stat.h>
+#include <thread>
+#include <unistd.h>
 #include <cstdlib>
 #include <fstream>
+#include <algorithm>
 #include <deque>
 #include <future>
 #include <memory>
@@ -37,10 +57,12 @@ static void usage()
     puts("warped_RGB \t [output] path to output warped image (.png), all intermediate directories must exist");
     puts("warped_Mask \t [output] path to output warped mask (.png), all intermediate directories must exist");
     puts("\n./arap_deform LISTFILE   (one such 6-tuple per line)");
+    puts("./arap_deform --serve SPOOLDIR   (resident worker: runs the list files that clients with ARAP_SERVER=SPOOLDIR submit)");
     puts("Environment: ARAP_PLAN = path of the ARAP energy file (default ./arap_plan.t); CUDA_VISIBLE_DEVICES selects the GPU;");
     puts("             ARAP_BATCH = problems solved together (default 9: three cooperative launches of three)");
     puts("             ARAP_PCG_RTOL = opt-in relative PCG tolerance, e.g. 1e-3 (default 0: fixed 400 iterations)");
     puts("             ARAP_GN_RTOL = opt-in relative cost-decrease tolerance of the Gauss-Newton steps (default 0: fixed 8 steps)");
+    puts("             ARAP_SERVER = spool directory of a running `arap_deform --serve`: hand the work to it instead of solving here");
 }
 
 struct Loaded {
@@ -51,41 +73,30 @@ struct Loaded {
     std::vector<uint8_t> wrgb, wmask;
 };
 
-int main(int argc, const char* argv[])
+// the GPU context that outlives a list file (and, in --serve mode, every client request)
+struct Context {
+    arapb200_batch* ctx = NULL;
+    int W = 0, H = 0;
+    long saved = 0;
+    ~Context() { if (ctx) arapb200_batch_destroy(ctx); }
+};
+
+static bool read_list(const char* path, std::vector<InputPaths>& lines)
 {
-    std::vector<InputPaths> lines;
-    if (argc == 7) {
-        lines.push_back({argv[1], argv[2], argv[3], argv[4], argv[5], argv[6]});
-    } else if (argc == 2) { // a list file: main.cpp:182-193
-        std::ifstream infile(argv[1]);
-        std::string line;
-        while (getline(infile, line)) {
-            std::stringstream s(line);
-            InputPaths p;
-            if (s >> p.rgb >> p.mask >> p.cstr >> p.flo >> p.wrgb >> p.wmask) lines.push_back(p);
-        }
-    } else {
-        printf("Invalid Input!\n");
-        usage();
-        return 1;
+    std::ifstream infile(path);
+    if (!infile) return false;
+    std::string line;
+    while (getline(infile, line)) {
+        std::stringstream s(line);
+        InputPaths p;
+        if (s >> p.rgb >> p.mask >> p.cstr >> p.flo >> p.wrgb >> p.wmask) lines.push_back(p);
     }
-    if (lines.empty()) {
-        printf("No file to be processed");
-        return 1;
-    }
-    const char* planPath = getenv("ARAP_PLAN") == NULL ? "arap_plan.t" : getenv("ARAP_PLAN");
-    printf("Optimization plan at %s\n", planPath);
-    {
-        Opt_InitializationParameters ip = {0, 0, 0, 0};
-        Opt_State* st = Opt_NewState(ip);
-        Opt_Problem* pr = st ? Opt_ProblemDefine(st, planPath, "gaussNewtonGPU") : NULL;
-        if (!pr) {
-            printf(" Not found! Please run export ARAP_PLAN=/path/to/plan.t or copy "
-                   "the file to the running folder with name arap_plan.t");
-            return 1;
-        }
-        Opt_ProblemDelete(st, pr);
-    }
+    return true;
+}
+
+// deformSingle for every entry (ARAP/deformation/src/main.cpp:223-238), batched and pipelined
+static int process(const std::vector<InputPaths>& lines, Context& C)
+{
     // the solver budget is a compile-time constant of the reference: main.cpp:215-221
     const int nCont = 19, nGN = 8, nPCG = 400;
     int batch = getenv("ARAP_BATCH") ? atoi(getenv("ARAP_BATCH")) : 9;
@@ -108,37 +119,35 @@ int main(int argc, const char* argv[])
         int W = 0, H = 0;
         std::vector<Loaded> items;
     };
-    arapb200_batch* ctx = NULL;
-    int ctxW = 0, ctxH = 0;
     auto gpu_stage = [&](std::shared_ptr<Group> g) -> int {
-        if (!ctx || g->W != ctxW || g->H != ctxH) {
-            if (ctx) {
+        if (!C.ctx || g->W != C.W || g->H != C.H) {
+            if (C.ctx) {
                 printf("Warning: Input image has different size to one in the prebuilt plan.\n"
                        "To avoid re-building the plan and to save time, put images of the "
                        "same size in the same list.\nStarting to re-build plan...\n");
-                arapb200_batch_destroy(ctx);
+                arapb200_batch_destroy(C.ctx);
             }
             const auto t0 = std::chrono::steady_clock::now();
-            ctx = arapb200_batch_create(g->W, g->H, batch, nCont, nGN, nPCG, ARAPB200_BACKEND_AUTO);
+            C.ctx = arapb200_batch_create(g->W, g->H, batch, nCont, nGN, nPCG, ARAPB200_BACKEND_AUTO);
             t_create += since(t0);
-            if (!ctx) return 1;
-            if (pcg_rtol > 0.0 && arapb200_batch_set_option(ctx, "pcg_rtol", pcg_rtol)) {
+            if (!C.ctx) return 1;
+            if (pcg_rtol > 0.0 && arapb200_batch_set_option(C.ctx, "pcg_rtol", pcg_rtol)) {
                 fprintf(stderr, "ARAP_PCG_RTOL must be in [0, 1)\n");
                 return 1;
             }
-            if (gn_rtol > 0.0 && arapb200_batch_set_option(ctx, "gn_rtol", gn_rtol)) {
+            if (gn_rtol > 0.0 && arapb200_batch_set_option(C.ctx, "gn_rtol", gn_rtol)) {
                 fprintf(stderr, "ARAP_GN_RTOL must be in [0, 1)\n");
                 return 1;
             }
-            ctxW = g->W; ctxH = g->H;
+            C.W = g->W; C.H = g->H;
         }
         for (size_t k = 0; k < g->items.size(); ++k) {
             Loaded& L = g->items[k];
-            if (arapb200_batch_submit(ctx, (int)k, g->W, g->H, L.rgb.px.data(), L.mask_red.data(), L.cstr.data(),
+            if (arapb200_batch_submit(C.ctx, (int)k, g->W, g->H, L.rgb.px.data(), L.mask_red.data(), L.cstr.data(),
                                       (int)(L.cstr.size() / 4), L.flow.data(), L.wrgb.data(), L.wmask.data(), NULL))
                 return 1;
         }
-        return arapb200_batch_run(ctx);
+        return arapb200_batch_run(C.ctx);
     };
     // decode / encode run one task per list entry (zlib dominates: ~0.1 s of CPU per pair at 854x480)
     auto save_one = [&](const Group& g, size_t k) -> bool {
@@ -154,7 +163,7 @@ int main(int argc, const char* argv[])
         for (size_t k = 0; k < g.items.size(); ++k) jobs.push_back(std::async(std::launch::async, save_one, std::cref(g), k));
         bool ok = true;
         for (auto& j : jobs) {
-            if (j.get()) printf("Saved\n"); // list order
+            if (j.get()) { printf("Saved\n"); ++C.saved; } // list order
             else ok = false;
         }
         return ok;
@@ -237,6 +246,153 @@ int main(int argc, const char* argv[])
     if (timing)
         fprintf(stderr, "arap_deform timing: total %.3f s | decode %.3f | waiting for the GPU %.3f (context + buffers %.3f) | "
                         "encode %.3f\n", since(t_begin), t_decode, t_gpu_wait, t_create, t_encode);
-    if (ctx) arapb200_batch_destroy(ctx);
     return 0;
+}
+
+static bool plan_ok(const char* planPath)
+{
+    Opt_InitializationParameters ip = {0, 0, 0, 0};
+    Opt_State* st = Opt_NewState(ip);
+    Opt_Problem* pr = st ? Opt_ProblemDefine(st, planPath, "gaussNewtonGPU") : NULL;
+    if (!pr) return false;
+    Opt_ProblemDelete(st, pr);
+    return true;
+}
+
+static bool exists(const std::string& p)
+{
+    struct stat sb;
+    return stat(p.c_str(), &sb) == 0;
+}
+
+static volatile sig_atomic_t g_stop = 0;
+static void on_signal(int) { g_stop = 1; }
+
+// ---- resident worker ----------------------------------------------------------------------------------
+static int serve(const std::string& dir)
+{
+    mkdir(dir.c_str(), 0777);
+    signal(SIGTERM, on_signal);
+    signal(SIGINT, on_signal);
+    Context C;
+    {   // pay for the CUDA context now, not on the first request
+        int sm = 0;
+        if (arapb200_device_info(&sm, NULL, NULL, NULL)) return 1;
+    }
+    {   // tell clients (and the driver that started us) that the worker is up
+        std::ofstream r(dir + "/ready.tmp");
+        r << getpid() << "\n";
+        r.close();
+        rename((dir + "/ready.tmp").c_str(), (dir + "/ready").c_str());
+    }
+    fprintf(stderr, "arap_deform: serving %s (pid %d)\n", dir.c_str(), (int)getpid());
+    while (!g_stop) {
+        if (exists(dir + "/stop")) break;
+        std::vector<std::string> jobs;
+        if (DIR* d = opendir(dir.c_str())) {
+            while (dirent* e = readdir(d)) {
+                const std::string n = e->d_name;
+                if (n.size() > 4 && n.compare(n.size() - 4, 4, ".job") == 0) jobs.push_back(n.substr(0, n.size() - 4));
+            }
+            closedir(d);
+        }
+        if (jobs.empty()) {
+            std::this_thread::sleep_for(std::chrono::milliseconds(2));
+            continue;
+        }
+        std::sort(jobs.begin(), jobs.end()); // ids start with a timestamp: oldest first
+        for (const std::string& id : jobs) {
+            const std::string job = dir + "/" + id + ".job", run = dir + "/" + id + ".run";
+            if (rename(job.c_str(), run.c_str()) != 0) continue; // somebody else took it
+            std::vector<InputPaths> lines;
+            int rc = 1;
+            C.saved = 0;
+            if (read_list(run.c_str(), lines) && !lines.empty()) rc = process(lines, C);
+            fflush(stdout);
+            std::ofstream o(dir + "/" + id + ".done.tmp");
+            o << rc << "\n" << C.saved << "\n";
+            o.close();
+            rename((dir + "/" + id + ".done.tmp").c_str(), (dir + "/" + id + ".done").c_str());
+            unlink(run.c_str());
+        }
+    }
+    unlink((dir + "/ready").c_str());
+    return 0;
+}
+
+// ---- thin client --------------------------------------------------------------------------------------
+static int submit(const std::string& dir, const std::vector<InputPaths>& lines)
+{
+    if (!exists(dir + "/ready")) {
+        fprintf(stderr, "arap_deform: no server is watching %s (start one with: arap_deform --serve %s)\n", dir.c_str(), dir.c_str());
+        return 1;
+    }
+    char id[128];
+    const long long now = std::chrono::duration_cast<std::chrono::microseconds>(
+                              std::chrono::system_clock::now().time_since_epoch()).count();
+    snprintf(id, sizeof(id), "%020lld_%d", now, (int)getpid());
+    const std::string base = dir + "/" + id;
+    {
+        std::ofstream o(base + ".job.tmp");
+        for (const InputPaths& p : lines)
+            o << p.rgb << " " << p.mask << " " << p.cstr << " " << p.flo << " " << p.wrgb << " " << p.wmask << "\n";
+        if (!o) return 1;
+    }
+    if (rename((base + ".job.tmp").c_str(), (base + ".job").c_str()) != 0) return 1;
+    while (!exists(base + ".done")) {
+        if (!exists(dir + "/ready") && !exists(base + ".done")) {
+            fprintf(stderr, "arap_deform: the server watching %s went away\n", dir.c_str());
+            unlink((base + ".job").c_str());
+            return 1;
+        }
+        std::this_thread::sleep_for(std::chrono::milliseconds(1));
+    }
+    int rc = 1;
+    long saved = 0;
+    {
+        std::ifstream in(base + ".done");
+        in >> rc >> saved;
+    }
+    unlink((base + ".done").c_str());
+    for (long k = 0; k < saved; ++k) printf("Saved\n");
+    return rc;
+}
+
+int main(int argc, const char* argv[])
+{
+    const char* planPath = getenv("ARAP_PLAN") == NULL ? "arap_plan.t" : getenv("ARAP_PLAN");
+    if (argc == 3 && strcmp(argv[1], "--serve") == 0) {
+        printf("Optimization plan at %s\n", planPath);
+        if (!plan_ok(planPath)) {
+            printf(" Not found! Please run export ARAP_PLAN=/path/to/plan.t or copy "
+                   "the file to the running folder with name arap_plan.t");
+            return 1;
+        }
+        return serve(argv[2]);
+    }
+    std::vector<InputPaths> lines;
+    if (argc == 7) {
+        lines.push_back({argv[1], argv[2], argv[3], argv[4], argv[5], argv[6]});
+    } else if (argc == 2) { // a list file: main.cpp:182-193
+        read_list(argv[1], lines);
+    } else {
+        printf("Invalid Input!\n");
+        usage();
+        return 1;
+    }
+    if (lines.empty()) {
+        printf("No file to be processed");
+        return 1;
+    }
+    printf("Optimization plan at %s\n", planPath);
+    if (!plan_ok(planPath)) {
+        printf(" Not found! Please run export ARAP_PLAN=/path/to/plan.t or copy "
+               "the file to the running folder with name arap_plan.t");
+        return 1;
+    }
+    if (const char* srv = getenv("ARAP_SERVER")) {
+        if (*srv) return submit(srv, lines);
+    }
+    Context C;
+    return process(lines, C);
 }

@@ -6,21 +6,37 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 
 namespace arapb200 {
 
-// CUDA failure inside the Opt_* entry points: message + exit, as the reference does
-// (ARAP/API/src/solverGPUGaussNewton.t:59-73, ARAP/shared/cudaUtil.h:26-31).
-#define ARAP_CUDA_OR_EXIT(call)                                                                        \
+// Failures inside the library surface as a C++ exception that every extern "C" entry point catches and turns into
+// its error convention (a non-zero return code for arapb200_*, NULL from Opt_ProblemPlan, "finished" from Opt_ProblemStep
+// plus a sticky error on the plan).  The reference prints and exits the process (ARAP/API/src/solverGPUGaussNewton.t:
+// 59-73, ARAP/shared/cudaUtil.h:26-31); a library embedded in somebody else's process must not.
+struct ArapError {
+    int code;
+    ArapError(int c) : code(c ? c : 1) {}
+};
+[[noreturn]] inline void arap_fail(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
+inline void arap_fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    fprintf(stderr, "arapb200: ");
+    vfprintf(stderr, fmt, ap);
+    fprintf(stderr, "\n");
+    va_end(ap);
+    throw ArapError(code);
+}
+#define ARAP_CUDA_CHECK(call)                                                                          \
     do {                                                                                               \
         cudaError_t e__ = (call);                                                                      \
-        if (e__ != cudaSuccess) {                                                                      \
-            fprintf(stderr, "arapb200: CUDA error %d (%s) at %s:%d: %s\n", (int)e__,                   \
-                    cudaGetErrorString(e__), __FILE__, __LINE__, #call);                               \
-            exit((int)e__);                                                                            \
-        }                                                                                              \
+        if (e__ != cudaSuccess)                                                                        \
+            ::arapb200::arap_fail((int)e__, "CUDA error %d (%s) at %s:%d: %s", (int)e__, cudaGetErrorString(e__), \
+                                  __FILE__, __LINE__, #call);                                          \
     } while (0)
 
 // Same, but returns the error code (flat arapb200_* API).

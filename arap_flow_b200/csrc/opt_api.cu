@@ -4,6 +4,7 @@
 // ARAP/API/src/o.t:2521-2558 (API bodies), ARAP/API/src/solverGPUGaussNewton.t:956-1007 (init),
 // :1016-1177 (step), :1179-1182 (cost), :1205-1221 (setSolverParameter), :1223-1284 (free/makePlan).
 #include "../../include/Opt.h"
+#include "../../include/arapb200.h"
 #include "plan.cuh"
 
 #include <cstring>
@@ -22,6 +23,22 @@ struct Opt_Problem {
 struct Opt_Plan {
     GnPlan* plan;
 };
+
+// These three have no error return in the ABI.  A failure (CUDA error, watchdog) is printed, recorded on the plan
+// (arapb200_plan_error, below) and makes Opt_ProblemCurrentCost return NaN; Opt_ProblemStep reports "finished" so that
+// a stepping caller's loop ends.  The reference exits the process instead (solverGPUGaussNewton.t:59-73).
+template <class F>
+static void plan_guard(Opt_Plan* plan, F&& f)
+{
+    if (!plan || !plan->plan) return;
+    try {
+        f();
+    } catch (const ArapError& e) {
+        plan->plan->set_error(e.code);
+    } catch (...) {
+        plan->plan->set_error(2);
+    }
+}
 
 extern "C" {
 
@@ -80,9 +97,15 @@ Opt_Plan* Opt_ProblemPlan(Opt_State* state, Opt_Problem* problem, unsigned int* 
         fprintf(stderr, "arapb200: bad plan dimensions %u x %u\n", W, H);
         return nullptr;
     }
-    Opt_Plan* pl = new Opt_Plan;
-    pl->plan = new GnPlan((int)W, (int)H, state->params.verbosityLevel, ARAPB200_BACKEND_AUTO);
-    return pl;
+    // failure => NULL, which the reference caller asserts on (ARAP/shared/OptSolver.h:54-56)
+    try {
+        Opt_Plan* pl = new Opt_Plan;
+        pl->plan = new GnPlan((int)W, (int)H, state->params.verbosityLevel, ARAPB200_BACKEND_AUTO);
+        return pl;
+    } catch (...) {
+        fprintf(stderr, "arapb200: Opt_ProblemPlan failed for %u x %u\n", W, H);
+        return nullptr;
+    }
 }
 
 void Opt_PlanFree(Opt_State*, Opt_Plan* plan)
@@ -99,16 +122,27 @@ void Opt_SetSolverParameter(Opt_State* state, Opt_Plan* plan, const char* name, 
         fprintf(stderr, "Warning: tried to set nonexistent solver parameter %s\n", name); // :1220
 }
 
-void Opt_ProblemInit(Opt_State*, Opt_Plan* plan, void** problemparams) { plan->plan->init(problemparams); }
+void Opt_ProblemInit(Opt_State*, Opt_Plan* plan, void** problemparams)
+{
+    plan_guard(plan, [&] { plan->plan->init(problemparams); });
+}
 
-int Opt_ProblemStep(Opt_State*, Opt_Plan* plan, void** problemparams) { return plan->plan->step(problemparams); }
+int Opt_ProblemStep(Opt_State*, Opt_Plan* plan, void** problemparams)
+{
+    int more = 0;
+    plan_guard(plan, [&] { more = plan->plan->step(problemparams); });
+    return (plan && plan->plan && plan->plan->error()) ? 0 : more;
+}
 
 void Opt_ProblemSolve(Opt_State*, Opt_Plan* plan, void** problemparams)
 {
     // o.t:2548-2551: init, then step until it reports completion
-    plan->plan->solve(problemparams);
+    plan_guard(plan, [&] { plan->plan->solve(problemparams); });
 }
 
 double Opt_ProblemCurrentCost(Opt_State*, Opt_Plan* plan) { return plan->plan->current_cost(); }
+
+// extension (not in the reference's Opt.h): 0, or the code of the first failure since the plan was made
+int arapb200_plan_error(Opt_Plan* plan) { return (plan && plan->plan) ? plan->plan->error() : 1; }
 
 } // extern "C"

@@ -115,25 +115,25 @@ BatchPipeline::BatchPipeline(int maxW, int maxH, int max_problems, int nCont, in
     : maxW_(maxW), maxH_(maxH), nCont_(nCont), nGN_(nGN), nPCG_(nPCG), backend_(backend)
 {
     const size_t N = (size_t)maxW * maxH;
-    ARAP_CUDA_OR_EXIT(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
-    for (auto& e : ev_) ARAP_CUDA_OR_EXIT(cudaEventCreate(&e));
+    ARAP_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    for (auto& e : ev_) ARAP_CUDA_CHECK(cudaEventCreate(&e));
     dev_.resize(max_problems > 0 ? max_problems : 1);
     const size_t cbytes = (size_t)nCont * (nGN + 1) * sizeof(float);
     for (Dev& d : dev_) {
-        ARAP_CUDA_OR_EXIT(cudaMalloc(&d.X, N * sizeof(float2)));
-        ARAP_CUDA_OR_EXIT(cudaMalloc(&d.U, N * sizeof(float2)));
-        ARAP_CUDA_OR_EXIT(cudaMalloc(&d.C, N * sizeof(float2)));
-        ARAP_CUDA_OR_EXIT(cudaMalloc(&d.flow, N * sizeof(float2)));
-        ARAP_CUDA_OR_EXIT(cudaMalloc(&d.A, N * sizeof(float)));
-        ARAP_CUDA_OR_EXIT(cudaMalloc(&d.M, N * sizeof(float)));
-        ARAP_CUDA_OR_EXIT(cudaMalloc(&d.costs, cbytes));
-        ARAP_CUDA_OR_EXIT(cudaMalloc(&d.rgb, 3 * N));
-        ARAP_CUDA_OR_EXIT(cudaMalloc(&d.mask, N));
-        ARAP_CUDA_OR_EXIT(cudaMalloc(&d.orgb, 3 * N));
-        ARAP_CUDA_OR_EXIT(cudaMalloc(&d.omask, N));
-        ARAP_CUDA_OR_EXIT(cudaMalloc(&d.z, N * sizeof(unsigned)));
-        ARAP_CUDA_OR_EXIT(cudaMallocHost(&d.h_in, 4 * N));
-        ARAP_CUDA_OR_EXIT(cudaMallocHost(&d.h_out, 12 * N + cbytes));
+        ARAP_CUDA_CHECK(cudaMalloc(&d.X, N * sizeof(float2)));
+        ARAP_CUDA_CHECK(cudaMalloc(&d.U, N * sizeof(float2)));
+        ARAP_CUDA_CHECK(cudaMalloc(&d.C, N * sizeof(float2)));
+        ARAP_CUDA_CHECK(cudaMalloc(&d.flow, N * sizeof(float2)));
+        ARAP_CUDA_CHECK(cudaMalloc(&d.A, N * sizeof(float)));
+        ARAP_CUDA_CHECK(cudaMalloc(&d.M, N * sizeof(float)));
+        ARAP_CUDA_CHECK(cudaMalloc(&d.costs, cbytes));
+        ARAP_CUDA_CHECK(cudaMalloc(&d.rgb, 3 * N));
+        ARAP_CUDA_CHECK(cudaMalloc(&d.mask, N));
+        ARAP_CUDA_CHECK(cudaMalloc(&d.orgb, 3 * N));
+        ARAP_CUDA_CHECK(cudaMalloc(&d.omask, N));
+        ARAP_CUDA_CHECK(cudaMalloc(&d.z, N * sizeof(unsigned)));
+        ARAP_CUDA_CHECK(cudaMallocHost(&d.h_in, 4 * N));
+        ARAP_CUDA_CHECK(cudaMallocHost(&d.h_out, 12 * N + cbytes));
     }
     if (backend_ != ARAPB200_BACKEND_STREAM) resident_ = new ResidentSolver(maxW, maxH, (int)dev_.size());
 }

@@ -48,6 +48,15 @@ public:
     float last_ms_warp() const { return ms_warp_; }
     int last_resident_count() const { return n_resident_; }
     int last_group_size() const { return group_size_; }
+    // {problems in the largest cooperative launch, variant max threads, variant min CTAs/SM, grid.x, grid.y, threads} of
+    // the last resident launch of the last run (zeros if everything streamed)
+    void last_launch_info(int out[6]) const
+    {
+        out[0] = group_size_;
+        int sh[5] = {0, 0, 0, 0, 0};
+        if (resident_ && n_resident_ > 0) resident_->last_launch_shape(sh);
+        for (int i = 0; i < 5; ++i) out[1 + i] = sh[i];
+    }
     int max_problems() const { return (int)dev_.size(); }
     // opt-in early exit of the PCG loops (resident back-end only; the streaming graph keeps the fixed budget)
     void set_pcg_rtol(float rtol);

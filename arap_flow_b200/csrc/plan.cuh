@@ -19,6 +19,9 @@ public:
     int step(void** problemparams);   // :1016-1177
     void solve(void** problemparams); // o.t:2548-2551, with a single host sync at the end
     double current_cost() const { return (double)prev_cost_; }
+    // sticky error of the Opt_* entry points (they have no error return): 0 = fine
+    int error() const { return error_; }
+    void set_error(int code) { error_ = code ? code : 1; prev_cost_ = __builtin_nanf(""); }
     long long launches() const;
     bool using_resident() const { return use_resident_; }
     bool general_urshape() const { return general_; }
@@ -29,8 +32,10 @@ private:
     void bind(void** problemparams);
     int W_, H_, verbosity_, backend_;
     int n_iterations_ = 10, l_iterations_ = 10; // solver_parameter_defaults, :26-39
-    float pcg_rtol_ = 0.0f;                     // extension, 0 = off
+    float pcg_rtol_ = 0.0f, gn_rtol_ = 0.0f;    // extensions, 0 = off
+    bool warned_rtol_ = false;
     int n_iter_ = 0;
+    int error_ = 0;
     float prev_cost_ = 0.f;
     cudaStream_t stream_h_ = nullptr;
     std::unique_ptr<StreamSolver> stream_;      // created on first use
@@ -39,7 +44,12 @@ private:
     bool general_ = false;                      // UrShape is not the pixel grid
     void** last_params_ = nullptr;
     float* d_costs_ = nullptr;                  // resident: cost log of the current launch
-    unsigned* d_bad_u_ = nullptr;
+    unsigned long long* d_check_ = nullptr;     // [0] non-grid UrShape count, [1..2] fingerprint of the active set
+    unsigned long long* h_check_ = nullptr;     // pinned copy
+    const void* mask_ptr_ = nullptr;            // Mask image + fingerprint the resident strip tables were built for
+    unsigned long long mask_key_[2] = {0, 0};
+    bool have_mask_key_ = false;
+    void order_after_caller();
     float* d_trace_ = nullptr;
     void choose_backend(void** problemparams);
     float run_resident(void** problemparams, int nGN, float* trace);

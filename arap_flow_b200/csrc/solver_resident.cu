@@ -20,8 +20,9 @@
 //    of arrival order.  Two buffers alternate; they are never reset inside a launch (readers subtract the
 //    total they saw two barriers ago).  S is predicted from the previous result of the same reduction and
 //    verified (overflow flag / magnitude of the result); a wrong guess costs one extra barrier.
-//  * Halo.  Outbox words are (float, tag) pairs written with plain 16-byte stores; the receiver spins until
-//    the tag equals the publication sequence number, so the data validates itself.
+//  * Halo.  Outbox words are (float, tag) pairs, each ONE 64-bit element of a st.relaxed.gpu.v2.b64; the receiver
+//    spins with ld.relaxed.gpu.v2.b64 until the tag equals the publication sequence number, so the data
+//    validates itself (64-bit elements are single-copy atomic: value and tag cannot tear).
 //
 // Per PCG iteration there are exactly two grid barriers (sum p.Ap, sum z.r).  The direction update
 // p = z + beta p that follows the second one needs the neighbours' NEW p; instead of a third barrier every
@@ -72,18 +73,21 @@ __device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long
 {
     asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ uint4 ld_u4_volatile(const uint4* p)
+// An outbox entry is four (float, tag) words.  Each word is ONE 64-bit element (float in the low half, tag in the high
+// half): 64-bit elements of a vector access are single-copy atomic in the PTX memory model, so a value can never be
+// observed with another publication's tag, and a relaxed store paired with a relaxed load is a morally strong pair (no
+// data race).  The uint4 view (x = float, y = tag, z = float, w = tag) is the same bytes.
+__device__ __forceinline__ uint4 ld_entry_relaxed(const uint4* p)
 {
-    uint4 v;
-    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "l"(p)
-                 : "memory");
-    return v;
+    unsigned long long a, b;
+    asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+    return make_uint4((unsigned)a, (unsigned)(a >> 32), (unsigned)b, (unsigned)(b >> 32));
 }
-__device__ __forceinline__ void st_u4(uint4* p, uint4 v)
+__device__ __forceinline__ void st_entry_relaxed(uint4* p, unsigned tag, float v0, float v1)
 {
-    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    const unsigned long long t = (unsigned long long)tag << 32;
+    const unsigned long long a = t | __float_as_uint(v0), b = t | __float_as_uint(v1);
+    asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
 __device__ __forceinline__ double pow2_f64(int e) // 2^e, e in the normal range
 {
@@ -309,8 +313,8 @@ __device__ __forceinline__ float grid_sum(Cta& c, float g0, float g1, int& S, bo
 // PCG iterations: the receiver already holds the neighbour's previous direction (it computed it one iteration ago).
 __device__ __forceinline__ void put_entry(uint4* e, unsigned tag, float a, float b, float c2, float d)
 {
-    st_u4(e, make_uint4(__float_as_uint(a), tag, __float_as_uint(b), tag));
-    st_u4(e + 1, make_uint4(__float_as_uint(c2), tag, __float_as_uint(d), tag));
+    st_entry_relaxed(e, tag, a, b);
+    st_entry_relaxed(e + 1, tag, c2, d);
 }
 
 // called once per row k (fully unrolled) with the entry of pixel (lane, k)
@@ -353,9 +357,9 @@ __device__ __forceinline__ void fetch_halo(const ResProb& P, Ctl* ctl, const Str
     unsigned spins = 0;
     for (;;) {
         uint4 u0 = fake, u1 = fake, d0 = fake, d1 = fake, s0 = fake, s1 = fake;
-        if (pu) { u0 = ld_u4_volatile(pu); u1 = ld_u4_volatile(pu + 1); }
-        if (pd) { d0 = ld_u4_volatile(pd); d1 = ld_u4_volatile(pd + 1); }
-        if (ps) { s0 = ld_u4_volatile(ps); s1 = ld_u4_volatile(ps + 1); }
+        if (pu) { u0 = ld_entry_relaxed(pu); u1 = ld_entry_relaxed(pu + 1); }
+        if (pd) { d0 = ld_entry_relaxed(pd); d1 = ld_entry_relaxed(pd + 1); }
+        if (ps) { s0 = ld_entry_relaxed(ps); s1 = ld_entry_relaxed(ps + 1); }
         if (entry_ok(u0, u1, tag) && entry_ok(d0, d1, tag) && entry_ok(s0, s1, tag)) {
             if (pu) entry_park(s.stage + 4 * lane, u0, u1, four);
             if (pd) entry_park(s.stage + 4 * (32 + lane), d0, d1, four);
@@ -546,7 +550,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
     for (int k = 0; k < RS_STRIP_H; ++k) { r0[k] = r1[k] = r2[k] = pa[k] = 0.f; cc[k] = 1.f; ss[k] = 0.f; q0[k] = q1[k] = qa[k] = 0.f; }
     // every tile cell must hold finite data (the masked stencil multiplies invalid neighbours by 0)
     for (int e = lane; e < TH * TW; e += 32) s.own[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-    int S_cost = 0, S_num = 0, S_den = 0, S_bnum = 0;
+    int S_cost = 0, S_num = 0, S_den = 0, S_bnum = 0, S_sep = 8;
     unsigned seq = 0; // publication sequence number == halo tag
     bool ok = true;
     __syncthreads();
@@ -688,6 +692,12 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
 
             // ======== PCG iterations ========
             RS_TICK(3);
+            // Outbox reuse is safe only when a full grid barrier separates two publications to the same entry (a
+            // neighbour fetches publication k between its arrival at and the completion of the barrier that follows
+            // k).  The fixed-budget loop guarantees that (the last iteration does not publish and the den barrier
+            // precedes it); an early exit, or no PCG iteration at all, leaves a publication without its separating
+            // barrier before the next prologue publishes again -- those two paths run one extra barrier.
+            bool need_sep = (P.nPCG == 0);
             for (int it = 0; it < P.nPCG; ++it) {
                 // ---- PCGStep1: q = J^T J p, den = sum p.q.  Inactive pixels hold zeros throughout.
                 float gs0 = 0.f, gs1 = 0.f;
@@ -756,7 +766,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                 const float beta = (num > 0.0f) ? bnum / num : 0.0f; // :544-547
                 num = bnum;                                          // :1091
                 if (it + 1 == P.nPCG) break; // the direction is not needed after the last iteration
-                if (bnum <= ctl.stop) break; // early exit (every CTA decodes the same bnum: a uniform decision)
+                if (bnum <= ctl.stop) { need_sep = true; break; } // early exit (every CTA decodes the same bnum: a uniform decision)
 
                 // ---- PCGStep3: p = z + beta p (own pixels, then the remote ring) ----
 #pragma unroll
@@ -774,6 +784,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                 RS_TICK(2);
             }
             if (!ok) break;
+            if (need_sep) {
+                (void)grid_sum(c, threadIdx.x == 0 ? 1.0f : 0.0f, 0.0f, S_sep, ok); // sum = G: never zero, scale settles at once
+                if (!ok) break;
+            }
 
             // ======== PCGLinearUpdate ========
 #pragma unroll
@@ -903,28 +917,30 @@ static int pick_variant(int nw, long long total_ctas, int sm_count)
 ResidentSolver::ResidentSolver(int maxW, int maxH, int max_slots) : maxW_(maxW), maxH_(maxH)
 {
     int dev = 0;
-    ARAP_CUDA_OR_EXIT(cudaGetDevice(&dev));
-    ARAP_CUDA_OR_EXIT(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, dev));
+    ARAP_CUDA_CHECK(cudaGetDevice(&dev));
+    ARAP_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, dev));
     const int SX = (maxW + RS_STRIP_W - 1) / RS_STRIP_W, SY = (maxH + RS_STRIP_H - 1) / RS_STRIP_H;
     strip_cap_ = (size_t)SX * SY;
     slots_.resize(max_slots > 0 ? max_slots : 1);
     for (Slot& sl : slots_) {
-        ARAP_CUDA_OR_EXIT(cudaMalloc(&sl.d_strip_xy, strip_cap_ * sizeof(int2)));
-        ARAP_CUDA_OR_EXIT(cudaMalloc(&sl.d_slot_of_strip, strip_cap_ * sizeof(int) + strip_cap_)); // + the active bytes
-        ARAP_CUDA_OR_EXIT(cudaMalloc(&sl.d_count, sizeof(int)));
+        ARAP_CUDA_CHECK(cudaMalloc(&sl.d_strip_xy, strip_cap_ * sizeof(int2)));
+        ARAP_CUDA_CHECK(cudaMalloc(&sl.d_slot_of_strip, strip_cap_ * sizeof(int) + strip_cap_)); // + the active bytes
+        ARAP_CUDA_CHECK(cudaMalloc(&sl.d_count, sizeof(int)));
         // the outbox only has to hold what can be resident: at most sm_count * max warps strips
         const size_t ob = std::min(strip_cap_, (size_t)sm_count_ * (RS_THREADS_MAX / 32));
-        ARAP_CUDA_OR_EXIT(cudaMalloc(&sl.d_outbox, ob * RS_OUTBOX_ENTRIES * 2 * sizeof(uint4)));
-        ARAP_CUDA_OR_EXIT(cudaMalloc(&sl.d_bar, 8 * BAR_STRIDE * sizeof(unsigned long long)));
+        ARAP_CUDA_CHECK(cudaMalloc(&sl.d_outbox, ob * RS_OUTBOX_ENTRIES * 2 * sizeof(uint4)));
+        ARAP_CUDA_CHECK(cudaMalloc(&sl.d_bar, 8 * BAR_STRIDE * sizeof(unsigned long long)));
     }
-    ARAP_CUDA_OR_EXIT(cudaMallocHost(&h_counts_, slots_.size() * sizeof(int)));
-    ARAP_CUDA_OR_EXIT(cudaMalloc(&d_status_, 2 * sizeof(int)));
-    ARAP_CUDA_OR_EXIT(cudaMemset(d_status_, 0, 2 * sizeof(int)));
-    ARAP_CUDA_OR_EXIT(cudaMalloc(&d_probs_, slots_.size() * sizeof(ResProb)));
+    ARAP_CUDA_CHECK(cudaMallocHost(&h_counts_, slots_.size() * sizeof(int)));
+    ARAP_CUDA_CHECK(cudaMalloc(&d_status_, 2 * sizeof(int)));
+    ARAP_CUDA_CHECK(cudaMemset(d_status_, 0, 2 * sizeof(int)));
+    // the memset ran on the legacy stream, all later work runs on non-blocking streams: finish it here
+    ARAP_CUDA_CHECK(cudaDeviceSynchronize());
+    ARAP_CUDA_CHECK(cudaMalloc(&d_probs_, slots_.size() * sizeof(ResProb)));
     for (int v = 0; v < g_nvariants; ++v) {
         const int smem = (int)((g_variants[v].max_threads / 32) * sizeof(StripSmem));
-        ARAP_CUDA_OR_EXIT(cudaFuncSetAttribute((const void*)g_variants[v].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        ARAP_CUDA_OR_EXIT(cudaFuncSetAttribute((const void*)g_variants[v].fn_prof, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ARAP_CUDA_CHECK(cudaFuncSetAttribute((const void*)g_variants[v].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ARAP_CUDA_CHECK(cudaFuncSetAttribute((const void*)g_variants[v].fn_prof, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
 }
 
@@ -951,7 +967,7 @@ void ResidentSolver::prepare_enqueue(int slot, int W, int H, const float* d_M, c
     k_strip_active<<<(sl.SX * sl.SY + 7) / 8, 256, 0, stream>>>(W, H, sl.SX, sl.SY, d_M, d_active);
     k_strip_compact<<<1, 1024, 0, stream>>>(sl.SX, sl.SY, d_active, sl.d_strip_xy, sl.d_slot_of_strip, sl.d_count);
     launches_ += 2;
-    ARAP_CUDA_OR_EXIT(cudaMemcpyAsync(&h_counts_[slot], sl.d_count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    ARAP_CUDA_CHECK(cudaMemcpyAsync(&h_counts_[slot], sl.d_count, sizeof(int), cudaMemcpyDeviceToHost, stream));
 }
 
 bool ResidentSolver::prepare_finish(int slot)
@@ -977,7 +993,7 @@ bool ResidentSolver::prepare_finish(int slot)
 bool ResidentSolver::prepare(int W, int H, const float* d_M, cudaStream_t stream)
 {
     prepare_enqueue(0, W, H, d_M, stream);
-    ARAP_CUDA_OR_EXIT(cudaStreamSynchronize(stream));
+    ARAP_CUDA_CHECK(cudaStreamSynchronize(stream));
     return prepare_finish(0);
 }
 
@@ -1025,17 +1041,14 @@ void ResidentSolver::enqueue_group(int first, int count, int nCont, int nGN, int
         ctas += sl.G;
         nwmax = std::max(nwmax, sl.NW);
         // barrier words start at zero; halo tags start at 1, so a zeroed outbox is "nothing published yet"
-        ARAP_CUDA_OR_EXIT(cudaMemsetAsync(sl.d_bar, 0, 8 * BAR_STRIDE * sizeof(unsigned long long), stream));
-        ARAP_CUDA_OR_EXIT(cudaMemsetAsync(sl.d_outbox, 0,
+        ARAP_CUDA_CHECK(cudaMemsetAsync(sl.d_bar, 0, 8 * BAR_STRIDE * sizeof(unsigned long long), stream));
+        ARAP_CUDA_CHECK(cudaMemsetAsync(sl.d_outbox, 0,
                                           (size_t)(sl.n_strips > 0 ? sl.n_strips : 1) * RS_OUTBOX_ENTRIES * 2 * sizeof(uint4), stream));
     }
-    ARAP_CUDA_OR_EXIT(cudaMemcpyAsync(d_probs_ + first, host.data(), count * sizeof(ResProb), cudaMemcpyHostToDevice, stream));
+    ARAP_CUDA_CHECK(cudaMemcpyAsync(d_probs_ + first, host.data(), count * sizeof(ResProb), cudaMemcpyHostToDevice, stream));
     // the live CTAs of all problems form one 1-D grid; the variant with the most registers that keeps them co-resident
     const int v = pick_variant(nwmax, ctas, sm_count_);
-    if (v < 0) {
-        fprintf(stderr, "arapb200: resident kernel cannot be co-resident (%lld CTAs of %d warps)\n", ctas, nwmax);
-        exit(1);
-    }
+    if (v < 0) arap_fail(1, "resident kernel cannot be co-resident (%lld CTAs of %d warps)", ctas, nwmax);
     last_variant_ = v;
     const int threads = nwmax * 32;
     const size_t smem = (size_t)nwmax * sizeof(StripSmem);
@@ -1048,7 +1061,9 @@ void ResidentSolver::enqueue_group(int first, int count, int nCont, int nGN, int
     bool equal = true;
     for (int i = 1; i < count; ++i) equal = equal && slots_[first + i].G == g0;
     const dim3 grid = equal ? dim3((unsigned)g0, (unsigned)count, 1) : dim3((unsigned)ctas, 1, 1);
-    ARAP_CUDA_OR_EXIT(cudaLaunchCooperativeKernel(fn, grid, dim3(threads, 1, 1), args, smem, stream));
+    last_shape_[0] = g_variants[v].max_threads; last_shape_[1] = g_variants[v].min_blocks;
+    last_shape_[2] = (int)grid.x; last_shape_[3] = (int)grid.y; last_shape_[4] = threads;
+    ARAP_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, grid, dim3(threads, 1, 1), args, smem, stream));
     launches_ += 1;
 }
 
@@ -1062,10 +1077,10 @@ void ResidentSolver::enqueue(float2* X, float* A, const float2* C, int lerp_mode
 int ResidentSolver::status(cudaStream_t stream)
 {
     int st[2] = {0, 0};
-    ARAP_CUDA_OR_EXIT(cudaMemcpyAsync(st, d_status_, sizeof(st), cudaMemcpyDeviceToHost, stream));
-    ARAP_CUDA_OR_EXIT(cudaStreamSynchronize(stream));
+    ARAP_CUDA_CHECK(cudaMemcpyAsync(st, d_status_, sizeof(st), cudaMemcpyDeviceToHost, stream));
+    ARAP_CUDA_CHECK(cudaStreamSynchronize(stream));
     if (st[0]) {
-        ARAP_CUDA_OR_EXIT(cudaMemsetAsync(d_status_, 0, sizeof(st), stream));
+        ARAP_CUDA_CHECK(cudaMemsetAsync(d_status_, 0, sizeof(st), stream));
         return st[1] ? st[1] : 1;
     }
     return 0;

@@ -76,6 +76,8 @@ public:
     int warps(int slot = 0) const { return slots_[slot].NW; }
     int max_slots() const { return (int)slots_.size(); }
     int last_variant() const { return last_variant_; }
+    // shape of the last cooperative launch: {max threads, min CTAs per SM of the kernel variant, grid.x, grid.y, threads}
+    void last_launch_shape(int out[5]) const { for (int i = 0; i < 5; ++i) out[i] = last_shape_[i]; }
     // debug: per-CTA cycle accounting of the next launches into d_prof ([ctas()][8] u64), or null to disable
     void set_profile(unsigned long long* d_prof) { d_prof_ = d_prof; }
     // opt-in convergence-aware schedule; 0 restores the reference's fixed iteration budget
@@ -104,6 +106,7 @@ private:
     long long launches_ = 0;
     unsigned long long* d_prof_ = nullptr;
     int last_variant_ = -1;
+    int last_shape_[5] = {0, 0, 0, 0, 0};
     float pcg_rtol_ = 0.0f, gn_rtol_ = 0.0f;
 };
 

@@ -705,15 +705,18 @@ StreamSolver::StreamSolver(int W, int H)
     h_.ty = (H + ST_TILE - 1) / ST_TILE;
     h_.ntiles = h_.tx * h_.ty;
     const size_t bytes = (size_t)h_.ntiles * ST_TILE_FLOATS * sizeof(float);
-    ARAP_CUDA_OR_EXIT(cudaMalloc(&h_.planes, bytes));
-    ARAP_CUDA_OR_EXIT(cudaMemset(h_.planes, 0, bytes));
-    ARAP_CUDA_OR_EXIT(cudaMalloc(&h_.tile_active, (size_t)h_.ntiles));
-    ARAP_CUDA_OR_EXIT(cudaMemset(h_.tile_active, 1, (size_t)h_.ntiles));
-    ARAP_CUDA_OR_EXIT(cudaMalloc(&h_.acc, ACC_BYTES));
-    ARAP_CUDA_OR_EXIT(cudaMemset(h_.acc, 0, ACC_BYTES));
-    ARAP_CUDA_OR_EXIT(cudaMalloc(&h_.sc, sizeof(StreamScalars)));
-    ARAP_CUDA_OR_EXIT(cudaMemset(h_.sc, 0, sizeof(StreamScalars)));
-    ARAP_CUDA_OR_EXIT(cudaMalloc(&d_, sizeof(StreamDev)));
+    ARAP_CUDA_CHECK(cudaMalloc(&h_.planes, bytes));
+    ARAP_CUDA_CHECK(cudaMemset(h_.planes, 0, bytes));
+    ARAP_CUDA_CHECK(cudaMalloc(&h_.tile_active, (size_t)h_.ntiles));
+    ARAP_CUDA_CHECK(cudaMemset(h_.tile_active, 1, (size_t)h_.ntiles));
+    ARAP_CUDA_CHECK(cudaMalloc(&h_.acc, ACC_BYTES));
+    ARAP_CUDA_CHECK(cudaMemset(h_.acc, 0, ACC_BYTES));
+    ARAP_CUDA_CHECK(cudaMalloc(&h_.sc, sizeof(StreamScalars)));
+    ARAP_CUDA_CHECK(cudaMemset(h_.sc, 0, sizeof(StreamScalars)));
+    ARAP_CUDA_CHECK(cudaMalloc(&d_, sizeof(StreamDev)));
+    // the memsets above ran on the legacy stream; the solver's kernels run on non-blocking streams that do not order
+    // behind it, and the branch-free kernels rely on "inactive pixels hold zeros": finish the clears here
+    ARAP_CUDA_CHECK(cudaDeviceSynchronize());
     h_.trace = nullptr;
     const char* e = getenv("ARAP_STREAM_SUB");
     sub16_ = !(e && atoi(e) == 32);
@@ -738,7 +741,7 @@ static size_t host_tiled_off(const StreamDev& h, int x, int y)
 void StreamSolver::download_plane(int plane, float* dst) const
 {
     std::vector<float> all((size_t)h_.ntiles * ST_TILE_FLOATS);
-    ARAP_CUDA_OR_EXIT(cudaMemcpy(all.data(), h_.planes, all.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    ARAP_CUDA_CHECK(cudaMemcpy(all.data(), h_.planes, all.size() * sizeof(float), cudaMemcpyDeviceToHost));
     for (int y = 0; y < h_.H; ++y)
         for (int x = 0; x < h_.W; ++x) dst[(size_t)y * h_.W + x] = all[host_tiled_off(h_, x, y) + (size_t)plane * ST_TILE_PX];
 }
@@ -746,7 +749,7 @@ void StreamSolver::download_plane(int plane, float* dst) const
 void StreamSolver::upload_plane(int plane, const float* src)
 {
     std::vector<float> all((size_t)h_.ntiles * ST_TILE_FLOATS);
-    ARAP_CUDA_OR_EXIT(cudaMemcpy(all.data(), h_.planes, all.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    ARAP_CUDA_CHECK(cudaMemcpy(all.data(), h_.planes, all.size() * sizeof(float), cudaMemcpyDeviceToHost));
     for (int y = 0; y < h_.H; ++y)
         for (int x = 0; x < h_.W; ++x) {
             const float v = src[(size_t)y * h_.W + x];
@@ -758,13 +761,13 @@ void StreamSolver::upload_plane(int plane, const float* src)
                 all[tile0 + (size_t)PL_EDGE * ST_TILE_PX + (size_t)(slot * 2 + ((x & 31) ? 1 : 0)) * ST_TILE + (y & 31)] = v;
             }
         }
-    ARAP_CUDA_OR_EXIT(cudaMemcpy(h_.planes, all.data(), all.size() * sizeof(float), cudaMemcpyHostToDevice));
+    ARAP_CUDA_CHECK(cudaMemcpy(h_.planes, all.data(), all.size() * sizeof(float), cudaMemcpyHostToDevice));
 }
 
 void StreamSolver::download_flags(unsigned char* dst) const
 {
     std::vector<float> all((size_t)h_.ntiles * ST_TILE_FLOATS);
-    ARAP_CUDA_OR_EXIT(cudaMemcpy(all.data(), h_.planes, all.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    ARAP_CUDA_CHECK(cudaMemcpy(all.data(), h_.planes, all.size() * sizeof(float), cudaMemcpyDeviceToHost));
     for (int y = 0; y < h_.H; ++y)
         for (int x = 0; x < h_.W; ++x) {
             const size_t tile0 = (size_t)((y >> 5) * h_.tx + (x >> 5)) * ST_TILE_FLOATS;
@@ -775,7 +778,7 @@ void StreamSolver::download_flags(unsigned char* dst) const
 
 void StreamSolver::upload(cudaStream_t stream)
 {
-    ARAP_CUDA_OR_EXIT(cudaMemcpyAsync(d_, &h_, sizeof(StreamDev), cudaMemcpyHostToDevice, stream));
+    ARAP_CUDA_CHECK(cudaMemcpyAsync(d_, &h_, sizeof(StreamDev), cudaMemcpyHostToDevice, stream));
 }
 
 void StreamSolver::bind(float2* X, float* A, const float2* U, const float2* C, const float* M, float wf,
@@ -789,7 +792,7 @@ void StreamSolver::bind(float2* X, float* A, const float2* U, const float2* C, c
 
 void StreamSolver::enqueue_prep(cudaStream_t stream)
 {
-    ARAP_CUDA_OR_EXIT(cudaMemsetAsync(h_.acc, 0, ACC_BYTES, stream));
+    ARAP_CUDA_CHECK(cudaMemsetAsync(h_.acc, 0, ACC_BYTES, stream));
     k_prep<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
     ++launches_;
 }
@@ -843,19 +846,19 @@ void StreamSolver::enqueue_step_a(bool first, int it, cudaStream_t stream)
 void StreamSolver::enqueue_init(cudaStream_t stream)
 {
     const StreamPlanes& pl = h_;
-    ARAP_CUDA_OR_EXIT(cudaMemsetAsync(&h_.sc->bad_u, 0, sizeof(unsigned), stream));
+    ARAP_CUDA_CHECK(cudaMemsetAsync(&h_.sc->bad_u, 0, sizeof(unsigned), stream));
     enqueue_prep(stream);
     if (general_) k_cost_gen<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
     else k_cost<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
     k_finish<<<1, 32, 0, stream>>>(pl, d_, -1);
     launches_ += 2;
-    ARAP_CUDA_OR_EXIT(cudaGetLastError());
+    ARAP_CUDA_CHECK(cudaGetLastError());
 }
 
 void StreamSolver::launch_gn_body(int nPCG, cudaStream_t stream, bool tracing)
 {
     const StreamPlanes& pl = h_;
-    ARAP_CUDA_OR_EXIT(cudaMemsetAsync(h_.acc, 0, ACC_BYTES, stream));
+    ARAP_CUDA_CHECK(cudaMemsetAsync(h_.acc, 0, ACC_BYTES, stream));
     // the caller may have changed the constraint image / mask between steps (Opt.h:58-60): refresh flags
     k_prep<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
     if (general_) k_init_gen<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
@@ -878,7 +881,7 @@ void StreamSolver::enqueue_gn_step(int nPCG, cudaStream_t stream, float* d_trace
         h_.trace = d_trace;
         upload(stream);
         launch_gn_body(nPCG, stream, true);
-        ARAP_CUDA_OR_EXIT(cudaGetLastError());
+        ARAP_CUDA_CHECK(cudaGetLastError());
         h_.trace = nullptr;
         upload(stream);
         launches_ += nodes;
@@ -887,26 +890,26 @@ void StreamSolver::enqueue_gn_step(int nPCG, cudaStream_t stream, float* d_trace
     if (!graph_ || graph_npcg_ != nPCG) {
         if (graph_) { cudaGraphExecDestroy(graph_); graph_ = nullptr; }
         cudaStream_t cap;
-        ARAP_CUDA_OR_EXIT(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+        ARAP_CUDA_CHECK(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
         cudaGraph_t g;
-        ARAP_CUDA_OR_EXIT(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+        ARAP_CUDA_CHECK(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
         launch_gn_body(nPCG, cap, false);
-        ARAP_CUDA_OR_EXIT(cudaStreamEndCapture(cap, &g));
-        ARAP_CUDA_OR_EXIT(cudaGraphInstantiate(&graph_, g, 0));
-        ARAP_CUDA_OR_EXIT(cudaGraphDestroy(g));
-        ARAP_CUDA_OR_EXIT(cudaStreamDestroy(cap));
+        ARAP_CUDA_CHECK(cudaStreamEndCapture(cap, &g));
+        ARAP_CUDA_CHECK(cudaGraphInstantiate(&graph_, g, 0));
+        ARAP_CUDA_CHECK(cudaGraphDestroy(g));
+        ARAP_CUDA_CHECK(cudaStreamDestroy(cap));
         graph_npcg_ = nPCG;
         graph_nodes_ = nodes;
     }
-    ARAP_CUDA_OR_EXIT(cudaGraphLaunch(graph_, stream));
+    ARAP_CUDA_CHECK(cudaGraphLaunch(graph_, stream));
     launches_ += graph_nodes_;
 }
 
 void StreamSolver::read_back(cudaStream_t stream, float* cost, unsigned* bad_u)
 {
     StreamScalars s;
-    ARAP_CUDA_OR_EXIT(cudaMemcpyAsync(&s, h_.sc, sizeof(s), cudaMemcpyDeviceToHost, stream));
-    ARAP_CUDA_OR_EXIT(cudaStreamSynchronize(stream));
+    ARAP_CUDA_CHECK(cudaMemcpyAsync(&s, h_.sc, sizeof(s), cudaMemcpyDeviceToHost, stream));
+    ARAP_CUDA_CHECK(cudaStreamSynchronize(stream));
     if (cost) *cost = s.cost;
     if (bad_u) *bad_u = s.bad_u;
 }

@@ -140,25 +140,25 @@ void enqueue_warp(int W, int H, const float2* d_pos, const unsigned char* d_rgb,
                   unsigned* d_z, unsigned char* d_out_rgb, unsigned char* d_out_mask, cudaStream_t stream)
 {
     const size_t N = (size_t)W * H;
-    ARAP_CUDA_OR_EXIT(cudaMemsetAsync(d_z, 0, N * sizeof(unsigned), stream));
+    ARAP_CUDA_CHECK(cudaMemsetAsync(d_z, 0, N * sizeof(unsigned), stream));
     dim3 g1((W + 31) / 32, (H + 7) / 8);
     k_splat<<<g1, 256, 0, stream>>>(W, H, d_pos, d_mask_red, d_z);
     k_resolve<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(W, H, d_pos, d_rgb, d_z, d_out_rgb, d_out_mask);
-    ARAP_CUDA_OR_EXIT(cudaGetLastError());
+    ARAP_CUDA_CHECK(cudaGetLastError());
 }
 
 void enqueue_flow_to_pos(int W, int H, const float2* d_flow, float2* d_pos, cudaStream_t stream)
 {
     const size_t N = (size_t)W * H;
     k_grid_add<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(W, H, d_flow, d_pos, 1.f);
-    ARAP_CUDA_OR_EXIT(cudaGetLastError());
+    ARAP_CUDA_CHECK(cudaGetLastError());
 }
 
 void enqueue_pos_to_flow(int W, int H, const float2* d_pos, float2* d_flow, cudaStream_t stream)
 {
     const size_t N = (size_t)W * H;
     k_grid_add<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(W, H, d_pos, d_flow, -1.f);
-    ARAP_CUDA_OR_EXIT(cudaGetLastError());
+    ARAP_CUDA_CHECK(cudaGetLastError());
 }
 
 } // namespace arapb200

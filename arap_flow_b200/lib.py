@@ -26,7 +26,8 @@ ARAP_SYMBOLS = [
     "arapb200_batch_timing", "arapb200_batch_launches", "arapb200_debug_gn_solve", "arapb200_debug_eval_jtf",
     "arapb200_debug_apply_jtj", "arapb200_debug_cost", "arapb200_debug_sincos", "arapb200_debug_exact_sum",
     "arapb200_debug_resident_profile", "arapb200_flatten", "arapb200_filter_matches", "arapb200_segment_mask",
-    "arapb200_batch_set_option", "arapb200_batch_resident_count", "arapb200_debug_wide_sum",
+    "arapb200_batch_set_option", "arapb200_batch_resident_count", "arapb200_debug_wide_sum", "arapb200_plan_error",
+    "arapb200_batch_launch_info",
 ]
 
 
@@ -247,6 +248,13 @@ class Batch:
         """Problems of the last run() that the resident back-end solved (the others streamed)."""
         self.L.arapb200_batch_resident_count.argtypes = [C.c_void_p]
         return int(self.L.arapb200_batch_resident_count(self.h))
+
+    def launch_info(self):
+        """Shape of the last cooperative launch of the last run() (zeros if every problem streamed)."""
+        info = (C.c_int * 6)()
+        self.L.arapb200_batch_launch_info.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+        _check(self.L.arapb200_batch_launch_info(self.h, info), "arapb200_batch_launch_info")
+        return dict(problems_per_launch=info[0], variant=(info[1], info[2]), grid=(info[3], info[4]), threads=info[5])
 
     def close(self):
         if self.h:

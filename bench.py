@@ -6,7 +6,8 @@ warp) over one batch of synthetic 854x480 pairs (config C1: single segment, fd=1
 matches) per GPU.  Pairs are independent: ranks shard them with no collective (para_gen.py --gpu style),
 so scaling is weak (per-GPU work fixed).
 
-  python bench.py [--gpus N --steps K --warmup W]            # our arm (libarapb200.so)
+  python bench.py [--gpus N --steps K --warmup W]            # our arm (libarapb200.so), batched API
+  python bench.py --path opt_h [...]                          # our arm through the reference's own Opt.h call sequence
   python bench.py --impl reference [...]                      # the reference arm: CPU oracle port
 Prints ONE JSON line (rank 0).
 """
@@ -29,25 +30,60 @@ B_ITER = 156.0            # algorithmic bytes / active pixel / PCG iteration (SU
 B_GN_EXTRA = 132.0        # init + update + cost per GN step
 NCONT, NGN, NPCG = 19, 8, 400
 WORKLOADS = {"C1": (854, 480, 1, 1, 1000), "C3": (1024, 436, 1, 5, 3000), "C0": (64, 64, 1, 1, 0),
-             "C4": (1920, 1080, 1, 1, 4000), "C2": (854, 480, 4, 3, 2000)}
+             "C4": (1920, 1080, 1, 1, 4000), "C2": (854, 480, 4, 3, 2000),
+             "C1s": (854, 480, 1, 1, 1000)}   # C1 geometry with a DAVIS-typical small object (8 % of the frame)
+AXES = {"C4": (0.46, 0.46),   # C4 enlarges the ellipse to 66 % coverage
+        "C1s": (0.15, 0.17)}
 
 
 def make_pairs(workload: str, count: int, first: int):
     from arap_flow_b200 import synth
     W, H, nseg, fd, seed0 = WORKLOADS[workload]
-    axes = (0.46, 0.46) if workload == "C4" else None   # C4 enlarges the ellipse to 66 % coverage
-    return [synth.synth(W, H, nseg, fd, seed0 + first + i, axes=axes) for i in range(count)]
+    return [synth.synth(W, H, nseg, fd, seed0 + first + i, axes=AXES.get(workload)) for i in range(count)]
+
+
+def workload_config(workload: str, pairs):
+    """The `config` object: identical for our arm and the reference arm (what is solved, not how)."""
+    W, H, nseg, fd, seed0 = WORKLOADS[workload]
+    act = [int(sum((m == 0).sum() for m in p.masks)) for p in pairs]
+    return {"workload": f"{workload} {W}x{H}, {nseg} segment(s) per pair, fd={fd}, synth seeds {seed0}+",
+            "schedule": f"{NCONT}x{NGN}x{NPCG}", "active_px_per_pair": float(np.mean(act)),
+            "matches_per_pair": float(np.mean([len(p.matches) for p in pairs])), "warp": "forward warp of RGB + mask per segment"}
 
 
 def measured_traffic(problems_per_launch: int):
     """DRAM bytes of one k_resident launch of that many co-resident problems, from the committed ncu captures
     (profiles/r1_traffic.json), or None."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    try:
-        with open(p) as f:
-            return int(json.load(f)["launches"][str(problems_per_launch)]["dram_bytes_per_launch"])
-    except Exception:
-        return None
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return int(json.load(f)["launches"][str(problems_per_launch)]["dram_bytes_per_launch"])
+        except Exception:
+            continue
+    return None
+
+
+def committed_profile_numbers():
+    """Numbers that only a profiler or a separate probe can give, read from committed files under profiles/ (never
+    measured under ncu in this run): issue-slot utilisation of k_resident and the L2-resident copy peak."""
+    out = {}
+    for name in ("r2_ncu_resident.json", "r1_ncu_resident.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                out["issue_active_pct"] = float(json.load(f)["smsp__issue_active.avg.pct_of_peak_sustained_active"])
+            out["issue_active_source"] = "profiles/" + name
+            break
+        except Exception:
+            continue
+    for name in ("r2_copy_peaks.json", "r1_copy_peaks.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                out["l2_copy_gbs"] = float(json.load(f)["l2_copy_gbs_32MiB"])
+            out["l2_peak_source"] = "profiles/" + name + " (32 MiB L2-resident copy, same method as MEASURED_PEAKS.json)"
+            break
+        except Exception:
+            continue
+    return out
 
 
 def measured_peak():
@@ -103,53 +139,135 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_leg(workload: str, cores_note=True):
-    """Oracle (CPU port of the reference algorithm) on a bounded sample: ONE continuation step
-    (8 GN x 400 PCG) of one pair, scaled x19 + one warp.  Returns (pairs_per_s, dict)."""
-    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU arm runs on rank 0 alone)
-    os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
-    from oracle import pyoracle as O
-    O.build()
-    sp = make_pairs(workload, 1, 0)[0]
-    m = O.with_border_pins(sp.matches, sp.W, sp.H)
-    U = O.grid(sp.W, sp.H)
-    t_cont = t_warp = 0.0
-    for mask in sp.masks:     # one independent solve + warp per segment (C2: 4, otherwise 1)
-        Cn = O.constraint_image(mask, m, 1.0 / NCONT)
+class CpuArm:
+    """The CPU arm: oracle/arap_oracle.c (port of the reference algorithm, OpenMP over all host threads) advancing the
+    solve of ONE pair one continuation step per call, state carried from step to step exactly as
+    CombinedSolverBase::singleSolve does (ARAP/shared/CombinedSolverBase.h:108-117).  19 consecutive calls are one full
+    solve; fewer are a sample of it (continuation steps cost the same: every one runs 8 x 400 PCG iterations)."""
+
+    def __init__(self, workload: str):
+        # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU arm runs on rank 0 alone)
+        # (ARAP_CPU_THREADS caps it, for trying the arm out on a machine that is busy with something else)
+        os.environ["OMP_NUM_THREADS"] = os.environ.get("ARAP_CPU_THREADS", str(len(os.sched_getaffinity(0))))
+        from oracle import pyoracle as O
+        O.build()
+        self.O = O
+        self.workload = workload
+        self.sp = make_pairs(workload, 1, 0)[0]
+        sp = self.sp
+        self.m = O.with_border_pins(sp.matches, sp.W, sp.H)
+        self.U = O.grid(sp.W, sp.H)
+        self.t = 0
+        self.reset()
+
+    def reset(self):
+        sp = self.sp
+        self.state = [(self.U.copy(), np.zeros((sp.H, sp.W), np.float32)) for _ in sp.masks]
+
+    def step(self) -> float:
+        """one continuation step of every segment of the pair; returns the seconds it took"""
+        O, sp = self.O, self.sp
+        if self.t == 0:
+            self.reset()
+        alpha = np.float32(self.t + 1) / np.float32(NCONT)
+        dt = 0.0
+        for k, mask in enumerate(sp.masks):
+            Cn = O.constraint_image(mask, self.m, alpha)
+            X, A = self.state[k]
+            t0 = time.perf_counter()
+            X, A, costs, _ = O.gn_solve(X, A, self.U, Cn, mask.astype(np.float32), NGN, NPCG)
+            dt += time.perf_counter() - t0
+            self.state[k] = (X, A)
+        self.t = (self.t + 1) % NCONT
+        return dt
+
+    def warp_seconds(self) -> float:
         t0 = time.perf_counter()
-        X, A, costs, _ = O.gn_solve(U.copy(), np.zeros((sp.H, sp.W), np.float32), U, Cn, mask.astype(np.float32), NGN, NPCG)
-        t_cont += time.perf_counter() - t0
-        t0 = time.perf_counter()
-        O.warp(X, sp.rgb, mask)
-        t_warp += time.perf_counter() - t0
-    per_pair = NCONT * t_cont + t_warp
-    info = {"value": 1.0 / per_pair, "unit": "pairs/s", "cores": O.num_threads(), "kind": "port",
-            "sample": f"{workload}: 1 of {NCONT} continuation steps ({NGN}x{NPCG} PCG iterations) of each of the pair's "
-                      f"{len(sp.masks)} segment(s) ({t_cont:.2f} s) scaled x{NCONT} + forward warp(s) ({t_warp:.3f} s); "
-                      f"oracle/arap_oracle.c, OpenMP"}
-    return 1.0 / per_pair, info
+        for k, mask in enumerate(self.sp.masks):
+            self.O.warp(self.state[k][0], self.sp.rgb, mask)
+        return time.perf_counter() - t0
+
+    def info(self, step_seconds, warp_s):
+        n = len(step_seconds)
+        per_pair = NCONT * float(np.mean(step_seconds)) + warp_s
+        return {"value": 1.0 / per_pair, "unit": "pairs/s", "cores": self.O.num_threads(), "kind": "port",
+                "extrapolated": n < NCONT, "sampled_seconds": float(np.sum(step_seconds)),
+                "sample": f"{self.workload}: {n} consecutive continuation step(s) of one pair's solve ({NGN}x{NPCG} PCG iterations "
+                          f"each, {len(self.sp.masks)} segment(s)), mean {np.mean(step_seconds):.2f} s per step; a pair = {NCONT} such steps "
+                          f"+ forward warp ({warp_s:.3f} s)" + ("" if n < NCONT else "; the timed steps contain a complete 19-step solve") +
+                          "; oracle/arap_oracle.c, OpenMP"}
+
+
+def cpu_leg(workload: str, n_steps: int = 3):
+    """cpu_baseline of our arm: a bounded sample (n_steps continuation steps, about 10 s) of one pair on the host cores."""
+    arm = CpuArm(workload)
+    secs = [arm.step() for _ in range(n_steps)]
+    return arm.info(secs, arm.warp_seconds())
 
 
 def run_reference_arm(args, rank, world):
+    """--impl reference.  A "step" here is ONE continuation step of one pair's solve (1/19 of a pair: the bounded sample
+    the contract asks for); `ms_per_step` is the time of that step as executed, `value` = 1 / (19 x mean step + warp).
+    With --steps >= 19 the timed region holds a complete solve and nothing is extrapolated."""
     if rank != 0:
         return
     W, H = WORKLOADS[args.workload][:2]
-    vals = []
-    info = None
-    for i in range(args.warmup + args.steps):
-        v, info = cpu_leg(args.workload)
-        if i >= args.warmup:
-            vals.append(v)
-    v = float(np.mean(vals))
-    info["value"] = v
+    arm = CpuArm(args.workload)
+    for _ in range(args.warmup):
+        arm.step()
+    arm.t = 0                   # the timed steps start a fresh solve
+    secs = [arm.step() for _ in range(args.steps)]
+    info = arm.info(secs, arm.warp_seconds())
+    v = info["value"]
     line = {"impl": "reference", "metric": f"flow pairs/sec @{W}x{H}", "value": v, "unit": "pairs/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * float(np.mean(secs)),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload} {W}x{H} {WORKLOADS[args.workload][2]} segment(s) per pair", "schedule": f"{NCONT}x{NGN}x{NPCG}",
-                       "note": "reference has no CPU path (SURVEY.md 8c); this is the oracle port on host cores"},
+            "config": workload_config(args.workload, [arm.sp]),
+            "step_definition": f"one of the {NCONT} continuation steps of one pair (bounded sample of the workload); "
+                               "pairs per step = 1/19",
+            "extrapolated": info["extrapolated"],
+            "note": "the reference has no CPU path (ARAP/API/src/o.t:121-124 accepts GPU solver kinds only; SURVEY.md 8c): "
+                    "this is the oracle port on the host cores; rank 0 alone runs it at any N",
             "cpu_baseline": info,
             "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def opt_h_image(cs, p, mask):
+    """one (image, segment) through the reference's own API sequence (CombinedSolver -> OptSolver -> Opt.h)"""
+    from arap_flow_b200.combined_solver import with_border_pins
+    cs.add_image(p.rgb, mask, with_border_pins(p.matches, p.W, p.H))
+    cs.solve_all()
+
+
+def single_problem_gn_step_ms(pair, mask):
+    """device time of ONE Opt_ProblemStep (PCGInit + 400 PCG iterations + update + cost) of ONE problem,
+    median over the steps of a few continuation steps -- through Opt_ProblemInit / Opt_ProblemStep, outside the timed region."""
+    import ctypes as C
+    import torch
+    from arap_flow_b200.combined_solver import CombinedSolver, with_border_pins
+    cs = CombinedSolver(pair.W, pair.H)
+    cs.add_image(pair.rgb, mask, with_border_pins(pair.matches, pair.W, pair.H))
+    cs._reset_gpu()
+    pp = (C.c_void_p * 7)(cs.d_offset.data_ptr(), cs.d_angle.data_ptr(), cs.d_urshape.data_ptr(),
+                          cs.d_constraints.data_ptr(), cs.d_mask.data_ptr(),
+                          C.cast(C.byref(cs.w_fit), C.c_void_p), C.cast(C.byref(cs.w_reg), C.c_void_p))
+    L, sv = cs.solver.L, cs.solver
+    L.Opt_SetSolverParameter(sv.state, sv.plan, b"nIterations", C.byref(cs.nIterations))
+    L.Opt_SetSolverParameter(sv.state, sv.plan, b"lIterations", C.byref(cs.lIterations))
+    ms = []
+    for t in range(3):
+        cs._set_constraint_image(np.float32(t + 1) / np.float32(NCONT))
+        torch.cuda.synchronize()
+        L.Opt_ProblemInit(sv.state, sv.plan, pp)
+        while True:
+            t0 = time.perf_counter()
+            more = L.Opt_ProblemStep(sv.state, sv.plan, pp)     # synchronous: returns after the step's cost read-back
+            if not more:
+                break
+            ms.append((time.perf_counter() - t0) * 1e3)
+    cs.close()
+    return float(np.median(ms)) if ms else None
 
 
 def main():
@@ -159,6 +277,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C1", choices=sorted(WORKLOADS))
+    ap.add_argument("--path", default="batch", choices=["batch", "opt_h"],
+                    help="batch: arapb200_batch_* (several problems per cooperative launch).  opt_h: the reference's own "
+                         "call sequence, one image at a time: 19 x Opt_ProblemSolve with the host-side constraint lerp and "
+                         "full-image upload per continuation step (CombinedSolver.h / OptSolver.h)")
     ap.add_argument("--batch", type=int, default=0, help="pairs per GPU per step (0 = backend default)")
     ap.add_argument("--backend", default="auto", choices=["auto", "stream", "resident"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -185,16 +307,21 @@ def main():
     lib.load()
     backend = {"auto": lib.BACKEND_AUTO, "stream": lib.BACKEND_STREAM, "resident": lib.BACKEND_RESIDENT}[args.backend]
     W, H = WORKLOADS[args.workload][:2]
+    opt_h = args.path == "opt_h"
     # resident back-end: 3 (168 registers) or 4 (128 registers) problems share one cooperative launch; 9 = three launches of
     # three, measured 2 % faster than two launches of four (profiles/r1_batch_choice.txt)
-    B = args.batch if args.batch > 0 else (1 if (args.backend == "stream" or args.workload == "C4") else
+    B = args.batch if args.batch > 0 else (1 if (args.backend == "stream" or args.workload == "C4" or opt_h) else
                                            (2 if args.workload == "C2" else 9))
     pairs = make_pairs(args.workload, B, first=rank * B)
     nseg = WORKLOADS[args.workload][2]
     # --multseg (C2): one independent problem per segment, all of them sharing the pair's constraint list
     problems = [(p, m) for p in pairs for m in p.masks]
     active_px = [int(sum((m == 0).sum() for m in p.masks)) for p in pairs]   # per pair
-    batch = lib.Batch(W, H, len(problems), NCONT, NGN, NPCG, backend)
+    batch = None if opt_h else lib.Batch(W, H, len(problems), NCONT, NGN, NPCG, backend)
+    cs = None
+    if opt_h:
+        from arap_flow_b200.combined_solver import CombinedSolver
+        cs = CombinedSolver(W, H)
 
     def barrier():
         torch.cuda.synchronize()
@@ -203,11 +330,23 @@ def main():
         torch.cuda.synchronize()
 
     out_bufs = [None] * len(problems)   # output arrays are allocated once and reused, as a caller looping over pairs would
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    io_bytes = [0, 0]
 
     def one_step():
-        outs = [batch.submit(i, p.rgb, m, p.matches, out=out_bufs[i]) for i, (p, m) in enumerate(problems)]
-        out_bufs[:] = outs
-        batch.run()
+        if opt_h:
+            # the library's kernels run on its own stream, but every Opt_ProblemSolve is synchronous and the uploads /
+            # download run on the current (default) stream, so events on the default stream bracket the device work
+            outs = []
+            for (p, m) in problems:
+                opt_h_image(cs, p, m)
+                io_bytes[0] += cs.h2d_bytes
+                io_bytes[1] += cs.d2h_bytes
+                outs.append({"flow": cs.warp_field(), "rgb": cs.warped_rgb, "mask": cs.warped_mask})
+        else:
+            outs = [batch.submit(i, p.rgb, m, p.matches, out=out_bufs[i]) for i, (p, m) in enumerate(problems)]
+            out_bufs[:] = outs
+            batch.run()
         if nseg > 1:  # layer flatten of every pair (para_gen.py:136-175) belongs to the pair's end-to-end time
             for k in range(len(pairs)):
                 o = outs[k * nseg:(k + 1) * nseg]
@@ -226,15 +365,26 @@ def main():
     sampler.start()
     barrier()
     dev_ms, solve_ms, launches = 0.0, 0.0, 0
+    io_bytes[:] = [0, 0]
     t0 = time.perf_counter()
     for _ in range(args.steps):
         flush_l2()
-        outs = one_step()
-        tm = batch.timing_ms()
-        dev_ms += tm["solve"] + tm["warp"]
-        solve_ms += tm["solve"]
-        launches += batch.launches()
-    streamed = batch.resident_count() == 0
+        if opt_h:
+            ev[0].record()
+            one_step()
+            ev[1].record()
+            ev[1].synchronize()
+            ms = ev[0].elapsed_time(ev[1])
+            dev_ms += ms
+            solve_ms += ms
+        else:
+            one_step()
+            tm = batch.timing_ms()
+            dev_ms += tm["solve"] + tm["warp"]
+            solve_ms += tm["solve"]
+            launches += batch.launches()
+    streamed = (batch.resident_count() == 0) if batch else (args.workload == "C4")
+    linfo = batch.launch_info() if batch else None
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
@@ -251,42 +401,74 @@ def main():
         e2e = total_pairs / (wall_ms_max / 1000.0)
         peak, peak_src = measured_peak()
         n_iter = NCONT * NGN * NPCG
-        alg_bytes = float(np.mean(active_px)) * (B_ITER * n_iter + B_GN_EXTRA * NCONT * NGN)   # per solve
+        alg_bytes = float(np.mean(active_px)) * (B_ITER * n_iter + B_GN_EXTRA * NCONT * NGN)   # per pair
         achieved = alg_bytes * B * args.steps / (solve_ms_max / 1000.0) / 1e9                  # this rank's GPU
         N = W * H
+        prof = committed_profile_numbers()
+        if opt_h:
+            # per image: 1 check + (first call: 2 strip kernels) + 1 cooperative launch per Opt_ProblemSolve, + 3 warp kernels
+            n_launch = len(problems) * args.steps * world * (NCONT * 2 + 2 + 3)
+            h2d, d2h = io_bytes[0] // args.steps, io_bytes[1] // args.steps
+        else:
+            n_launch = int(lt.cpu()[0])
+            h2d = int(len(problems) * (4 * N) + nseg * sum(16 * (len(p.matches) + 2 * (W + H)) for p in pairs))
+            d2h = int(len(problems) * (12 * N + 4 * NCONT * (NGN + 1)))
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": (measured_traffic(3 if B % 3 == 0 else 4) if not streamed and not opt_h and (B % 3 == 0 or B % 4 == 0) and args.workload == "C1" else None),
+                "peak_source": peak_src}
+        if streamed:
+            roof["kernel"] = "k_step_a + k_step_b (streaming PCG iteration; 156 B/active px/iteration algorithmic)"
+            roof["model"] = "streaming-HBM: state in HBM/L2, this is the bound that applies"
+        else:
+            roof["kernel"] = "k_resident (persistent fused GN/PCG solve; 156 B/active px/PCG iteration algorithmic)"
+            roof["model"] = ("streaming-HBM figure for comparison only: NOT a bound for the resident kernel, whose PCG state never "
+                             "leaves registers/shared memory (traffic << algorithmic bytes, so frac may exceed 1); the bound that "
+                             "applies is issue-slot throughput: see issue_active_pct")
+            if "l2_copy_gbs" in prof:
+                roof["l2_frac"] = achieved / prof["l2_copy_gbs"]
+                roof["l2_peak"] = prof["l2_copy_gbs"]
+                roof["l2_peak_source"] = prof["l2_peak_source"]
+            if "issue_active_pct" in prof:
+                roof["issue_active_pct"] = prof["issue_active_pct"]
+                roof["issue_active_source"] = prof["issue_active_source"]
         line = {
             "metric": f"flow pairs/sec @{W}x{H}", "value": value, "unit": "pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload} {W}x{H} {nseg} segment(s) per pair, synth seeds {WORKLOADS[args.workload][4]}+",
-                       "pairs_per_gpu_per_step": B, "schedule": f"{NCONT}x{NGN}x{NPCG}",
-                       "backend": args.backend + (" (streaming)" if streamed else " (resident)"),
-                       "active_px_mean": float(np.mean(active_px)), "parallelism": f"independent pairs x{world}, no collective",
-                       "l2_policy": "L2 flushed between steps by writing a 256 MiB buffer; every step also re-uploads its inputs "
-                                    "(host->device) and restarts from the reset grid, nothing is reused across steps; within a "
-                                    "solve the PCG state lives " + ("in HBM/L2 (tile-interleaved planes)" if streamed else
-                                                                    "in registers/shared memory")},
-            "e2e": {"value": e2e, "unit": "pairs/s",
-                    "h2d_bytes_per_step": int(len(problems) * (4 * N) + nseg * sum(16 * (len(p.matches) + 2 * (W + H)) for p in pairs)),
-                    "d2h_bytes_per_step": int(len(problems) * (12 * N + 4 * NCONT * (NGN + 1)))},
-            "gpu_launches": int(lt.cpu()[0]),
-            "ms_per_gn_solve": solve_ms_max / (B * args.steps * NCONT * NGN),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (measured_traffic(3 if B % 3 == 0 else 4) if not streamed and (B % 3 == 0 or B % 4 == 0) and args.workload == "C1" else None),
-                         "peak_source": peak_src,
-                         "kernel": "k_resident (persistent fused GN/PCG solve; 156 B/active px/PCG iteration algorithmic, "
-                                   "state on chip so a fraction > 1 of the STREAMING roofline is possible)" if not streamed
-                                   else "k_step_a + k_step_b (streaming PCG iteration; 156 B/active px/iteration algorithmic)"},
+            "config": workload_config(args.workload, pairs),
+            "run": {"path": ("opt_h: CombinedSolver/OptSolver sequence, 19 synchronous Opt_ProblemSolve calls per image, host-side "
+                             "constraint lerp + full-image upload per continuation step, one problem per launch" if opt_h else
+                             "batch: arapb200_batch_* (whole 19x8x400 schedules, several problems per cooperative launch)"),
+                    "pairs_per_gpu_per_step": B, "backend": args.backend + (" (streaming)" if streamed else " (resident)"),
+                    "launch": linfo, "parallelism": f"independent pairs x{world}, no collective",
+                    "l2_policy": "L2 flushed between steps by writing a 256 MiB buffer; every step also re-uploads its inputs "
+                                 "(host->device) and restarts from the reset grid, nothing is reused across steps; within a "
+                                 "solve the PCG state lives " + ("in HBM/L2 (tile-interleaved planes)" if streamed else
+                                                                 "in registers/shared memory")},
+            "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": n_launch,
+            # amortised: solve time of the whole step / (problems x GN steps) -- co-resident problems overlap, so this is
+            # NOT the latency of one Gauss-Newton step; that is ms_per_gn_step_single_problem below
+            "ms_per_gn_step_amortised": solve_ms_max / (B * args.steps * NCONT * NGN),
+            "roofline": roof,
             "clocks": clocks,
         }
+        if world == 1 and not streamed:
+            try:   # SURVEY.md 8d (ii), measured after the timed region
+                line["ms_per_gn_step_single_problem"] = single_problem_gn_step_ms(pairs[0], pairs[0].masks[0])
+            except Exception as e:
+                line["ms_per_gn_step_single_problem"] = None
+                print("single-problem GN step timing failed:", e, file=sys.stderr)
         if not args.no_cpu_baseline and world == 1:
             try:
-                _, info = cpu_leg(args.workload)
-                line["cpu_baseline"] = info
+                line["cpu_baseline"] = cpu_leg(args.workload)
             except Exception as e:  # the oracle is a checker; never let it sink the GPU number
                 line["cpu_baseline"] = {"error": str(e)}
         print(json.dumps(line), flush=True)
-    batch.close()
+    if batch:
+        batch.close()
+    if cs:
+        cs.close()
     if world > 1:
         dist.destroy_process_group()
 

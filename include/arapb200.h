@@ -4,8 +4,8 @@
  * ARAP/warping/src/main.cpp), as whole-image calls with plain pointers and sizes.  This is the
  * surface a Terra host reaches with terralib.includec and the one bench.py / the
  * Python mirror bind with ctypes.  All functions return 0 on success, non-zero on failure (message on
- * stderr); CUDA errors inside the Opt_* entry points follow the reference instead and exit
- * (solverGPUGaussNewton.t:59-73).
+ * stderr); nothing in the library calls exit(): failures inside the Opt_* entry points are recorded on the
+ * plan (arapb200_plan_error).
  */
 #ifndef ARAPB200_H
 #define ARAPB200_H
@@ -90,6 +90,11 @@ ARAPB200_API long long arapb200_batch_launches(arapb200_batch* b);
 /* how many problems of the last run were solved by the resident (on-chip) back-end; the rest took the streaming one */
 ARAPB200_API int arapb200_batch_resident_count(arapb200_batch* b);
 
+/* shape of the last cooperative launch of the last run: info6 = {problems sharing the launch, kernel variant's max
+ * threads, variant's min CTAs per SM, grid.x, grid.y, threads per CTA}; zeros when every problem streamed.  Lets a test
+ * assert that it exercised the launch shape a benchmark times. */
+ARAPB200_API int arapb200_batch_launch_info(arapb200_batch* b, int* info6);
+
 /* Options beyond the reference's behaviour; every one defaults to "off" and none is on the parity path.
  *   "pcg_rtol" (SURVEY.md 8f N4): 0 <= value < 1.  > 0: a PCG loop ends as soon as r.z <= value^2 * (r.z at its start)
  *   instead of always running lIterations iterations.  Changes results (by design); resident back-end only --
@@ -99,6 +104,13 @@ ARAPB200_API int arapb200_batch_resident_count(arapb200_batch* b);
  *   out_costs repeat the last cost.  Same scope and caveats as "pcg_rtol".
  * Returns non-zero for unknown names / bad values. */
 ARAPB200_API int arapb200_batch_set_option(arapb200_batch* b, const char* name, double value);
+
+/* Error state of a plan made by Opt_ProblemPlan (include/Opt.h).  Opt_ProblemInit / Step / Solve have no error return
+ * in the reference's ABI (ARAP/API/release/include/Opt.h:60-68) and the reference exits the process on a CUDA failure
+ * (ARAP/API/src/solverGPUGaussNewton.t:59-73); this library records the failure instead: 0 = fine, otherwise the code of
+ * the first failure (Opt_ProblemCurrentCost then returns NaN and Opt_ProblemStep reports "finished"). */
+struct Opt_Plan;
+ARAPB200_API int arapb200_plan_error(struct Opt_Plan* plan);
 
 /* ---- debug / parity entry points (unit-level comparison against the oracle) ----------------- */
 /* one Opt_ProblemSolve on host buffers: X float2[N] and A float[N] in/out; U, C float2[N]; M float[N];

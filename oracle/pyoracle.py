@@ -184,3 +184,37 @@ def warp(pos, rgb, mask_red):
 
 def num_threads() -> int:
     return int(lib().arap_oracle_num_threads())
+
+
+# ---- the independently-ordered "literal" implementation (oracle/arap_literal.c) ---------------------------------
+_LIT = os.path.join(_HERE, "libliteral.so")
+LIT_SINCOS_EVERY_ITER, LIT_ORDERED_ATOMICS = 1, 2
+_lit = None
+
+
+def literal_lib():
+    global _lit
+    if _lit is None:
+        src = os.path.join(_HERE, "arap_literal.c")
+        if not os.path.exists(_LIT) or os.path.getmtime(src) > os.path.getmtime(_LIT):
+            subprocess.check_call(["make", "-C", _HERE, "--no-print-directory", "libliteral.so"], stdout=subprocess.DEVNULL)
+        L = C.CDLL(_LIT)
+        L.arap_literal_solve.argtypes = [C.c_int, C.c_int, _u8p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_ulonglong, C.c_int, _f32p, _f32p, C.c_void_p]
+        L.arap_literal_solve.restype = C.c_int
+        _lit = L
+    return _lit
+
+
+def literal_solve(mask_red, matches, nCont=19, nGN=8, nPCG=400, seed=0, flags=0):
+    """Same interface as solve(); reference-like unfused schedule, libm sin/cos, compiler-chosen contraction, fp32
+    per-warp partial sums accumulated in a seeded shuffled order (arap_literal.c header)."""
+    H, W = mask_red.shape
+    X = np.zeros((H, W, 2), np.float32)
+    A = np.zeros((H, W), np.float32)
+    costs = np.zeros((nCont, nGN + 1), np.float32)
+    m = _c(matches, np.int32).reshape(-1, 4)
+    rc = literal_lib().arap_literal_solve(W, H, _c(mask_red, np.uint8), m, len(m), nCont, nGN, nPCG, seed, flags, X, A,
+                                          costs.ctypes.data)
+    assert rc == 0
+    return X, A, costs

@@ -100,3 +100,36 @@ def test_sharded_run_is_byte_identical_to_single_gpu(tmp_path):
         for k in (3, 4, 5):
             assert open(a[k], "rb").read() == open(b[k], "rb").read()
     assert not os.listdir(tmp_path / "tmp")  # temporary list files are always removed (para_gen.py:197-200)
+
+
+def test_resident_worker_serves_clients_byte_identically(tmp_path):
+    """N2: `arap_deform --serve` keeps context + plan + buffers; clients (the same binary, same argv contract, with
+    ARAP_SERVER set) hand their list files over.  Several dispatches, two image sizes, a single-item argv call: every
+    output file equals the one a stand-alone process writes, the "Saved" lines and exit codes are the same."""
+    sps = [synth.synth(96, 80, 1, 2, 30 + i) for i in range(5)] + [synth.synth(128, 96, 2, 3, 40)]
+    jobs = [(s, s.masks[0]) for s in sps] + [(sps[-1], sps[-1].masks[1])]
+    d1, d2 = tmp_path / "direct", tmp_path / "served"
+    d1.mkdir(); d2.mkdir()
+    it1 = [_write_case(d1, f"p{i}", s, m) for i, (s, m) in enumerate(jobs)]
+    it2 = [_write_case(d2, f"p{i}", s, m) for i, (s, m) in enumerate(jobs)]
+    driver.do_arap(it1, 0, str(tmp_path / "tmp"))
+    spool = str(tmp_path / "spool")
+    env = dict(os.environ, ARAP_PLAN=driver.PLAN, ARAP_SERVER=spool)
+    # no server yet: the client fails loudly instead of solving on its own
+    r = subprocess.run([driver.ARAP_BIN] + list(it2[0]), capture_output=True, text=True, env=env)
+    assert r.returncode == 1 and "no server" in r.stderr
+    with driver.Server(0, spool) as srv:
+        driver.do_arap(it2[:3], 0, str(tmp_path / "tmp"), server=spool)        # dispatch 1
+        driver.do_arap(it2[3:6], 0, str(tmp_path / "tmp"), server=spool)       # dispatch 2: ends with a size change
+        r = subprocess.run([driver.ARAP_BIN] + list(it2[6]), capture_output=True, text=True, env=env)   # argv form
+        assert r.returncode == 0 and r.stdout.count("Saved") == 1, r.stdout + r.stderr
+        # a bad request is answered with a non-zero code and does not take the worker down
+        bad = list(it2[0]); bad[0] = str(tmp_path / "missing.png")
+        r = subprocess.run([driver.ARAP_BIN] + bad, capture_output=True, text=True, env=env)
+        assert r.returncode != 0
+        driver.do_arap(it2[:1], 0, str(tmp_path / "tmp"), server=spool)
+        assert srv.proc.poll() is None
+    for a, b in zip(it1, it2):
+        for k in (3, 4, 5):
+            assert open(a[k], "rb").read() == open(b[k], "rb").read()
+    assert not [f for f in os.listdir(spool) if f.endswith((".job", ".run", ".done"))]

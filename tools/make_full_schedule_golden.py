@@ -1,0 +1,98 @@
+#!/usr/bin/env python
+"""Record FULL-schedule (19 x 8 x 400) oracle results of the BASELINE configurations as small fixtures:
+per problem the 19 x 9 cost table (bit patterns) and SHA-256 digests of the flow and of the warped RGB / mask --
+not the images themselves.  tests/test_gpu_full_schedule.py runs exactly the launch shapes bench.py times and
+asserts equality with these.
+
+Runs the CPU oracle (oracle/arap_oracle.c) only; minutes of CPU per case, resumable: a case already present in
+tests/golden/full_schedule.json is skipped.
+
+  python tools/make_full_schedule_golden.py                 # the default case list, in priority order
+  python tools/make_full_schedule_golden.py C1:1000 C3:3001 # chosen cases (workload:seed)
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from arap_flow_b200 import synth  # noqa: E402
+from oracle import pyoracle as O  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden", "full_schedule.json")
+
+# workload -> (W, H, nseg, fd, axes, schedule)
+WORKLOADS = {
+    "C0": (64, 64, 1, 1, None, (19, 8, 400)),
+    "C1": (854, 480, 1, 1, None, (19, 8, 400)),
+    "C2": (854, 480, 4, 3, None, (19, 8, 400)),
+    "C3": (1024, 436, 1, 5, None, (19, 8, 400)),
+    "C4": (1920, 1080, 1, 1, (0.46, 0.46), (1, 8, 400)),   # one full continuation step
+    # DAVIS-typical small object (about 8 % of the frame): bench.py --workload C1s
+    "C1s": (854, 480, 1, 1, (0.15, 0.17), (19, 8, 400)),
+}
+DEFAULT = (["C1:%d" % s for s in range(1000, 1004)] + ["C2:2000"] + ["C3:%d" % s for s in range(3000, 3003)] + ["C4:4000"] +
+           ["C1s:1000", "C1s:1001"] + ["C1:%d" % s for s in range(1004, 1009)] + ["C2:2001"] +
+           ["C3:%d" % s for s in range(3003, 3008)] + ["C0:%d" % s for s in range(0, 8)])
+
+
+def digest(a: np.ndarray) -> str:
+    a = np.ascontiguousarray(a)
+    if a.dtype == np.float32:
+        a = a + np.float32(0.0)       # -0 -> +0: the digest is over VALUES
+    return hashlib.sha256(a.tobytes()).hexdigest()
+
+
+def make_pair(workload: str, seed: int):
+    W, H, nseg, fd, axes, _ = WORKLOADS[workload]
+    return synth.synth(W, H, nseg, fd, seed, axes=axes)
+
+
+def main():
+    cases = sys.argv[1:] or DEFAULT
+    O.build()
+    db = json.load(open(OUT)) if os.path.exists(OUT) else {}
+    # single-segment pairs of one workload share mask and matches (the seed only changes the texture), so they share the
+    # solve: cache (X, costs) by a digest of what the solve depends on; only the warp is redone per seed
+    solved = {}
+    for case in cases:
+        wl, seed = case.split(":")
+        seed = int(seed)
+        nCont, nGN, nPCG = WORKLOADS[wl][5]
+        sp = make_pair(wl, seed)
+        for s, mask in enumerate(sp.masks):
+            key = f"{wl}:{seed}:{s}"
+            if key in db:
+                continue
+            t0 = time.time()
+            sk = hashlib.sha256(mask.tobytes() + np.ascontiguousarray(sp.matches, np.int32).tobytes() +
+                                repr((sp.W, sp.H, nCont, nGN, nPCG)).encode()).hexdigest()
+            if sk not in solved:
+                solved[sk] = O.solve(mask, sp.matches, nCont=nCont, nGN=nGN, nPCG=nPCG)
+            X, A, costs = solved[sk]
+            fl = O.flow(X)
+            rgb, wm, _ = O.warp(X, sp.rgb, mask)
+            db[key] = {
+                "W": sp.W, "H": sp.H, "schedule": [nCont, nGN, nPCG], "active_px": int((mask == 0).sum()),
+                "n_matches": int(len(sp.matches)), "solve_inputs_sha256": sk,
+                "costs_bits": np.ascontiguousarray(costs, np.float32).view(np.uint32).tolist(),
+                "final_cost": float(costs[-1, -1]),
+                "flow_sha256": digest(fl), "rgb_sha256": digest(rgb), "mask_sha256": digest(wm),
+                "flow_abs_mean": float(np.abs(fl[mask == 0]).mean()) if (mask == 0).any() else 0.0,
+                "oracle_seconds": round(time.time() - t0, 1), "oracle_threads": O.num_threads(),
+            }
+            tmp = OUT + ".tmp"
+            with open(tmp, "w") as f:
+                json.dump(db, f, indent=0, sort_keys=True)
+            os.replace(tmp, OUT)
+            print(key, "done in %.0f s, final cost %.6f" % (time.time() - t0, costs[-1, -1]), flush=True)
+
+
+if __name__ == "__main__":
+    main()
