@@ -98,6 +98,7 @@ class CombinedSolver:
         self.w_reg = C.c_float(float(np.sqrt(np.float32(0.01))))
         self.costs = []
         self.h2d_bytes = self.d2h_bytes = 0
+        self.seconds = {"reset": 0.0, "constraints": 0.0, "solve": 0.0, "download+warp": 0.0}   # wall time per stage, last image
 
     # ---- addImage (:139-170): keep the inputs, resolve which constraint wins at every source pixel once -------------
     def add_image(self, rgb, mask_red, constraints):
@@ -138,16 +139,26 @@ class CombinedSolver:
 
     def solve_all(self):
         """CombinedSolverBase::singleSolve (CombinedSolverBase.h:99-120)"""
+        import time
         self.h2d_bytes = self.d2h_bytes = 0
+        t0 = time.perf_counter()
         self._reset_gpu()                                             # preSingleSolve
+        t1 = time.perf_counter()
+        sec = {"reset": t1 - t0, "constraints": 0.0, "solve": 0.0, "download+warp": 0.0}
         pp = (C.c_void_p * 7)(self.d_offset.data_ptr(), self.d_angle.data_ptr(), self.d_urshape.data_ptr(),
                               self.d_constraints.data_ptr(), self.d_mask.data_ptr(),
                               C.cast(C.byref(self.w_fit), C.c_void_p), C.cast(C.byref(self.w_reg), C.c_void_p))
         sp = {"nIterations": self.nIterations, "lIterations": self.lIterations}
         self.costs = []
         for i in range(self.numIter):
+            t0 = time.perf_counter()
             self._set_constraint_image(np.float32(i + 1) / np.float32(self.numIter))   # preNonlinearSolve (:199-201)
+            t1 = time.perf_counter()
             self.costs.append(self.solver.solve(sp, pp))
+            t2 = time.perf_counter()
+            sec["constraints"] += t1 - t0
+            sec["solve"] += t2 - t1
+        t0 = time.perf_counter()
         # postSingleSolve -> copyResultToCPU (:280-342): download the warp field, rasterise
         self.h_field.copy_(self.d_offset)
         self.d2h_bytes += self.h_field.numpy().nbytes
@@ -156,6 +167,8 @@ class CombinedSolver:
         N = self.W * self.H
         self.h2d_bytes += 8 * N + 3 * N + N
         self.d2h_bytes += 3 * N + N
+        sec["download+warp"] = time.perf_counter() - t0
+        self.seconds = sec
         return self.costs[-1]
 
     def warp_field(self):

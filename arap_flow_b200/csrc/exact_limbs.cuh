@@ -1,0 +1,98 @@
+// exact_limbs.cuh -- integer helpers of the resident kernel's exact grid-wide sums (contract C3):
+// a binary32 term <-> four signed 24-bit limbs of a 96-bit fixed-point number, and the 4-limb total -> binary32 with one
+// rounding.  Plain integer code, host + device, so that tests/test_exact_limbs.py can check it against exact rational
+// arithmetic without a GPU (tests/exact_limbs_host.cpp).
+#pragma once
+#include <cstdint>
+#include <cstring>
+
+#if defined(__CUDACC__)
+#define ARAP_HD __host__ __device__ __forceinline__
+#else
+#define ARAP_HD inline
+#endif
+
+#ifndef ARAP_RS_INT_LIMBS
+#define ARAP_RS_INT_LIMBS 1
+#endif
+#ifndef ARAP_RS_INT_FOLD
+#define ARAP_RS_INT_FOLD 1
+#endif
+
+namespace arapb200 {
+
+ARAP_HD int clz64(unsigned long long v) // v != 0
+{
+#if defined(__CUDA_ARCH__)
+    return __clzll((long long)v);
+#else
+    return __builtin_clzll(v);
+#endif
+}
+
+// One binary32 term -> four signed 24-bit limbs (units 2^(S-18), 2^(S-42), 2^(S-66), 2^(S-90)), in integer arithmetic
+// (the float formulation is a chain of 4 x {FMUL, F2I, I2F, FSUB} on the slow conversion pipe, in front of every
+// barrier arrival).  Exact for |g| < 2^(S+6) and ulp(g) >= 2^(S-90); bits below the LSB are rounded to nearest;
+// |g| >= 2^(S+6), Inf and NaN report ovf and contribute nothing.
+ARAP_HD void to_limbs(float g, int S, int& l0, int& l1, int& l2, int& l3, bool& ovf)
+{
+    unsigned b;
+    memcpy(&b, &g, 4);
+    const int e = (int)((b >> 23) & 0xffu);
+    unsigned m = (b & 0x7fffffu) | (e ? 0x800000u : 0u);
+    int p = (e > 1 ? e : 1) - 60 - S; // bit position of m's LSB: value = m * 2^(max(e,1) - 150), unit 2^(S - 90)
+    ovf = (e == 255) || (m != 0u && p > 72);
+    if (p < 0) { // below the LSB: round to nearest
+        const int r = -p;
+        m = (r <= 25) ? ((m + (1u << (r - 1))) >> r) : 0u;
+        p = 0;
+    }
+    if (ovf) m = 0u;
+    if (p > 72) p = 72;
+    const int j = (p * 43) >> 10; // p / 24 for 0 <= p < 96
+    const int o = p - 24 * j;
+    const unsigned long long w = (unsigned long long)m << o; // < 2^48
+    int lo = (int)(w & 0xffffffull), hi = (int)(w >> 24);
+    if ((int)b < 0) { lo = -lo; hi = -hi; }
+    l3 = (j == 0) ? lo : 0;
+    l2 = (j == 0) ? hi : ((j == 1) ? lo : 0);
+    l1 = (j == 1) ? hi : ((j == 2) ? lo : 0);
+    l0 = (j == 2) ? hi : ((j == 3) ? lo : 0);
+}
+
+// T = L0*2^72 + L1*2^48 + L2*2^24 + L3 (|Lj| < 2^45 => |T| < 2^118, units 2^e_unit) -> binary32, rounded ONCE to
+// nearest-even.  Returns false (nothing computed) when the result would leave binary32's normal range by a wide margin:
+// the caller then takes the binary64 route.
+ARAP_HD bool limbs_to_float_int(const long long L[4], int e_unit, bool& is_zero, float& out)
+{
+    const __int128 T = ((__int128)L[0] << 72) + ((__int128)L[1] << 48) + ((__int128)L[2] << 24) + (__int128)L[3];
+    is_zero = (T == 0);
+    out = 0.0f;
+    if (is_zero) return true;
+    const bool neg = T < 0;
+    const unsigned __int128 a = neg ? (unsigned __int128)(-T) : (unsigned __int128)T;
+    const unsigned long long hi = (unsigned long long)(a >> 64), lo = (unsigned long long)a;
+    const int nb = hi ? 128 - clz64(hi) : 64 - clz64(lo); // significant bits of |T|
+    if (nb + e_unit < -120 || nb + e_unit > 120) return false;
+    unsigned q;
+    int sh = nb - 24;
+    if (sh <= 0) {
+        q = (unsigned)lo;
+        sh = 0;
+    } else {
+        const unsigned t25 = (unsigned)(a >> (sh - 1)); // q and the round bit
+        const bool sticky = (a & ((((unsigned __int128)1) << (sh - 1)) - 1)) != 0;
+        q = t25 >> 1;
+        if ((t25 & 1u) && (sticky || (q & 1u))) ++q; // nearest, ties to even (q may become 2^24: still exact below)
+    }
+    // q * 2^(sh + e_unit): q <= 2^24 and the exponent keeps the product a normal binary32 => exact
+    const int ex = sh + e_unit; // in [-144, 120]
+    unsigned long long dbits = (unsigned long long)(ex + 1023) << 52;
+    double scale;
+    memcpy(&scale, &dbits, 8);
+    const float r = (float)((double)q * scale);
+    out = neg ? -r : r;
+    return true;
+}
+
+} // namespace arapb200

@@ -30,6 +30,7 @@
 #include "solver_resident.cuh"
 #include "grid_math.cuh"
 #include "solver_stream.cuh" // FLAG_* bit layout
+#include "exact_limbs.cuh"
 #include <algorithm>
 
 namespace arapb200 {
@@ -41,6 +42,11 @@ constexpr int OB_LEFT = 64, OB_RIGHT = 64 + RS_STRIP_H;
 static_assert(RS_STRIP_H == 4 || RS_STRIP_H == 8, "strip height must be 4 or 8");
 constexpr long long LIMB_BIAS = 1ll << 36;
 constexpr int BAR_STRIDE = 128; // u64 words between barrier words (1 KiB): separate L2 slices, parallel atomics
+#ifndef ARAP_RS_BAR_REPLICAS
+#define ARAP_RS_BAR_REPLICAS 1 // every CTA adds its contribution to R copies of the barrier words and polls copy (cta % R)
+#endif
+constexpr int BAR_R = ARAP_RS_BAR_REPLICAS;
+constexpr int BAR_WORDS = 2 * BAR_R * 4; // [buffer][replica][limb]
 constexpr int S_MIN = -100, S_MAX = 100;
 
 struct __align__(16) StripSmem {
@@ -51,16 +57,15 @@ struct __align__(16) StripSmem {
     float2 pre[RS_STRIP_H][32];        // (1/(1+sqrt(D_X))^2, 1/(1+sqrt(D_a))^2) per pixel, constant during a GN step
 };
 
-struct Ctl {
+struct __align__(16) Ctl {
     int limb[RS_THREADS_MAX / 32][4];
     int ovf[RS_THREADS_MAX / 32];
     unsigned long long prev[2][4]; // totals last seen in each barrier buffer
-    float bc;                      // broadcast result
+    unsigned long long local[4];   // G == 1: this CTA's contribution stays here, the barrier never leaves the SM
+    int4 bc4;                      // broadcast of a finished barrier: (result bits, 0 accept / 1 redo, new scale, abort)
     float stop;                    // opt-in early exit: leave the PCG loop once r.z <= stop (-1: never)
     float prev_cost;               // opt-in early exit of the Gauss-Newton loop: cost before the last step
-    int bc_code;                   // 0 accept, 1 redo with bc_S
-    int bc_S;
-    int abort;
+    int abort_halo;                // a halo fetch of this CTA hit its watchdog
 };
 
 __device__ __forceinline__ unsigned long long ld_u64_volatile(const unsigned long long* p)
@@ -77,14 +82,26 @@ __device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long
 // half): 64-bit elements of a vector access are single-copy atomic in the PTX memory model, so a value can never be
 // observed with another publication's tag, and a relaxed store paired with a relaxed load is a morally strong pair (no
 // data race).  The uint4 view (x = float, y = tag, z = float, w = tag) is the same bytes.
+#ifndef ARAP_RS_HALO_WEAK
+#define ARAP_RS_HALO_WEAK 0 // 1 = round 1's accesses (weak st.v4.u32 / ld.relaxed.v4.u32), kept only to measure the fix's cost
+#endif
 __device__ __forceinline__ uint4 ld_entry_relaxed(const uint4* p)
 {
+#if ARAP_RS_HALO_WEAK
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+#endif
     unsigned long long a, b;
     asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
     return make_uint4((unsigned)a, (unsigned)(a >> 32), (unsigned)b, (unsigned)(b >> 32));
 }
 __device__ __forceinline__ void st_entry_relaxed(uint4* p, unsigned tag, float v0, float v1)
 {
+#if ARAP_RS_HALO_WEAK
+    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(__float_as_uint(v0)), "r"(tag), "r"(__float_as_uint(v1)), "r"(tag) : "memory");
+    return;
+#endif
     const unsigned long long t = (unsigned long long)tag << 32;
     const unsigned long long a = t | __float_as_uint(v0), b = t | __float_as_uint(v1);
     asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
@@ -105,7 +122,7 @@ __device__ __forceinline__ void two_sum(double a, double b, double& s, double& e
 // L0*2^72 + L1*2^48 + L2*2^24 + L3 (|Lj| < 2^45, units 2^e_unit) -> binary32 with ONE rounding: the four terms
 // are exact doubles; they are added error-free (s + e), s + e is rounded to odd in binary64 (53 >= 24 + 2 bits)
 // and only then to binary32.
-__device__ __forceinline__ float limbs_to_float_rn(const long long L[4], int e_unit, bool& is_zero)
+__device__ __forceinline__ float limbs_to_float_rn_f64(const long long L[4], int e_unit, bool& is_zero)
 {
     const double a = __ll2double_rn(L[0]) * 4722366482869645213696.0; // 2^72
     const double b = __ll2double_rn(L[1]) * 281474976710656.0;        // 2^48
@@ -123,6 +140,19 @@ __device__ __forceinline__ float limbs_to_float_rn(const long long L[4], int e_u
     if (zd != zu) z = __longlong_as_double(__double_as_longlong(z) | 1ll);
     e_unit = max(-900, min(900, e_unit));
     return (float)(z * pow2_f64(e_unit)); // exact scaling (barring binary32 underflow), single rounding
+}
+
+// The integer version (exact_limbs.cuh) is the default: the decode sits on the critical path of every grid barrier and
+// the binary64 version is a chain of ~25 dependent DADDs.  Totals near binary32's subnormal / overflow range take the
+// binary64 route (one rounding there needs the round-to-odd trick).
+__device__ __forceinline__ float limbs_to_float_rn(const long long L[4], int e_unit, bool& is_zero)
+{
+#if ARAP_RS_INT_FOLD
+    float r;
+    e_unit = max(-900, min(900, e_unit));
+    if (limbs_to_float_int(L, e_unit, is_zero, r)) return r;
+#endif
+    return limbs_to_float_rn_f64(L, e_unit, is_zero);
 }
 
 // Everything a warp needs to know about its strip
@@ -161,10 +191,22 @@ __device__ __forceinline__ void grid_arrive(Cta& c, float g0, float g1, int S, l
     Ctl* ctl = c.ctl;
     if (c.prof) t0 = clock64();
     // ---- thread -> four signed 24-bit limbs in units 2^(S-18), 2^(S-42), 2^(S-66), 2^(S-90) ----
-    // (binary32 only: scaling by powers of two and the remainders are exact)
-    const float sc = __int_as_float((127 + 18 - S) << 23);
     int l0, l1, l2, l3;
     bool ovf;
+#if ARAP_RS_INT_LIMBS
+    {
+        int m0, m1, m2, m3;
+        bool o1;
+        to_limbs(g0, S, l0, l1, l2, l3, ovf);
+        if (RS_STRIP_H == 8) {
+            to_limbs(g1, S, m0, m1, m2, m3, o1);
+            l0 += m0; l1 += m1; l2 += m2; l3 += m3;
+            ovf = ovf || o1;
+        }
+    }
+#else
+    // (binary32 only: scaling by powers of two and the remainders are exact)
+    const float sc = __int_as_float((127 + 18 - S) << 23);
     {
         const float v = g0 * sc;
         ovf = !(fabsf(v) < 16777216.0f); // |g| >= 2^(S+6), Inf or NaN
@@ -190,6 +232,7 @@ __device__ __forceinline__ void grid_arrive(Cta& c, float g0, float g1, int S, l
         const float v3 = (v2 - (float)m2) * 16777216.0f;
         l0 += m0; l1 += m1; l2 += m2; l3 += __float2int_rn(v3);
     }
+#endif
     const int s0 = __reduce_add_sync(0xffffffffu, l0);
     const int s1 = __reduce_add_sync(0xffffffffu, l1);
     const int s2 = __reduce_add_sync(0xffffffffu, l2);
@@ -203,33 +246,100 @@ __device__ __forceinline__ void grid_arrive(Cta& c, float g0, float g1, int S, l
         ctl->ovf[c.wid] = wovf ? 1 : 0;
     }
     __syncthreads();
-    if (c.wid == 0 && c.lane < 4) {
-        unsigned long long* buf = c.P->bar + (size_t)(c.epoch & 1u) * 4 * BAR_STRIDE;
+    if (c.wid == 0 && c.lane < 4 * BAR_R) { // lane = 4 * replica + limb
+        unsigned long long* buf = c.P->bar + (size_t)(c.epoch & 1u) * (4 * BAR_R) * BAR_STRIDE;
+        const int limb = c.lane & 3;
         long long sum = 0;
         int any = 0;
         for (int w = 0; w < c.nw; ++w) {
-            sum += (long long)ctl->limb[w][c.lane];
+            sum += (long long)ctl->limb[w][limb];
             any |= ctl->ovf[w];
         }
         unsigned long long contrib = (1ull << 48) + (unsigned long long)(sum + LIMB_BIAS);
-        if (c.lane == 0 && any) contrib += (1ull << 56);
-        red_add_u64(buf + (size_t)c.lane * BAR_STRIDE, contrib);
+        if (limb == 0 && any) contrib += (1ull << 56);
+        if (c.G == 1) { if (c.lane < 4) ctl->local[limb] = contrib; } // a problem that fits one CTA: CTA-local all-reduce, no L2 round trip
+        else red_add_u64(buf + (size_t)c.lane * BAR_STRIDE, contrib);
     }
+    __syncwarp(); // (G == 1) lane 0 reads ctl->local[0..3] in grid_wait
     if (c.prof) t1 = clock64();
 }
 
 // grid_wait: poll the barrier words until all G CTAs have arrived, decode, verify the scale, broadcast.
 // Returns 0 = accepted (result in res, S updated for the next reduction of this kind), 1 = redo with the new S.
+#ifndef ARAP_RS_WARP_POLL
+#define ARAP_RS_WARP_POLL 1 // 0 = round 1's poller: lane 0 of warp 0 loads and decodes all four words
+#endif
 __device__ __forceinline__ int grid_wait(Cta& c, int& S, bool& grown, float& res, bool& ok, long long t0, long long t1)
 {
     Ctl* ctl = c.ctl;
     const ResProb& P = *c.P;
     long long t2 = 0;
+#if ARAP_RS_WARP_POLL
+    // Warp 0 polls as a warp: lane l looks at word (l & 3), so one load instruction covers the four words (the same four
+    // sectors as before: lanes that share a word coalesce) and the poll loop is a quarter of the instructions -- they
+    // compete for issue slots with the compute warps of the co-resident problems.  The four limbs are then gathered
+    // with shuffles and every lane decodes the total redundantly.
+    if (c.wid == 0) {
+        const int j = c.lane & 3;
+        unsigned long long d;
+        bool aborted = false;
+        if (c.G == 1) {
+            d = ctl->local[j]; // written by lanes 0..3 of this warp before the __syncwarp in grid_arrive
+        } else {
+            const unsigned long long* w = P.bar + ((size_t)(c.epoch & 1u) * (4 * BAR_R) + (c.cta % BAR_R) * 4 + j) * BAR_STRIDE;
+            const unsigned long long pv = ctl->prev[c.epoch & 1u][j];
+            unsigned spins = 0;
+            for (;;) {
+                d = ld_u64_volatile(w) - pv;
+                if (__all_sync(0xffffffffu, (int)((d >> 48) & 0xFF) == c.G)) break;
+                if ((++spins & 0xffu) == 0) {
+                    // watchdog: a peer's abort or ~seconds of polling => leave instead of hanging the GPU
+                    if (*(volatile int*)P.status || spins > (1u << 23)) {
+                        aborted = true;
+                        break;
+                    }
+                }
+            }
+            if (c.lane < 4) ctl->prev[c.epoch & 1u][j] = pv + d;
+        }
+        if (c.prof) t2 = clock64();
+        const long long Lm = (long long)(d & ((1ull << 48) - 1)) - (long long)c.G * LIMB_BIAS;
+        long long L[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) L[k] = __shfl_sync(0xffffffffu, Lm, k);
+        const int novf = (int)((__shfl_sync(0xffffffffu, d, 0) >> 56) & 0xFF);
+        bool T_is_zero;
+        const float r = limbs_to_float_rn(L, S - 90, T_is_zero);
+        int code = 0, newS = S;
+        if (novf) {
+            code = 1; newS = min(S + 24, S_MAX);
+            if (S >= S_MAX) code = 0; // Inf/NaN terms: give up, the result is garbage anyway
+        } else if (T_is_zero) {
+            if (!grown && S > S_MIN) { code = 1; newS = max(S - 64, S_MIN); }
+        } else {
+            const int e = ilogb_f32(fabsf(r));
+            if (!grown && e < S - 24 && S > S_MIN) { code = 1; newS = max(e + 4, S_MIN); }
+            else newS = max(min(e + 4, S_MAX), S_MIN);
+        }
+        if (c.lane == 0) {
+            if (aborted) {
+                atomicExch(P.status, 1);
+                atomicCAS(P.status + 1, 0, 100 + (int)(c.epoch & 0xffff));
+            }
+            ctl->bc4 = make_int4(__float_as_int(r), code, newS, (aborted || ctl->abort_halo) ? 1 : ctl->bc4.w); // one store, one load per reader
+        }
+    }
+#else
     if (c.wid == 0 && c.lane == 0) {
-        unsigned long long* buf = P.bar + (size_t)(c.epoch & 1u) * 4 * BAR_STRIDE;
+        unsigned long long* buf = P.bar + ((size_t)(c.epoch & 1u) * (4 * BAR_R) + (c.cta % BAR_R) * 4) * BAR_STRIDE;
         unsigned long long* prev = ctl->prev[c.epoch & 1u];
         unsigned long long d[4];
         unsigned spins = 0;
+        bool aborted = false;
+        if (c.G == 1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) d[j] = ctl->local[j]; // written by lanes 0..3 of this warp before the __syncwarp in grid_arrive
+        } else
         for (;;) {
             bool done = true;
 #pragma unroll
@@ -243,7 +353,7 @@ __device__ __forceinline__ int grid_wait(Cta& c, int& S, bool& grown, float& res
                 if (*(volatile int*)P.status || spins > (1u << 23)) {
                     atomicExch(P.status, 1);
                     atomicCAS(P.status + 1, 0, 100 + (int)(c.epoch & 0xffff));
-                    ctl->abort = 1;
+                    aborted = true;
                     break;
                 }
             }
@@ -252,7 +362,7 @@ __device__ __forceinline__ int grid_wait(Cta& c, int& S, bool& grown, float& res
         long long L[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            prev[j] += d[j];
+            if (c.G != 1) prev[j] += d[j];
             L[j] = (long long)(d[j] & ((1ull << 48) - 1)) - (long long)c.G * LIMB_BIAS;
         }
         const int novf = (int)((d[0] >> 56) & 0xFF);
@@ -269,10 +379,9 @@ __device__ __forceinline__ int grid_wait(Cta& c, int& S, bool& grown, float& res
             if (!grown && e < S - 24 && S > S_MIN) { code = 1; newS = max(e + 4, S_MIN); }
             else newS = max(min(e + 4, S_MAX), S_MIN);
         }
-        ctl->bc = r;
-        ctl->bc_code = code;
-        ctl->bc_S = newS;
+        ctl->bc4 = make_int4(__float_as_int(r), code, newS, (aborted || ctl->abort_halo) ? 1 : ctl->bc4.w);
     }
+#endif
     __syncthreads();
     if (c.prof && threadIdx.x == 0) {
         const long long t3 = clock64();
@@ -281,13 +390,12 @@ __device__ __forceinline__ int grid_wait(Cta& c, int& S, bool& grown, float& res
         c.acc[2] += (unsigned long long)(t3 - t2);
     }
     ++c.epoch;
-    if (ctl->abort) { ok = false; res = 0.f; return 0; }
-    const int code = ctl->bc_code;
-    const int newS = ctl->bc_S;
-    res = ctl->bc;
-    if (newS > S) grown = true;
-    S = newS;
-    return code;
+    const int4 bc = ctl->bc4; // (result, code, new scale, abort)
+    if (bc.w) { ok = false; res = 0.f; return 0; }
+    res = __int_as_float(bc.x);
+    if (bc.z > S) grown = true;
+    S = bc.z;
+    return bc.y;
 }
 
 // arrive + wait (+ the rare redo with a corrected scale).  Returns the exact sum rounded once to binary32.
@@ -369,7 +477,7 @@ __device__ __forceinline__ void fetch_halo(const ResProb& P, Ctl* ctl, const Str
         if ((++spins & 0xffu) == 0 && (*(volatile int*)P.status || spins > (1u << 22))) {
             atomicExch(P.status, 1);
             atomicCAS(P.status + 1, 0, 200);
-            ctl->abort = 1;
+            ctl->abort_halo = 1; // folded into the broadcast of the next barrier (grid_wait)
             return;
         }
     }
@@ -482,7 +590,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
     const int W = P.W, H = P.H;
     const float wr = P.wr, wf = P.wf, wr2 = P.wr2, wf2 = P.wf2;
 
-    if (threadIdx.x == 0) ctl.abort = 0;
+    if (threadIdx.x == 0) { ctl.bc4 = make_int4(0, 0, 0, 0); ctl.abort_halo = 0; }
     if (threadIdx.x < 8) ctl.prev[threadIdx.x >> 2][threadIdx.x & 3] = 0ull; // the host zeroes P.bar before the launch
 
     // ---- which strip is mine, who are my neighbours ----
@@ -916,6 +1024,7 @@ static int pick_variant(int nw, long long total_ctas, int sm_count)
 
 ResidentSolver::ResidentSolver(int maxW, int maxH, int max_slots) : maxW_(maxW), maxH_(maxH)
 {
+    if (const char* e = getenv("ARAP_RS_ONE_CTA")) small_one_cta_ = atoi(e) != 0; // experiments: 0 = always spread
     int dev = 0;
     ARAP_CUDA_CHECK(cudaGetDevice(&dev));
     ARAP_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, dev));
@@ -929,7 +1038,7 @@ ResidentSolver::ResidentSolver(int maxW, int maxH, int max_slots) : maxW_(maxW),
         // the outbox only has to hold what can be resident: at most sm_count * max warps strips
         const size_t ob = std::min(strip_cap_, (size_t)sm_count_ * (RS_THREADS_MAX / 32));
         ARAP_CUDA_CHECK(cudaMalloc(&sl.d_outbox, ob * RS_OUTBOX_ENTRIES * 2 * sizeof(uint4)));
-        ARAP_CUDA_CHECK(cudaMalloc(&sl.d_bar, 8 * BAR_STRIDE * sizeof(unsigned long long)));
+        ARAP_CUDA_CHECK(cudaMalloc(&sl.d_bar, BAR_WORDS * BAR_STRIDE * sizeof(unsigned long long)));
     }
     ARAP_CUDA_CHECK(cudaMallocHost(&h_counts_, slots_.size() * sizeof(int)));
     ARAP_CUDA_CHECK(cudaMalloc(&d_status_, 2 * sizeof(int)));
@@ -981,6 +1090,9 @@ bool ResidentSolver::prepare_finish(int slot)
     sl.NW = (sl.n_strips + sm_count_ - 1) / sm_count_;
     if (sl.NW < 4) sl.NW = 4;
     if (sl.NW > max_warps) return false; // does not fit on chip
+    // a small problem (a DAVIS segment of a few percent of the frame, the 64x64 plumbing case) runs in ONE CTA: its two
+    // reductions per PCG iteration then never leave the SM (CTA-local all-reduce in grid_arrive / grid_wait)
+    if (sl.n_strips <= max_warps && small_one_cta_) sl.NW = std::max(sl.n_strips, 4);
     sl.G = (sl.n_strips + sl.NW - 1) / sl.NW;
     if (sl.G > sm_count_) sl.G = sm_count_;
     if (sl.G > RS_MAX_CTAS) return false;
@@ -1041,7 +1153,7 @@ void ResidentSolver::enqueue_group(int first, int count, int nCont, int nGN, int
         ctas += sl.G;
         nwmax = std::max(nwmax, sl.NW);
         // barrier words start at zero; halo tags start at 1, so a zeroed outbox is "nothing published yet"
-        ARAP_CUDA_CHECK(cudaMemsetAsync(sl.d_bar, 0, 8 * BAR_STRIDE * sizeof(unsigned long long), stream));
+        ARAP_CUDA_CHECK(cudaMemsetAsync(sl.d_bar, 0, BAR_WORDS * BAR_STRIDE * sizeof(unsigned long long), stream));
         ARAP_CUDA_CHECK(cudaMemsetAsync(sl.d_outbox, 0,
                                           (size_t)(sl.n_strips > 0 ? sl.n_strips : 1) * RS_OUTBOX_ENTRIES * 2 * sizeof(uint4), stream));
     }

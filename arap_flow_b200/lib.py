@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libarapb200.so")
+# ARAPB200_LIB selects another build of the same library (A/B measurements, tools/build_variant.sh)
+LIB_PATH = os.environ.get("ARAPB200_LIB") or os.path.join(_HERE, "libarapb200.so")
 
 BACKEND_AUTO, BACKEND_STREAM, BACKEND_RESIDENT = 0, 1, 2
 

@@ -440,7 +440,7 @@ def main():
                              "constraint lerp + full-image upload per continuation step, one problem per launch" if opt_h else
                              "batch: arapb200_batch_* (whole 19x8x400 schedules, several problems per cooperative launch)"),
                     "pairs_per_gpu_per_step": B, "backend": args.backend + (" (streaming)" if streamed else " (resident)"),
-                    "launch": linfo, "parallelism": f"independent pairs x{world}, no collective",
+                    "launch": linfo, "opt_h_seconds_last_image": (cs.seconds if cs else None), "parallelism": f"independent pairs x{world}, no collective",
                     "l2_policy": "L2 flushed between steps by writing a 256 MiB buffer; every step also re-uploads its inputs "
                                  "(host->device) and restarts from the reset grid, nothing is reused across steps; within a "
                                  "solve the PCG state lives " + ("in HBM/L2 (tile-interleaved planes)" if streamed else

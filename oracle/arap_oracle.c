@@ -481,6 +481,18 @@ static float cost_all(const Prob *P, Work *w, const float *X, const float *A)
     return 0.5f * reduce_terms(P, w->T, w->gb);
 }
 
+/* Opt-in convergence-aware schedule (NOT reference behaviour, default off): the same two rules the
+ * resident CUDA kernel implements, so that the early-exit path is checked against this oracle and not against itself.
+ *   pcg_rtol > 0: a PCG loop ends after the iteration whose r.z <= pcg_rtol^2 * (r.z at PCGInit1)
+ *   gn_rtol  > 0: the Gauss-Newton steps of one Opt_ProblemSolve end once a step lowers the cost by less than gn_rtol
+ *                 (relative); the remaining cost entries repeat the last cost */
+static float g_pcg_rtol = 0.0f, g_gn_rtol = 0.0f;
+ORACLE_API void arap_oracle_set_rtol(float pcg_rtol, float gn_rtol)
+{
+    g_pcg_rtol = pcg_rtol > 0.0f ? pcg_rtol : 0.0f;
+    g_gn_rtol = gn_rtol > 0.0f ? gn_rtol : 0.0f;
+}
+
 /* One Gauss-Newton step = solverGPUGaussNewton.t:1016-1177 with UsesLambda()==false.
  * Optional trace: scal[3*it+0..2] = (den, alpha-numerator used, beta numerator) per PCG iteration. */
 static void gn_step(const Prob *P, Work *w, float *X, float *A, int nPCG, float *scal)
@@ -506,6 +518,8 @@ static void gn_step(const Prob *P, Work *w, float *X, float *A, int nPCG, float 
                 T[i] = dot3(&r[3 * i], &p[3 * i]);
             }
     float num = reduce_terms(P, T, w->gb);
+    const float rtol2 = g_pcg_rtol * g_pcg_rtol;
+    const float stop = (rtol2 > 0.0f) ? rtol2 * num : -1.0f;
     for (int it = 0; it < nPCG; ++it) {
         /* PCGStep1 (:421-434) */
 #pragma omp parallel for schedule(static)
@@ -534,6 +548,10 @@ static void gn_step(const Prob *P, Work *w, float *X, float *A, int nPCG, float 
                 }
         float bnum = reduce_terms(P, T, w->gb);
         float beta = (num > 0.0f) ? bnum / num : 0.0f; /* :537-550 */
+        if (it + 1 < nPCG && bnum <= stop) { /* opt-in early exit: the direction is not needed any more */
+            if (scal) { scal[3 * it] = den; scal[3 * it + 1] = num; scal[3 * it + 2] = bnum; }
+            break;
+        }
 #pragma omp parallel for schedule(static)
         for (int y = P->y0; y <= P->y1; ++y)
             for (int x = P->x0; x <= P->x1; ++x)
@@ -571,10 +589,17 @@ ORACLE_API int arap_oracle_gn_solve(int W, int H, float *X, float *A, const floa
     if (!work_alloc(&w, &P)) return -1;
     float c0 = cost_all(&P, &w, X, A);
     if (costs) costs[0] = c0;
+    float prev = c0;
     for (int g = 0; g < nGN; ++g) {
         gn_step(&P, &w, X, A, nPCG, scal ? scal + (size_t)3 * nPCG * g : NULL);
         float c = cost_all(&P, &w, X, A);
         if (costs) costs[g + 1] = c;
+        if (g_gn_rtol > 0.0f && g + 1 < nGN && !((prev - c) > g_gn_rtol * prev)) { /* opt-in: this step gained too little */
+            if (costs)
+                for (int gg = g + 2; gg <= nGN; ++gg) costs[gg] = c;
+            break;
+        }
+        prev = c;
     }
     work_free(&w);
     return 0;

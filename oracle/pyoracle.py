@@ -62,6 +62,8 @@ def lib():
         L.arap_oracle_warp.argtypes = [C.c_int, C.c_int, _f32p, _u8p, _u8p, _u8p, _u8p, _u32p]
         L.arap_oracle_flow_to_pos.argtypes = [C.c_int, C.c_int, _f32p, _f32p]
         L.arap_oracle_num_threads.restype = C.c_int
+        L.arap_oracle_set_rtol.argtypes = [C.c_float, C.c_float]
+        L.arap_oracle_set_rtol.restype = None
         _lib = L
     return _lib
 
@@ -156,6 +158,11 @@ def solve(mask_red, matches, nCont=19, nGN=8, nPCG=400):
                                  costs.ctypes.data)
     assert rc == 0
     return X, A, costs
+
+
+def set_rtol(pcg_rtol=0.0, gn_rtol=0.0):
+    """Opt-in early exits (N4), mirrored from the resident kernel; (0, 0) restores the reference's fixed budget."""
+    lib().arap_oracle_set_rtol(np.float32(pcg_rtol), np.float32(gn_rtol))
 
 
 def flow(X):

@@ -453,12 +453,22 @@ def test_opt_in_pcg_tolerance_n4(oracle):
     assert _eq(same["flow"], full["flow"]) and _eq(same["costs"], full["costs"])
     b.set_option("pcg_rtol", 1e-2)
     fast, t_fast = run()
+    # the early-exit path against the ORACLE's implementation of the same rule (not against itself): bit-exact
+    try:
+        oracle.set_rtol(1e-2, 0.0)
+        Xe, Ae, ce = oracle.solve(sp.masks[0], sp.matches, **kw)
+        assert _eq(fast["flow"], oracle.flow(Xe)) and _eq(fast["costs"], ce)
+        oracle.set_rtol(1e-2, 1e-2)
+        Xe2, Ae2, ce2 = oracle.solve(sp.masks[0], sp.matches, **kw)
+    finally:
+        oracle.set_rtol(0.0, 0.0)
     act = sp.masks[0] == 0
     d = np.linalg.norm(fast["flow"] - full["flow"], axis=-1)[act]
     assert t_fast < 0.8 * t_full, (t_fast, t_full)
     assert d.mean() < 0.5 and abs(fast["costs"][-1, -1] - full["costs"][-1, -1]) < 0.2 * abs(full["costs"][-1, -1]) + 1e-3, (d.mean(), fast["costs"][-1], full["costs"][-1])
     b.set_option("gn_rtol", 1e-2)
     faster, t_faster = run()
+    assert _eq(faster["flow"], oracle.flow(Xe2)) and _eq(faster["costs"], ce2)
     d2 = np.linalg.norm(faster["flow"] - full["flow"], axis=-1)[act]
     assert t_faster <= t_fast * 1.05 and d2.mean() < 0.5, (t_faster, t_fast, d2.mean())
     assert np.all(np.diff(faster["costs"], axis=1) <= 1e-6 * np.abs(faster["costs"][:, :-1]) + 1e-9)  # skipped steps repeat the cost
