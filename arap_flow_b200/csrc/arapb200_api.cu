@@ -384,10 +384,10 @@ int arapb200_debug_resident_profile(int W, int H, const uint8_t* mask_red, const
         DevBuf<float2> dX(N), dU(N), dC(N);
         DevBuf<float> dA(N), dM(N), dcost((size_t)nCont * (nGN + 1));
         DevBuf<MatchRec> dm(recs.size());
-        DevBuf<unsigned long long> dprof(RS_MAX_CTAS * 8);
+        DevBuf<unsigned long long> dprof(RS_MAX_CTAS * RS_PROF_SLOTS);
         dmask.up(mask_red);
         if (!recs.empty()) dm.up(recs.data());
-        ARAP_CUDA_OR_RETURN(cudaMemset(dprof.p, 0, RS_MAX_CTAS * 8 * sizeof(unsigned long long)));
+        ARAP_CUDA_OR_RETURN(cudaMemset(dprof.p, 0, RS_MAX_CTAS * RS_PROF_SLOTS * sizeof(unsigned long long)));
         enqueue_reset_state(W, H, dmask.p, dX.p, dU.p, dA.p, dM.p, nullptr);
         enqueue_target_image(W, H, dm.p, (int)recs.size(), dC.p, nullptr);
         ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());

@@ -12,11 +12,14 @@
 #define ARAP_HD inline
 #endif
 
+// Both default to 0: on the B200 the integer formulations are SLOWER than the float / double chains they were meant
+// to replace (64- and 128-bit shifts by variable amounts are long 32-bit instruction sequences): C1 7.0 vs 7.8 pairs/s,
+// profiles/r2_barrier_ab.txt.  Kept as measured alternatives.
 #ifndef ARAP_RS_INT_LIMBS
-#define ARAP_RS_INT_LIMBS 1
+#define ARAP_RS_INT_LIMBS 0
 #endif
 #ifndef ARAP_RS_INT_FOLD
-#define ARAP_RS_INT_FOLD 1
+#define ARAP_RS_INT_FOLD 0
 #endif
 
 namespace arapb200 {

@@ -46,7 +46,14 @@ constexpr int BAR_STRIDE = 128; // u64 words between barrier words (1 KiB): sepa
 #define ARAP_RS_BAR_REPLICAS 1 // every CTA adds its contribution to R copies of the barrier words and polls copy (cta % R)
 #endif
 constexpr int BAR_R = ARAP_RS_BAR_REPLICAS;
-constexpr int BAR_WORDS = 2 * BAR_R * 4; // [buffer][replica][limb]
+#ifndef ARAP_RS_WARP_ARRIVE
+#define ARAP_RS_WARP_ARRIVE 0 // 1: every WARP adds its limb sums to the barrier words itself (no CTA-level staging / sync)
+#endif
+// per-warp arrival: five words per buffer -- four limbs + an overflow counter --, 12-bit arrival count in bits 63..52
+constexpr int BAR_WORDS = ARAP_RS_WARP_ARRIVE ? 2 * 5 : 2 * BAR_R * 4; // [buffer][replica][limb]
+#if ARAP_RS_WARP_ARRIVE
+constexpr long long WARP_BIAS = 1ll << 32;
+#endif
 constexpr int S_MIN = -100, S_MAX = 100;
 
 struct __align__(16) StripSmem {
@@ -60,7 +67,7 @@ struct __align__(16) StripSmem {
 struct __align__(16) Ctl {
     int limb[RS_THREADS_MAX / 32][4];
     int ovf[RS_THREADS_MAX / 32];
-    unsigned long long prev[2][4]; // totals last seen in each barrier buffer
+    unsigned long long prev[2][5]; // totals last seen in each barrier buffer
     unsigned long long local[4];   // G == 1: this CTA's contribution stays here, the barrier never leaves the SM
     int4 bc4;                      // broadcast of a finished barrier: (result bits, 0 accept / 1 redo, new scale, abort)
     float stop;                    // opt-in early exit: leave the PCG loop once r.z <= stop (-1: never)
@@ -178,7 +185,8 @@ struct Cta {
     Ctl* ctl;
     int cta, G, lane, wid, nw;
     unsigned epoch;
-    unsigned long long acc[3]; // optional cycle accounting (thread 0): reduce+arrive, poll, decode+broadcast
+    unsigned long long acc[8]; // optional cycle accounting (thread 0): reduce+arrive, poll, decode+broadcast; [3..7] finer split
+    long long tq[4];           // scratch time stamps of the current barrier
     bool prof;
 };
 
@@ -233,11 +241,24 @@ __device__ __forceinline__ void grid_arrive(Cta& c, float g0, float g1, int S, l
         l0 += m0; l1 += m1; l2 += m2; l3 += __float2int_rn(v3);
     }
 #endif
+    if (c.prof) c.tq[0] = clock64();
     const int s0 = __reduce_add_sync(0xffffffffu, l0);
     const int s1 = __reduce_add_sync(0xffffffffu, l1);
     const int s2 = __reduce_add_sync(0xffffffffu, l2);
     const int s3 = __reduce_add_sync(0xffffffffu, l3);
     const bool wovf = __any_sync(0xffffffffu, ovf);
+#if ARAP_RS_WARP_ARRIVE
+    if (c.G != 1) {
+        // this warp arrives on its own: lanes 0..3 add (count 1 | limb sum + bias), lane 4 adds (count 1 | overflow)
+        if (c.lane < 5) {
+            const int mine = c.lane == 0 ? s0 : (c.lane == 1 ? s1 : (c.lane == 2 ? s2 : s3));
+            const unsigned long long v = (c.lane < 4) ? (unsigned long long)((long long)mine + WARP_BIAS) : (wovf ? 1ull : 0ull);
+            red_add_u64(c.P->bar + ((size_t)(c.epoch & 1u) * 5 + c.lane) * BAR_STRIDE, (1ull << 52) + v);
+        }
+        if (c.prof) t1 = clock64();
+        return;
+    }
+#endif
     if (c.lane == 0) {
         ctl->limb[c.wid][0] = s0;
         ctl->limb[c.wid][1] = s1;
@@ -245,7 +266,9 @@ __device__ __forceinline__ void grid_arrive(Cta& c, float g0, float g1, int S, l
         ctl->limb[c.wid][3] = s3;
         ctl->ovf[c.wid] = wovf ? 1 : 0;
     }
+    if (c.prof) c.tq[1] = clock64();
     __syncthreads();
+    if (c.prof) c.tq[2] = clock64();
     if (c.wid == 0 && c.lane < 4 * BAR_R) { // lane = 4 * replica + limb
         unsigned long long* buf = c.P->bar + (size_t)(c.epoch & 1u) * (4 * BAR_R) * BAR_STRIDE;
         const int limb = c.lane & 3;
@@ -267,7 +290,7 @@ __device__ __forceinline__ void grid_arrive(Cta& c, float g0, float g1, int S, l
 // grid_wait: poll the barrier words until all G CTAs have arrived, decode, verify the scale, broadcast.
 // Returns 0 = accepted (result in res, S updated for the next reduction of this kind), 1 = redo with the new S.
 #ifndef ARAP_RS_WARP_POLL
-#define ARAP_RS_WARP_POLL 1 // 0 = round 1's poller: lane 0 of warp 0 loads and decodes all four words
+#define ARAP_RS_WARP_POLL 0 // 1 = warp 0 polls as a warp (one load instruction for the four words): measured SLOWER, see DESIGN.md 4.1
 #endif
 __device__ __forceinline__ int grid_wait(Cta& c, int& S, bool& grown, float& res, bool& ok, long long t0, long long t1)
 {
@@ -280,18 +303,33 @@ __device__ __forceinline__ int grid_wait(Cta& c, int& S, bool& grown, float& res
     // compete for issue slots with the compute warps of the co-resident problems.  The four limbs are then gathered
     // with shuffles and every lane decodes the total redundantly.
     if (c.wid == 0) {
+#if ARAP_RS_WARP_ARRIVE
+        const bool per_warp = c.G != 1;
+        const int j = per_warp ? min(c.lane & 7, 4) : (c.lane & 3);
+        const int target = c.G * c.nw; // every warp of every CTA arrives
+#else
+        const bool per_warp = false;
         const int j = c.lane & 3;
+#endif
         unsigned long long d;
         bool aborted = false;
         if (c.G == 1) {
             d = ctl->local[j]; // written by lanes 0..3 of this warp before the __syncwarp in grid_arrive
         } else {
+#if ARAP_RS_WARP_ARRIVE
+            const unsigned long long* w = P.bar + ((size_t)(c.epoch & 1u) * 5 + j) * BAR_STRIDE;
+#else
             const unsigned long long* w = P.bar + ((size_t)(c.epoch & 1u) * (4 * BAR_R) + (c.cta % BAR_R) * 4 + j) * BAR_STRIDE;
+#endif
             const unsigned long long pv = ctl->prev[c.epoch & 1u][j];
             unsigned spins = 0;
             for (;;) {
                 d = ld_u64_volatile(w) - pv;
+#if ARAP_RS_WARP_ARRIVE
+                if (__all_sync(0xffffffffu, (int)(d >> 52) == target)) break;
+#else
                 if (__all_sync(0xffffffffu, (int)((d >> 48) & 0xFF) == c.G)) break;
+#endif
                 if ((++spins & 0xffu) == 0) {
                     // watchdog: a peer's abort or ~seconds of polling => leave instead of hanging the GPU
                     if (*(volatile int*)P.status || spins > (1u << 23)) {
@@ -300,14 +338,24 @@ __device__ __forceinline__ int grid_wait(Cta& c, int& S, bool& grown, float& res
                     }
                 }
             }
-            if (c.lane < 4) ctl->prev[c.epoch & 1u][j] = pv + d;
+            if (c.lane < (per_warp ? 5 : 4)) ctl->prev[c.epoch & 1u][j] = pv + d;
         }
         if (c.prof) t2 = clock64();
+#if ARAP_RS_WARP_ARRIVE
+        const long long Lm = per_warp ? (long long)(d & ((1ull << 52) - 1)) - (long long)target * WARP_BIAS
+                                      : (long long)(d & ((1ull << 48) - 1)) - (long long)c.G * LIMB_BIAS;
+#else
         const long long Lm = (long long)(d & ((1ull << 48) - 1)) - (long long)c.G * LIMB_BIAS;
+#endif
         long long L[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) L[k] = __shfl_sync(0xffffffffu, Lm, k);
+#if ARAP_RS_WARP_ARRIVE
+        const int novf = per_warp ? (int)(__shfl_sync(0xffffffffu, d, 4) & 0xffffu)
+                                  : (int)((__shfl_sync(0xffffffffu, d, 0) >> 56) & 0xFF);
+#else
         const int novf = (int)((__shfl_sync(0xffffffffu, d, 0) >> 56) & 0xFF);
+#endif
         bool T_is_zero;
         const float r = limbs_to_float_rn(L, S - 90, T_is_zero);
         int code = 0, newS = S;
@@ -327,6 +375,7 @@ __device__ __forceinline__ int grid_wait(Cta& c, int& S, bool& grown, float& res
                 atomicCAS(P.status + 1, 0, 100 + (int)(c.epoch & 0xffff));
             }
             ctl->bc4 = make_int4(__float_as_int(r), code, newS, (aborted || ctl->abort_halo) ? 1 : ctl->bc4.w); // one store, one load per reader
+            if (c.prof) c.tq[3] = clock64();
         }
     }
 #else
@@ -380,6 +429,7 @@ __device__ __forceinline__ int grid_wait(Cta& c, int& S, bool& grown, float& res
             else newS = max(min(e + 4, S_MAX), S_MIN);
         }
         ctl->bc4 = make_int4(__float_as_int(r), code, newS, (aborted || ctl->abort_halo) ? 1 : ctl->bc4.w);
+        if (c.prof) c.tq[3] = clock64();
     }
 #endif
     __syncthreads();
@@ -388,6 +438,11 @@ __device__ __forceinline__ int grid_wait(Cta& c, int& S, bool& grown, float& res
         c.acc[0] += (unsigned long long)(t1 - t0);
         c.acc[1] += (unsigned long long)(t2 - t1);
         c.acc[2] += (unsigned long long)(t3 - t2);
+        c.acc[3] += (unsigned long long)(c.tq[0] - t0);      // limb conversion
+        c.acc[4] += (unsigned long long)(c.tq[1] - c.tq[0]); // REDUX x4 + vote + staging stores
+        c.acc[5] += (unsigned long long)(c.tq[2] - c.tq[1]); // __syncthreads
+        c.acc[6] += (unsigned long long)(t1 - c.tq[2]);      // sum over warps + red
+        c.acc[7] += (unsigned long long)(c.tq[3] - t2);      // decode (before the broadcast sync)
     }
     ++c.epoch;
     const int4 bc = ctl->bc4; // (result, code, new scale, abort)
@@ -581,7 +636,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
     Cta c;
     c.P = &P; c.ctl = &ctl; c.cta = cta_in_problem; c.G = P.G;
     c.lane = threadIdx.x & 31; c.wid = threadIdx.x >> 5; c.nw = blockDim.x >> 5; c.epoch = 0;
-    c.acc[0] = c.acc[1] = c.acc[2] = 0; c.prof = PROF && (P.prof != nullptr);
+    for (int k = 0; k < 8; ++k) c.acc[k] = 0;
+    c.prof = PROF && (P.prof != nullptr);
     unsigned long long ph[4] = {0, 0, 0, 0}; // cycles in PCG phase 1, 2, 3 and everything else (thread 0)
     long long tk = c.prof ? clock64() : 0;
 #define RS_TICK(slot) do { if (c.prof && threadIdx.x == 0) { const long long tn = clock64(); ph[slot] += (unsigned long long)(tn - tk); tk = tn; } } while (0)
@@ -591,7 +647,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
     const float wr = P.wr, wf = P.wf, wr2 = P.wr2, wf2 = P.wf2;
 
     if (threadIdx.x == 0) { ctl.bc4 = make_int4(0, 0, 0, 0); ctl.abort_halo = 0; }
-    if (threadIdx.x < 8) ctl.prev[threadIdx.x >> 2][threadIdx.x & 3] = 0ull; // the host zeroes P.bar before the launch
+    if (threadIdx.x < 10) ctl.prev[threadIdx.x / 5][threadIdx.x % 5] = 0ull; // the host zeroes P.bar before the launch
 
     // ---- which strip is mine, who are my neighbours ----
     const int n = P.n_strips;
@@ -913,9 +969,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
         }
     }
     if (c.prof && threadIdx.x == 0) {
-        unsigned long long* o = P.prof + (size_t)c.cta * 8;
+        unsigned long long* o = P.prof + (size_t)c.cta * RS_PROF_SLOTS;
         o[0] = ph[0]; o[1] = ph[1]; o[2] = ph[2]; o[3] = ph[3];
         o[4] = c.acc[0]; o[5] = c.acc[1]; o[6] = c.acc[2]; o[7] = c.epoch;
+        for (int k = 3; k < 8; ++k) o[5 + k] = c.acc[k]; // [8..12]: limb conversion, warp reduce, CTA sync, sum + red, decode
     }
 #undef RS_TICK
 #undef RS_TOCK

@@ -16,6 +16,7 @@ constexpr int RS_STRIP_W = 32;   // a strip is 32 x RS_STRIP_H pixels: one warp,
 constexpr int RS_STRIP_H = ARAP_RS_STRIP_H; // 4 (one contract-C3 group per lane) or 8 (two)
 constexpr int RS_MAX_WARPS = 16; // strips per CTA
 constexpr int RS_MAX_CTAS = 160; // CTAs per problem (8-bit arrival count per barrier word)
+constexpr int RS_PROF_SLOTS = 16; // u64 per CTA of the optional cycle accounting (arapb200_debug_resident_profile)
 constexpr int RS_OUTBOX_ENTRIES = 64 + 2 * RS_STRIP_H; // top row, bottom row, left column, right column; 32 bytes each
 
 // One problem as the kernel sees it (device memory, one per blockIdx.y)
@@ -39,7 +40,7 @@ struct ResProb {
     int nCont, nGN, nPCG;
     float gn_rtol;             // 0 = every GN step runs; > 0: a continuation step ends once a GN step gains less than this (relative)
     float pcg_rtol2;           // 0 = fixed budget (reference behaviour); > 0: leave a PCG loop once r.z <= rtol^2 * r0.z0
-    unsigned long long* prof;  // optional [G][8] cycle counters (debug)
+    unsigned long long* prof;  // optional [G][RS_PROF_SLOTS] cycle counters (debug)
 };
 
 class ResidentSolver {
@@ -78,7 +79,7 @@ public:
     int last_variant() const { return last_variant_; }
     // shape of the last cooperative launch: {max threads, min CTAs per SM of the kernel variant, grid.x, grid.y, threads}
     void last_launch_shape(int out[5]) const { for (int i = 0; i < 5; ++i) out[i] = last_shape_[i]; }
-    // debug: per-CTA cycle accounting of the next launches into d_prof ([ctas()][8] u64), or null to disable
+    // debug: per-CTA cycle accounting of the next launches into d_prof ([ctas()][RS_PROF_SLOTS] u64), or null to disable
     void set_profile(unsigned long long* d_prof) { d_prof_ = d_prof; }
     // opt-in convergence-aware schedule; 0 restores the reference's fixed iteration budget
     void set_pcg_rtol(float rtol) { pcg_rtol_ = rtol > 0.0f ? rtol : 0.0f; }

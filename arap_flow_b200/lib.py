@@ -312,7 +312,7 @@ def debug_resident_profile(mask_red, matches, nCont, nGN, nPCG):
     """Cycle accounting of the resident kernel (thread 0 of every CTA).  Returns (prof[G, 8], info, ms)."""
     H, W = mask_red.shape
     m = _c(matches, np.int32).reshape(-1, 4)
-    prof = np.zeros((160, 8), np.uint64)
+    prof = np.zeros((160, 16), np.uint64)
     info = (C.c_int * 3)()
     ms = C.c_float()
     L = load()

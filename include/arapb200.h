@@ -126,7 +126,7 @@ ARAPB200_API int arapb200_debug_apply_jtj(int W, int H, const float* A, const fl
 /* cost per the contract */
 ARAPB200_API int arapb200_debug_cost(int W, int H, const float* X, const float* A, const float* U, const float* C,
                         const float* M, float wf, float wr, float* cost);
-/* cycle accounting of the resident kernel: prof uint64[160*8] (per CTA: cycles in PCG phase 1/2/3, other,
+/* cycle accounting of the resident kernel: prof uint64[160*16] (per CTA: cycles in PCG phase 1/2/3, other,
  * barrier skew / poll / fold, barrier count), info int[3] = {strips, CTAs, warps per CTA}, *ms = launch time */
 ARAPB200_API int arapb200_debug_resident_profile(int W, int H, const uint8_t* mask_red, const int32_t* matches,
                                                  int n_matches, int nCont, int nGN, int nPCG,

@@ -88,3 +88,48 @@ def test_argv_contracts_without_gpu(tmp_path):
     env = dict(os.environ, ARAP_PLAN=str(tmp_path / "missing.t"))
     r = subprocess.run([os.path.join(BIN, "arap_deform"), "a", "b", "c", "d", "e", "f"], capture_output=True, text=True, env=env)
     assert r.returncode == 1 and "Optimization plan at" in r.stdout and "Not found!" in r.stdout
+
+
+def test_resident_worker_contracts_without_gpu(tmp_path):
+    """`arap_deform --serve` / ARAP_SERVER on a box without a GPU: the client refuses to run when no
+    worker watches the spool directory (it never falls back to solving in-process), the worker refuses to start without a
+    plan, and without a CUDA device it exits non-zero instead of signalling `ready`."""
+    from arap_flow_b200 import driver
+    exe = os.path.join(BIN, "arap_deform")
+    spool = str(tmp_path / "spool")
+    env = dict(os.environ, ARAP_PLAN=driver.PLAN, ARAP_SERVER=spool)
+    r = subprocess.run([exe, "a", "b", "c", "d", "e", "f"], capture_output=True, text=True, env=env)
+    assert r.returncode == 1 and "no server is watching" in r.stderr
+    r = subprocess.run([exe, "--serve", spool], capture_output=True, text=True, env=dict(os.environ, ARAP_PLAN=str(tmp_path / "nope.t")))
+    assert r.returncode == 1 and "Not found!" in r.stdout
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            driver.Server(0, spool, timeout=20.0)
+        assert not os.path.exists(os.path.join(spool, "ready"))
+
+
+def test_dispatch_queue_hands_every_dispatch_to_a_free_gpu(tmp_path, monkeypatch):
+    """driver.run_dispatches mirrors para_gen's free-GPU queue (para_gen.py:441-445, 560-567): every dispatch runs exactly
+    once, never two at a time on one GPU."""
+    import threading
+    import time
+    from arap_flow_b200 import driver
+    lock, busy, seen, overlap = threading.Lock(), set(), [], []
+
+    def fake_do_arap(items, gpu, tmp_dir, server=None, **kw):
+        with lock:
+            if gpu in busy:
+                overlap.append(gpu)
+            busy.add(gpu)
+        time.sleep(0.01)
+        with lock:
+            busy.discard(gpu)
+            seen.append((gpu, tuple(items), server))
+        return 0.01
+
+    monkeypatch.setattr(driver, "do_arap", fake_do_arap)
+    dispatches = [[("r%d" % k, "m", "c", "f", "wr", "wm")] for k in range(11)]
+    driver.run_dispatches(dispatches, [0, 1, 2], str(tmp_path), servers=["s0", "s1", "s2"])
+    assert not overlap and sorted(s[1][0][0] for s in seen) == sorted("r%d" % k for k in range(11))
+    assert all(s[2] == "s%d" % s[0] for s in seen)

@@ -11,9 +11,12 @@ sp = synth.config(cfg)
 for rep in range(2):
     prof, info, ms = lib.debug_resident_profile(sp.masks[0], sp.matches, 1, 2, nPCG)
 it = 2 * nPCG
-names = ["phase1(JTJ)", "phase2(update)", "phase3(p,halo)", "other", "bar:skew", "bar:poll", "bar:fold"]
+names = ["phase1(JTJ)", "phase2(update)", "phase3(p,halo)", "other", "bar:arrive", "bar:poll", "bar:fold", None,
+         " arrive:limbs", " arrive:redux+stage", " arrive:cta-sync", " arrive:sum+red", " fold:decode"]
 print(f"{cfg}: {info}, launch {ms:.3f} ms, {ms * 1e3 / it:.2f} us per PCG iteration, barriers/CTA {int(prof[0, 7])}")
 clk = 1.9e3  # cycles per us (approx.)
 for i, n in enumerate(names):
+    if n is None:
+        continue
     v = prof[:, i].astype(np.float64) / it
     print(f"  {n:16s} cycles/iter: mean {v.mean():9.0f}  min {v.min():9.0f}  max {v.max():9.0f}   (~{v.mean() / clk:.2f} us)")
