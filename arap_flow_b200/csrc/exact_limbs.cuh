@@ -12,12 +12,11 @@
 #define ARAP_HD inline
 #endif
 
-// Both default to 0: on the B200 the integer formulations are SLOWER than the float / double chains they were meant
-// to replace (64- and 128-bit shifts by variable amounts are long 32-bit instruction sequences): C1 7.0 vs 7.8 pairs/s,
-// profiles/r2_barrier_ab.txt.  Kept as measured alternatives.
-#ifndef ARAP_RS_INT_LIMBS
-#define ARAP_RS_INT_LIMBS 0
-#endif
+// On the B200 the integer limb conversion (to_limbs) and the 128-bit decode (limbs_to_float_int) are SLOWER than the
+// float / double chains they were meant to replace (64- and 128-bit shifts by variable amounts are long 32-bit
+// instruction sequences): C1 7.0 vs 7.8 pairs/s, profiles/r2_barrier_ab.txt.  They stay here, with their host-side
+// exactness tests, as measured alternatives; the kernel can select a decode with ARAP_RS_INT_FOLD (0 = binary64 chain,
+// 1 = 128-bit, 2 = the 64-bit fast path below).
 #ifndef ARAP_RS_INT_FOLD
 #define ARAP_RS_INT_FOLD 0
 #endif
@@ -90,6 +89,50 @@ ARAP_HD bool limbs_to_float_int(const long long L[4], int e_unit, bool& is_zero,
     }
     // q * 2^(sh + e_unit): q <= 2^24 and the exponent keeps the product a normal binary32 => exact
     const int ex = sh + e_unit; // in [-144, 120]
+    unsigned long long dbits = (unsigned long long)(ex + 1023) << 52;
+    double scale;
+    memcpy(&scale, &dbits, 8);
+    const float r = (float)((double)q * scale);
+    out = neg ? -r : r;
+    return true;
+}
+
+// A lighter integer decode (ARAP_RS_INT_FOLD == 2).  The scale prediction keeps the total's leading bit inside the top two
+// limbs, so: fold the carries of the low limbs upward with constant shifts, H = L0*2^24 + L1 + carries (64-bit), low part
+// 0 <= Lo < 2^48 as a sticky bit only, then ONE variable 64-bit shift.  Everything 64-bit (the 128-bit version above needs
+// 128-bit variable shifts: measured slower than the binary64 chain).  Returns false -- caller falls back to the binary64
+// route -- when the fast path's preconditions do not hold (|L0| >= 2^37, fewer than 25 significant bits in H, or a result
+// outside the comfortable binary32 range).
+ARAP_HD bool limbs_to_float_i64(const long long L[4], int e_unit, bool& is_zero, float& out)
+{
+    out = 0.0f;
+    is_zero = false;
+    if (L[0] >= (1ll << 37) || L[0] <= -(1ll << 37)) return false;
+    // low part: Lo = l2 * 2^24 + L3 with l2 = L2 mod 2^24 (floor), carries go up
+    const long long c2 = L[2] >> 24;                 // floor
+    const long long l2 = L[2] - (c2 << 24);          // [0, 2^24)
+    long long Lo = (l2 << 24) + L[3];                // |L3| < 2^45  =>  -2^45 < Lo < 2^48 + 2^45
+    const long long c = Lo >> 48;                    // floor: -1, 0 or 1
+    Lo -= c << 48;                                   // [0, 2^48)
+    const long long H = (L[0] << 24) + L[1] + c2 + c; // |.| < 2^61 + 2^45 + 2^21 + 1
+    // total T = H * 2^48 + Lo, 0 <= Lo < 2^48
+    const bool neg = H < 0;
+    const bool low = Lo != 0;
+    // |T| = a * 2^48 + (low ? something in (0, 2^48) : 0)
+    const unsigned long long a = neg ? (unsigned long long)(-H) - (low ? 1ull : 0ull) : (unsigned long long)H;
+    if (a == 0) {
+        if (!low) { is_zero = true; return true; }
+        return false; // the whole total sits in the low limbs: leave it to the general route
+    }
+    const int nb = 64 - clz64(a);
+    if (nb < 25) return false;
+    if (nb + 48 + e_unit < -120 || nb + 48 + e_unit > 120) return false;
+    const int sh = nb - 24; // >= 1
+    unsigned q = (unsigned)(a >> sh);
+    const bool rbit = ((a >> (sh - 1)) & 1ull) != 0;
+    const bool sticky = low || (a & ((1ull << (sh - 1)) - 1ull)) != 0;
+    if (rbit && (sticky || (q & 1u))) ++q;
+    const int ex = sh + 48 + e_unit;
     unsigned long long dbits = (unsigned long long)(ex + 1023) << 52;
     double scale;
     memcpy(&scale, &dbits, 8);

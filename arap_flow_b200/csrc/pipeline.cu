@@ -184,11 +184,13 @@ void BatchPipeline::solve_streaming(const HostProblem& hp, Dev& d)
 
 void BatchPipeline::set_pcg_rtol(float rtol)
 {
+    pcg_rtol_ = rtol > 0.0f ? rtol : 0.0f;
     if (resident_) resident_->set_pcg_rtol(rtol);
 }
 
 void BatchPipeline::set_gn_rtol(float rtol)
 {
+    gn_rtol_ = rtol > 0.0f ? rtol : 0.0f;
     if (resident_) resident_->set_gn_rtol(rtol);
 }
 
@@ -254,6 +256,11 @@ int BatchPipeline::run(const HostProblem* problems, int count)
     for (int i = 0; i < count;) {
         Dev& d = dev_[i];
         if (!d.resident) {
+            if ((pcg_rtol_ > 0.0f || gn_rtol_ > 0.0f) && !warned_rtol_) { // never silently: the caller asked for an early exit
+                warned_rtol_ = true;
+                fprintf(stderr, "arapb200: warning: pcg_rtol / gn_rtol are honoured by the resident back-end only; a %dx%d problem "
+                                "streams and runs the full iteration budget\n", problems[i].W, problems[i].H);
+            }
             solve_streaming(problems[i], d);
             ++i;
             continue;

@@ -85,6 +85,8 @@ private:
     long long launches_ = 0;
     float ms_total_ = 0, ms_solve_ = 0, ms_warp_ = 0;
     int n_resident_ = 0, group_size_ = 0;
+    float pcg_rtol_ = 0.0f, gn_rtol_ = 0.0f;
+    bool warned_rtol_ = false;
 };
 
 // shared small kernels

@@ -42,19 +42,16 @@ constexpr int OB_LEFT = 64, OB_RIGHT = 64 + RS_STRIP_H;
 static_assert(RS_STRIP_H == 4 || RS_STRIP_H == 8, "strip height must be 4 or 8");
 constexpr long long LIMB_BIAS = 1ll << 36;
 constexpr int BAR_STRIDE = 128; // u64 words between barrier words (1 KiB): separate L2 slices, parallel atomics
-#ifndef ARAP_RS_BAR_REPLICAS
-#define ARAP_RS_BAR_REPLICAS 1 // every CTA adds its contribution to R copies of the barrier words and polls copy (cta % R)
-#endif
-constexpr int BAR_R = ARAP_RS_BAR_REPLICAS;
-#ifndef ARAP_RS_WARP_ARRIVE
-#define ARAP_RS_WARP_ARRIVE 0 // 1: every WARP adds its limb sums to the barrier words itself (no CTA-level staging / sync)
-#endif
-// per-warp arrival: five words per buffer -- four limbs + an overflow counter --, 12-bit arrival count in bits 63..52
-constexpr int BAR_WORDS = ARAP_RS_WARP_ARRIVE ? 2 * 5 : 2 * BAR_R * 4; // [buffer][replica][limb]
-#if ARAP_RS_WARP_ARRIVE
-constexpr long long WARP_BIAS = 1ll << 32;
-#endif
 constexpr int S_MIN = -100, S_MAX = 100;
+// Measured alternatives of the barrier code (tools/build_variant.sh + tools/ab_sweep.sh, profiles/r2_barrier_ab.txt).
+// The barrier is ~55 % of a lone problem's PCG iteration, and its code is so latency-critical that harmless-looking
+// changes move C1 by several percent either way: every switch here is kept only with a measurement next to it.
+#ifndef ARAP_RS_SUM_UNROLL
+#define ARAP_RS_SUM_UNROLL 0 // 1: the CTA-level sum over the warps' limb sums is unrolled (all shared-memory loads in flight)
+#endif
+#ifndef ARAP_RS_G1_LOCAL
+#define ARAP_RS_G1_LOCAL 0   // 1: a problem that runs in ONE CTA keeps its barrier in shared memory (no L2 round trip)
+#endif
 
 struct __align__(16) StripSmem {
     float4 T[TH][TW];              // tile + ring: (p_x, p_y, sin*p_a, cos*p_a) or (X_x, X_y, cos, sin)
@@ -64,15 +61,19 @@ struct __align__(16) StripSmem {
     float2 pre[RS_STRIP_H][32];        // (1/(1+sqrt(D_X))^2, 1/(1+sqrt(D_a))^2) per pixel, constant during a GN step
 };
 
-struct __align__(16) Ctl {
+struct Ctl {
     int limb[RS_THREADS_MAX / 32][4];
     int ovf[RS_THREADS_MAX / 32];
-    unsigned long long prev[2][5]; // totals last seen in each barrier buffer
+    unsigned long long prev[2][4]; // totals last seen in each barrier buffer
+#if ARAP_RS_G1_LOCAL
     unsigned long long local[4];   // G == 1: this CTA's contribution stays here, the barrier never leaves the SM
-    int4 bc4;                      // broadcast of a finished barrier: (result bits, 0 accept / 1 redo, new scale, abort)
+#endif
+    float bc;                      // broadcast result
     float stop;                    // opt-in early exit: leave the PCG loop once r.z <= stop (-1: never)
     float prev_cost;               // opt-in early exit of the Gauss-Newton loop: cost before the last step
-    int abort_halo;                // a halo fetch of this CTA hit its watchdog
+    int bc_code;                   // 0 accept, 1 redo with bc_S
+    int bc_S;
+    int abort;
 };
 
 __device__ __forceinline__ unsigned long long ld_u64_volatile(const unsigned long long* p)
@@ -89,26 +90,14 @@ __device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long
 // half): 64-bit elements of a vector access are single-copy atomic in the PTX memory model, so a value can never be
 // observed with another publication's tag, and a relaxed store paired with a relaxed load is a morally strong pair (no
 // data race).  The uint4 view (x = float, y = tag, z = float, w = tag) is the same bytes.
-#ifndef ARAP_RS_HALO_WEAK
-#define ARAP_RS_HALO_WEAK 0 // 1 = round 1's accesses (weak st.v4.u32 / ld.relaxed.v4.u32), kept only to measure the fix's cost
-#endif
 __device__ __forceinline__ uint4 ld_entry_relaxed(const uint4* p)
 {
-#if ARAP_RS_HALO_WEAK
-    uint4 v;
-    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
-#endif
     unsigned long long a, b;
     asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
     return make_uint4((unsigned)a, (unsigned)(a >> 32), (unsigned)b, (unsigned)(b >> 32));
 }
 __device__ __forceinline__ void st_entry_relaxed(uint4* p, unsigned tag, float v0, float v1)
 {
-#if ARAP_RS_HALO_WEAK
-    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(__float_as_uint(v0)), "r"(tag), "r"(__float_as_uint(v1)), "r"(tag) : "memory");
-    return;
-#endif
     const unsigned long long t = (unsigned long long)tag << 32;
     const unsigned long long a = t | __float_as_uint(v0), b = t | __float_as_uint(v1);
     asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
@@ -149,15 +138,15 @@ __device__ __forceinline__ float limbs_to_float_rn_f64(const long long L[4], int
     return (float)(z * pow2_f64(e_unit)); // exact scaling (barring binary32 underflow), single rounding
 }
 
-// The integer version (exact_limbs.cuh) is the default: the decode sits on the critical path of every grid barrier and
-// the binary64 version is a chain of ~25 dependent DADDs.  Totals near binary32's subnormal / overflow range take the
-// binary64 route (one rounding there needs the round-to-odd trick).
+// ARAP_RS_INT_FOLD == 2 (exact_limbs.cuh): a 64-bit integer fast path in front of the binary64 route
 __device__ __forceinline__ float limbs_to_float_rn(const long long L[4], int e_unit, bool& is_zero)
 {
-#if ARAP_RS_INT_FOLD
+#if ARAP_RS_INT_FOLD == 2
     float r;
-    e_unit = max(-900, min(900, e_unit));
-    if (limbs_to_float_int(L, e_unit, is_zero, r)) return r;
+    if (limbs_to_float_i64(L, max(-900, min(900, e_unit)), is_zero, r)) return r;
+#elif ARAP_RS_INT_FOLD == 1
+    float r;
+    if (limbs_to_float_int(L, max(-900, min(900, e_unit)), is_zero, r)) return r;
 #endif
     return limbs_to_float_rn_f64(L, e_unit, is_zero);
 }
@@ -182,11 +171,12 @@ struct StripCtx {
 
 struct Cta {
     const ResProb* P;
+    unsigned long long* bar; // = P->bar
+    int* status;             // = P->status
     Ctl* ctl;
     int cta, G, lane, wid, nw;
     unsigned epoch;
-    unsigned long long acc[8]; // optional cycle accounting (thread 0): reduce+arrive, poll, decode+broadcast; [3..7] finer split
-    long long tq[4];           // scratch time stamps of the current barrier
+    unsigned long long acc[3]; // optional cycle accounting (thread 0): reduce+arrive, poll, decode+broadcast
     bool prof;
 };
 
@@ -199,22 +189,10 @@ __device__ __forceinline__ void grid_arrive(Cta& c, float g0, float g1, int S, l
     Ctl* ctl = c.ctl;
     if (c.prof) t0 = clock64();
     // ---- thread -> four signed 24-bit limbs in units 2^(S-18), 2^(S-42), 2^(S-66), 2^(S-90) ----
-    int l0, l1, l2, l3;
-    bool ovf;
-#if ARAP_RS_INT_LIMBS
-    {
-        int m0, m1, m2, m3;
-        bool o1;
-        to_limbs(g0, S, l0, l1, l2, l3, ovf);
-        if (RS_STRIP_H == 8) {
-            to_limbs(g1, S, m0, m1, m2, m3, o1);
-            l0 += m0; l1 += m1; l2 += m2; l3 += m3;
-            ovf = ovf || o1;
-        }
-    }
-#else
     // (binary32 only: scaling by powers of two and the remainders are exact)
     const float sc = __int_as_float((127 + 18 - S) << 23);
+    int l0, l1, l2, l3;
+    bool ovf;
     {
         const float v = g0 * sc;
         ovf = !(fabsf(v) < 16777216.0f); // |g| >= 2^(S+6), Inf or NaN
@@ -240,25 +218,11 @@ __device__ __forceinline__ void grid_arrive(Cta& c, float g0, float g1, int S, l
         const float v3 = (v2 - (float)m2) * 16777216.0f;
         l0 += m0; l1 += m1; l2 += m2; l3 += __float2int_rn(v3);
     }
-#endif
-    if (c.prof) c.tq[0] = clock64();
     const int s0 = __reduce_add_sync(0xffffffffu, l0);
     const int s1 = __reduce_add_sync(0xffffffffu, l1);
     const int s2 = __reduce_add_sync(0xffffffffu, l2);
     const int s3 = __reduce_add_sync(0xffffffffu, l3);
     const bool wovf = __any_sync(0xffffffffu, ovf);
-#if ARAP_RS_WARP_ARRIVE
-    if (c.G != 1) {
-        // this warp arrives on its own: lanes 0..3 add (count 1 | limb sum + bias), lane 4 adds (count 1 | overflow)
-        if (c.lane < 5) {
-            const int mine = c.lane == 0 ? s0 : (c.lane == 1 ? s1 : (c.lane == 2 ? s2 : s3));
-            const unsigned long long v = (c.lane < 4) ? (unsigned long long)((long long)mine + WARP_BIAS) : (wovf ? 1ull : 0ull);
-            red_add_u64(c.P->bar + ((size_t)(c.epoch & 1u) * 5 + c.lane) * BAR_STRIDE, (1ull << 52) + v);
-        }
-        if (c.prof) t1 = clock64();
-        return;
-    }
-#endif
     if (c.lane == 0) {
         ctl->limb[c.wid][0] = s0;
         ctl->limb[c.wid][1] = s1;
@@ -266,129 +230,55 @@ __device__ __forceinline__ void grid_arrive(Cta& c, float g0, float g1, int S, l
         ctl->limb[c.wid][3] = s3;
         ctl->ovf[c.wid] = wovf ? 1 : 0;
     }
-    if (c.prof) c.tq[1] = clock64();
     __syncthreads();
-    if (c.prof) c.tq[2] = clock64();
-    if (c.wid == 0 && c.lane < 4 * BAR_R) { // lane = 4 * replica + limb
-        unsigned long long* buf = c.P->bar + (size_t)(c.epoch & 1u) * (4 * BAR_R) * BAR_STRIDE;
-        const int limb = c.lane & 3;
+    if (c.wid == 0 && c.lane < 4) {
+        unsigned long long* buf = c.bar + (size_t)(c.epoch & 1u) * 4 * BAR_STRIDE;
         long long sum = 0;
         int any = 0;
+#if ARAP_RS_SUM_UNROLL
+#pragma unroll
+        for (int w = 0; w < RS_THREADS_MAX / 32; ++w) {
+            const bool in = w < c.nw;
+            sum += in ? (long long)ctl->limb[w][c.lane] : 0ll;
+            any |= in ? ctl->ovf[w] : 0;
+        }
+#else
         for (int w = 0; w < c.nw; ++w) {
-            sum += (long long)ctl->limb[w][limb];
+            sum += (long long)ctl->limb[w][c.lane];
             any |= ctl->ovf[w];
         }
+#endif
         unsigned long long contrib = (1ull << 48) + (unsigned long long)(sum + LIMB_BIAS);
-        if (limb == 0 && any) contrib += (1ull << 56);
-        if (c.G == 1) { if (c.lane < 4) ctl->local[limb] = contrib; } // a problem that fits one CTA: CTA-local all-reduce, no L2 round trip
-        else red_add_u64(buf + (size_t)c.lane * BAR_STRIDE, contrib);
+        if (c.lane == 0 && any) contrib += (1ull << 56);
+#if ARAP_RS_G1_LOCAL
+        if (c.G == 1) ctl->local[c.lane] = contrib;
+        else
+#endif
+        red_add_u64(buf + (size_t)c.lane * BAR_STRIDE, contrib);
     }
+#if ARAP_RS_G1_LOCAL
     __syncwarp(); // (G == 1) lane 0 reads ctl->local[0..3] in grid_wait
+#endif
     if (c.prof) t1 = clock64();
 }
 
 // grid_wait: poll the barrier words until all G CTAs have arrived, decode, verify the scale, broadcast.
 // Returns 0 = accepted (result in res, S updated for the next reduction of this kind), 1 = redo with the new S.
-#ifndef ARAP_RS_WARP_POLL
-#define ARAP_RS_WARP_POLL 0 // 1 = warp 0 polls as a warp (one load instruction for the four words): measured SLOWER, see DESIGN.md 4.1
-#endif
 __device__ __forceinline__ int grid_wait(Cta& c, int& S, bool& grown, float& res, bool& ok, long long t0, long long t1)
 {
     Ctl* ctl = c.ctl;
-    const ResProb& P = *c.P;
     long long t2 = 0;
-#if ARAP_RS_WARP_POLL
-    // Warp 0 polls as a warp: lane l looks at word (l & 3), so one load instruction covers the four words (the same four
-    // sectors as before: lanes that share a word coalesce) and the poll loop is a quarter of the instructions -- they
-    // compete for issue slots with the compute warps of the co-resident problems.  The four limbs are then gathered
-    // with shuffles and every lane decodes the total redundantly.
-    if (c.wid == 0) {
-#if ARAP_RS_WARP_ARRIVE
-        const bool per_warp = c.G != 1;
-        const int j = per_warp ? min(c.lane & 7, 4) : (c.lane & 3);
-        const int target = c.G * c.nw; // every warp of every CTA arrives
-#else
-        const bool per_warp = false;
-        const int j = c.lane & 3;
-#endif
-        unsigned long long d;
-        bool aborted = false;
-        if (c.G == 1) {
-            d = ctl->local[j]; // written by lanes 0..3 of this warp before the __syncwarp in grid_arrive
-        } else {
-#if ARAP_RS_WARP_ARRIVE
-            const unsigned long long* w = P.bar + ((size_t)(c.epoch & 1u) * 5 + j) * BAR_STRIDE;
-#else
-            const unsigned long long* w = P.bar + ((size_t)(c.epoch & 1u) * (4 * BAR_R) + (c.cta % BAR_R) * 4 + j) * BAR_STRIDE;
-#endif
-            const unsigned long long pv = ctl->prev[c.epoch & 1u][j];
-            unsigned spins = 0;
-            for (;;) {
-                d = ld_u64_volatile(w) - pv;
-#if ARAP_RS_WARP_ARRIVE
-                if (__all_sync(0xffffffffu, (int)(d >> 52) == target)) break;
-#else
-                if (__all_sync(0xffffffffu, (int)((d >> 48) & 0xFF) == c.G)) break;
-#endif
-                if ((++spins & 0xffu) == 0) {
-                    // watchdog: a peer's abort or ~seconds of polling => leave instead of hanging the GPU
-                    if (*(volatile int*)P.status || spins > (1u << 23)) {
-                        aborted = true;
-                        break;
-                    }
-                }
-            }
-            if (c.lane < (per_warp ? 5 : 4)) ctl->prev[c.epoch & 1u][j] = pv + d;
-        }
-        if (c.prof) t2 = clock64();
-#if ARAP_RS_WARP_ARRIVE
-        const long long Lm = per_warp ? (long long)(d & ((1ull << 52) - 1)) - (long long)target * WARP_BIAS
-                                      : (long long)(d & ((1ull << 48) - 1)) - (long long)c.G * LIMB_BIAS;
-#else
-        const long long Lm = (long long)(d & ((1ull << 48) - 1)) - (long long)c.G * LIMB_BIAS;
-#endif
-        long long L[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) L[k] = __shfl_sync(0xffffffffu, Lm, k);
-#if ARAP_RS_WARP_ARRIVE
-        const int novf = per_warp ? (int)(__shfl_sync(0xffffffffu, d, 4) & 0xffffu)
-                                  : (int)((__shfl_sync(0xffffffffu, d, 0) >> 56) & 0xFF);
-#else
-        const int novf = (int)((__shfl_sync(0xffffffffu, d, 0) >> 56) & 0xFF);
-#endif
-        bool T_is_zero;
-        const float r = limbs_to_float_rn(L, S - 90, T_is_zero);
-        int code = 0, newS = S;
-        if (novf) {
-            code = 1; newS = min(S + 24, S_MAX);
-            if (S >= S_MAX) code = 0; // Inf/NaN terms: give up, the result is garbage anyway
-        } else if (T_is_zero) {
-            if (!grown && S > S_MIN) { code = 1; newS = max(S - 64, S_MIN); }
-        } else {
-            const int e = ilogb_f32(fabsf(r));
-            if (!grown && e < S - 24 && S > S_MIN) { code = 1; newS = max(e + 4, S_MIN); }
-            else newS = max(min(e + 4, S_MAX), S_MIN);
-        }
-        if (c.lane == 0) {
-            if (aborted) {
-                atomicExch(P.status, 1);
-                atomicCAS(P.status + 1, 0, 100 + (int)(c.epoch & 0xffff));
-            }
-            ctl->bc4 = make_int4(__float_as_int(r), code, newS, (aborted || ctl->abort_halo) ? 1 : ctl->bc4.w); // one store, one load per reader
-            if (c.prof) c.tq[3] = clock64();
-        }
-    }
-#else
     if (c.wid == 0 && c.lane == 0) {
-        unsigned long long* buf = P.bar + ((size_t)(c.epoch & 1u) * (4 * BAR_R) + (c.cta % BAR_R) * 4) * BAR_STRIDE;
+        unsigned long long* buf = c.bar + (size_t)(c.epoch & 1u) * 4 * BAR_STRIDE;
         unsigned long long* prev = ctl->prev[c.epoch & 1u];
         unsigned long long d[4];
         unsigned spins = 0;
-        bool aborted = false;
+#if ARAP_RS_G1_LOCAL
         if (c.G == 1) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) d[j] = ctl->local[j]; // written by lanes 0..3 of this warp before the __syncwarp in grid_arrive
         } else
+#endif
         for (;;) {
             bool done = true;
 #pragma unroll
@@ -399,10 +289,10 @@ __device__ __forceinline__ int grid_wait(Cta& c, int& S, bool& grown, float& res
             if (done) break;
             if ((++spins & 0xffu) == 0) {
                 // watchdog: a peer's abort or ~seconds of polling => leave instead of hanging the GPU
-                if (*(volatile int*)P.status || spins > (1u << 23)) {
-                    atomicExch(P.status, 1);
-                    atomicCAS(P.status + 1, 0, 100 + (int)(c.epoch & 0xffff));
-                    aborted = true;
+                if (*(volatile int*)c.status || spins > (1u << 23)) {
+                    atomicExch(c.status, 1);
+                    atomicCAS(c.status + 1, 0, 100 + (int)(c.epoch & 0xffff));
+                    ctl->abort = 1;
                     break;
                 }
             }
@@ -411,7 +301,10 @@ __device__ __forceinline__ int grid_wait(Cta& c, int& S, bool& grown, float& res
         long long L[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            if (c.G != 1) prev[j] += d[j];
+#if ARAP_RS_G1_LOCAL
+            if (c.G != 1)
+#endif
+            prev[j] += d[j];
             L[j] = (long long)(d[j] & ((1ull << 48) - 1)) - (long long)c.G * LIMB_BIAS;
         }
         const int novf = (int)((d[0] >> 56) & 0xFF);
@@ -428,46 +321,96 @@ __device__ __forceinline__ int grid_wait(Cta& c, int& S, bool& grown, float& res
             if (!grown && e < S - 24 && S > S_MIN) { code = 1; newS = max(e + 4, S_MIN); }
             else newS = max(min(e + 4, S_MAX), S_MIN);
         }
-        ctl->bc4 = make_int4(__float_as_int(r), code, newS, (aborted || ctl->abort_halo) ? 1 : ctl->bc4.w);
-        if (c.prof) c.tq[3] = clock64();
+        ctl->bc = r;
+        ctl->bc_code = code;
+        ctl->bc_S = newS;
     }
-#endif
     __syncthreads();
     if (c.prof && threadIdx.x == 0) {
         const long long t3 = clock64();
         c.acc[0] += (unsigned long long)(t1 - t0);
         c.acc[1] += (unsigned long long)(t2 - t1);
         c.acc[2] += (unsigned long long)(t3 - t2);
-        c.acc[3] += (unsigned long long)(c.tq[0] - t0);      // limb conversion
-        c.acc[4] += (unsigned long long)(c.tq[1] - c.tq[0]); // REDUX x4 + vote + staging stores
-        c.acc[5] += (unsigned long long)(c.tq[2] - c.tq[1]); // __syncthreads
-        c.acc[6] += (unsigned long long)(t1 - c.tq[2]);      // sum over warps + red
-        c.acc[7] += (unsigned long long)(c.tq[3] - t2);      // decode (before the broadcast sync)
     }
     ++c.epoch;
-    const int4 bc = ctl->bc4; // (result, code, new scale, abort)
-    if (bc.w) { ok = false; res = 0.f; return 0; }
-    res = __int_as_float(bc.x);
-    if (bc.z > S) grown = true;
-    S = bc.z;
-    return bc.y;
+    if (ctl->abort) { ok = false; res = 0.f; return 0; }
+    const int code = ctl->bc_code;
+    const int newS = ctl->bc_S;
+    res = ctl->bc;
+    if (newS > S) grown = true;
+    S = newS;
+    return code;
 }
+
+// ARAP_RS_NOINLINE_BARRIER: one out-of-line copy of the arrival and of the wait instead of four / two inlined ones.  The
+// PCG loop of this kernel is ~50 KB of code shared by the warps of three co-resident problems that sit in different phases;
+// measurements (profiles/r2_barrier_ab.txt) show that its SIZE matters more than its instruction count.
+#ifndef ARAP_RS_NOINLINE_BARRIER
+#define ARAP_RS_NOINLINE_BARRIER 0
+#endif
+#if ARAP_RS_NOINLINE_BARRIER
+__device__ __noinline__ void grid_arrive_ni(Ctl* ctl, unsigned long long* bar, int G, unsigned epoch, float g0, float g1, int S)
+{
+    Cta c;
+    c.P = nullptr; c.bar = bar; c.status = nullptr; c.ctl = ctl; c.cta = 0; c.G = G;
+    c.lane = threadIdx.x & 31; c.wid = threadIdx.x >> 5; c.nw = blockDim.x >> 5; c.epoch = epoch; c.prof = false;
+    long long t0 = 0, t1 = 0;
+    grid_arrive(c, g0, g1, S, t0, t1);
+}
+// returns (result bits, 0 accept / 1 redo, new scale, bit 0: abort, bit 1: grown)
+__device__ __noinline__ int4 grid_wait_ni(Ctl* ctl, unsigned long long* bar, int* status, int G, unsigned epoch, int S, int grown)
+{
+    Cta c;
+    c.P = nullptr; c.bar = bar; c.status = status; c.ctl = ctl; c.cta = 0; c.G = G;
+    c.lane = threadIdx.x & 31; c.wid = threadIdx.x >> 5; c.nw = blockDim.x >> 5; c.epoch = epoch; c.prof = false;
+    bool gr = grown != 0, ok = true;
+    float res = 0.f;
+    const int code = grid_wait(c, S, gr, res, ok, 0, 0);
+    return make_int4(__float_as_int(res), code, S, (ok ? 0 : 1) | (gr ? 2 : 0));
+}
+__device__ __forceinline__ void arrive_x(Cta& c, float g0, float g1, int S, long long& t0, long long& t1)
+{
+    if (c.prof) t0 = clock64();
+    grid_arrive_ni(c.ctl, c.bar, c.G, c.epoch, g0, g1, S);
+    if (c.prof) t1 = clock64();
+}
+__device__ __forceinline__ int wait_x(Cta& c, int& S, bool& grown, float& res, bool& ok, long long t0, long long t1)
+{
+    const int4 w = grid_wait_ni(c.ctl, c.bar, c.status, c.G, c.epoch, S, grown ? 1 : 0);
+    if (c.prof && threadIdx.x == 0) {
+        c.acc[0] += (unsigned long long)(t1 - t0);
+        c.acc[1] += (unsigned long long)(clock64() - t1); // poll + decode + broadcast together
+    }
+    ++c.epoch;
+    res = __int_as_float(w.x);
+    S = w.z;
+    grown = (w.w & 2) != 0;
+    if (w.w & 1) { ok = false; res = 0.f; return 0; }
+    return w.y;
+}
+#else
+__device__ __forceinline__ void arrive_x(Cta& c, float g0, float g1, int S, long long& t0, long long& t1) { grid_arrive(c, g0, g1, S, t0, t1); }
+__device__ __forceinline__ int wait_x(Cta& c, int& S, bool& grown, float& res, bool& ok, long long t0, long long t1)
+{
+    return grid_wait(c, S, grown, res, ok, t0, t1);
+}
+#endif
 
 // arrive + wait (+ the rare redo with a corrected scale).  Returns the exact sum rounded once to binary32.
 __device__ __forceinline__ float grid_finish(Cta& c, float g0, float g1, int& S, bool& ok, long long t0, long long t1)
 {
     bool grown = false;
     float res;
-    while (grid_wait(c, S, grown, res, ok, t0, t1)) {
+    while (wait_x(c, S, grown, res, ok, t0, t1)) {
         __syncthreads(); // everybody has read the broadcast before the redo overwrites it
-        grid_arrive(c, g0, g1, S, t0, t1);
+        arrive_x(c, g0, g1, S, t0, t1);
     }
     return res;
 }
 __device__ __forceinline__ float grid_sum(Cta& c, float g0, float g1, int& S, bool& ok)
 {
     long long t0 = 0, t1 = 0;
-    grid_arrive(c, g0, g1, S, t0, t1);
+    arrive_x(c, g0, g1, S, t0, t1);
     return grid_finish(c, g0, g1, S, ok, t0, t1);
 }
 
@@ -532,7 +475,7 @@ __device__ __forceinline__ void fetch_halo(const ResProb& P, Ctl* ctl, const Str
         if ((++spins & 0xffu) == 0 && (*(volatile int*)P.status || spins > (1u << 22))) {
             atomicExch(P.status, 1);
             atomicCAS(P.status + 1, 0, 200);
-            ctl->abort_halo = 1; // folded into the broadcast of the next barrier (grid_wait)
+            ctl->abort = 1;
             return;
         }
     }
@@ -634,10 +577,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
     StripSmem* S = reinterpret_cast<StripSmem*>(smem_raw);
 
     Cta c;
-    c.P = &P; c.ctl = &ctl; c.cta = cta_in_problem; c.G = P.G;
+    c.P = &P; c.bar = P.bar; c.status = P.status; c.ctl = &ctl; c.cta = cta_in_problem; c.G = P.G;
     c.lane = threadIdx.x & 31; c.wid = threadIdx.x >> 5; c.nw = blockDim.x >> 5; c.epoch = 0;
-    for (int k = 0; k < 8; ++k) c.acc[k] = 0;
-    c.prof = PROF && (P.prof != nullptr);
+    c.acc[0] = c.acc[1] = c.acc[2] = 0; c.prof = PROF && (P.prof != nullptr);
     unsigned long long ph[4] = {0, 0, 0, 0}; // cycles in PCG phase 1, 2, 3 and everything else (thread 0)
     long long tk = c.prof ? clock64() : 0;
 #define RS_TICK(slot) do { if (c.prof && threadIdx.x == 0) { const long long tn = clock64(); ph[slot] += (unsigned long long)(tn - tk); tk = tn; } } while (0)
@@ -646,8 +588,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
     const int W = P.W, H = P.H;
     const float wr = P.wr, wf = P.wf, wr2 = P.wr2, wf2 = P.wf2;
 
-    if (threadIdx.x == 0) { ctl.bc4 = make_int4(0, 0, 0, 0); ctl.abort_halo = 0; }
-    if (threadIdx.x < 10) ctl.prev[threadIdx.x / 5][threadIdx.x % 5] = 0ull; // the host zeroes P.bar before the launch
+    if (threadIdx.x == 0) ctl.abort = 0;
+    if (threadIdx.x < 8) ctl.prev[threadIdx.x >> 2][threadIdx.x & 3] = 0ull; // the host zeroes P.bar before the launch
 
     // ---- which strip is mine, who are my neighbours ----
     const int n = P.n_strips;
@@ -835,7 +777,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                     }
                 }
                 long long ta0 = 0, ta1 = 0;
-                grid_arrive(c, gs0, gs1, S_num, ta0, ta1);
+                arrive_x(c, gs0, gs1, S_num, ta0, ta1);
                 if (any_rem) fetch_halo(P, &ctl, s, lane, seq, false); // overlaps the barrier latency
                 num = grid_finish(c, gs0, gs1, S_num, ok, ta0, ta1); // solverGPUGaussNewton.t:395 scanAlphaNumerator
                 if (!ok) break;
@@ -918,7 +860,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                 }
                 RS_TICK(1);
                 long long tb0 = 0, tb1 = 0;
-                grid_arrive(c, gs0, gs1, S_bnum, tb0, tb1);
+                arrive_x(c, gs0, gs1, S_bnum, tb0, tb1);
                 if (pub) fetch_halo(P, &ctl, s, lane, seq, false); // overlaps the barrier latency
                 const float bnum = grid_finish(c, gs0, gs1, S_bnum, ok, tb0, tb1);
                 RS_TOCK();
@@ -972,7 +914,6 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
         unsigned long long* o = P.prof + (size_t)c.cta * RS_PROF_SLOTS;
         o[0] = ph[0]; o[1] = ph[1]; o[2] = ph[2]; o[3] = ph[3];
         o[4] = c.acc[0]; o[5] = c.acc[1]; o[6] = c.acc[2]; o[7] = c.epoch;
-        for (int k = 3; k < 8; ++k) o[5 + k] = c.acc[k]; // [8..12]: limb conversion, warp reduce, CTA sync, sum + red, decode
     }
 #undef RS_TICK
 #undef RS_TOCK
@@ -1081,7 +1022,6 @@ static int pick_variant(int nw, long long total_ctas, int sm_count)
 
 ResidentSolver::ResidentSolver(int maxW, int maxH, int max_slots) : maxW_(maxW), maxH_(maxH)
 {
-    if (const char* e = getenv("ARAP_RS_ONE_CTA")) small_one_cta_ = atoi(e) != 0; // experiments: 0 = always spread
     int dev = 0;
     ARAP_CUDA_CHECK(cudaGetDevice(&dev));
     ARAP_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, dev));
@@ -1095,7 +1035,7 @@ ResidentSolver::ResidentSolver(int maxW, int maxH, int max_slots) : maxW_(maxW),
         // the outbox only has to hold what can be resident: at most sm_count * max warps strips
         const size_t ob = std::min(strip_cap_, (size_t)sm_count_ * (RS_THREADS_MAX / 32));
         ARAP_CUDA_CHECK(cudaMalloc(&sl.d_outbox, ob * RS_OUTBOX_ENTRIES * 2 * sizeof(uint4)));
-        ARAP_CUDA_CHECK(cudaMalloc(&sl.d_bar, BAR_WORDS * BAR_STRIDE * sizeof(unsigned long long)));
+        ARAP_CUDA_CHECK(cudaMalloc(&sl.d_bar, 8 * BAR_STRIDE * sizeof(unsigned long long)));
     }
     ARAP_CUDA_CHECK(cudaMallocHost(&h_counts_, slots_.size() * sizeof(int)));
     ARAP_CUDA_CHECK(cudaMalloc(&d_status_, 2 * sizeof(int)));
@@ -1147,9 +1087,11 @@ bool ResidentSolver::prepare_finish(int slot)
     sl.NW = (sl.n_strips + sm_count_ - 1) / sm_count_;
     if (sl.NW < 4) sl.NW = 4;
     if (sl.NW > max_warps) return false; // does not fit on chip
+#if ARAP_RS_G1_LOCAL
     // a small problem (a DAVIS segment of a few percent of the frame, the 64x64 plumbing case) runs in ONE CTA: its two
-    // reductions per PCG iteration then never leave the SM (CTA-local all-reduce in grid_arrive / grid_wait)
-    if (sl.n_strips <= max_warps && small_one_cta_) sl.NW = std::max(sl.n_strips, 4);
+    // reductions per PCG iteration then never leave the SM
+    if (sl.n_strips <= max_warps) sl.NW = std::max(sl.n_strips, 4);
+#endif
     sl.G = (sl.n_strips + sl.NW - 1) / sl.NW;
     if (sl.G > sm_count_) sl.G = sm_count_;
     if (sl.G > RS_MAX_CTAS) return false;
@@ -1210,7 +1152,7 @@ void ResidentSolver::enqueue_group(int first, int count, int nCont, int nGN, int
         ctas += sl.G;
         nwmax = std::max(nwmax, sl.NW);
         // barrier words start at zero; halo tags start at 1, so a zeroed outbox is "nothing published yet"
-        ARAP_CUDA_CHECK(cudaMemsetAsync(sl.d_bar, 0, BAR_WORDS * BAR_STRIDE * sizeof(unsigned long long), stream));
+        ARAP_CUDA_CHECK(cudaMemsetAsync(sl.d_bar, 0, 8 * BAR_STRIDE * sizeof(unsigned long long), stream));
         ARAP_CUDA_CHECK(cudaMemsetAsync(sl.d_outbox, 0,
                                           (size_t)(sl.n_strips > 0 ? sl.n_strips : 1) * RS_OUTBOX_ENTRIES * 2 * sizeof(uint4), stream));
     }

@@ -109,7 +109,6 @@ private:
     int last_variant_ = -1;
     int last_shape_[5] = {0, 0, 0, 0, 0};
     float pcg_rtol_ = 0.0f, gn_rtol_ = 0.0f;
-    bool small_one_cta_ = true;
 };
 
 } // namespace arapb200

@@ -15,4 +15,11 @@ int el_fold(const long long* L4, int e_unit, float* out)
     if (!arapb200::limbs_to_float_int(L4, e_unit, z, *out)) return 1;
     return z ? 2 : 0;
 }
+// the lighter 64-bit decode: 0 = computed, 1 = preconditions not met (fallback), 2 = computed and zero
+int el_fold64(const long long* L4, int e_unit, float* out)
+{
+    bool z;
+    if (!arapb200::limbs_to_float_i64(L4, e_unit, z, *out)) return 1;
+    return z ? 2 : 0;
+}
 }

@@ -20,6 +20,7 @@ def el(tmp_path_factory):
     L = C.CDLL(so)
     L.el_to_limbs.argtypes = [C.c_float, C.c_int, C.POINTER(C.c_int)]
     L.el_fold.argtypes = [C.POINTER(C.c_longlong), C.c_int, C.POINTER(C.c_float)]
+    L.el_fold64.argtypes = [C.POINTER(C.c_longlong), C.c_int, C.POINTER(C.c_float)]
     return L
 
 
@@ -117,3 +118,43 @@ def test_fold_rounds_once_to_nearest_even(el):
             assert rc == (2 if T == 0 else 0)
             want = float(np.float32(_rn_even(T, e_unit)))
             assert got == want and math.copysign(1.0, got) == math.copysign(1.0, want if T != 0 else 0.0), (L, e_unit, got, want)
+
+
+def test_fold64_fast_path_agrees_or_declines(el):
+    """The 64-bit decode either declines (preconditions) or returns the correctly rounded result; on totals shaped like the
+    kernel's (leading bit inside the two top limbs, signed limb sums of every sign combination) it must not decline."""
+    rng = np.random.default_rng(3)
+    out = C.c_float()
+    taken = 0
+    cases = []
+    for _ in range(20000):
+        L = [int(rng.integers(-(1 << 22), 1 << 22)), int(rng.integers(-(1 << 39), 1 << 39)),
+             int(rng.integers(-(1 << 39), 1 << 39)), int(rng.integers(-(1 << 39), 1 << 39))]
+        r = rng.random()
+        if r < 0.15:
+            L[0] = int(rng.integers(-3, 4))
+        elif r < 0.25:
+            L[0] = 0; L[1] = int(rng.integers(-(1 << 30), 1 << 30))
+        elif r < 0.30:
+            L[2] = 0; L[3] = 0                                  # exact ties possible
+        elif r < 0.35:
+            L[2] = -(1 << 24) * int(rng.integers(0, 3)); L[3] = int(rng.integers(-2, 3))
+        cases.append(L)
+    cases += [[0, 1 << 24, 0, 0], [0, (1 << 24) | 1, 0, 0], [0, (1 << 25) | 1, 0, 0], [0, (1 << 25) | 1, 0, 1], [0, (1 << 25) | 1, 0, -1],
+              [0, (1 << 25) | 3, 0, 0], [0, -((1 << 25) | 1), 0, 0], [0, -((1 << 25) | 1), 0, 1], [0, -((1 << 25) | 3), -1, (1 << 24)],
+              [1, -(1 << 24), 0, 0], [1 << 36, 0, 0, 1], [0, 0, 0, 0]]
+    for L in cases:
+        T = (L[0] << 72) + (L[1] << 48) + (L[2] << 24) + L[3]
+        for e_unit in (-150, -90, -30, 10):
+            arr = (C.c_longlong * 4)(*L)
+            rc = el.el_fold64(arr, e_unit, C.byref(out))
+            if rc == 1:
+                continue
+            taken += 1
+            assert rc == (2 if T == 0 else 0), (L, rc)
+            want = float(np.float32(_rn_even(T, e_unit)))
+            assert float(out.value) == want, (L, e_unit, float(out.value), want)
+            # kernel-shaped totals must take the fast path
+    assert taken > 0.7 * len(cases) * 4
+    arr = (C.c_longlong * 4)(1 << 14, 123456, -98765, 4242)
+    assert el.el_fold64(arr, -60, C.byref(out)) == 0

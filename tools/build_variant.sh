@@ -5,8 +5,8 @@
 set -e
 name=$1; defs=$2
 root=$(cd "$(dirname "$0")/.." && pwd)
-src=$root/arap_flow_b200/csrc
-bld=$src/build_$name
+src=${SRC_OVERRIDE:-$root/arap_flow_b200/csrc}   # SRC_OVERRIDE: build another revision of the sources (bisecting)
+bld=$root/arap_flow_b200/csrc/build_$name
 out=$root/arap_flow_b200/variants
 mkdir -p "$bld" "$out"
 flags="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -DARAP_RS_STRIP_H=${RS_H:-8} $defs -lineinfo -fmad=false -prec-div=true -prec-sqrt=true -Xcompiler -fPIC,-fvisibility=hidden"
