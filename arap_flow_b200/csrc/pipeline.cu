@@ -267,6 +267,24 @@ int BatchPipeline::run(const HostProblem* problems, int count)
         }
         int run_len = 0; // consecutive resident problems
         while (i + run_len < count && dev_[i + run_len].resident) ++run_len;
+        // small problems (each fits one thread-block cluster) share ONE launch, however many they are: their barriers run
+        // through distributed shared memory and the problems need not be co-resident
+        if (const int ncl = resident_->cluster_run(i, run_len)) {
+            for (int j = 0; j < ncl; ++j) {
+                Dev& dj = dev_[i + j];
+                const HostProblem& hp = problems[i + j];
+                enqueue_target_image(hp.W, hp.H, dj.matches, (int)dj.recs.size(), dj.C, stream_);
+                launches_ += dj.recs.empty() ? 1 : 2;
+                resident_->set_problem(i + j, dj.X, dj.A, dj.C, 1, wf, wr, dj.costs, nullptr);
+            }
+            resident_->enqueue_cluster(i, ncl, nCont_, nGN_, nPCG_, stream_);
+            if (ncl > group_size_) group_size_ = ncl;
+            i += ncl;
+            continue;
+        }
+        // the cluster-eligible problems further down this run get their own launch: stop the co-resident group before them
+        for (int j = 1; j < run_len; ++j)
+            if (resident_->cluster_run(i + j, 1)) { run_len = j; break; }
         int gsz = resident_->group_size(i, run_len);
         if (gsz < run_len) { // several launches: split the run evenly instead of one full launch and a small remainder
             const int ngroups = (run_len + gsz - 1) / gsz;

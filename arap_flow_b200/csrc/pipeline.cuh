@@ -61,6 +61,7 @@ public:
     // opt-in early exit of the PCG loops (resident back-end only; the streaming graph keeps the fixed budget)
     void set_pcg_rtol(float rtol);
     void set_gn_rtol(float rtol);
+    void set_cluster_barrier(bool on) { if (resident_) resident_->set_cluster_barrier(on); }
 
 private:
     struct Dev { // device + pinned staging of one problem slot

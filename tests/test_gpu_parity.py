@@ -531,3 +531,41 @@ def test_conditioning_bounds_the_gap_to_any_rounding_order():
     spec.loader.exec_module(mod)
     res = mod.run("C3", 6, 4, 150)
     assert res["worst_mean_epe_px"] < 1e-4 and res["worst_rel_cost_diff"] < 1e-5, res
+
+
+def test_cluster_scope_barrier_equals_l2_barrier(oracle):
+    """Opt-in: small problems (each fits one thread-block cluster) run with a cluster-scope barrier -- limb sums pushed
+    through distributed shared memory, mbarrier completion -- instead of the L2 barrier.  Same bits as the L2 path and as the
+    oracle; any number of problems per launch; mixed with a large problem in one batch."""
+    sps = [synth.synth(160, 120, 1, 2, 500 + i) for i in range(5)] + [synth.synth(320, 200, 2, 3, 600)]
+    jobs = [(s, s.masks[0]) for s in sps] + [(sps[-1], sps[-1].masks[1])]
+    kw = dict(nCont=2, nGN=2, nPCG=60)
+    b = lib.Batch(320, 200, len(jobs), **kw)
+    res = {}
+    for mode in (1, 0):
+        b.set_option("cluster_barrier", mode)
+        outs = [b.submit(i, s.rgb, m, s.matches) for i, (s, m) in enumerate(jobs)]
+        b.run()
+        info = b.launch_info()
+        res[mode] = ([{k: v.copy() for k, v in o.items()} for o in outs], info)
+    assert res[1][1]["variant"][1] == 0 and res[1][1]["problems_per_launch"] == len(jobs), res[1][1]   # ONE cluster launch
+    assert res[0][1]["variant"][1] != 0, res[0][1]
+    for a, c in zip(res[1][0], res[0][0]):
+        assert _eq(a["flow"], c["flow"]) and _eq(a["costs"], c["costs"]) and _eq(a["rgb"], c["rgb"])
+    for o, (s, m) in zip(res[1][0], jobs):
+        Xo, Ao, co = oracle.solve(m, s.matches, **kw)
+        assert _eq(o["flow"], oracle.flow(Xo)) and _eq(o["costs"], co)
+    b.close()
+    # a batch that mixes small problems with one that needs the L2 barrier (C1 size)
+    big = synth.config("C1")
+    small = synth.synth(854, 480, 1, 1, 77, axes=(0.1, 0.1))
+    kw = dict(nCont=1, nGN=1, nPCG=30)
+    b = lib.Batch(854, 480, 3, **kw)
+    b.set_option("cluster_barrier", 1)
+    outs = [b.submit(0, small.rgb, small.masks[0], small.matches), b.submit(1, big.rgb, big.masks[0], big.matches),
+            b.submit(2, small.rgb, small.masks[0], small.matches)]
+    b.run()
+    for o, s in zip(outs, (small, big, small)):
+        Xo, Ao, co = oracle.solve(s.masks[0], s.matches, **kw)
+        assert _eq(o["flow"], oracle.flow(Xo)) and _eq(o["costs"], co)
+    b.close()
