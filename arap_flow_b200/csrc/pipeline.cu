@@ -166,6 +166,7 @@ void BatchPipeline::solve_streaming(const HostProblem& hp, Dev& d)
     }
     const long long l0 = solver_->launches();
     const float wf = sqrtf(100.0f), wr = sqrtf(0.01f); // CombinedSolver.h:172-177
+    solver_->set_pcg_rtol(pcg_rtol_);
     solver_->bind(d.X, d.A, d.U, d.C, d.M, wf, wr, stream_);
     for (int t = 0; t < nCont_; ++t) {
         const float alpha = (float)(t + 1) / (float)nCont_; // CombinedSolver.h:199-201
@@ -256,10 +257,10 @@ int BatchPipeline::run(const HostProblem* problems, int count)
     for (int i = 0; i < count;) {
         Dev& d = dev_[i];
         if (!d.resident) {
-            if ((pcg_rtol_ > 0.0f || gn_rtol_ > 0.0f) && !warned_rtol_) { // never silently: the caller asked for an early exit
+            if (gn_rtol_ > 0.0f && !warned_rtol_) { // never silently: the caller asked for an early exit
                 warned_rtol_ = true;
-                fprintf(stderr, "arapb200: warning: pcg_rtol / gn_rtol are honoured by the resident back-end only; a %dx%d problem "
-                                "streams and runs the full iteration budget\n", problems[i].W, problems[i].H);
+                fprintf(stderr, "arapb200: warning: gn_rtol is honoured by the resident back-end only; a %dx%d problem streams "
+                                "and runs every Gauss-Newton step (pcg_rtol is honoured)\n", problems[i].W, problems[i].H);
             }
             solve_streaming(problems[i], d);
             ++i;

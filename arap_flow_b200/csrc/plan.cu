@@ -129,10 +129,11 @@ void GnPlan::choose_backend(void** pp)
     if (!use_resident_) {
         if (!stream_) stream_.reset(new StreamSolver(W_, H_));
         stream_->set_general(general_);
-        if ((pcg_rtol_ > 0.0f || gn_rtol_ > 0.0f) && !warned_rtol_) {
+        stream_->set_pcg_rtol(general_ ? 0.0f : pcg_rtol_);
+        if ((gn_rtol_ > 0.0f || (general_ && pcg_rtol_ > 0.0f)) && !warned_rtol_) {
             warned_rtol_ = true;
-            fprintf(stderr, "arapb200: warning: pcg_rtol / gn_rtol are honoured by the resident back-end only; this %dx%d "
-                            "problem streams and runs the full iteration budget\n", W_, H_);
+            fprintf(stderr, "arapb200: warning: gn_rtol (and, for a non-grid UrShape, pcg_rtol) is honoured by the resident "
+                            "back-end only; this %dx%d problem streams\n", W_, H_);
         }
     }
 }

@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_prep(const StreamDev* __restrict
     if (bad) atomicAdd(&dp.sc->bad_u, 1u);
     any = __syncthreads_or(any);
     if (threadIdx.x == 0) dp.tile_active[blockIdx.x] = any ? 1 : 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { dp.sc->conv = 0u; dp.sc->stop = -1.0f; } // opt-in early exit: re-armed per GN step
 }
 
 // Stage (X_x, X_y, cos, sin) of a tile + halo.  Inactive / out-of-image entries are never used.
@@ -209,7 +210,10 @@ __global__ void __launch_bounds__(ST_THREADS) k_init(const StreamDev* __restrict
 // ping-ponged).  Every global load of the block is issued before the first use; beta is decoded under them.
 // SUB = rows per block (32: one block per tile, 256 threads; 16: two blocks per tile, 128 threads -- shorter blocks leave
 // less idle time at the end of the grid).
-template <bool FIRST, int SUB>
+// RT (opt-in early exit, separate instantiation so that the default kernels compile exactly as before): once r.z of the
+// previous iteration is <= sc->stop, this launch and every later k_step_a / k_step_b of the Gauss-Newton step return at
+// once -- every block decodes the same scalar, so the decision is uniform; block 0 makes it sticky (sc->conv).
+template <bool FIRST, int SUB, bool RT = false>
 __global__ void __launch_bounds__(SUB * 8) k_step_a(const __grid_constant__ StreamPlanes pl,
                                                     const StreamDev* __restrict__ dpp, int it)
 {
@@ -217,6 +221,7 @@ __global__ void __launch_bounds__(SUB * 8) k_step_a(const __grid_constant__ Stre
     __shared__ float4 T[TSY][TS]; // (p_x, p_y, sin*p_a, cos*p_a) of the block's rows + ring
     __shared__ double red[64];
     __shared__ float s_beta;
+    __shared__ int s_skip;
     const int tile = blockIdx.x / NSUB, sub = blockIdx.x % NSUB;
     const bool tile_on = pl.tile_active[tile] != 0; // tiles without object pixels have nothing to add
     if (!tile_on && blockIdx.x != 0) return;
@@ -285,9 +290,15 @@ __global__ void __launch_bounds__(SUB * 8) k_step_a(const __grid_constant__ Stre
             if (threadIdx.x == 0) {
                 s_beta = (num > 0.0f) ? bnum / num : 0.0f; // :544-547
                 if (blockIdx.x == 0 && dpp->trace) dpp->trace[3 * (it - 1) + 2] = bnum;
+                if (RT) {
+                    const bool skip = pl.sc->conv != 0u || bnum <= pl.sc->stop;
+                    s_skip = skip ? 1 : 0;
+                    if (skip && blockIdx.x == 0) pl.sc->conv = 1u;
+                }
             }
         }
         __syncthreads();
+        if (RT && s_skip) return;
         beta = s_beta;
     }
 
@@ -346,13 +357,14 @@ __global__ void __launch_bounds__(SUB * 8) k_step_a(const __grid_constant__ Stre
 // PCGStep2 (solverGPUGaussNewton.t:446-489).  Branch-free: the planes of inactive pixels hold zeros (they are
 // zero-initialised and never written), so they flow through as exact zeros and add +0 to the group term;
 // every load of the four rows is issued before the first use.
-template <int SUB>
+template <int SUB, bool RT = false>
 __global__ void __launch_bounds__(SUB * 8) k_step_b(const __grid_constant__ StreamPlanes pl,
                                                     const StreamDev* __restrict__ dpp, int it)
 {
     constexpr int NSUB = ST_TILE / SUB;
     __shared__ double red[64];
     __shared__ float s_alpha;
+    __shared__ int s_skip;
     const int tile = blockIdx.x / NSUB, sub = blockIdx.x % NSUB;
     const bool tile_on = pl.tile_active[tile] != 0;
     if (!tile_on && blockIdx.x != 0) return;
@@ -378,11 +390,20 @@ __global__ void __launch_bounds__(SUB * 8) k_step_b(const __grid_constant__ Stre
         const float num = __shfl_sync(0xffffffffu, v, 0), den = __shfl_sync(0xffffffffu, v, 16);
         if (threadIdx.x == 0) {
             s_alpha = (den > 0.0f) ? num / den : 0.0f; // :456-459
-            if (blockIdx.x == 0 && dpp->trace) {
+            if (RT) {
+                // it == 0: num is r.p of PCGInit1 -> the threshold of this Gauss-Newton step; later: num is r.z of iteration it-1
+                if (it == 0) { if (blockIdx.x == 0) pl.sc->stop = (dpp->pcg_rtol2 > 0.0f) ? dpp->pcg_rtol2 * num : -1.0f; s_skip = 0; }
+                else s_skip = (pl.sc->conv != 0u || num <= pl.sc->stop) ? 1 : 0;
+            }
+            if (blockIdx.x == 0 && dpp->trace && !(RT && s_skip)) {
                 dpp->trace[3 * it] = den;
                 dpp->trace[3 * it + 1] = num;
             }
         }
+    }
+    if (RT) {
+        __syncthreads();
+        if (s_skip) return;
     }
     if (blockIdx.x == 0) { // recycle the accumulators nobody reads any more (their next writers are later kernels)
         for (int w = threadIdx.x; w < WA_WORDS; w += blockDim.x) {
@@ -787,6 +808,7 @@ void StreamSolver::bind(float2* X, float* A, const float2* U, const float2* C, c
     h_.X = X; h_.A = A; h_.U = U; h_.C = C; h_.M = M;
     h_.wf = wf; h_.wr = wr; h_.wf2 = wf * wf; h_.wr2 = wr * wr;
     h_.trace = nullptr;
+    h_.pcg_rtol2 = pcg_rtol_ * pcg_rtol_;
     upload(stream);
 }
 
@@ -811,11 +833,14 @@ void StreamSolver::launch_step_a(bool first, int it, cudaStream_t stream)
         if (first) k_step_a_gen<true><<<h_.ntiles, ST_THREADS, 0, stream>>>(pl, d_, it);
         else k_step_a_gen<false><<<h_.ntiles, ST_THREADS, 0, stream>>>(pl, d_, it);
     } else {
+        const bool rt = pcg_rtol_ > 0.0f; // opt-in early exit: its own instantiations
         if (sub16_) {
             if (first) k_step_a<true, 16><<<2 * h_.ntiles, 128, 0, stream>>>(pl, d_, it);
+            else if (rt) k_step_a<false, 16, true><<<2 * h_.ntiles, 128, 0, stream>>>(pl, d_, it);
             else k_step_a<false, 16><<<2 * h_.ntiles, 128, 0, stream>>>(pl, d_, it);
         } else {
             if (first) k_step_a<true, 32><<<h_.ntiles, 256, 0, stream>>>(pl, d_, it);
+            else if (rt) k_step_a<false, 32, true><<<h_.ntiles, 256, 0, stream>>>(pl, d_, it);
             else k_step_a<false, 32><<<h_.ntiles, 256, 0, stream>>>(pl, d_, it);
         }
     }
@@ -824,8 +849,23 @@ void StreamSolver::launch_step_a(bool first, int it, cudaStream_t stream)
 void StreamSolver::launch_step_b(int it, cudaStream_t stream)
 {
     const StreamPlanes& pl = h_;
-    if (sub16_) k_step_b<16><<<2 * h_.ntiles, 128, 0, stream>>>(pl, d_, it);
-    else k_step_b<32><<<h_.ntiles, 256, 0, stream>>>(pl, d_, it);
+    const bool rt = pcg_rtol_ > 0.0f && !general_;
+    if (sub16_) {
+        if (rt) k_step_b<16, true><<<2 * h_.ntiles, 128, 0, stream>>>(pl, d_, it);
+        else k_step_b<16><<<2 * h_.ntiles, 128, 0, stream>>>(pl, d_, it);
+    } else {
+        if (rt) k_step_b<32, true><<<h_.ntiles, 256, 0, stream>>>(pl, d_, it);
+        else k_step_b<32><<<h_.ntiles, 256, 0, stream>>>(pl, d_, it);
+    }
+}
+
+void StreamSolver::set_pcg_rtol(float rtol)
+{
+    rtol = rtol > 0.0f ? rtol : 0.0f;
+    if ((rtol > 0.0f) != (pcg_rtol_ > 0.0f) && graph_) { // other kernel instantiations: re-capture
+        cudaGraphExecDestroy(graph_); graph_ = nullptr; graph_npcg_ = -1;
+    }
+    pcg_rtol_ = rtol;
 }
 
 void StreamSolver::set_general(bool general)

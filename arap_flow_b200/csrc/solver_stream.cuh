@@ -15,7 +15,11 @@ constexpr unsigned FLAG_ACTIVE = 0x20u;
 struct StreamScalars {
     float num, den, bnum, cost;
     unsigned bad_u; // number of pixels whose UrShape is not the pixel grid
-    unsigned pad[3];
+    // opt-in early exit of the PCG loop: threshold on r.z, set once per Gauss-Newton step, and the sticky
+    // "converged" flag that turns the remaining k_step_a / k_step_b launches of the captured graph into no-ops
+    float stop;
+    unsigned conv;
+    unsigned pad;
 };
 
 // Accumulator sets (common.cuh: wide fixed-point accumulators).  r.z of PCG iteration j lives in set (j + 3) % 3
@@ -62,6 +66,7 @@ struct StreamDev : StreamPlanes {
     const float* M;       // Mask
     float wf, wr, wf2, wr2;
     float* trace;         // optional: (den, num, bnum) per PCG iteration of the current GN step
+    float pcg_rtol2;      // 0 = fixed budget (reference behaviour); > 0: the PCG loop ends once r.z <= pcg_rtol2 * (r.z at PCGInit1)
 };
 
 class StreamSolver {
@@ -87,6 +92,8 @@ public:
     void enqueue_step_a(bool first, int it, cudaStream_t stream); // also decodes p.q into scalars().den
     // UrShape is not the pixel grid: use the general-d kernels (slower; same arithmetic contract)
     void set_general(bool general);
+    // opt-in (never on the parity path): relative tolerance of the PCG loops; takes effect with the next bind()
+    void set_pcg_rtol(float rtol);
     bool general() const { return general_; }
     const StreamDev& host_view() const { return h_; }
     // debug / parity tests: one plane (PL_*) <-> a row-major host image; blocking
@@ -104,6 +111,7 @@ private:
     void launch_step_a(bool first, int it, cudaStream_t stream);
     void launch_step_b(int it, cudaStream_t stream);
     bool general_ = false;
+    float pcg_rtol_ = 0.0f;
     bool sub16_ = true; // two 128-thread blocks per tile in the PCG kernels (ARAP_STREAM_SUB=32: one 256-thread block)
     StreamDev h_{};
     StreamDev* d_ = nullptr;

@@ -97,8 +97,8 @@ ARAPB200_API int arapb200_batch_launch_info(arapb200_batch* b, int* info6);
 
 /* Options beyond the reference's behaviour; every one defaults to "off" and none is on the parity path.
  *   "pcg_rtol" (SURVEY.md 8f N4): 0 <= value < 1.  > 0: a PCG loop ends as soon as r.z <= value^2 * (r.z at its start)
- *   instead of always running lIterations iterations.  Changes results (by design); resident back-end only --
- *   problems that take the streaming back-end keep the fixed budget.
+ *   instead of always running lIterations iterations.  Changes results (by design).  Both back-ends honour it (the
+ *   streaming one turns the remaining kernels of its captured graph into no-ops).
  *   "gn_rtol": 0 <= value < 1.  > 0: the Gauss-Newton steps of a continuation step end as soon as one of them lowers
  *   the cost by less than value (relative) instead of always running nIterations steps; the skipped entries of
  *   out_costs repeat the last cost.  Same scope and caveats as "pcg_rtol".

@@ -479,6 +479,19 @@ def test_opt_in_pcg_tolerance_n4(oracle):
     with pytest.raises(RuntimeError):
         b.set_option("no_such_option", 1.0)
     b.close()
+    # the streaming back-end honours pcg_rtol too (the rest of its captured graph turns into no-ops): same bits as the
+    # oracle's early exit, and back to the fixed-budget result when switched off again
+    bs = lib.Batch(sp.W, sp.H, 1, backend=lib.BACKEND_STREAM, **kw)
+    bs.set_option("pcg_rtol", 1e-2)
+    o = bs.submit(0, sp.rgb, sp.masks[0], sp.matches)
+    bs.run()
+    t_s_fast = bs.timing_ms()["solve"]
+    assert _eq(o["flow"], oracle.flow(Xe)) and _eq(o["costs"], ce)
+    bs.set_option("pcg_rtol", 0.0)
+    o = bs.submit(0, sp.rgb, sp.masks[0], sp.matches)
+    bs.run()
+    assert _eq(o["flow"], full["flow"]) and _eq(o["costs"], full["costs"]) and t_s_fast < 0.9 * bs.timing_ms()["solve"]
+    bs.close()
 
 
 @pytest.mark.parametrize("W,H,seed", [(70, 45, 0), (128, 96, 1)])
