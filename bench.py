@@ -308,10 +308,12 @@ def main():
     backend = {"auto": lib.BACKEND_AUTO, "stream": lib.BACKEND_STREAM, "resident": lib.BACKEND_RESIDENT}[args.backend]
     W, H = WORKLOADS[args.workload][:2]
     opt_h = args.path == "opt_h"
-    # resident back-end: 3 (168 registers) or 4 (128 registers) problems share one cooperative launch; 9 = three launches of
-    # three, measured 2 % faster than two launches of four (profiles/r1_batch_choice.txt)
+    # resident back-end: 3 (168 registers) or 4 (128 registers) C1-sized problems share one cooperative launch; 9 = three
+    # launches of three, measured 2 % faster than two launches of four (profiles/r1_batch_choice.txt).  Smaller problems: as
+    # many as fill the CTA slots of ONE launch (profiles/r2_batch_sweep.txt): 3 multi-segment pairs = 12 problems, 14 C1s pairs
+    DEFAULT_B = {"C2": 3, "C1s": 14}
     B = args.batch if args.batch > 0 else (1 if (args.backend == "stream" or args.workload == "C4" or opt_h) else
-                                           (2 if args.workload == "C2" else 9))
+                                           DEFAULT_B.get(args.workload, 9))
     pairs = make_pairs(args.workload, B, first=rank * B)
     nseg = WORKLOADS[args.workload][2]
     # --multseg (C2): one independent problem per segment, all of them sharing the pair's constraint list

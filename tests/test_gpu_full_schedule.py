@@ -100,17 +100,22 @@ def test_c2_ragged_compact_grid_one_pair():
     _run_and_check("C2", [2000], expect_compact=True)
 
 
-def test_c2_default_bench_two_pairs_eight_problems():
-    """exactly bench.py --workload C2: 2 pairs = 8 ragged problems in one compact grid"""
+def test_c2_two_pairs_eight_problems():
+    """2 pairs = 8 ragged problems in one compact grid (168-register variant)"""
     _run_and_check("C2", [2000, 2001], expect_compact=True)
+
+
+def test_c2_default_bench_three_pairs_twelve_problems():
+    """exactly bench.py --workload C2: 3 pairs = 12 ragged problems in one compact grid (128-register variant)"""
+    _run_and_check("C2", [2000, 2001, 2002], expect_compact=True)
 
 
 def test_c3_batch_three():
     _run_and_check("C3", [3000, 3001, 3002])
 
 
-def test_c3_default_bench_batch_of_eight():
-    """exactly bench.py --workload C3 --batch 8"""
+def test_c3_batch_of_eight():
+    """3 + 3 + 2 (bench.py --workload C3 runs launches of three whatever the batch: test_c3_batch_three is its launch shape)"""
     _run_and_check("C3", list(range(3000, 3008)))
 
 
@@ -120,8 +125,13 @@ def test_c4_streaming_one_full_continuation_step():
 
 
 def test_c1s_small_objects_share_a_launch():
-    """DAVIS-typical small object (8 % coverage): bench.py --workload C1s"""
+    """DAVIS-typical small object (8 % coverage)"""
     _run_and_check("C1s", [1000, 1001])
+
+
+def test_c1s_default_bench_batch_of_fourteen():
+    """exactly bench.py --workload C1s: fourteen problems of 41 CTAs in one (41, 14) launch, 128-register variant"""
+    _run_and_check("C1s", list(range(1000, 1014)), expect_variant=(160, 3), expect_grid_y=14)
 
 
 def test_c0_batch_of_eight():
