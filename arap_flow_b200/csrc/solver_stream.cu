@@ -16,6 +16,14 @@
 #include "solver_stream.cuh"
 #include "grid_math.cuh"
 
+// occupancy experiments (tools/build_variant.sh): minimum resident blocks per SM of the two PCG kernels; 0 = let ptxas choose
+#ifndef ARAP_ST_MINB_A
+#define ARAP_ST_MINB_A 0
+#endif
+#ifndef ARAP_ST_MINB_B
+#define ARAP_ST_MINB_B 0
+#endif
+
 namespace arapb200 {
 
 namespace {
@@ -214,7 +222,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_init(const StreamDev* __restrict
 // previous iteration is <= sc->stop, this launch and every later k_step_a / k_step_b of the Gauss-Newton step return at
 // once -- every block decodes the same scalar, so the decision is uniform; block 0 makes it sticky (sc->conv).
 template <bool FIRST, int SUB, bool RT = false>
-__global__ void __launch_bounds__(SUB * 8) k_step_a(const __grid_constant__ StreamPlanes pl,
+__global__ void __launch_bounds__(SUB * 8, ARAP_ST_MINB_A) k_step_a(const __grid_constant__ StreamPlanes pl,
                                                     const StreamDev* __restrict__ dpp, int it)
 {
     constexpr int NSUB = ST_TILE / SUB, TSY = SUB + 2;
@@ -358,7 +366,7 @@ __global__ void __launch_bounds__(SUB * 8) k_step_a(const __grid_constant__ Stre
 // zero-initialised and never written), so they flow through as exact zeros and add +0 to the group term;
 // every load of the four rows is issued before the first use.
 template <int SUB, bool RT = false>
-__global__ void __launch_bounds__(SUB * 8) k_step_b(const __grid_constant__ StreamPlanes pl,
+__global__ void __launch_bounds__(SUB * 8, ARAP_ST_MINB_B) k_step_b(const __grid_constant__ StreamPlanes pl,
                                                     const StreamDev* __restrict__ dpp, int it)
 {
     constexpr int NSUB = ST_TILE / SUB;
