@@ -88,8 +88,9 @@ def main():
                 "oracle_seconds": round(time.time() - t0, 1), "oracle_threads": O.num_threads(),
             }
             tmp = OUT + ".tmp"
-            with open(tmp, "w") as f:
-                json.dump(db, f, indent=0, sort_keys=True)
+            with open(tmp, "w") as f:     # one line per problem
+                ks = sorted(db)
+                f.write("{\n" + ",\n".join(json.dumps(k) + ": " + json.dumps(db[k], sort_keys=True, separators=(", ", ": ")) for k in ks) + "\n}\n")
             os.replace(tmp, OUT)
             print(key, "done in %.0f s, final cost %.6f" % (time.time() - t0, costs[-1, -1]), flush=True)
 
