@@ -8,8 +8,10 @@
 // (para_gen.py:178-200), and every process pays CUDA context creation + buffer allocation (0.6-4 s) before
 // its first pair -- more than the GPU work of a handful of pairs.  Two extra invocations remove that cost
 // without touching the driver's calling convention:
-//   arap_deform --serve SPOOLDIR     one long-lived process per GPU: keeps the context, the plan and the
-//                                    device buffers, and runs every list file dropped into SPOOLDIR
+//   arap_deform --serve SPOOLDIR [--warm WxH]
+//                                    one long-lived process per GPU: keeps the context, the plan and the
+//                                    device buffers, and runs every list file dropped into SPOOLDIR; --warm
+//                                    builds plan + buffers for that image size at start-up
 //   ARAP_SERVER=SPOOLDIR arap_deform LISTFILE | RGB MASK CSTR FLO WRGB WMASK
 //                                    thin client: same argv contract, same "Saved" lines, same exit code;
 //                                    the work is done by the server that watches SPOOLDIR
@@ -57,7 +59,8 @@ static void usage()
     puts("warped_RGB \t [output] path to output warped image (.png), all intermediate directories must exist");
     puts("warped_Mask \t [output] path to output warped mask (.png), all intermediate directories must exist");
     puts("\n./arap_deform LISTFILE   (one such 6-tuple per line)");
-    puts("./arap_deform --serve SPOOLDIR   (resident worker: runs the list files that clients with ARAP_SERVER=SPOOLDIR submit)");
+    puts("./arap_deform --serve SPOOLDIR [--warm WxH]   (resident worker: runs the list files that clients with ARAP_SERVER=SPOOLDIR");
+    puts("                                               submit; --warm pre-builds the plan and buffers for that image size)");
     puts("Environment: ARAP_PLAN = path of the ARAP energy file (default ./arap_plan.t); CUDA_VISIBLE_DEVICES selects the GPU;");
     puts("             ARAP_BATCH = problems solved together (default 9: three cooperative launches of three)");
     puts("             ARAP_PCG_RTOL = opt-in relative PCG tolerance, e.g. 1e-3 (default 0: fixed 400 iterations)");
@@ -94,18 +97,54 @@ static bool read_list(const char* path, std::vector<InputPaths>& lines)
     return true;
 }
 
+struct Settings {
+    // the solver budget is a compile-time constant of the reference: main.cpp:215-221
+    int nCont = 19, nGN = 8, nPCG = 400;
+    int batch = 9;
+    // opt-in, off by default: convergence-aware PCG loops (changes results; include/arapb200.h)
+    double pcg_rtol = 0.0, gn_rtol = 0.0;
+    bool timing = false; // ARAP_TIMING=1: per-stage wall times on stderr
+    Settings()
+    {
+        if (getenv("ARAP_BATCH")) batch = atoi(getenv("ARAP_BATCH"));
+        if (batch < 1) batch = 1;
+        if (getenv("ARAP_PCG_RTOL")) pcg_rtol = atof(getenv("ARAP_PCG_RTOL"));
+        if (getenv("ARAP_GN_RTOL")) gn_rtol = atof(getenv("ARAP_GN_RTOL"));
+        timing = getenv("ARAP_TIMING") != NULL;
+    }
+};
+
+// (re)build the batch context -- the "plan" of the reference -- for images of W x H; 0 = ok
+static int ensure_context(Context& C, const Settings& S, int W, int H)
+{
+    if (C.ctx && W == C.W && H == C.H) return 0;
+    if (C.ctx) {
+        printf("Warning: Input image has different size to one in the prebuilt plan.\n"
+               "To avoid re-building the plan and to save time, put images of the "
+               "same size in the same list.\nStarting to re-build plan...\n");
+        arapb200_batch_destroy(C.ctx);
+        C.ctx = NULL;
+    }
+    C.ctx = arapb200_batch_create(W, H, S.batch, S.nCont, S.nGN, S.nPCG, ARAPB200_BACKEND_AUTO);
+    if (!C.ctx) return 1;
+    if (S.pcg_rtol > 0.0 && arapb200_batch_set_option(C.ctx, "pcg_rtol", S.pcg_rtol)) {
+        fprintf(stderr, "ARAP_PCG_RTOL must be in [0, 1)\n");
+        return 1;
+    }
+    if (S.gn_rtol > 0.0 && arapb200_batch_set_option(C.ctx, "gn_rtol", S.gn_rtol)) {
+        fprintf(stderr, "ARAP_GN_RTOL must be in [0, 1)\n");
+        return 1;
+    }
+    C.W = W; C.H = H;
+    return 0;
+}
+
 // deformSingle for every entry (ARAP/deformation/src/main.cpp:223-238), batched and pipelined
 static int process(const std::vector<InputPaths>& lines, Context& C)
 {
-    // the solver budget is a compile-time constant of the reference: main.cpp:215-221
-    const int nCont = 19, nGN = 8, nPCG = 400;
-    int batch = getenv("ARAP_BATCH") ? atoi(getenv("ARAP_BATCH")) : 9;
-    if (batch < 1) batch = 1;
-    // opt-in, off by default: convergence-aware PCG loops (changes results; include/arapb200.h)
-    const double pcg_rtol = getenv("ARAP_PCG_RTOL") ? atof(getenv("ARAP_PCG_RTOL")) : 0.0;
-    const double gn_rtol = getenv("ARAP_GN_RTOL") ? atof(getenv("ARAP_GN_RTOL")) : 0.0;
-    // ARAP_TIMING=1: per-stage wall times on stderr
-    const bool timing = getenv("ARAP_TIMING") != NULL;
+    const Settings S;
+    const int batch = S.batch;
+    const bool timing = S.timing;
     const auto t_begin = std::chrono::steady_clock::now();
     auto since = [&](std::chrono::steady_clock::time_point t0) {
         return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -121,25 +160,10 @@ static int process(const std::vector<InputPaths>& lines, Context& C)
     };
     auto gpu_stage = [&](std::shared_ptr<Group> g) -> int {
         if (!C.ctx || g->W != C.W || g->H != C.H) {
-            if (C.ctx) {
-                printf("Warning: Input image has different size to one in the prebuilt plan.\n"
-                       "To avoid re-building the plan and to save time, put images of the "
-                       "same size in the same list.\nStarting to re-build plan...\n");
-                arapb200_batch_destroy(C.ctx);
-            }
             const auto t0 = std::chrono::steady_clock::now();
-            C.ctx = arapb200_batch_create(g->W, g->H, batch, nCont, nGN, nPCG, ARAPB200_BACKEND_AUTO);
+            const int rc = ensure_context(C, S, g->W, g->H);
             t_create += since(t0);
-            if (!C.ctx) return 1;
-            if (pcg_rtol > 0.0 && arapb200_batch_set_option(C.ctx, "pcg_rtol", pcg_rtol)) {
-                fprintf(stderr, "ARAP_PCG_RTOL must be in [0, 1)\n");
-                return 1;
-            }
-            if (gn_rtol > 0.0 && arapb200_batch_set_option(C.ctx, "gn_rtol", gn_rtol)) {
-                fprintf(stderr, "ARAP_GN_RTOL must be in [0, 1)\n");
-                return 1;
-            }
-            C.W = g->W; C.H = g->H;
+            if (rc) return rc;
         }
         for (size_t k = 0; k < g->items.size(); ++k) {
             Loaded& L = g->items[k];
@@ -269,15 +293,30 @@ static volatile sig_atomic_t g_stop = 0;
 static void on_signal(int) { g_stop = 1; }
 
 // ---- resident worker ----------------------------------------------------------------------------------
-static int serve(const std::string& dir)
+static int serve(const std::string& dir, int warmW, int warmH)
 {
     mkdir(dir.c_str(), 0777);
     signal(SIGTERM, on_signal);
     signal(SIGINT, on_signal);
+    // a worker pays every one-time cost at start-up, not on the first request: all kernels are loaded with the context
+    // (the default is lazy loading at first launch) ...
+    setenv("CUDA_MODULE_LOADING", "EAGER", 0);
     Context C;
-    {   // pay for the CUDA context now, not on the first request
+    {
         int sm = 0;
         if (arapb200_device_info(&sm, NULL, NULL, NULL)) return 1;
+    }
+    if (warmW > 0 && warmH > 0) {
+        // ... and, when the image size is known (--warm WxH: para_gen's --size), so are the device and pinned buffers and
+        // the first launch: one empty problem (no object pixel) through the whole path
+        const Settings S;
+        if (ensure_context(C, S, warmW, warmH)) return 1;
+        const size_t N = (size_t)warmW * warmH;
+        std::vector<uint8_t> rgb(3 * N, 0), mask(N, 255), wrgb(3 * N), wmask(N);
+        std::vector<float> flow(2 * N);
+        if (arapb200_batch_submit(C.ctx, 0, warmW, warmH, rgb.data(), mask.data(), NULL, 0, flow.data(), wrgb.data(), wmask.data(), NULL) ||
+            arapb200_batch_run(C.ctx))
+            return 1;
     }
     {   // tell clients (and the driver that started us) that the worker is up
         std::ofstream r(dir + "/ready.tmp");
@@ -361,14 +400,20 @@ static int submit(const std::string& dir, const std::vector<InputPaths>& lines)
 int main(int argc, const char* argv[])
 {
     const char* planPath = getenv("ARAP_PLAN") == NULL ? "arap_plan.t" : getenv("ARAP_PLAN");
-    if (argc == 3 && strcmp(argv[1], "--serve") == 0) {
+    if ((argc == 3 || argc == 5) && strcmp(argv[1], "--serve") == 0) {
+        int ww = 0, wh = 0;
+        if (argc == 5 && (strcmp(argv[3], "--warm") != 0 || sscanf(argv[4], "%dx%d", &ww, &wh) != 2 || ww <= 0 || wh <= 0)) {
+            printf("Invalid Input!\n");
+            usage();
+            return 1;
+        }
         printf("Optimization plan at %s\n", planPath);
         if (!plan_ok(planPath)) {
             printf(" Not found! Please run export ARAP_PLAN=/path/to/plan.t or copy "
                    "the file to the running folder with name arap_plan.t");
             return 1;
         }
-        return serve(argv[2]);
+        return serve(argv[2], ww, wh);
     }
     std::vector<InputPaths> lines;
     if (argc == 7) {

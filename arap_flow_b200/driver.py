@@ -53,14 +53,18 @@ class Server:
     para_gen.py keeps calling the binary with a list file (para_gen.py:190-195); with ARAP_SERVER set that call is a thin
     client of this worker."""
 
-    def __init__(self, gpu: int, spool: str, arap_bin: str = ARAP_BIN, plan: str = PLAN, batch: int = 9, timeout: float = 120.0):
+    def __init__(self, gpu: int, spool: str, arap_bin: str = ARAP_BIN, plan: str = PLAN, batch: int = 9, timeout: float = 120.0,
+                 warm=None):
+        """warm = (W, H): build the plan and the buffers for that image size at start-up (para_gen's --size), so that the
+        first dispatch already runs at steady state."""
         self.gpu, self.spool = gpu, spool
         os.makedirs(spool, exist_ok=True)
         for f in os.listdir(spool):                       # leftovers of a previous worker
             os.remove(os.path.join(spool, f))
         env = dict(os.environ, CUDA_VISIBLE_DEVICES=str(gpu), ARAP_PLAN=plan, ARAP_BATCH=str(batch))
         env.pop("ARAP_SERVER", None)
-        self.proc = subprocess.Popen([arap_bin, "--serve", spool], env=env, stdout=subprocess.DEVNULL)
+        cmd = [arap_bin, "--serve", spool] + (["--warm", "%dx%d" % tuple(warm)] if warm else [])
+        self.proc = subprocess.Popen(cmd, env=env, stdout=subprocess.DEVNULL)
         t0 = time.time()
         while not os.path.exists(os.path.join(spool, "ready")):
             if self.proc.poll() is not None:

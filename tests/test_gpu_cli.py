@@ -118,7 +118,7 @@ def test_resident_worker_serves_clients_byte_identically(tmp_path):
     # no server yet: the client fails loudly instead of solving on its own
     r = subprocess.run([driver.ARAP_BIN] + list(it2[0]), capture_output=True, text=True, env=env)
     assert r.returncode == 1 and "no server" in r.stderr
-    with driver.Server(0, spool) as srv:
+    with driver.Server(0, spool, warm=(96, 80)) as srv:                        # plan + buffers pre-built for the first size
         driver.do_arap(it2[:3], 0, str(tmp_path / "tmp"), server=spool)        # dispatch 1
         driver.do_arap(it2[3:6], 0, str(tmp_path / "tmp"), server=spool)       # dispatch 2: ends with a size change
         r = subprocess.run([driver.ARAP_BIN] + list(it2[6]), capture_output=True, text=True, env=env)   # argv form

@@ -45,6 +45,7 @@ def main():
     ap.add_argument("--gpus", type=int, nargs="+", default=[1])
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--served-only", action="store_true", help="dispatch mode: skip the process-per-dispatch baseline")
+    ap.add_argument("--no-warm", action="store_true", help="start the workers without --warm WxH")
     a = ap.parse_args()
     d = tempfile.mkdtemp(prefix="arapcli_")
     tmp = os.path.join(d, "tmp")
@@ -66,14 +67,15 @@ def main():
             # (b) resident worker
             spool = os.path.join(d, "spool")
             t0 = time.time()
-            with driver.Server(0, spool, batch=batch):
+            wh = None if a.no_warm else (synth.config(wl).W, synth.config(wl).H)
+            with driver.Server(0, spool, batch=batch, warm=wh):
                 t_up = time.time() - t0
                 t1 = time.time()
                 for disp in dispatches:
                     driver.do_arap(disp, 0, tmp, server=spool)
                 dt = time.time() - t1
             print(json.dumps({"mode": "resident worker (arap_deform --serve)", "workload": wl, "dispatches": a.dispatches,
-                              "pairs_per_dispatch": per, "batch": batch, "seconds": dt, "pairs_per_s": len(items) / dt,
+                              "pairs_per_dispatch": per, "batch": batch, "warm": wh, "seconds": dt, "pairs_per_s": len(items) / dt,
                               "worker_start_seconds_once": t_up, "pairs_per_s_including_worker_start": len(items) / (dt + t_up)}),
                   flush=True)
         else:
@@ -86,14 +88,15 @@ def main():
                 batch = a.batch or 8
                 dt = driver.run_sharded(items, gpus, tmp, batch=batch)
                 spools = [os.path.join(d, f"spool{r}") for r in gpus]
-                servers = [driver.Server(r, spools[r], batch=batch) for r in gpus]
+                wh = None if a.no_warm else (synth.config(wl).W, synth.config(wl).H)
+                servers = [driver.Server(r, spools[r], batch=batch, warm=wh) for r in gpus]
                 try:
                     dts = driver.run_sharded(items, gpus, tmp, servers=spools)
                 finally:
                     for s in servers:
                         s.close()
                 base = base or (dt, dts)
-                print(json.dumps({"mode": "shard", "workload": wl, "pairs": n, "gpus": g, "scaling": "strong",
+                print(json.dumps({"mode": "shard", "workload": wl, "pairs": n, "gpus": g, "scaling": "strong", "batch": batch, "warm": wh,
                                   "process_per_gpu": {"seconds": dt, "pairs_per_s": n / dt, "efficiency_vs_1gpu": base[0] / (g * dt)},
                                   "resident_worker_per_gpu": {"seconds": dts, "pairs_per_s": n / dts,
                                                               "efficiency_vs_1gpu": base[1] / (g * dts)}}), flush=True)
