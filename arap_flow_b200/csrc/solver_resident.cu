@@ -46,6 +46,15 @@ constexpr int S_MIN = -100, S_MAX = 100;
 // Measured alternatives of the barrier code (tools/build_variant.sh + tools/ab_sweep.sh, profiles/r2_barrier_ab.txt).
 // The barrier is ~55 % of a lone problem's PCG iteration, and its code is so latency-critical that harmless-looking
 // changes move C1 by several percent either way: every switch here is kept only with a measurement next to it.
+#ifndef ARAP_RS_HOIST
+#define ARAP_RS_HOIST 1 // phases 2 and 3 issue all their shared-memory loads before their first store (0: row by row, round 1)
+#endif
+#ifndef ARAP_RS_STAGE_V4
+#define ARAP_RS_STAGE_V4 0
+#endif
+#ifndef ARAP_RS_SUM_UNROLL4
+#define ARAP_RS_SUM_UNROLL4 1 // the CTA-level limb sum runs four warps per trip: its shared-memory loads overlap
+#endif
 #ifndef ARAP_RS_SUM_UNROLL
 #define ARAP_RS_SUM_UNROLL 0 // 1: the CTA-level sum over the warps' limb sums is unrolled (all shared-memory loads in flight)
 #endif
@@ -61,7 +70,7 @@ struct __align__(16) StripSmem {
     float2 pre[RS_STRIP_H][32];        // (1/(1+sqrt(D_X))^2, 1/(1+sqrt(D_a))^2) per pixel, constant during a GN step
 };
 
-struct Ctl {
+struct __align__(16) Ctl {
     int limb[RS_THREADS_MAX / 32][4];
     int ovf[RS_THREADS_MAX / 32];
     unsigned long long prev[2][4]; // totals last seen in each barrier buffer
@@ -224,10 +233,14 @@ __device__ __forceinline__ void limbs_to_smem(Cta& c, float g0, float g1, int S)
     const int s3 = __reduce_add_sync(0xffffffffu, l3);
     const bool wovf = __any_sync(0xffffffffu, ovf);
     if (c.lane == 0) {
+#if ARAP_RS_STAGE_V4
+        *reinterpret_cast<int4*>(&ctl->limb[c.wid][0]) = make_int4(s0, s1, s2, s3);
+#else
         ctl->limb[c.wid][0] = s0;
         ctl->limb[c.wid][1] = s1;
         ctl->limb[c.wid][2] = s2;
         ctl->limb[c.wid][3] = s3;
+#endif
         ctl->ovf[c.wid] = wovf ? 1 : 0;
     }
     __syncthreads();
@@ -247,6 +260,12 @@ __device__ __forceinline__ void grid_arrive(Cta& c, float g0, float g1, int S, l
             const bool in = w < c.nw;
             sum += in ? (long long)ctl->limb[w][c.lane] : 0ll;
             any |= in ? ctl->ovf[w] : 0;
+        }
+#elif ARAP_RS_SUM_UNROLL4
+#pragma unroll 4
+        for (int w = 0; w < c.nw; ++w) {
+            sum += (long long)ctl->limb[w][c.lane];
+            any |= ctl->ovf[w];
         }
 #else
         for (int w = 0; w < c.nw; ++w) {
@@ -704,18 +723,55 @@ __device__ __forceinline__ void ring_update(float4* cell, float* st, float beta,
 }
 
 // ring <- neighbours' new direction
+#ifndef ARAP_RS_HOIST_RING
+#define ARAP_RS_HOIST_RING 0 // 1: the (up to three) ring pixels of a lane are loaded together before the first is stored
+#endif
 template <bool FIRST>
 __device__ __forceinline__ void apply_p(const StripCtx& s, int lane, float beta)
 {
+    const bool lft = lane < RS_STRIP_H;
+    const int row = lft ? lane : lane - 8;
+    const bool side = (lft && s.rem[2] >= 0) || (!lft && lane >= 8 && lane < 8 + RS_STRIP_H && s.rem[3] >= 0);
+    const int slot = (lft ? OB_LEFT : OB_RIGHT) + row;
+#if ARAP_RS_HOIST_RING
+    // same arithmetic as ring_update, loads first (the stores of one ring pixel may alias the loads of the next as far as the
+    // compiler can tell, which would serialise three shared-memory round trips)
+    const bool top = s.rem[0] >= 0, bot = s.rem[1] >= 0;
+    float4* const ct = &s.own[0 * TW + lane + 1];
+    float4* const cb = &s.own[(TH - 1) * TW + lane + 1];
+    float4* const cd = &s.own[(row + 1) * TW + (lft ? 0 : TW - 1)];
+    float4* const st_t = reinterpret_cast<float4*>(s.stage + 4 * lane);
+    float4* const st_b = reinterpret_cast<float4*>(s.stage + 4 * (32 + lane));
+    float4* const st_d = reinterpret_cast<float4*>(s.stage + 4 * slot);
+    float4 vt = make_float4(0.f, 0.f, 0.f, 0.f), vb = vt, vd = vt, ot = vt, ob = vt, od = vt;
+    float2 rt = make_float2(0.f, 0.f), rb = rt, rd = rt;
+    if (top) { vt = *st_t; rt = s.rcs[lane]; if (!FIRST) ot = *ct; }
+    if (bot) { vb = *st_b; rb = s.rcs[32 + lane]; if (!FIRST) ob = *cb; }
+    if (side) { vd = *st_d; rd = s.rcs[slot]; if (!FIRST) od = *cd; }
+    if (top) {
+        float p0 = vt.x, p1 = vt.y, pa = vt.z;
+        if (!FIRST) { p0 = fmaf(beta, ot.x, p0); p1 = fmaf(beta, ot.y, p1); pa = fmaf(beta, vt.w, pa); }
+        s.stage[4 * lane + 3] = pa;
+        *ct = make_float4(p0, p1, rt.y * pa, rt.x * pa);
+    }
+    if (bot) {
+        float p0 = vb.x, p1 = vb.y, pa = vb.z;
+        if (!FIRST) { p0 = fmaf(beta, ob.x, p0); p1 = fmaf(beta, ob.y, p1); pa = fmaf(beta, vb.w, pa); }
+        s.stage[4 * (32 + lane) + 3] = pa;
+        *cb = make_float4(p0, p1, rb.y * pa, rb.x * pa);
+    }
+    if (side) {
+        float p0 = vd.x, p1 = vd.y, pa = vd.z;
+        if (!FIRST) { p0 = fmaf(beta, od.x, p0); p1 = fmaf(beta, od.y, p1); pa = fmaf(beta, vd.w, pa); }
+        s.stage[4 * slot + 3] = pa;
+        *cd = make_float4(p0, p1, rd.y * pa, rd.x * pa);
+    }
+#else
     if (s.rem[0] >= 0) ring_update<FIRST>(&s.own[0 * TW + lane + 1], s.stage + 4 * lane, beta, s.rcs[lane]);
     if (s.rem[1] >= 0) ring_update<FIRST>(&s.own[(TH - 1) * TW + lane + 1], s.stage + 4 * (32 + lane), beta, s.rcs[32 + lane]);
     // left column (lanes 0..H-1) and right column (lanes 8..8+H-1) in one predicated block
-    const bool lft = lane < RS_STRIP_H;
-    const int row = lft ? lane : lane - 8;
-    if ((lft && s.rem[2] >= 0) || (!lft && lane >= 8 && lane < 8 + RS_STRIP_H && s.rem[3] >= 0)) {
-        const int slot = (lft ? OB_LEFT : OB_RIGHT) + row;
-        ring_update<FIRST>(&s.own[(row + 1) * TW + (lft ? 0 : TW - 1)], s.stage + 4 * slot, beta, s.rcs[slot]);
-    }
+    if (side) ring_update<FIRST>(&s.own[(row + 1) * TW + (lft ? 0 : TW - 1)], s.stage + 4 * slot, beta, s.rcs[slot]);
+#endif
 }
 
 // constraint of a pixel for the current continuation weight (CombinedSolver.h:236-239)
@@ -1027,6 +1083,36 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                 gs0 = 0.f; gs1 = 0.f;
                 const bool pub = any_rem && (it + 1 < P.nPCG);
                 ++seq;
+#if ARAP_RS_HOIST
+                // every shared-memory load of the phase first: the compiler cannot move a later row's loads above an earlier
+                // row's delta stores (it cannot prove that D, the tile and pre do not alias), so written row by row the phase
+                // pays the shared-memory latency eight times over
+                float hx[RS_STRIP_H], hy[RS_STRIP_H], hd0[RS_STRIP_H], hd1[RS_STRIP_H], hd2[RS_STRIP_H];
+                float2 hpre[RS_STRIP_H];
+#pragma unroll
+                for (int k = 0; k < RS_STRIP_H; ++k) {
+                    const float4 e = s.own[(k + 1) * TW + lane + 1];
+                    const float* Dk = s.D + k * 32;
+                    hx[k] = e.x; hy[k] = e.y;
+                    hd0[k] = Dk[0 * RS_STRIP_H * 32]; hd1[k] = Dk[1 * RS_STRIP_H * 32]; hd2[k] = Dk[2 * RS_STRIP_H * 32];
+                    hpre[k] = s.pre[k * 32];
+                }
+#pragma unroll
+                for (int k = 0; k < RS_STRIP_H; ++k) {
+                    float* Dk = s.D + k * 32;
+                    Dk[0 * RS_STRIP_H * 32] = fmaf(alpha, hx[k], hd0[k]);
+                    Dk[1 * RS_STRIP_H * 32] = fmaf(alpha, hy[k], hd1[k]);
+                    Dk[2 * RS_STRIP_H * 32] = fmaf(alpha, pa[k], hd2[k]);
+                    r0[k] = fmaf(-alpha, q0[k], r0[k]);
+                    r1[k] = fmaf(-alpha, q1[k], r1[k]);
+                    r2[k] = fmaf(-alpha, qa[k], r2[k]);
+                    const float pX = hpre[k].x, pA = hpre[k].y;
+                    const float z0 = pX * r0[k], z1 = pX * r1[k], z2 = pA * r2[k];
+                    const float term = dot3(z0, z1, z2, r0[k], r1[k], r2[k]);
+                    if (k < 4) gs0 = gs0 + term; else gs1 = gs1 + term;
+                    if (pub) publish_rowcol(s, lane, k, seq, z0, z1, z2, 0.f);
+                }
+#else
 #pragma unroll
                 for (int k = 0; k < RS_STRIP_H; ++k) {
                     const float4 e = s.own[(k + 1) * TW + lane + 1];
@@ -1044,6 +1130,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                     if (k < 4) gs0 = gs0 + term; else gs1 = gs1 + term;
                     if (pub) publish_rowcol(s, lane, k, seq, z0, z1, z2, 0.f);
                 }
+#endif
                 RS_TICK(1);
                 long long tb0 = 0, tb1 = 0;
                 arrive_t<CL>(c, gs0, gs1, S_bnum, tb0, tb1);
@@ -1061,6 +1148,26 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                 if (bnum <= ctl.stop) { need_sep = true; break; } // early exit (every CTA decodes the same bnum: a uniform decision)
 
                 // ---- PCGStep3: p = z + beta p (own pixels, then the remote ring) ----
+#if ARAP_RS_HOIST
+                {
+                    float hx[RS_STRIP_H], hy[RS_STRIP_H];
+                    float2 hpre[RS_STRIP_H];
+#pragma unroll
+                    for (int k = 0; k < RS_STRIP_H; ++k) {
+                        const float4 e = s.own[(k + 1) * TW + lane + 1];
+                        hx[k] = e.x; hy[k] = e.y;
+                        hpre[k] = s.pre[k * 32];
+                    }
+#pragma unroll
+                    for (int k = 0; k < RS_STRIP_H; ++k) {
+                        const float pX = hpre[k].x, pA = hpre[k].y;
+                        const float p0 = fmaf(beta, hx[k], pX * r0[k]);
+                        const float p1 = fmaf(beta, hy[k], pX * r1[k]);
+                        pa[k] = fmaf(beta, pa[k], pA * r2[k]);
+                        s.own[(k + 1) * TW + lane + 1] = make_float4(p0, p1, ss[k] * pa[k], cc[k] * pa[k]);
+                    }
+                }
+#else
 #pragma unroll
                 for (int k = 0; k < RS_STRIP_H; ++k) {
                     const float4 e = s.own[(k + 1) * TW + lane + 1];
@@ -1071,6 +1178,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                     pa[k] = fmaf(beta, pa[k], pA * r2[k]);
                     s.own[(k + 1) * TW + lane + 1] = make_float4(p0, p1, ss[k] * pa[k], cc[k] * pa[k]);
                 }
+#endif
                 if (any_rem) apply_p<false>(s, lane, beta);
                 __syncthreads();
                 RS_TICK(2);
