@@ -47,13 +47,16 @@ constexpr int S_MIN = -100, S_MAX = 100;
 // The barrier is ~55 % of a lone problem's PCG iteration, and its code is so latency-critical that harmless-looking
 // changes move C1 by several percent either way: every switch here is kept only with a measurement next to it.
 #ifndef ARAP_RS_HOIST
-#define ARAP_RS_HOIST 1 // phases 2 and 3 issue all their shared-memory loads before their first store (0: row by row, round 1)
+#define ARAP_RS_HOIST 1 // the 168-register variants issue all shared-memory loads of phases 2 and 3 before the first store
+                        // (0: row by row everywhere, round 1).  NOT the 128-register variants: the extra temporaries spill there
+                        // (C1s 28.4 -> 26.6, C2 6.04 -> 5.76, C3 6.00 -> 5.79 pairs/s when hoisted)
 #endif
 #ifndef ARAP_RS_STAGE_V4
 #define ARAP_RS_STAGE_V4 0
 #endif
 #ifndef ARAP_RS_SUM_UNROLL4
-#define ARAP_RS_SUM_UNROLL4 1 // the CTA-level limb sum runs four warps per trip: its shared-memory loads overlap
+#define ARAP_RS_SUM_UNROLL4 2 // the CTA-level limb sum runs four warps per trip (its shared-memory loads overlap): 1 = in the
+                              // 168-register variants, 2 = everywhere, 0 = nowhere
 #endif
 #ifndef ARAP_RS_SUM_UNROLL
 #define ARAP_RS_SUM_UNROLL 0 // 1: the CTA-level sum over the warps' limb sums is unrolled (all shared-memory loads in flight)
@@ -183,6 +186,7 @@ struct Cta {
     unsigned long long* bar; // = P->bar
     int* status;             // = P->status
     Ctl* ctl;
+    bool u4;                 // CTA-level limb sum four warps per trip (compile-time constant per kernel variant)
     struct ClusterCtl* xc;   // cluster-scope barrier only (null otherwise)
     int cta, G, lane, wid, nw;
     unsigned epoch;
@@ -261,16 +265,18 @@ __device__ __forceinline__ void grid_arrive(Cta& c, float g0, float g1, int S, l
             sum += in ? (long long)ctl->limb[w][c.lane] : 0ll;
             any |= in ? ctl->ovf[w] : 0;
         }
-#elif ARAP_RS_SUM_UNROLL4
-#pragma unroll 4
-        for (int w = 0; w < c.nw; ++w) {
-            sum += (long long)ctl->limb[w][c.lane];
-            any |= ctl->ovf[w];
-        }
 #else
-        for (int w = 0; w < c.nw; ++w) {
-            sum += (long long)ctl->limb[w][c.lane];
-            any |= ctl->ovf[w];
+        if (c.u4) {
+#pragma unroll 4
+            for (int w = 0; w < c.nw; ++w) {
+                sum += (long long)ctl->limb[w][c.lane];
+                any |= ctl->ovf[w];
+            }
+        } else {
+            for (int w = 0; w < c.nw; ++w) {
+                sum += (long long)ctl->limb[w][c.lane];
+                any |= ctl->ovf[w];
+            }
         }
 #endif
         unsigned long long contrib = (1ull << 48) + (unsigned long long)(sum + LIMB_BIAS);
@@ -539,7 +545,7 @@ __device__ __forceinline__ int cl_wait(Cta& c, int& S, bool& grown, float& res, 
 __device__ __noinline__ void grid_arrive_ni(Ctl* ctl, unsigned long long* bar, int G, unsigned epoch, float g0, float g1, int S)
 {
     Cta c;
-    c.P = nullptr; c.bar = bar; c.status = nullptr; c.ctl = ctl; c.xc = nullptr; c.cta = 0; c.G = G;
+    c.P = nullptr; c.bar = bar; c.status = nullptr; c.ctl = ctl; c.xc = nullptr; c.u4 = false; c.cta = 0; c.G = G;
     c.lane = threadIdx.x & 31; c.wid = threadIdx.x >> 5; c.nw = blockDim.x >> 5; c.epoch = epoch; c.prof = false;
     long long t0 = 0, t1 = 0;
     grid_arrive(c, g0, g1, S, t0, t1);
@@ -548,7 +554,7 @@ __device__ __noinline__ void grid_arrive_ni(Ctl* ctl, unsigned long long* bar, i
 __device__ __noinline__ int4 grid_wait_ni(Ctl* ctl, unsigned long long* bar, int* status, int G, unsigned epoch, int S, int grown)
 {
     Cta c;
-    c.P = nullptr; c.bar = bar; c.status = status; c.ctl = ctl; c.xc = nullptr; c.cta = 0; c.G = G;
+    c.P = nullptr; c.bar = bar; c.status = status; c.ctl = ctl; c.xc = nullptr; c.u4 = false; c.cta = 0; c.G = G;
     c.lane = threadIdx.x & 31; c.wid = threadIdx.x >> 5; c.nw = blockDim.x >> 5; c.epoch = epoch; c.prof = false;
     bool gr = grown != 0, ok = true;
     float res = 0.f;
@@ -813,7 +819,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
     const ResProb& P = sP;
     StripSmem* S = reinterpret_cast<StripSmem*>(smem_raw);
 
+    constexpr bool LEAN = (MINB >= 3);               // the 128-register variants
+    constexpr bool HOIST = ARAP_RS_HOIST && !LEAN;
     Cta c;
+    c.u4 = ARAP_RS_SUM_UNROLL4 && (ARAP_RS_SUM_UNROLL4 > 1 || !LEAN);
     c.P = &P; c.bar = P.bar; c.status = P.status; c.ctl = &ctl; c.xc = nullptr; c.cta = cta_in_problem; c.G = P.G;
     c.lane = threadIdx.x & 31; c.wid = threadIdx.x >> 5; c.nw = blockDim.x >> 5; c.epoch = 0;
     c.acc[0] = c.acc[1] = c.acc[2] = 0; c.prof = PROF && (P.prof != nullptr);
@@ -1083,7 +1092,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                 gs0 = 0.f; gs1 = 0.f;
                 const bool pub = any_rem && (it + 1 < P.nPCG);
                 ++seq;
-#if ARAP_RS_HOIST
+                if constexpr (HOIST) {
                 // every shared-memory load of the phase first: the compiler cannot move a later row's loads above an earlier
                 // row's delta stores (it cannot prove that D, the tile and pre do not alias), so written row by row the phase
                 // pays the shared-memory latency eight times over
@@ -1112,7 +1121,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                     if (k < 4) gs0 = gs0 + term; else gs1 = gs1 + term;
                     if (pub) publish_rowcol(s, lane, k, seq, z0, z1, z2, 0.f);
                 }
-#else
+                } else {
 #pragma unroll
                 for (int k = 0; k < RS_STRIP_H; ++k) {
                     const float4 e = s.own[(k + 1) * TW + lane + 1];
@@ -1130,7 +1139,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                     if (k < 4) gs0 = gs0 + term; else gs1 = gs1 + term;
                     if (pub) publish_rowcol(s, lane, k, seq, z0, z1, z2, 0.f);
                 }
-#endif
+                }
                 RS_TICK(1);
                 long long tb0 = 0, tb1 = 0;
                 arrive_t<CL>(c, gs0, gs1, S_bnum, tb0, tb1);
@@ -1148,8 +1157,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                 if (bnum <= ctl.stop) { need_sep = true; break; } // early exit (every CTA decodes the same bnum: a uniform decision)
 
                 // ---- PCGStep3: p = z + beta p (own pixels, then the remote ring) ----
-#if ARAP_RS_HOIST
-                {
+                if constexpr (HOIST) {
                     float hx[RS_STRIP_H], hy[RS_STRIP_H];
                     float2 hpre[RS_STRIP_H];
 #pragma unroll
@@ -1166,8 +1174,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                         pa[k] = fmaf(beta, pa[k], pA * r2[k]);
                         s.own[(k + 1) * TW + lane + 1] = make_float4(p0, p1, ss[k] * pa[k], cc[k] * pa[k]);
                     }
-                }
-#else
+                } else {
 #pragma unroll
                 for (int k = 0; k < RS_STRIP_H; ++k) {
                     const float4 e = s.own[(k + 1) * TW + lane + 1];
@@ -1178,7 +1185,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                     pa[k] = fmaf(beta, pa[k], pA * r2[k]);
                     s.own[(k + 1) * TW + lane + 1] = make_float4(p0, p1, ss[k] * pa[k], cc[k] * pa[k]);
                 }
-#endif
+                }
                 if (any_rem) apply_p<false>(s, lane, beta);
                 __syncthreads();
                 RS_TICK(2);
