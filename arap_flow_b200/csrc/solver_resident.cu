@@ -48,11 +48,15 @@ constexpr int S_MIN = -100, S_MAX = 100;
 // changes move C1 by several percent either way: every switch here is kept only with a measurement next to it.
 #ifndef ARAP_RS_HOIST
 #define ARAP_RS_HOIST 1 // the 168-register variants issue all shared-memory loads of phases 2 and 3 before the first store
-                        // (0: row by row everywhere, round 1).  NOT the 128-register variants: the extra temporaries spill there
-                        // (C1s 28.4 -> 26.6, C2 6.04 -> 5.76, C3 6.00 -> 5.79 pairs/s when hoisted)
+                        // (0: row by row everywhere, round 1).  The 128-register variants hoist in groups of ARAP_RS_HOIST_LEAN rows:
+                        // all eight at once spill there (C1s 28.4 -> 26.6, C2 6.04 -> 5.76, C3 6.00 -> 5.79 pairs/s)
 #endif
 #ifndef ARAP_RS_STAGE_V4
 #define ARAP_RS_STAGE_V4 0
+#endif
+#ifndef ARAP_RS_HOIST_LEAN
+#define ARAP_RS_HOIST_LEAN 4 // rows per hoisted group in the 128-register variants (0: not hoisted there; 8 spills: C1s -6 %;
+                             // 4: C1s / C2 / C3 +1.3 ... 1.9 %, 2: the same within noise)
 #endif
 #ifndef ARAP_RS_SUM_UNROLL4
 #define ARAP_RS_SUM_UNROLL4 2 // the CTA-level limb sum runs four warps per trip (its shared-memory loads overlap): 1 = in the
@@ -820,7 +824,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
     StripSmem* S = reinterpret_cast<StripSmem*>(smem_raw);
 
     constexpr bool LEAN = (MINB >= 3);               // the 128-register variants
-    constexpr bool HOIST = ARAP_RS_HOIST && !LEAN;
+    constexpr bool HOIST = ARAP_RS_HOIST && (!LEAN || ARAP_RS_HOIST_LEAN > 0);
+    constexpr int HG = (LEAN && ARAP_RS_HOIST_LEAN > 0) ? ARAP_RS_HOIST_LEAN : RS_STRIP_H; // rows whose loads are issued together
     Cta c;
     c.u4 = ARAP_RS_SUM_UNROLL4 && (ARAP_RS_SUM_UNROLL4 > 1 || !LEAN);
     c.P = &P; c.bar = P.bar; c.status = P.status; c.ctl = &ctl; c.xc = nullptr; c.cta = cta_in_problem; c.G = P.G;
@@ -1096,30 +1101,36 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                 // every shared-memory load of the phase first: the compiler cannot move a later row's loads above an earlier
                 // row's delta stores (it cannot prove that D, the tile and pre do not alias), so written row by row the phase
                 // pays the shared-memory latency eight times over
-                float hx[RS_STRIP_H], hy[RS_STRIP_H], hd0[RS_STRIP_H], hd1[RS_STRIP_H], hd2[RS_STRIP_H];
-                float2 hpre[RS_STRIP_H];
+                // (HG rows per group: all eight in the 168-register variants, fewer where registers are tight)
 #pragma unroll
-                for (int k = 0; k < RS_STRIP_H; ++k) {
-                    const float4 e = s.own[(k + 1) * TW + lane + 1];
-                    const float* Dk = s.D + k * 32;
-                    hx[k] = e.x; hy[k] = e.y;
-                    hd0[k] = Dk[0 * RS_STRIP_H * 32]; hd1[k] = Dk[1 * RS_STRIP_H * 32]; hd2[k] = Dk[2 * RS_STRIP_H * 32];
-                    hpre[k] = s.pre[k * 32];
-                }
+                for (int kb = 0; kb < RS_STRIP_H; kb += HG) {
+                    float hx[HG], hy[HG], hd0[HG], hd1[HG], hd2[HG];
+                    float2 hpre[HG];
 #pragma unroll
-                for (int k = 0; k < RS_STRIP_H; ++k) {
-                    float* Dk = s.D + k * 32;
-                    Dk[0 * RS_STRIP_H * 32] = fmaf(alpha, hx[k], hd0[k]);
-                    Dk[1 * RS_STRIP_H * 32] = fmaf(alpha, hy[k], hd1[k]);
-                    Dk[2 * RS_STRIP_H * 32] = fmaf(alpha, pa[k], hd2[k]);
-                    r0[k] = fmaf(-alpha, q0[k], r0[k]);
-                    r1[k] = fmaf(-alpha, q1[k], r1[k]);
-                    r2[k] = fmaf(-alpha, qa[k], r2[k]);
-                    const float pX = hpre[k].x, pA = hpre[k].y;
-                    const float z0 = pX * r0[k], z1 = pX * r1[k], z2 = pA * r2[k];
-                    const float term = dot3(z0, z1, z2, r0[k], r1[k], r2[k]);
-                    if (k < 4) gs0 = gs0 + term; else gs1 = gs1 + term;
-                    if (pub) publish_rowcol(s, lane, k, seq, z0, z1, z2, 0.f);
+                    for (int j = 0; j < HG; ++j) {
+                        const int k = kb + j;
+                        const float4 e = s.own[(k + 1) * TW + lane + 1];
+                        const float* Dk = s.D + k * 32;
+                        hx[j] = e.x; hy[j] = e.y;
+                        hd0[j] = Dk[0 * RS_STRIP_H * 32]; hd1[j] = Dk[1 * RS_STRIP_H * 32]; hd2[j] = Dk[2 * RS_STRIP_H * 32];
+                        hpre[j] = s.pre[k * 32];
+                    }
+#pragma unroll
+                    for (int j = 0; j < HG; ++j) {
+                        const int k = kb + j;
+                        float* Dk = s.D + k * 32;
+                        Dk[0 * RS_STRIP_H * 32] = fmaf(alpha, hx[j], hd0[j]);
+                        Dk[1 * RS_STRIP_H * 32] = fmaf(alpha, hy[j], hd1[j]);
+                        Dk[2 * RS_STRIP_H * 32] = fmaf(alpha, pa[k], hd2[j]);
+                        r0[k] = fmaf(-alpha, q0[k], r0[k]);
+                        r1[k] = fmaf(-alpha, q1[k], r1[k]);
+                        r2[k] = fmaf(-alpha, qa[k], r2[k]);
+                        const float pX = hpre[j].x, pA = hpre[j].y;
+                        const float z0 = pX * r0[k], z1 = pX * r1[k], z2 = pA * r2[k];
+                        const float term = dot3(z0, z1, z2, r0[k], r1[k], r2[k]);
+                        if (k < 4) gs0 = gs0 + term; else gs1 = gs1 + term;
+                        if (pub) publish_rowcol(s, lane, k, seq, z0, z1, z2, 0.f);
+                    }
                 }
                 } else {
 #pragma unroll
@@ -1158,21 +1169,25 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
 
                 // ---- PCGStep3: p = z + beta p (own pixels, then the remote ring) ----
                 if constexpr (HOIST) {
-                    float hx[RS_STRIP_H], hy[RS_STRIP_H];
-                    float2 hpre[RS_STRIP_H];
 #pragma unroll
-                    for (int k = 0; k < RS_STRIP_H; ++k) {
-                        const float4 e = s.own[(k + 1) * TW + lane + 1];
-                        hx[k] = e.x; hy[k] = e.y;
-                        hpre[k] = s.pre[k * 32];
-                    }
+                    for (int kb = 0; kb < RS_STRIP_H; kb += HG) {
+                        float hx[HG], hy[HG];
+                        float2 hpre[HG];
 #pragma unroll
-                    for (int k = 0; k < RS_STRIP_H; ++k) {
-                        const float pX = hpre[k].x, pA = hpre[k].y;
-                        const float p0 = fmaf(beta, hx[k], pX * r0[k]);
-                        const float p1 = fmaf(beta, hy[k], pX * r1[k]);
-                        pa[k] = fmaf(beta, pa[k], pA * r2[k]);
-                        s.own[(k + 1) * TW + lane + 1] = make_float4(p0, p1, ss[k] * pa[k], cc[k] * pa[k]);
+                        for (int j = 0; j < HG; ++j) {
+                            const float4 e = s.own[(kb + j + 1) * TW + lane + 1];
+                            hx[j] = e.x; hy[j] = e.y;
+                            hpre[j] = s.pre[(kb + j) * 32];
+                        }
+#pragma unroll
+                        for (int j = 0; j < HG; ++j) {
+                            const int k = kb + j;
+                            const float pX = hpre[j].x, pA = hpre[j].y;
+                            const float p0 = fmaf(beta, hx[j], pX * r0[k]);
+                            const float p1 = fmaf(beta, hy[j], pX * r1[k]);
+                            pa[k] = fmaf(beta, pa[k], pA * r2[k]);
+                            s.own[(k + 1) * TW + lane + 1] = make_float4(p0, p1, ss[k] * pa[k], cc[k] * pa[k]);
+                        }
                     }
                 } else {
 #pragma unroll
