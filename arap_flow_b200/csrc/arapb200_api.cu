@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <vector>
 
 using namespace arapb200;
@@ -29,27 +30,67 @@ struct DevBuf {
     }
 };
 
+// Device workspace of the stand-alone warp calls (warp_image, the Opt.h mirror's copyResultToCPU): grown on demand, kept
+// for the life of the process -- seven cudaMalloc/cudaFree pairs per call cost more than the warp itself (and cudaFree
+// synchronises the device).  One per device; the mutex also serialises concurrent callers on it.
+struct WarpArena {
+    std::mutex mu;
+    unsigned char* base = nullptr;
+    size_t cap = 0;
+    cudaStream_t stream = nullptr;
+    unsigned char* reserve(size_t bytes)
+    {
+        if (bytes > cap) {
+            if (base) ARAP_CUDA_CHECK(cudaFree(base));
+            base = nullptr; cap = 0;
+            ARAP_CUDA_CHECK(cudaMalloc(&base, bytes));
+            cap = bytes;
+        }
+        if (!stream) ARAP_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        return base;
+    }
+};
+
+WarpArena& warp_arena()
+{
+    static std::mutex table_mu;
+    static WarpArena* table[64] = {};          // never freed: outlives the CUDA context teardown at exit
+    int dev = 0;
+    ARAP_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) arap_fail(1, "warp: device ordinal %d out of range", dev);
+    std::lock_guard<std::mutex> g(table_mu);
+    if (!table[dev]) table[dev] = new WarpArena;
+    return *table[dev];
+}
+
 int warp_common(int W, int H, const float* pos_or_flow, bool is_flow, const uint8_t* rgb, const uint8_t* mask_red,
                 uint8_t* out_rgb, uint8_t* out_mask, uint32_t* out_splat)
 {
     if (W <= 0 || H <= 0 || !pos_or_flow || !rgb || !mask_red || !out_rgb || !out_mask) return 1;
     const size_t N = (size_t)W * H;
-    DevBuf<float2> d_in(N), d_pos(is_flow ? N : 0);
-    DevBuf<unsigned char> d_rgb(3 * N), d_m(N), d_orgb(3 * N), d_om(N);
-    DevBuf<unsigned> d_z(N);
-    d_in.up((const float2*)pos_or_flow);
-    d_rgb.up(rgb);
-    d_m.up(mask_red);
-    const float2* pos = d_in.p;
+    auto up256 = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t o_in = 0, o_pos = o_in + up256(8 * N), o_z = o_pos + up256(8 * N), o_rgb = o_z + up256(4 * N),
+                 o_orgb = o_rgb + up256(3 * N), o_m = o_orgb + up256(3 * N), o_om = o_m + up256(N), total = o_om + up256(N);
+    WarpArena& ar = warp_arena();
+    std::lock_guard<std::mutex> g(ar.mu);
+    unsigned char* b = ar.reserve(total);
+    cudaStream_t s = ar.stream;
+    float2* d_in = (float2*)(b + o_in);
+    float2* d_pos = (float2*)(b + o_pos);
+    unsigned* d_z = (unsigned*)(b + o_z);
+    ARAP_CUDA_CHECK(cudaMemcpyAsync(d_in, pos_or_flow, 8 * N, cudaMemcpyHostToDevice, s));
+    ARAP_CUDA_CHECK(cudaMemcpyAsync(b + o_rgb, rgb, 3 * N, cudaMemcpyHostToDevice, s));
+    ARAP_CUDA_CHECK(cudaMemcpyAsync(b + o_m, mask_red, N, cudaMemcpyHostToDevice, s));
+    const float2* pos = d_in;
     if (is_flow) {
-        enqueue_flow_to_pos(W, H, d_in.p, d_pos.p, nullptr);
-        pos = d_pos.p;
+        enqueue_flow_to_pos(W, H, d_in, d_pos, s);
+        pos = d_pos;
     }
-    enqueue_warp(W, H, pos, d_rgb.p, d_m.p, d_z.p, d_orgb.p, d_om.p, nullptr);
-    d_orgb.down(out_rgb);
-    d_om.down(out_mask);
-    if (out_splat) d_z.down(out_splat);
-    ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
+    enqueue_warp(W, H, pos, b + o_rgb, b + o_m, d_z, b + o_orgb, b + o_om, s);
+    ARAP_CUDA_CHECK(cudaMemcpyAsync(out_rgb, b + o_orgb, 3 * N, cudaMemcpyDeviceToHost, s));
+    ARAP_CUDA_CHECK(cudaMemcpyAsync(out_mask, b + o_om, N, cudaMemcpyDeviceToHost, s));
+    if (out_splat) ARAP_CUDA_CHECK(cudaMemcpyAsync(out_splat, d_z, 4 * N, cudaMemcpyDeviceToHost, s));
+    ARAP_CUDA_OR_RETURN(cudaStreamSynchronize(s));
     return 0;
 }
 

@@ -334,6 +334,7 @@ def main():
     out_bufs = [None] * len(problems)   # output arrays are allocated once and reused, as a caller looping over pairs would
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     io_bytes = [0, 0]
+    opt_h_stage_log = []     # wall seconds per stage of every image, warm-up included
 
     def one_step():
         if opt_h:
@@ -342,6 +343,7 @@ def main():
             outs = []
             for (p, m) in problems:
                 opt_h_image(cs, p, m)
+                opt_h_stage_log.append({k: round(v, 4) for k, v in cs.seconds.items()})
                 io_bytes[0] += cs.h2d_bytes
                 io_bytes[1] += cs.d2h_bytes
                 outs.append({"flow": cs.warp_field(), "rgb": cs.warped_rgb, "mask": cs.warped_mask})
@@ -442,7 +444,7 @@ def main():
                              "constraint lerp + full-image upload per continuation step, one problem per launch" if opt_h else
                              "batch: arapb200_batch_* (whole 19x8x400 schedules, several problems per cooperative launch)"),
                     "pairs_per_gpu_per_step": B, "backend": args.backend + (" (streaming)" if streamed else " (resident)"),
-                    "launch": linfo, "opt_h_seconds_last_image": (cs.seconds if cs else None), "parallelism": f"independent pairs x{world}, no collective",
+                    "launch": linfo, "opt_h_seconds_last_image": (cs.seconds if cs else None), "opt_h_seconds_every_image": (opt_h_stage_log if cs else None), "parallelism": f"independent pairs x{world}, no collective",
                     "l2_policy": "L2 flushed between steps by writing a 256 MiB buffer; every step also re-uploads its inputs "
                                  "(host->device) and restarts from the reset grid, nothing is reused across steps; within a "
                                  "solve the PCG state lives " + ("in HBM/L2 (tile-interleaved planes)" if streamed else
