@@ -18,6 +18,7 @@ struct Opt_State {
 
 struct Opt_Problem {
     std::string filename;
+    bool lm = false; // solver kind "LMGPU"
 };
 
 struct Opt_Plan {
@@ -73,9 +74,10 @@ static bool looks_like_arap_plan(const char* filename)
 Opt_Problem* Opt_ProblemDefine(Opt_State* state, const char* filename, const char* solverkind)
 {
     if (!state || !filename || !solverkind) return nullptr;
-    if (strcmp(solverkind, "gaussNewtonGPU") != 0) {
-        // o.t:121-124 asserts gaussNewtonGPU or LMGPU; the app only ever asks for the former
-        fprintf(stderr, "arapb200: solver kind '%s' not supported (only gaussNewtonGPU)\n", solverkind);
+    // o.t:121-124 asserts gaussNewtonGPU or LMGPU; the app only ever asks for the former (CombinedSolverBase.h:76)
+    const bool lm = strcmp(solverkind, "LMGPU") == 0;
+    if (!lm && strcmp(solverkind, "gaussNewtonGPU") != 0) {
+        fprintf(stderr, "arapb200: solver kind '%s' not supported (gaussNewtonGPU or LMGPU)\n", solverkind);
         return nullptr;
     }
     if (!looks_like_arap_plan(filename)) {
@@ -84,6 +86,7 @@ Opt_Problem* Opt_ProblemDefine(Opt_State* state, const char* filename, const cha
     }
     Opt_Problem* p = new Opt_Problem;
     p->filename = filename;
+    p->lm = lm;
     return p;
 }
 
@@ -100,7 +103,7 @@ Opt_Plan* Opt_ProblemPlan(Opt_State* state, Opt_Problem* problem, unsigned int* 
     // failure => NULL, which the reference caller asserts on (ARAP/shared/OptSolver.h:54-56)
     try {
         Opt_Plan* pl = new Opt_Plan;
-        pl->plan = new GnPlan((int)W, (int)H, state->params.verbosityLevel, ARAPB200_BACKEND_AUTO);
+        pl->plan = new GnPlan((int)W, (int)H, state->params.verbosityLevel, ARAPB200_BACKEND_AUTO, problem->lm);
         return pl;
     } catch (...) {
         fprintf(stderr, "arapb200: Opt_ProblemPlan failed for %u x %u\n", W, H);
@@ -144,5 +147,17 @@ double Opt_ProblemCurrentCost(Opt_State*, Opt_Plan* plan) { return plan->plan->c
 
 // extension (not in the reference's Opt.h): 0, or the code of the first failure since the plan was made
 int arapb200_plan_error(Opt_Plan* plan) { return (plan && plan->plan) ? plan->plan->error() : 1; }
+
+// extension: what the last Opt_ProblemStep of an "LMGPU" plan did.  info6 = trust-region radius after the step, linear
+// iterations run, verdict (1 accepted, 0 reverted, 2 function tolerance reached, 3 radius below minimum), model cost,
+// cost at the trial point, last Q.  Returns 0, or 1 when the plan is not an LM plan.
+int arapb200_plan_lm_info(Opt_Plan* plan, float info6[6])
+{
+    const LmStepInfo* st = (plan && plan->plan) ? plan->plan->lm_last_step() : nullptr;
+    if (!st || !info6) return 1;
+    info6[0] = st->radius_after; info6[1] = (float)st->pcg_iterations; info6[2] = (float)st->verdict;
+    info6[3] = st->model_cost; info6[4] = st->new_cost; info6[5] = st->q_last;
+    return 0;
+}
 
 } // extern "C"

@@ -41,9 +41,10 @@ __global__ void __launch_bounds__(256) k_check_grid(int W, int H, const float2* 
 }
 } // namespace
 
-GnPlan::GnPlan(int W, int H, int verbosity, int backend)
+GnPlan::GnPlan(int W, int H, int verbosity, int backend, bool lm)
     : W_(W), H_(H), verbosity_(verbosity), backend_(backend)
 {
+    if (lm) lm_.reset(new LmSolver(W, H));
     ARAP_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_h_, cudaStreamNonBlocking));
     ARAP_CUDA_CHECK(cudaMalloc(&d_costs_, kMaxCostLog * sizeof(float)));
     ARAP_CUDA_CHECK(cudaMalloc(&d_check_, 3 * sizeof(unsigned long long)));
@@ -63,7 +64,7 @@ void GnPlan::order_after_caller()
 
 long long GnPlan::launches() const
 {
-    return (stream_ ? stream_->launches() : 0) + (resident_ ? resident_->launches() : 0);
+    return (stream_ ? stream_->launches() : 0) + (resident_ ? resident_->launches() : 0) + (lm_ ? lm_->launches() : 0);
 }
 
 GnPlan::~GnPlan()
@@ -92,6 +93,7 @@ bool GnPlan::set_parameter(const char* name, const void* value)
         (name[0] == 'p' ? pcg_rtol_ : gn_rtol_) = v;
         return true;
     }
+    if (lm_ && lm_->set_parameter(name, value)) return true;
     // Levenberg-Marquardt knobs of SolverParameters (:26-39): valid names, unused by gaussNewtonGPU
     static const char* lm[] = {"residual_reset_period", "min_relative_decrease", "min_trust_region_radius",
                                "max_trust_region_radius", "q_tolerance", "function_tolerance",
@@ -161,8 +163,21 @@ void GnPlan::bind(void** pp)
                   *(const float*)pp[5], *(const float*)pp[6], stream_h_);
 }
 
+void GnPlan::lm_bind(void** pp)
+{
+    lm_->bind((float2*)pp[0], (float*)pp[1], (const float2*)pp[2], (const float2*)pp[3], (const float*)pp[4],
+              *(const float*)pp[5], *(const float*)pp[6]);
+}
+
 void GnPlan::init(void** pp)
 {
+    if (lm_) {
+        order_after_caller();
+        lm_bind(pp);
+        n_iter_ = 0;
+        prev_cost_ = lm_->init(stream_h_);
+        return;
+    }
     choose_backend(pp);
     n_iter_ = 0;
     if (use_resident_) {
@@ -177,6 +192,23 @@ void GnPlan::init(void** pp)
 int GnPlan::step(void** pp)
 {
     if (n_iter_ >= n_iterations_) return 0;
+    order_after_caller();
+    if (lm_) {
+        lm_bind(pp);
+        const float before = prev_cost_;
+        const int more = lm_->step(l_iterations_, stream_h_, &prev_cost_);
+        if (verbosity_ > 0) {
+            const LmStepInfo& st = lm_->last_step();
+            printf("cost: %f -> %f (model %f, %d linear iterations, %s, trust_region_radius=%f)\n", before, st.new_cost,
+                   st.model_cost, st.pcg_iterations,
+                   st.verdict == 1 ? "accepted" : st.verdict == 0 ? "REVERT" : st.verdict == 2 ? "function tolerance reached"
+                                                                                              : "radius below the minimum",
+                   st.radius_after);
+        }
+        if (!more) return 0; // tolerance / minimum radius: nIter does not advance (:1129-1133, :1149-1153)
+        ++n_iter_;
+        return 1;
+    }
     float* tr = d_trace_ ? d_trace_ + (size_t)3 * l_iterations_ * n_iter_ : nullptr;
     float c;
     if (use_resident_) {
@@ -194,7 +226,7 @@ int GnPlan::step(void** pp)
 
 void GnPlan::solve(void** pp)
 {
-    if (verbosity_ > 0) { // keep the per-step prints: go through the stepwise path
+    if (verbosity_ > 0 || lm_) { // per-step prints, or per-step host decisions: go through the stepwise path
         init(pp);
         while (step(pp)) {}
         return;

@@ -5,13 +5,15 @@
 #include "../../include/arapb200.h"
 #include "solver_stream.cuh"
 #include "solver_resident.cuh"
+#include "solver_lm.cuh"
 #include <memory>
 
 namespace arapb200 {
 
 class GnPlan {
 public:
-    GnPlan(int W, int H, int verbosity, int backend);
+    // lm: the "LMGPU" solver kind (Levenberg-Marquardt, solver_lm.cuh) instead of "gaussNewtonGPU"
+    GnPlan(int W, int H, int verbosity, int backend, bool lm = false);
     ~GnPlan();
     // solverGPUGaussNewton.t:1205-1221.  false = unknown name.
     bool set_parameter(const char* name, const void* value);
@@ -25,6 +27,8 @@ public:
     long long launches() const;
     bool using_resident() const { return use_resident_; }
     bool general_urshape() const { return general_; }
+    bool is_lm() const { return lm_ != nullptr; }
+    const LmStepInfo* lm_last_step() const { return lm_ ? &lm_->last_step() : nullptr; }
     // parity/debug: device buffer of 3*lIterations floats per GN step, or null
     void set_trace(float* d_trace) { d_trace_ = d_trace; }
 
@@ -40,6 +44,8 @@ private:
     cudaStream_t stream_h_ = nullptr;
     std::unique_ptr<StreamSolver> stream_;      // created on first use
     std::unique_ptr<ResidentSolver> resident_;  // created on first use
+    std::unique_ptr<LmSolver> lm_;              // "LMGPU" plans only
+    void lm_bind(void** problemparams);
     bool use_resident_ = false;
     bool general_ = false;                      // UrShape is not the pixel grid
     void** last_params_ = nullptr;

@@ -115,6 +115,17 @@ ARAPB200_API int arapb200_batch_set_option(arapb200_batch* b, const char* name, 
 struct Opt_Plan;
 ARAPB200_API int arapb200_plan_error(struct Opt_Plan* plan);
 
+/* Opt_ProblemDefine(state, file, "LMGPU") selects the reference's other solver kind (ARAP/API/src/o.t:121-124,
+ * ARAP/API/src/solverGPUGaussNewton.t with UsesLambda(): Levenberg-Marquardt trust region around the same PCG, Q-based
+ * early exit of the linear loop, step acceptance / revert; never requested by the ARAP app).  Its solver parameters
+ * (Opt_SetSolverParameter, :26-39, :140-157) are floats -- min_relative_decrease, min_trust_region_radius,
+ * max_trust_region_radius, q_tolerance, function_tolerance, trust_region_radius, radius_decrease_factor,
+ * min_lm_diagonal, max_lm_diagonal -- and the int residual_reset_period.  This call reports what the last
+ * Opt_ProblemStep of such a plan did: info6 = trust-region radius after the step, linear iterations run, verdict
+ * (1 accepted, 0 reverted, 2 function tolerance reached, 3 radius below the minimum), model cost, cost at the trial
+ * point, last Q.  Returns 0, or 1 when the plan is not an LM plan. */
+ARAPB200_API int arapb200_plan_lm_info(struct Opt_Plan* plan, float info6[6]);
+
 /* ---- debug / parity entry points (unit-level comparison against the oracle) ----------------- */
 /* one Opt_ProblemSolve on host buffers: X float2[N] and A float[N] in/out; U, C float2[N]; M float[N];
  * costs float[nGN+1] (may be NULL); scal float[nGN*nPCG*3] (den, num, bnum per PCG iteration; may be NULL) */

@@ -605,6 +605,297 @@ ORACLE_API int arap_oracle_gn_solve(int W, int H, float *X, float *A, const floa
     return 0;
 }
 
+/* ------------------------------------------------------------------ Levenberg-Marquardt ---- */
+/* The reference's dormant "LMGPU" solver kind: solverGPUGaussNewton.t with UsesLambda() == true.
+ * The ARAP app never requests it (CombinedSolverBase.h:76), the tree holds no vectors for it: PARITY UNPINNED, this
+ * restatement and the CUDA path (csrc/solver_lm.cu) are checked against each other only.  Same arithmetic contract as
+ * the Gauss-Newton path; the additional per-pixel expressions are fixed here:
+ *   unclamped CtC_k = D_k * (1 / radius)                         (o.t:2255-2288; D = diag(J^T J) of jtf_pixel)
+ *   (J^T J + CtC) v = fmaf(CtC_k, v_k, (J^T J v)_k)              (o.t:2076-2082)
+ *   model cost term = sum over the pixel's residuals of (F + J delta)^2, accumulated like cost_pixel (o.t:2174-2202)
+ *   Q term          = 0.5 * (delta . (r + b))                    (solverGPUGaussNewton.t:483, :527)
+ * Host-side trust-region arithmetic is the reference's: binary32 fields, binary64 where its literals promote. */
+typedef struct {
+    float min_relative_decrease, min_trust_region_radius, max_trust_region_radius, q_tolerance, function_tolerance,
+        trust_region_radius, radius_decrease_factor, min_lm_diagonal, max_lm_diagonal;
+    int residual_reset_period;
+} LmParams;
+
+static void lm_defaults(LmParams *p) /* solverGPUGaussNewton.t:26-39 */
+{
+    p->min_relative_decrease = (float)1e-3;
+    p->min_trust_region_radius = (float)1e-32;
+    p->max_trust_region_radius = (float)1e16;
+    p->q_tolerance = (float)0.0001;
+    p->function_tolerance = (float)0.000001;
+    p->trust_region_radius = (float)1e4;
+    p->radius_decrease_factor = (float)2.0;
+    p->min_lm_diagonal = (float)1e-6;
+    p->max_lm_diagonal = (float)1e32;
+    p->residual_reset_period = 10;
+}
+
+/* sum over the residuals owned by pixel (x, y) of (F + J delta)^2; delta = float3[N] (dX0, dX1, dA) */
+static inline float modelcost_pixel(const Prob *P, const float *X, const float *cs, const float *delta, int x, int y)
+{
+    const int W = P->W;
+    size_t i = (size_t)y * W + x;
+    float ci = cs[2 * i], si = cs[2 * i + 1];
+    float di0 = delta[3 * i], di1 = delta[3 * i + 1], dai = delta[3 * i + 2];
+    float acc = 0.0f;
+    for (int n = 0; n < 4; ++n) {
+        int xj, yj;
+        if (!nb_valid(P, x, y, n, &xj, &yj)) continue;
+        size_t j = (size_t)yj * W + xj;
+        float dx = P->U[2 * i] - P->U[2 * j], dy = P->U[2 * i + 1] - P->U[2 * j + 1];
+        float dX0 = X[2 * i] - X[2 * j], dX1 = X[2 * i + 1] - X[2 * j + 1];
+        float Ri0 = ci * dx - si * dy, Ri1 = si * dx + ci * dy;
+        float e0 = dX0 - Ri0, e1 = dX1 - Ri1;
+        float dd0 = di0 - delta[3 * j], dd1 = di1 - delta[3 * j + 1];
+        float Q0 = (-(si * dx)) - ci * dy, Q1 = ci * dx - si * dy; /* R'(a_i) d */
+        float m0 = (e0 + dd0) - Q0 * dai, m1 = (e1 + dd1) - Q1 * dai;
+        float w0 = P->wr * m0, w1 = P->wr * m1;
+        acc = fmaf(w0, w0, acc);
+        acc = fmaf(w1, w1, acc);
+    }
+    if (has_fit(P, i)) {
+        float f0 = P->wf * ((X[2 * i] - P->C[2 * i]) + di0);
+        float f1 = P->wf * ((X[2 * i + 1] - P->C[2 * i + 1]) + di1);
+        acc = fmaf(f0, f0, acc);
+        acc = fmaf(f1, f1, acc);
+    }
+    return acc;
+}
+
+typedef struct {
+    float *ctc, *b, *ssq, *adelta, *prevX, *prevA, *T2;
+} LmWork;
+
+/* out = (J^T J + CtC) v for every active pixel */
+static void lm_apply(const Prob *P, Work *w, const LmWork *lw, const float *v, float *out)
+{
+    const int W = P->W;
+#pragma omp parallel for schedule(static)
+    for (int y = P->y0; y <= P->y1; ++y)
+        for (int x = P->x0; x <= P->x1; ++x)
+            if (active(P, x, y)) {
+                size_t i = (size_t)y * W + x;
+                float q[3];
+                jtj_pixel(P, w->cs, v, x, y, q);
+                for (int k = 0; k < 3; ++k) out[3 * i + k] = fmaf(lw->ctc[3 * i + k], v[3 * i + k], q[k]);
+            }
+}
+
+/* One LM iteration = solverGPUGaussNewton.t:1016-1177 with UsesLambda() == true.  Returns 1 to continue, 0 when the
+ * solver decided to stop (function tolerance / minimum radius).  stat[0..5] = radius after the step, PCG iterations
+ * run, verdict (1 accepted, 0 reverted, 2 function tolerance reached, 3 radius below minimum), model cost, new cost,
+ * last Q. */
+static int lm_step(const Prob *P, Work *w, LmWork *lw, LmParams *lp, float *X, float *A, int nPCG, int first,
+                   float *prevCost, float *stat)
+{
+    const int W = P->W;
+    float *r = w->r, *p = w->p, *q = w->q, *pre = w->pre, *delta = w->delta, *T = w->T, *T2 = lw->T2;
+    const float radius = lp->trust_region_radius;
+    const float inv_radius = 1.0f / radius;
+    fill_cs(P, A, w->cs);
+    /* PCGInit1 (:361-397), PCGSaveSSq (:624-629), PCGComputeCtC (:616-622), PCGFinalizeDiagonal (:631-664) */
+#pragma omp parallel for schedule(static)
+    for (int y = P->y0; y <= P->y1; ++y)
+        for (int x = P->x0; x <= P->x1; ++x)
+            if (active(P, x, y)) {
+                size_t i = (size_t)y * W + x;
+                float g[3], D2[2];
+                jtf_pixel(P, X, w->cs, x, y, g, D2);
+                const float D[3] = {D2[0], D2[0], D2[1]};
+                for (int k = 0; k < 3; ++k) {
+                    if (first) lw->ssq[3 * i + k] = guarded_invert(D[k]); /* jacobiScaling ONCE_PER_SOLVE */
+                    float u = D[k] * inv_radius;
+                    float invS = 1.0f / lw->ssq[3 * i + k];
+                    float mult = invS / radius;
+                    float lo = lp->min_lm_diagonal * mult, hi = lp->max_lm_diagonal * mult;
+                    float c = fminf(fmaxf(u, lo), hi);
+                    lw->ctc[3 * i + k] = c;
+                    pre[3 * i + k] = 1.0f / (c + radius * u);
+                    r[3 * i + k] = -g[k];
+                    lw->b[3 * i + k] = r[3 * i + k];
+                    p[3 * i + k] = pre[3 * i + k] * r[3 * i + k];
+                    delta[3 * i + k] = 0.0f;
+                }
+                T[i] = dot3(&r[3 * i], &p[3 * i]);
+                float rr[3] = {r[3 * i] + r[3 * i], r[3 * i + 1] + r[3 * i + 1], r[3 * i + 2] + r[3 * i + 2]};
+                T2[i] = 0.5f * dot3(&delta[3 * i], rr);
+            }
+    float num = reduce_terms(P, T, w->gb);
+    float Q0 = reduce_terms(P, T2, w->gb);
+    float Q1 = Q0;
+    int it = 0;
+    for (; it < nPCG;) {
+        lm_apply(P, w, lw, p, q); /* PCGStep1 (:421-434) */
+#pragma omp parallel for schedule(static)
+        for (int y = P->y0; y <= P->y1; ++y)
+            for (int x = P->x0; x <= P->x1; ++x)
+                if (active(P, x, y)) {
+                    size_t i = (size_t)y * W + x;
+                    T[i] = dot3(&p[3 * i], &q[3 * i]);
+                }
+        float den = reduce_terms(P, T, w->gb);
+        float alpha = (den > 0.0f) ? num / den : 0.0f;
+        const int reset = ((it + 1) % lp->residual_reset_period) == 0; /* :1077-1086 */
+        if (reset) {
+#pragma omp parallel for schedule(static)
+            for (int y = P->y0; y <= P->y1; ++y)
+                for (int x = P->x0; x <= P->x1; ++x)
+                    if (active(P, x, y)) {
+                        size_t i = (size_t)y * W + x;
+                        for (int k = 0; k < 3; ++k) delta[3 * i + k] = fmaf(alpha, p[3 * i + k], delta[3 * i + k]);
+                    }
+            lm_apply(P, w, lw, delta, lw->adelta); /* computeAdelta (:566-571) */
+        }
+#pragma omp parallel for schedule(static)
+        for (int y = P->y0; y <= P->y1; ++y)
+            for (int x = P->x0; x <= P->x1; ++x)
+                if (active(P, x, y)) {
+                    size_t i = (size_t)y * W + x;
+                    float z[3], rb[3];
+                    for (int k = 0; k < 3; ++k) {
+                        if (reset) {
+                            r[3 * i + k] = lw->b[3 * i + k] - lw->adelta[3 * i + k]; /* PCGStep2_2ndHalf (:505-534) */
+                        } else {
+                            delta[3 * i + k] = fmaf(alpha, p[3 * i + k], delta[3 * i + k]); /* PCGStep2 (:446-489) */
+                            r[3 * i + k] = fmaf(-alpha, q[3 * i + k], r[3 * i + k]);
+                        }
+                        z[k] = pre[3 * i + k] * r[3 * i + k];
+                        rb[k] = r[3 * i + k] + lw->b[3 * i + k];
+                    }
+                    T[i] = dot3(z, &r[3 * i]);
+                    T2[i] = 0.5f * dot3(&delta[3 * i], rb);
+                }
+        float bnum = reduce_terms(P, T, w->gb);
+        Q1 = reduce_terms(P, T2, w->gb);
+        float beta = (num > 0.0f) ? bnum / num : 0.0f;
+#pragma omp parallel for schedule(static)
+        for (int y = P->y0; y <= P->y1; ++y)
+            for (int x = P->x0; x <= P->x1; ++x)
+                if (active(P, x, y)) {
+                    size_t i = (size_t)y * W + x;
+                    for (int k = 0; k < 3; ++k) {
+                        float z = pre[3 * i + k] * r[3 * i + k];
+                        p[3 * i + k] = fmaf(beta, p[3 * i + k], z);
+                    }
+                }
+        num = bnum;
+        ++it;
+        float zeta = ((float)it * (Q1 - Q0)) / Q1; /* :1093-1101 */
+        if (zeta < lp->q_tolerance) break;
+        Q0 = Q1;
+    }
+    /* computeModelCostChange (:818-827), before the update */
+#pragma omp parallel for schedule(static)
+    for (int y = P->y0; y <= P->y1; ++y)
+        for (int x = P->x0; x <= P->x1; ++x)
+            if (active(P, x, y)) T[(size_t)y * W + x] = modelcost_pixel(P, X, w->cs, delta, x, y);
+    float model_cost = 0.5f * reduce_terms(P, T, w->gb);
+    float model_cost_change = *prevCost - model_cost;
+    /* savePreviousUnknowns (:573-578), PCGLinearUpdate (:552-557) */
+#pragma omp parallel for schedule(static)
+    for (int y = P->y0; y <= P->y1; ++y)
+        for (int x = P->x0; x <= P->x1; ++x)
+            if (active(P, x, y)) {
+                size_t i = (size_t)y * W + x;
+                lw->prevX[2 * i] = X[2 * i]; lw->prevX[2 * i + 1] = X[2 * i + 1]; lw->prevA[i] = A[i];
+                X[2 * i] = X[2 * i] + delta[3 * i];
+                X[2 * i + 1] = X[2 * i + 1] + delta[3 * i + 1];
+                A[i] = A[i] + delta[3 * i + 2];
+            }
+    float newCost = cost_all(P, w, X, A);
+    stat[1] = (float)it; stat[3] = model_cost; stat[4] = newCost; stat[5] = Q1;
+    float cost_change = *prevCost - newCost;
+    float relative_decrease = cost_change / model_cost_change;
+    if (cost_change >= 0.0f && relative_decrease > lp->min_relative_decrease) { /* :1127-1142 */
+        float absolute_function_tolerance = *prevCost * lp->function_tolerance;
+        if (cost_change <= absolute_function_tolerance) {
+            stat[0] = lp->trust_region_radius; stat[2] = 2.0f;
+            return 0; /* the update stays, prevCost does not move: the reference returns before both */
+        }
+        double step_quality = (double)relative_decrease;
+        double min_factor = 1.0 / 3.0;
+        double tmp_factor = 1.0 - pow(2.0 * step_quality - 1.0, 3.0);
+        lp->trust_region_radius = (float)((double)lp->trust_region_radius / fmax(min_factor, tmp_factor));
+        lp->trust_region_radius = (float)fmin((double)lp->trust_region_radius, (double)lp->max_trust_region_radius);
+        lp->radius_decrease_factor = 2.0f;
+        *prevCost = newCost;
+        stat[2] = 1.0f;
+    } else { /* :1143-1155 */
+#pragma omp parallel for schedule(static)
+        for (int y = P->y0; y <= P->y1; ++y)
+            for (int x = P->x0; x <= P->x1; ++x)
+                if (active(P, x, y)) {
+                    size_t i = (size_t)y * W + x;
+                    X[2 * i] = lw->prevX[2 * i]; X[2 * i + 1] = lw->prevX[2 * i + 1]; A[i] = lw->prevA[i];
+                }
+        lp->trust_region_radius = lp->trust_region_radius / lp->radius_decrease_factor;
+        lp->radius_decrease_factor = (float)(2.0 * (double)lp->radius_decrease_factor);
+        if (lp->trust_region_radius <= lp->min_trust_region_radius) {
+            stat[0] = lp->trust_region_radius; stat[2] = 3.0f;
+            return 0;
+        }
+        stat[2] = 0.0f;
+    }
+    stat[0] = lp->trust_region_radius;
+    return 1;
+}
+
+/* == Opt_ProblemSolve on an "LMGPU" plan: init (:956-1007: parameters from the solver parameters, prevCost) then
+ * steps until one returns 0 or nGN were taken.  params10 (may be NULL = defaults): the nine float parameters in the
+ * order of LmParams, then residual_reset_period as a float.  costs[0..nGN] = prevCost after init and after every step
+ * (entries of steps not taken repeat the last one); stats (may be NULL) = 6 floats per step taken.
+ * Returns the number of steps taken, or -1. */
+ORACLE_API int arap_oracle_lm_solve(int W, int H, float *X, float *A, const float *U, const float *C, const float *M,
+                                    float wf, float wr, int nGN, int nPCG, const float *params10, float *costs,
+                                    float *stats)
+{
+    Prob P; prob_init(&P, W, H, U, C, M, wf, wr);
+    Work w;
+    if (!work_alloc(&w, &P)) return -1;
+    size_t N = (size_t)W * H;
+    LmWork lw;
+    lw.ctc = (float *)calloc(3 * N, sizeof(float));
+    lw.b = (float *)calloc(3 * N, sizeof(float));
+    lw.ssq = (float *)calloc(3 * N, sizeof(float));
+    lw.adelta = (float *)calloc(3 * N, sizeof(float));
+    lw.prevX = (float *)calloc(2 * N, sizeof(float));
+    lw.prevA = (float *)calloc(N, sizeof(float));
+    lw.T2 = (float *)calloc(N, sizeof(float));
+    if (!lw.ctc || !lw.b || !lw.ssq || !lw.adelta || !lw.prevX || !lw.prevA || !lw.T2) return -1;
+    LmParams lp;
+    lm_defaults(&lp);
+    if (params10) {
+        lp.min_relative_decrease = params10[0]; lp.min_trust_region_radius = params10[1];
+        lp.max_trust_region_radius = params10[2]; lp.q_tolerance = params10[3]; lp.function_tolerance = params10[4];
+        lp.trust_region_radius = params10[5]; lp.radius_decrease_factor = params10[6];
+        lp.min_lm_diagonal = params10[7]; lp.max_lm_diagonal = params10[8];
+        lp.residual_reset_period = (int)params10[9];
+        if (lp.residual_reset_period < 1) lp.residual_reset_period = 1;
+    }
+    float prevCost = cost_all(&P, &w, X, A);
+    if (costs) costs[0] = prevCost;
+    int taken = 0;
+    for (int g = 0; g < nGN; ++g) {
+        float st[6] = {0, 0, 0, 0, 0, 0};
+        int more = lm_step(&P, &w, &lw, &lp, X, A, nPCG, g == 0, &prevCost, st);
+        if (stats) memcpy(stats + 6 * (size_t)g, st, sizeof(st));
+        if (costs) costs[g + 1] = prevCost;
+        ++taken;
+        if (!more) {
+            if (costs) for (int gg = g + 2; gg <= nGN; ++gg) costs[gg] = prevCost;
+            break;
+        }
+    }
+    free(lw.ctc); free(lw.b); free(lw.ssq); free(lw.adelta); free(lw.prevX); free(lw.prevA); free(lw.T2);
+    work_free(&w);
+    return taken;
+}
+
 /* constraint image for continuation weight alpha (CombinedSolver.h:223-242) */
 ORACLE_API void arap_oracle_constraint_image(int W, int H, const uint8_t *mask_red, const int *matches,
                                              int n_matches, float alpha, float *C)

@@ -52,6 +52,9 @@ def lib():
         L.arap_oracle_gn_solve.argtypes = [C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_float,
                                            C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.arap_oracle_gn_solve.restype = C.c_int
+        L.arap_oracle_lm_solve.argtypes = [C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_float,
+                                           C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.arap_oracle_lm_solve.restype = C.c_int
         L.arap_oracle_constraint_image.argtypes = [C.c_int, C.c_int, _u8p, _i32p, C.c_int, C.c_float, _f32p]
         L.arap_oracle_border_pin_count.argtypes = [C.c_int, C.c_int]
         L.arap_oracle_border_pin_count.restype = C.c_int
@@ -130,6 +133,33 @@ def gn_solve(X, A, U, Cn, M, nGN, nPCG, wf=WF, wr=WR, trace=False):
                                     costs.ctypes.data, scal.ctypes.data if trace else None)
     assert rc == 0
     return X, A, costs, scal
+
+
+# solverGPUGaussNewton.t:26-39, in the order arap_oracle_lm_solve takes them
+LM_DEFAULTS = {"min_relative_decrease": 1e-3, "min_trust_region_radius": 1e-32, "max_trust_region_radius": 1e16,
+               "q_tolerance": 0.0001, "function_tolerance": 0.000001, "trust_region_radius": 1e4,
+               "radius_decrease_factor": 2.0, "min_lm_diagonal": 1e-6, "max_lm_diagonal": 1e32,
+               "residual_reset_period": 10}
+
+
+def lm_solve(X, A, U, Cn, M, nGN, nPCG, wf=WF, wr=WR, **params):
+    """One Opt_ProblemSolve on an "LMGPU" plan (the reference's dormant Levenberg-Marquardt kind).  Returns
+    (X, A, costs[nGN+1], stats[steps, 6]); stats rows = (radius after, PCG iterations, verdict 1 accepted / 0 reverted /
+    2 function tolerance / 3 minimum radius, model cost, new cost, last Q).  Inputs untouched."""
+    H, W = M.shape
+    X = _c(X).copy()
+    A = _c(A).copy()
+    pv = dict(LM_DEFAULTS)
+    for k, v in params.items():
+        assert k in pv, k
+        pv[k] = v
+    p10 = np.array([pv[k] for k in LM_DEFAULTS], np.float32)
+    costs = np.zeros(nGN + 1, np.float32)
+    stats = np.zeros((max(nGN, 1), 6), np.float32)
+    n = lib().arap_oracle_lm_solve(W, H, X, A, _c(U), _c(Cn), _c(M), wf, wr, nGN, nPCG, p10.ctypes.data,
+                                   costs.ctypes.data, stats.ctypes.data)
+    assert n >= 0
+    return X, A, costs, stats[:n]
 
 
 def constraint_image(mask_red, matches, alpha):

@@ -42,7 +42,10 @@ def test_problem_define_refuses_foreign_plans(tmp_path):
     assert not L.Opt_ProblemDefine(st, str(bad).encode(), b"gaussNewtonGPU")
     assert not L.Opt_ProblemDefine(st, b"/nonexistent/arap_plan.t", b"gaussNewtonGPU")
     good = os.path.join(ROOT, "arap_flow_b200", "arap_plan.t")
-    assert not L.Opt_ProblemDefine(st, good.encode(), b"LMGPU")
+    assert not L.Opt_ProblemDefine(st, good.encode(), b"lbfgsGPU")      # o.t:121-124: gaussNewtonGPU or LMGPU
+    lm = L.Opt_ProblemDefine(st, good.encode(), b"LMGPU")
+    assert lm
+    L.Opt_ProblemDelete(st, lm)
     p = L.Opt_ProblemDefine(st, good.encode(), b"gaussNewtonGPU")
     assert p
     L.Opt_ProblemDelete(st, p)
