@@ -273,6 +273,10 @@ int arapb200_batch_set_option(arapb200_batch* b, const char* name, double value)
             b->pipe->set_gn_rtol((float)value);
             return 0;
         }
+        if (strcmp(name, "lm") == 0) { // 1: solver kind "LMGPU" for every Opt_ProblemSolve of the schedule; 0 (default): gaussNewtonGPU
+            b->pipe->set_lm(value != 0.0);
+            return 0;
+        }
         return 1;
     });
 }

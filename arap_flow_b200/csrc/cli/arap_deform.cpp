@@ -64,6 +64,7 @@ static void usage()
     puts("Environment: ARAP_PLAN = path of the ARAP energy file (default ./arap_plan.t); CUDA_VISIBLE_DEVICES selects the GPU;");
     puts("             ARAP_BATCH = problems solved together (default 9: three cooperative launches of three)");
     puts("             ARAP_PCG_RTOL = opt-in relative PCG tolerance, e.g. 1e-3 (default 0: fixed 400 iterations)");
+    puts("             ARAP_SOLVER = gaussNewtonGPU (default) | LMGPU (opt-in: trust region + Q-based exit of the linear loops)");
     puts("             ARAP_GN_RTOL = opt-in relative cost-decrease tolerance of the Gauss-Newton steps (default 0: fixed 8 steps)");
     puts("             ARAP_SERVER = spool directory of a running `arap_deform --serve`: hand the work to it instead of solving here");
 }
@@ -103,6 +104,7 @@ struct Settings {
     int batch = 9;
     // opt-in, off by default: convergence-aware PCG loops (changes results; include/arapb200.h)
     double pcg_rtol = 0.0, gn_rtol = 0.0;
+    bool lm = false;     // ARAP_SOLVER=LMGPU: the reference's other solver kind (o.t:121-124), default gaussNewtonGPU
     bool timing = false; // ARAP_TIMING=1: per-stage wall times on stderr
     Settings()
     {
@@ -111,6 +113,13 @@ struct Settings {
         if (getenv("ARAP_PCG_RTOL")) pcg_rtol = atof(getenv("ARAP_PCG_RTOL"));
         if (getenv("ARAP_GN_RTOL")) gn_rtol = atof(getenv("ARAP_GN_RTOL"));
         timing = getenv("ARAP_TIMING") != NULL;
+        if (const char* k = getenv("ARAP_SOLVER")) {
+            if (strcmp(k, "LMGPU") == 0) lm = true;
+            else if (strcmp(k, "gaussNewtonGPU") != 0) {
+                fprintf(stderr, "ARAP_SOLVER must be gaussNewtonGPU or LMGPU\n");
+                exit(1);
+            }
+        }
     }
 };
 
@@ -135,6 +144,7 @@ static int ensure_context(Context& C, const Settings& S, int W, int H)
         fprintf(stderr, "ARAP_GN_RTOL must be in [0, 1)\n");
         return 1;
     }
+    if (S.lm && arapb200_batch_set_option(C.ctx, "lm", 1.0)) return 1;
     C.W = W; C.H = H;
     return 0;
 }

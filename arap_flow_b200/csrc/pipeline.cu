@@ -143,6 +143,7 @@ BatchPipeline::~BatchPipeline()
     cudaStreamSynchronize(stream_);
     delete solver_;
     delete resident_;
+    delete lm_;
     for (Dev& d : dev_) {
         cudaFree(d.X); cudaFree(d.U); cudaFree(d.C); cudaFree(d.flow); cudaFree(d.A); cudaFree(d.M);
         cudaFree(d.costs); cudaFree(d.rgb); cudaFree(d.mask); cudaFree(d.orgb); cudaFree(d.omask);
@@ -181,6 +182,44 @@ void BatchPipeline::solve_streaming(const HostProblem& hp, Dev& d)
         launches_ += 1 + nGN_;
     }
     launches_ += solver_->launches() - l0;
+}
+
+// the "LMGPU" solver kind: per continuation step one Opt_ProblemSolve = init + up to nGN steps (o.t:2548-2551), the host
+// deciding acceptance after each (solver_lm.cu).  Cost log: prevCost after init and after every step; entries of steps the
+// solver did not take repeat the last one.
+void BatchPipeline::solve_lm(const HostProblem& hp, Dev& d)
+{
+    const int W = hp.W, H = hp.H;
+    if (!lm_ || lmW_ != W || lmH_ != H) {
+        if (lm_) launches_ += lm_->launches();
+        delete lm_;
+        lm_ = nullptr;
+        lm_ = new LmSolver(W, H);
+        lmW_ = W;
+        lmH_ = H;
+    }
+    const long long l0 = lm_->launches();
+    const float wf = sqrtf(100.0f), wr = sqrtf(0.01f); // CombinedSolver.h:172-177
+    lm_->bind(d.X, d.A, d.U, d.C, d.M, wf, wr);
+    lm_costs_.assign((size_t)nCont_ * (nGN_ + 1), 0.0f);
+    for (int t = 0; t < nCont_; ++t) {
+        const float alpha = (float)(t + 1) / (float)nCont_; // CombinedSolver.h:199-201
+        enqueue_constraint_image(W, H, d.matches, (int)d.recs.size(), alpha, d.C, stream_);
+        launches_ += d.recs.empty() ? 1 : 2;
+        float* c = lm_costs_.data() + (size_t)t * (nGN_ + 1);
+        float prev = lm_->init(stream_);
+        c[0] = prev;
+        int g = 0;
+        while (g < nGN_) {
+            const int more = lm_->step(nPCG_, stream_, &prev);
+            c[++g] = prev;
+            if (!more) break;
+        }
+        for (int k = g + 1; k <= nGN_; ++k) c[k] = prev;
+    }
+    ARAP_CUDA_CHECK(cudaMemcpyAsync(d.costs, lm_costs_.data(), lm_costs_.size() * sizeof(float), cudaMemcpyHostToDevice, stream_));
+    ARAP_CUDA_CHECK(cudaStreamSynchronize(stream_)); // lm_costs_ is reused by the next problem
+    launches_ += lm_->launches() - l0;
 }
 
 void BatchPipeline::set_pcg_rtol(float rtol)
@@ -236,10 +275,10 @@ int BatchPipeline::run(const HostProblem* problems, int count)
         enqueue_reset_state(hp.W, hp.H, d.mask, d.X, d.U, d.A, d.M, stream_);
         launches_ += 1;
         d.resident = false;
-        if (resident_) resident_->prepare_enqueue(i, hp.W, hp.H, d.M, stream_);
+        if (resident_ && !lm_on_) resident_->prepare_enqueue(i, hp.W, hp.H, d.M, stream_);
     }
     n_resident_ = 0;
-    if (resident_) {
+    if (resident_ && !lm_on_) {
         ARAP_CUDA_OR_RETURN(cudaStreamSynchronize(stream_)); // strip counts are needed to size the launches
         for (int i = 0; i < count; ++i) {
             dev_[i].resident = resident_->prepare_finish(i);
@@ -256,6 +295,11 @@ int BatchPipeline::run(const HostProblem* problems, int count)
     group_size_ = 0;
     for (int i = 0; i < count;) {
         Dev& d = dev_[i];
+        if (lm_on_) {
+            solve_lm(problems[i], d);
+            ++i;
+            continue;
+        }
         if (!d.resident) {
             if (gn_rtol_ > 0.0f && !warned_rtol_) { // never silently: the caller asked for an early exit
                 warned_rtol_ = true;

@@ -62,6 +62,9 @@ public:
     void set_pcg_rtol(float rtol);
     void set_gn_rtol(float rtol);
     void set_cluster_barrier(bool on) { if (resident_) resident_->set_cluster_barrier(on); }
+    // opt-in: every Opt_ProblemSolve of the schedule runs the reference's other solver kind, "LMGPU" (solver_lm.cuh:
+    // trust region + Q-based exit of the linear loops) with its default parameters, one problem at a time
+    void set_lm(bool on) { lm_on_ = on; }
 
 private:
     struct Dev { // device + pinned staging of one problem slot
@@ -76,6 +79,11 @@ private:
         bool resident = false;
     };
     void solve_streaming(const HostProblem& hp, Dev& d);
+    void solve_lm(const HostProblem& hp, Dev& d);
+    LmSolver* lm_ = nullptr;
+    int lmW_ = 0, lmH_ = 0;
+    bool lm_on_ = false;
+    std::vector<float> lm_costs_;
     int maxW_, maxH_, nCont_, nGN_, nPCG_, backend_;
     std::vector<Dev> dev_;
     StreamSolver* solver_ = nullptr;

@@ -105,6 +105,12 @@ ARAPB200_API int arapb200_batch_launch_info(arapb200_batch* b, int* info6);
  *   "cluster_barrier": 1 = problems that fit one thread-block cluster (<= 16 CTAs of <= 12 strips) run with a cluster-scope
  *   barrier (limb sums pushed through distributed shared memory, mbarrier completion); 0 (default) = every resident
  *   problem uses the L2 barrier.  Same results bit for bit; measured slower on B200, kept as an option.
+ *   "lm": 1 = every Opt_ProblemSolve of the schedule is run by the reference's other solver kind, "LMGPU"
+ *   (Levenberg-Marquardt trust region, Q-based exit of the linear loops, step acceptance / revert;
+ *   ARAP/API/src/solverGPUGaussNewton.t with UsesLambda()) with its default solver parameters (:26-39), one problem at a
+ *   time; nIterations / lIterations stay upper bounds.  Changes results (a different algorithm); out_costs holds the
+ *   accepted cost after init and after every step, entries of steps not taken repeat the last one.  0 (default) =
+ *   gaussNewtonGPU, what the ARAP app requests (CombinedSolverBase.h:76).
  * Returns non-zero for unknown names / bad values. */
 ARAPB200_API int arapb200_batch_set_option(arapb200_batch* b, const char* name, double value);
 

@@ -190,6 +190,24 @@ def solve(mask_red, matches, nCont=19, nGN=8, nPCG=400):
     return X, A, costs
 
 
+def solve_lm(mask_red, matches, nCont=19, nGN=8, nPCG=400, **params):
+    """The arap_deform schedule with every Opt_ProblemSolve run by the "LMGPU" solver kind (default parameters unless
+    given): resetGPU, then per continuation step the constraint image and one lm_solve.  Returns
+    (X[H,W,2], A[H,W], costs[nCont, nGN+1], linear iterations per continuation step)."""
+    H, W = mask_red.shape
+    m = with_border_pins(matches, W, H)
+    U = grid(W, H)
+    M = _c(mask_red, np.uint8).astype(np.float32)
+    X, A = U.copy(), np.zeros((H, W), np.float32)
+    costs = np.zeros((nCont, nGN + 1), np.float32)
+    its = []
+    for t in range(nCont):
+        alpha = np.float32(t + 1) / np.float32(nCont)
+        X, A, costs[t], st = lm_solve(X, A, U, constraint_image(mask_red, m, alpha), M, nGN, nPCG, **params)
+        its.append(int(st[:, 1].sum()))
+    return X, A, costs, its
+
+
 def set_rtol(pcg_rtol=0.0, gn_rtol=0.0):
     """Opt-in early exits (N4), mirrored from the resident kernel; (0, 0) restores the reference's fixed budget."""
     lib().arap_oracle_set_rtol(np.float32(pcg_rtol), np.float32(gn_rtol))

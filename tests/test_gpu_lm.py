@@ -150,3 +150,47 @@ def test_lm_c1_sized_problem(oracle):
     pr = dict(W=sp.W, H=sp.H, M=sp.masks[0].astype(np.float32), U=U, X=U.copy(), A=np.zeros((sp.H, sp.W), np.float32),
               C=oracle.constraint_image(sp.masks[0], m, 1.0 / 19))
     _check(oracle, pr, 3, 400)
+
+
+def test_lm_through_the_batch_pipeline_and_cli_option(oracle, tmp_path):
+    """arapb200_batch_set_option("lm", 1) / ARAP_SOLVER=LMGPU: the whole arap_deform schedule with the LM solver kind ==
+    the oracle's (constraint image per continuation step + arap_oracle_lm_solve), flow / warp / cost table bit for bit."""
+    import subprocess
+    from arap_flow_b200 import flowio, synth
+    sp = synth.synth(160, 120, 2, 2, 31)
+    nCont, nGN, nPCG = 5, 4, 100
+    b = lib.Batch(160, 120, 2, nCont, nGN, nPCG)
+    b.set_option("lm", 1)
+    outs = [b.submit(i, sp.rgb, m, sp.matches) for i, m in enumerate(sp.masks)]
+    b.run()
+    its_total = 0
+    for m, o in zip(sp.masks, outs):
+        Xo, Ao, co, its = oracle.solve_lm(m, sp.matches, nCont, nGN, nPCG)
+        its_total += sum(its)
+        assert np.array_equal(o["costs"].view(np.uint32), co.view(np.uint32))
+        assert np.array_equal(o["flow"], oracle.flow(Xo))
+        rgb_o, m_o, _ = oracle.warp(Xo, sp.rgb, m)
+        assert np.array_equal(o["rgb"], rgb_o) and np.array_equal(o["mask"], m_o)
+    assert its_total < 0.5 * 2 * nCont * nGN * nPCG          # the schedule really is convergence-aware
+    b.set_option("lm", 0)                                    # and back: the default solver kind on the same batch
+    o = b.submit(0, sp.rgb, sp.masks[0], sp.matches)
+    b.run()
+    Xo, Ao, co = oracle.solve(sp.masks[0], sp.matches, nCont, nGN, nPCG)
+    assert np.array_equal(o["costs"], co) and np.array_equal(o["flow"], oracle.flow(Xo))
+    b.close()
+    # the command-line tool: ARAP_SOLVER=LMGPU, full default schedule on a small image
+    sp = synth.synth(96, 80, 1, 2, 32)
+    p = {k: str(tmp_path / k) for k in ("rgb.png", "msk.png", "cstr.txt", "out.flo", "wrgb.png", "wmsk.png")}
+    flowio.write_png(p["rgb.png"], sp.rgb)
+    flowio.write_png(p["msk.png"], np.repeat(sp.masks[0][..., None], 3, axis=2))
+    flowio.write_constraints(p["cstr.txt"], sp.matches)
+    exe = os.path.join(os.path.dirname(lib.LIB_PATH), "bin", "arap_deform")
+    env = dict(os.environ, ARAP_PLAN=PLAN, ARAP_SOLVER="LMGPU")
+    r = subprocess.run([exe] + [p[k] for k in ("rgb.png", "msk.png", "cstr.txt", "out.flo", "wrgb.png", "wmsk.png")],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    Xo, Ao, co, its = oracle.solve_lm(sp.masks[0], sp.matches)
+    assert np.array_equal(flowio.read_flo(p["out.flo"]), oracle.flow(Xo))
+    r = subprocess.run([exe, p["rgb.png"], p["msk.png"], p["cstr.txt"], p["out.flo"], p["wrgb.png"], p["wmsk.png"]],
+                       env=dict(env, ARAP_SOLVER="nope"), capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "ARAP_SOLVER" in r.stderr
