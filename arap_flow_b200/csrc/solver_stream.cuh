@@ -112,6 +112,7 @@ private:
     void launch_step_b(int it, cudaStream_t stream);
     bool general_ = false;
     float pcg_rtol_ = 0.0f;
+    int tma_ = 0;       // ARAP_STREAM_TMA=1 / 2: k_step_a_tma<true / false> instead of k_step_a<false, 16>
     bool sub16_ = true; // two 128-thread blocks per tile in the PCG kernels (ARAP_STREAM_SUB=32: one 256-thread block)
     StreamDev h_{};
     StreamDev* d_ = nullptr;

@@ -581,3 +581,22 @@ def test_cluster_scope_barrier_equals_l2_barrier(oracle):
         Xo, Ao, co = oracle.solve(s.masks[0], s.matches, **kw)
         assert _eq(o["flow"], oracle.flow(Xo)) and _eq(o["costs"], co)
     b.close()
+
+
+@pytest.mark.parametrize("mode", ["1", "2"])
+@pytest.mark.parametrize("W,H,seed", [(203, 77, 3), (160, 120, 4), (854, 480, 1000)])
+def test_streaming_tma_variant_bit_exact(oracle, monkeypatch, W, H, seed, mode):
+    """ARAP_STREAM_TMA=1: k_step_a's inputs arrive by cp.async.bulk + mbarrier instead of per-thread loads.
+    Same bits as the default kernel and as the oracle, per-iteration (den, num, bnum) traces included; ragged right / bottom
+    tiles, images smaller than a tile row, C1 size."""
+    pr = synth_gn_problem(oracle, W, H, seed=seed, fd=2)
+    nGN, nPCG = 2, (25 if W < 800 else 12)
+    monkeypatch.setenv("ARAP_STREAM_TMA", mode)
+    Xt, At, ct, st = lib.debug_gn_solve(pr["X"], pr["A"], pr["U"], pr["C"], pr["M"], nGN, nPCG, oracle.WF, oracle.WR,
+                                        backend=lib.BACKEND_STREAM, trace=True)
+    monkeypatch.delenv("ARAP_STREAM_TMA")
+    Xd, Ad, cd, sd = lib.debug_gn_solve(pr["X"], pr["A"], pr["U"], pr["C"], pr["M"], nGN, nPCG, oracle.WF, oracle.WR,
+                                        backend=lib.BACKEND_STREAM, trace=True)
+    assert np.array_equal(Xt, Xd) and np.array_equal(At, Ad) and np.array_equal(ct, cd) and np.array_equal(st, sd)
+    Xo, Ao, co, so = oracle.gn_solve(pr["X"], pr["A"], pr["U"], pr["C"], pr["M"], nGN, nPCG, trace=True)
+    assert np.array_equal(Xt, Xo) and np.array_equal(At, Ao) and np.array_equal(ct, co) and np.array_equal(st, so)
