@@ -33,11 +33,12 @@ end
 
 -- the Opt.h level, as the reference's wrapper exposes it (ARAP/shared/OptSolver.h:43-91): one Opt_ProblemSolve on the
 -- caller's device images; params = {Offset, Angle, UrShape, Constraints, Mask (device), &w_fitSqrt, &w_regSqrt (host)}
-terra M.solve_once(plan_file : rawstring, dims : &uint32, params : &&opaque) : double
+-- solver_kind: "gaussNewtonGPU" (what the ARAP app asks for) or "LMGPU" (the reference's other kind, o.t:121-124)
+terra M.solve_kind(plan_file : rawstring, solver_kind : rawstring, dims : &uint32, params : &&opaque) : double
   var init : C.Opt_InitializationParameters
   init.doublePrecision, init.verbosityLevel, init.collectPerKernelTimingInfo, init.threadsPerBlock = 0, 0, 0, 0
   var st = C.Opt_NewState(init)
-  var pr = C.Opt_ProblemDefine(st, plan_file, "gaussNewtonGPU")
+  var pr = C.Opt_ProblemDefine(st, plan_file, solver_kind)
   if pr == nil then return -1.0 end
   var pl = C.Opt_ProblemPlan(st, pr, dims)
   if pl == nil then C.Opt_ProblemDelete(st, pr); return -1.0 end
@@ -50,6 +51,10 @@ terra M.solve_once(plan_file : rawstring, dims : &uint32, params : &&opaque) : d
   C.Opt_PlanFree(st, pl)
   C.Opt_ProblemDelete(st, pr)
   return c
+end
+
+terra M.solve_once(plan_file : rawstring, dims : &uint32, params : &&opaque) : double
+  return M.solve_kind(plan_file, "gaussNewtonGPU", dims, params)
 end
 
 return M
