@@ -103,7 +103,8 @@ Opt_Plan* Opt_ProblemPlan(Opt_State* state, Opt_Problem* problem, unsigned int* 
     // failure => NULL, which the reference caller asserts on (ARAP/shared/OptSolver.h:54-56)
     try {
         Opt_Plan* pl = new Opt_Plan;
-        pl->plan = new GnPlan((int)W, (int)H, state->params.verbosityLevel, ARAPB200_BACKEND_AUTO, problem->lm);
+        pl->plan = new GnPlan((int)W, (int)H, state->params.verbosityLevel, ARAPB200_BACKEND_AUTO, problem->lm,
+                              state->params.collectPerKernelTimingInfo != 0);
         return pl;
     } catch (...) {
         fprintf(stderr, "arapb200: Opt_ProblemPlan failed for %u x %u\n", W, H);
@@ -147,6 +148,21 @@ double Opt_ProblemCurrentCost(Opt_State*, Opt_Plan* plan) { return plan->plan->c
 
 // extension (not in the reference's Opt.h): 0, or the code of the first failure since the plan was made
 int arapb200_plan_error(Opt_Plan* plan) { return (plan && plan->plan) ? plan->plan->error() : 1; }
+
+// extension: the kernel-timing table of the last finished solve of a plan whose state was created with
+// collectPerKernelTimingInfo (or verbosityLevel > 0: then only the "overall" row) -- the text the reference prints at the
+// end of a solve (util.t:469-508).  Copies at most cap - 1 characters, returns the full length.
+size_t arapb200_plan_timing_report(Opt_Plan* plan, char* buf, size_t cap)
+{
+    if (!plan || !plan->plan) return 0;
+    const std::string& r = plan->plan->timing_report();
+    if (buf && cap) {
+        const size_t n = r.size() < cap - 1 ? r.size() : cap - 1;
+        memcpy(buf, r.data(), n);
+        buf[n] = 0;
+    }
+    return r.size();
+}
 
 // extension: what the last Opt_ProblemStep of an "LMGPU" plan did.  info6 = trust-region radius after the step, linear
 // iterations run, verdict (1 accepted, 0 reverted, 2 function tolerance reached, 3 radius below minimum), model cost,

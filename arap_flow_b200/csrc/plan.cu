@@ -41,8 +41,8 @@ __global__ void __launch_bounds__(256) k_check_grid(int W, int H, const float2* 
 }
 } // namespace
 
-GnPlan::GnPlan(int W, int H, int verbosity, int backend, bool lm)
-    : W_(W), H_(H), verbosity_(verbosity), backend_(backend)
+GnPlan::GnPlan(int W, int H, int verbosity, int backend, bool lm, bool collect_timing)
+    : W_(W), H_(H), verbosity_(verbosity), backend_(backend), collect_timing_(collect_timing)
 {
     if (lm) lm_.reset(new LmSolver(W, H));
     ARAP_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_h_, cudaStreamNonBlocking));
@@ -121,7 +121,8 @@ void GnPlan::choose_backend(void** pp)
     mask_ptr_ = pp[4]; mask_key_[0] = h_check_[1]; mask_key_[1] = h_check_[2]; have_mask_key_ = true;
     const bool was_resident = use_resident_;
     use_resident_ = false;
-    if (backend_ != ARAPB200_BACKEND_STREAM && !general_) {
+    // per-kernel timing needs kernels to time: the streaming back-end (same results bit for bit), launched eagerly
+    if (backend_ != ARAPB200_BACKEND_STREAM && !general_ && !collect_timing_) {
         if (!resident_) resident_.reset(new ResidentSolver(W_, H_));
         // same Mask image as the previous call: the strip tables are still valid
         use_resident_ = (same_mask && was_resident) ? true : resident_->prepare(W_, H_, (const float*)pp[4], stream_h_);
@@ -131,6 +132,7 @@ void GnPlan::choose_backend(void** pp)
     if (!use_resident_) {
         if (!stream_) stream_.reset(new StreamSolver(W_, H_));
         stream_->set_general(general_);
+        stream_->set_timer(collect_timing_ ? timer_.get() : nullptr);
         stream_->set_pcg_rtol(general_ ? 0.0f : pcg_rtol_);
         if ((gn_rtol_ > 0.0f || (general_ && pcg_rtol_ > 0.0f)) && !warned_rtol_) {
             warned_rtol_ = true;
@@ -163,6 +165,29 @@ void GnPlan::bind(void** pp)
                   *(const float*)pp[5], *(const float*)pp[6], stream_h_);
 }
 
+void GnPlan::timer_begin()
+{
+    timer_.reset();
+    if (verbosity_ > 0 || collect_timing_) {
+        timer_.reset(new KernelTimer);
+        overall_idx_ = timer_->start("overall", stream_h_);
+    }
+    if (lm_) lm_->set_timer(collect_timing_ ? timer_.get() : nullptr);
+}
+
+// solverGPUGaussNewton.t:1009-1014: end of a solve -- "final cost", then the timer table
+void GnPlan::cleanup()
+{
+    if (verbosity_ > 0) printf("final cost=%f\n", prev_cost_);
+    if (!timer_) return;
+    timer_->stop_at(overall_idx_, stream_h_);
+    timing_report_ = KernelTimer::format(timer_->aggregate());
+    if (verbosity_ > 0) fputs(timing_report_.c_str(), stdout); // Timer:evaluate prints under verbosity only (util.t:452)
+    if (stream_) stream_->set_timer(nullptr);
+    if (lm_) lm_->set_timer(nullptr);
+    timer_.reset();
+}
+
 void GnPlan::lm_bind(void** pp)
 {
     lm_->bind((float2*)pp[0], (float*)pp[1], (const float2*)pp[2], (const float2*)pp[3], (const float*)pp[4],
@@ -171,6 +196,7 @@ void GnPlan::lm_bind(void** pp)
 
 void GnPlan::init(void** pp)
 {
+    timer_begin();
     if (lm_) {
         order_after_caller();
         lm_bind(pp);
@@ -191,7 +217,7 @@ void GnPlan::init(void** pp)
 
 int GnPlan::step(void** pp)
 {
-    if (n_iter_ >= n_iterations_) return 0;
+    if (n_iter_ >= n_iterations_) { cleanup(); return 0; }
     order_after_caller();
     if (lm_) {
         lm_bind(pp);
@@ -205,7 +231,7 @@ int GnPlan::step(void** pp)
                                                                                               : "radius below the minimum",
                    st.radius_after);
         }
-        if (!more) return 0; // tolerance / minimum radius: nIter does not advance (:1129-1133, :1149-1153)
+        if (!more) { cleanup(); return 0; } // tolerance / minimum radius: nIter does not advance (:1129-1133, :1149-1153)
         ++n_iter_;
         return 1;
     }
@@ -226,7 +252,7 @@ int GnPlan::step(void** pp)
 
 void GnPlan::solve(void** pp)
 {
-    if (verbosity_ > 0 || lm_) { // per-step prints, or per-step host decisions: go through the stepwise path
+    if (verbosity_ > 0 || lm_ || collect_timing_) { // per-step prints / host decisions / per-kernel events: the stepwise path
         init(pp);
         while (step(pp)) {}
         return;

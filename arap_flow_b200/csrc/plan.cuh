@@ -7,13 +7,15 @@
 #include "solver_resident.cuh"
 #include "solver_lm.cuh"
 #include <memory>
+#include <string>
 
 namespace arapb200 {
 
 class GnPlan {
 public:
     // lm: the "LMGPU" solver kind (Levenberg-Marquardt, solver_lm.cuh) instead of "gaussNewtonGPU"
-    GnPlan(int W, int H, int verbosity, int backend, bool lm = false);
+    // collect_timing: Opt_InitializationParameters.collectPerKernelTimingInfo (kernel_timer.cuh)
+    GnPlan(int W, int H, int verbosity, int backend, bool lm = false, bool collect_timing = false);
     ~GnPlan();
     // solverGPUGaussNewton.t:1205-1221.  false = unknown name.
     bool set_parameter(const char* name, const void* value);
@@ -31,6 +33,8 @@ public:
     const LmStepInfo* lm_last_step() const { return lm_ ? &lm_->last_step() : nullptr; }
     // parity/debug: device buffer of 3*lIterations floats per GN step, or null
     void set_trace(float* d_trace) { d_trace_ = d_trace; }
+    // the table the reference prints at the end of a solve (util.t:469-508), of the last finished solve; empty if none
+    const std::string& timing_report() const { return timing_report_; }
 
 private:
     void bind(void** problemparams);
@@ -45,6 +49,12 @@ private:
     std::unique_ptr<StreamSolver> stream_;      // created on first use
     std::unique_ptr<ResidentSolver> resident_;  // created on first use
     std::unique_ptr<LmSolver> lm_;              // "LMGPU" plans only
+    bool collect_timing_ = false;
+    std::unique_ptr<KernelTimer> timer_;        // verbosity > 0 or collect_timing_: "overall" (+ per-kernel) events
+    size_t overall_idx_ = 0;
+    std::string timing_report_;
+    void timer_begin();                         // init: Timer:init + startEvent("overall") (:958-960)
+    void cleanup();                             // :1009-1014
     void lm_bind(void** problemparams);
     bool use_resident_ = false;
     bool general_ = false;                      // UrShape is not the pixel grid

@@ -507,8 +507,8 @@ void LmSolver::enqueue_cost(cudaStream_t s, int acc)
 {
     const unsigned nb = (unsigned)((d_->N + 255) / 256);
     const dim3 grid((W_ + 31) / 32, (H_ + 15) / 16);
-    k_lm_cs<<<nb, 256, 0, s>>>(*d_);
-    k_lm_cost<<<grid, LM_THREADS, 0, s>>>(*d_, acc);
+    ARAP_TIMED(timer_, "precompute", s, (k_lm_cs<<<nb, 256, 0, s>>>(*d_)));
+    ARAP_TIMED(timer_, "computeCost", s, (k_lm_cost<<<grid, LM_THREADS, 0, s>>>(*d_, acc)));
     launches_ += 2;
 }
 
@@ -542,25 +542,27 @@ int LmSolver::step(int L, cudaStream_t s, float* prev_cost)
     const int set_model = 2 + 3 * L, set_cost = set_model + 1;
     ARAP_CUDA_CHECK(cudaMemsetAsync(acc_, 0, (size_t)(set_cost + 1) * WA_WORDS * sizeof(unsigned long long), s));
     k_lm_flags<<<nb, 256, 0, s>>>(d);
-    k_lm_cs<<<nb, 256, 0, s>>>(d);
-    k_lm_init<<<grid, LM_THREADS, 0, s>>>(d, first_ ? 1 : 0, radius_, 1.0f / radius_, min_diag_, max_diag_, 0, 1);
+    ARAP_TIMED(timer_, "precompute", s, (k_lm_cs<<<nb, 256, 0, s>>>(d)));
+    // PCGInit1 + PCGSaveSSq + PCGComputeCtC + PCGFinalizeDiagonal in one kernel
+    ARAP_TIMED(timer_, "PCGInit1", s,
+               (k_lm_init<<<grid, LM_THREADS, 0, s>>>(d, first_ ? 1 : 0, radius_, 1.0f / radius_, min_diag_, max_diag_, 0, 1)));
     k_lm_begin<<<1, 32, 0, s>>>(d, 0, 1);
     launches_ += 4;
     first_ = false;
     for (int it = 0; it < L; ++it) {
         const int base = 2 + 3 * it;
-        k_lm_apply<0><<<grid, LM_THREADS, 0, s>>>(d, base);
+        ARAP_TIMED(timer_, "PCGStep1", s, (k_lm_apply<0><<<grid, LM_THREADS, 0, s>>>(d, base)));
         k_lm_alpha<<<1, 32, 0, s>>>(d, base);
         if (((it + 1) % sp_.residual_reset_period) == 0) { // :1077-1086
-            k_lm_axpy<<<nb, 256, 0, s>>>(d);
-            k_lm_apply<1><<<grid, LM_THREADS, 0, s>>>(d, 0);
-            k_lm_step2<true><<<grid, LM_THREADS, 0, s>>>(d, base + 1, base + 2);
+            ARAP_TIMED(timer_, "PCGStep2_1stHalf", s, (k_lm_axpy<<<nb, 256, 0, s>>>(d)));
+            ARAP_TIMED(timer_, "computeAdelta", s, (k_lm_apply<1><<<grid, LM_THREADS, 0, s>>>(d, 0)));
+            ARAP_TIMED(timer_, "PCGStep2_2ndHalf", s, (k_lm_step2<true><<<grid, LM_THREADS, 0, s>>>(d, base + 1, base + 2)));
             launches_ += 2;
         } else {
-            k_lm_step2<false><<<grid, LM_THREADS, 0, s>>>(d, base + 1, base + 2);
+            ARAP_TIMED(timer_, "PCGStep2", s, (k_lm_step2<false><<<grid, LM_THREADS, 0, s>>>(d, base + 1, base + 2)));
         }
         k_lm_beta<<<1, 32, 0, s>>>(d, base + 1, base + 2, it, sp_.q_tolerance);
-        k_lm_step3<<<nb, 256, 0, s>>>(d);
+        ARAP_TIMED(timer_, "PCGStep3", s, (k_lm_step3<<<nb, 256, 0, s>>>(d)));
         launches_ += 5;
         if ((it & 15) == 15 && it + 1 < L) { // has the Q test ended the loop?  (the remaining launches would be no-ops)
             ARAP_CUDA_CHECK(cudaMemcpyAsync(&h_sc_->conv, &sc_->conv, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
@@ -568,8 +570,8 @@ int LmSolver::step(int L, cudaStream_t s, float* prev_cost)
             if (h_sc_->conv) break;
         }
     }
-    k_lm_model<<<grid, LM_THREADS, 0, s>>>(d, set_model); // before the update (:1106-1112)
-    k_lm_update<<<nb, 256, 0, s>>>(d);
+    ARAP_TIMED(timer_, "computeModelCost", s, (k_lm_model<<<grid, LM_THREADS, 0, s>>>(d, set_model))); // before the update (:1106-1112)
+    ARAP_TIMED(timer_, "PCGLinearUpdate", s, (k_lm_update<<<nb, 256, 0, s>>>(d))); // + savePreviousUnknowns
     enqueue_cost(s, set_cost);
     k_lm_finish<<<1, 32, 0, s>>>(d, set_model, set_cost);
     launches_ += 3;
@@ -604,7 +606,7 @@ int LmSolver::step(int L, cudaStream_t s, float* prev_cost)
             info_.verdict = 1;
         }
     } else {
-        k_lm_revert<<<nb, 256, 0, s>>>(d);
+        ARAP_TIMED(timer_, "revertUpdate", s, (k_lm_revert<<<nb, 256, 0, s>>>(d)));
         ++launches_;
         ARAP_CUDA_CHECK(cudaGetLastError());
         ARAP_CUDA_CHECK(cudaStreamSynchronize(s));

@@ -6,6 +6,7 @@
 // bit for bit against oracle/arap_oracle.c (arap_oracle_lm_solve).
 #pragma once
 #include "common.cuh"
+#include "kernel_timer.cuh"
 
 namespace arapb200 {
 
@@ -55,6 +56,7 @@ public:
     int step(int lIterations, cudaStream_t s, float* prev_cost);
     const LmStepInfo& last_step() const { return info_; }
     long long launches() const { return launches_; }
+    void set_timer(KernelTimer* t) { timer_ = t; } // per-kernel timing under the reference's kernel names; null = off
     struct Dev; // the kernels' argument block (solver_lm.cu)
 
 private:
@@ -74,6 +76,7 @@ private:
     LmScalars* h_sc_ = nullptr;             // pinned
     LmStepInfo info_{};
     long long launches_ = 0;
+    KernelTimer* timer_ = nullptr;
 };
 
 } // namespace arapb200

@@ -1114,9 +1114,9 @@ void StreamSolver::enqueue_init(cudaStream_t stream)
 {
     const StreamPlanes& pl = h_;
     ARAP_CUDA_CHECK(cudaMemsetAsync(&h_.sc->bad_u, 0, sizeof(unsigned), stream));
-    enqueue_prep(stream);
-    if (general_) k_cost_gen<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
-    else k_cost<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
+    ARAP_TIMED(timer_, "precompute", stream, enqueue_prep(stream));
+    if (general_) ARAP_TIMED(timer_, "computeCost", stream, (k_cost_gen<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_)));
+    else ARAP_TIMED(timer_, "computeCost", stream, (k_cost<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_)));
     k_finish<<<1, 32, 0, stream>>>(pl, d_, -1);
     launches_ += 2;
     ARAP_CUDA_CHECK(cudaGetLastError());
@@ -1125,25 +1125,32 @@ void StreamSolver::enqueue_init(cudaStream_t stream)
 void StreamSolver::launch_gn_body(int nPCG, cudaStream_t stream, bool tracing)
 {
     const StreamPlanes& pl = h_;
+    KernelTimer* const tm = tracing ? timer_ : nullptr; // never inside a graph capture
     ARAP_CUDA_CHECK(cudaMemsetAsync(h_.acc, 0, ACC_BYTES, stream));
     // the caller may have changed the constraint image / mask between steps (Opt.h:58-60): refresh flags
-    k_prep<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
-    if (general_) k_init_gen<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
-    else k_init<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
+    ARAP_TIMED(tm, "precompute", stream, (k_prep<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_)));
+    if (general_) ARAP_TIMED(tm, "PCGInit1", stream, (k_init_gen<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_)));
+    else ARAP_TIMED(tm, "PCGInit1", stream, (k_init<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_)));
     for (int it = 0; it < nPCG; ++it) {
-        launch_step_a(it == 0, it, stream);
-        launch_step_b(it, stream);
+        // PCGStep3 of the previous iteration is fused into this kernel (k_step_a)
+        ARAP_TIMED(tm, "PCGStep1", stream, launch_step_a(it == 0, it, stream));
+        ARAP_TIMED(tm, "PCGStep2", stream, launch_step_b(it, stream));
     }
-    k_update<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
-    if (general_) k_cost_gen<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
-    else k_cost<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_);
+    ARAP_TIMED(tm, "PCGLinearUpdate", stream, (k_update<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_)));
+    if (general_) ARAP_TIMED(tm, "computeCost", stream, (k_cost_gen<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_)));
+    else ARAP_TIMED(tm, "computeCost", stream, (k_cost<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_)));
     k_finish<<<1, 32, 0, stream>>>(pl, d_, nPCG - 1);
-    (void)tracing;
 }
 
 void StreamSolver::enqueue_gn_step(int nPCG, cudaStream_t stream, float* d_trace)
 {
     const long long nodes = 2LL * nPCG + 5;
+    if (timer_ && !d_trace) { // per-kernel timing: eager launches, one event pair each
+        launch_gn_body(nPCG, stream, true);
+        ARAP_CUDA_CHECK(cudaGetLastError());
+        launches_ += nodes;
+        return;
+    }
     if (d_trace) {
         h_.trace = d_trace;
         upload(stream);

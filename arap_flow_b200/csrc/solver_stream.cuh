@@ -3,6 +3,7 @@
 // does not fit on chip (1920x1080) and as the general-size path behind Opt.h.
 #pragma once
 #include "common.cuh"
+#include "kernel_timer.cuh"
 #include <vector>
 
 namespace arapb200 {
@@ -94,6 +95,9 @@ public:
     void set_general(bool general);
     // opt-in (never on the parity path): relative tolerance of the PCG loops; takes effect with the next bind()
     void set_pcg_rtol(float rtol);
+    // per-kernel timing (Opt_InitializationParameters.collectPerKernelTimingInfo): every launch of a Gauss-Newton step is
+    // bracketed by an event pair under the reference's kernel name; bypasses the graph.  Null = off.
+    void set_timer(KernelTimer* t) { timer_ = t; }
     bool general() const { return general_; }
     const StreamDev& host_view() const { return h_; }
     // debug / parity tests: one plane (PL_*) <-> a row-major host image; blocking
@@ -111,6 +115,7 @@ private:
     void launch_step_a(bool first, int it, cudaStream_t stream);
     void launch_step_b(int it, cudaStream_t stream);
     bool general_ = false;
+    KernelTimer* timer_ = nullptr;
     float pcg_rtol_ = 0.0f;
     int tma_ = 0;       // ARAP_STREAM_TMA=1 / 2: k_step_a_tma<true / false> instead of k_step_a<false, 16>
     bool sub16_ = true; // two 128-thread blocks per tile in the PCG kernels (ARAP_STREAM_SUB=32: one 256-thread block)

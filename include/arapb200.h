@@ -121,6 +121,14 @@ ARAPB200_API int arapb200_batch_set_option(arapb200_batch* b, const char* name, 
 struct Opt_Plan;
 ARAPB200_API int arapb200_plan_error(struct Opt_Plan* plan);
 
+/* Opt_InitializationParameters.collectPerKernelTimingInfo (ARAP/API/release/include/Opt.h:22-24, util.t:404-510): every
+ * kernel launch of a solve is bracketed by a CUDA event pair under the reference's kernel name and aggregated at the end of
+ * the solve (when Opt_ProblemStep returns 0 / Opt_ProblemSolve returns).  Such a plan runs on the streaming back-end with
+ * eager launches (a persistent kernel has nothing to time per kernel; results are the same bits).  With verbosityLevel > 0
+ * the table is printed like the reference's Timer:evaluate does; this call returns it in any case: copies at most
+ * cap - 1 characters into buf (may be NULL), returns the full length (0 = no finished solve / no timing). */
+ARAPB200_API size_t arapb200_plan_timing_report(struct Opt_Plan* plan, char* buf, size_t cap);
+
 /* Opt_ProblemDefine(state, file, "LMGPU") selects the reference's other solver kind (ARAP/API/src/o.t:121-124,
  * ARAP/API/src/solverGPUGaussNewton.t with UsesLambda(): Levenberg-Marquardt trust region around the same PCG, Q-based
  * early exit of the linear loop, step acceptance / revert; never requested by the ARAP app).  Its solver parameters
