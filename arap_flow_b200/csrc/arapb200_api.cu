@@ -461,6 +461,62 @@ int arapb200_debug_resident_profile(int W, int H, const uint8_t* mask_red, const
     });
 }
 
+// The same accounting for the first of `copies` identical problems sharing one cooperative launch: what the phases and
+// the barriers of one problem cost while its co-resident neighbours compete for the SM and for L2.
+int arapb200_debug_resident_profile_group(int W, int H, const uint8_t* mask_red, const int32_t* matches, int n_matches,
+                                          int copies, int nCont, int nGN, int nPCG, unsigned long long* prof, int* info,
+                                          float* ms)
+{
+    return guarded([&]() -> int {
+        if (copies < 1 || copies > 16) return 1;
+        const size_t N = (size_t)W * H;
+        std::vector<MatchRec> recs;
+        build_match_records(W, H, mask_red, matches, n_matches, recs);
+        DevBuf<unsigned char> dmask(N);
+        DevBuf<float2> dU(N);
+        DevBuf<float> dM(N);
+        DevBuf<MatchRec> dm(recs.size());
+        DevBuf<unsigned long long> dprof(RS_MAX_CTAS * RS_PROF_SLOTS);
+        std::vector<std::unique_ptr<DevBuf<float2>>> dX, dC;
+        std::vector<std::unique_ptr<DevBuf<float>>> dA, dcost;
+        dmask.up(mask_red);
+        if (!recs.empty()) dm.up(recs.data());
+        ARAP_CUDA_OR_RETURN(cudaMemset(dprof.p, 0, RS_MAX_CTAS * RS_PROF_SLOTS * sizeof(unsigned long long)));
+        ResidentSolver rs(W, H, copies);
+        for (int i = 0; i < copies; ++i) {
+            dX.emplace_back(new DevBuf<float2>(N));
+            dC.emplace_back(new DevBuf<float2>(N));
+            dA.emplace_back(new DevBuf<float>(N));
+            dcost.emplace_back(new DevBuf<float>((size_t)nCont * (nGN + 1)));
+            enqueue_reset_state(W, H, dmask.p, dX[i]->p, dU.p, dA[i]->p, dM.p, nullptr);
+            enqueue_target_image(W, H, dm.p, (int)recs.size(), dC[i]->p, nullptr);
+            rs.prepare_enqueue(i, W, H, dM.p, nullptr);
+        }
+        ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
+        for (int i = 0; i < copies; ++i) {
+            if (!rs.prepare_finish(i)) return 3;
+            rs.set_problem(i, dX[i]->p, dA[i]->p, dC[i]->p, 1, sqrtf(100.f), sqrtf(0.01f), dcost[i]->p, nullptr);
+        }
+        if (rs.group_size(0, copies) < copies) return 4; // they must share ONE launch
+        rs.set_profile(dprof.p);
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, nullptr);
+        rs.enqueue_group(0, copies, nCont, nGN, nPCG, nullptr);
+        cudaEventRecord(e1, nullptr);
+        ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
+        if (ms) cudaEventElapsedTime(ms, e0, e1);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        if (int st = rs.status(nullptr)) return 100 + st;
+        dprof.down(prof);
+        ARAP_CUDA_OR_RETURN(cudaDeviceSynchronize());
+        if (info) { info[0] = rs.n_strips(); info[1] = rs.ctas(); info[2] = rs.warps(); }
+        return 0;
+    });
+}
+
 } // extern "C"
 
 // device-side sincos / exact-sum probes

@@ -26,7 +26,7 @@ ARAP_SYMBOLS = [
     "arapb200_batch_create", "arapb200_batch_destroy", "arapb200_batch_submit", "arapb200_batch_run",
     "arapb200_batch_timing", "arapb200_batch_launches", "arapb200_debug_gn_solve", "arapb200_debug_eval_jtf",
     "arapb200_debug_apply_jtj", "arapb200_debug_cost", "arapb200_debug_sincos", "arapb200_debug_exact_sum",
-    "arapb200_debug_resident_profile", "arapb200_flatten", "arapb200_filter_matches", "arapb200_segment_mask",
+    "arapb200_debug_resident_profile", "arapb200_debug_resident_profile_group", "arapb200_flatten", "arapb200_filter_matches", "arapb200_segment_mask",
     "arapb200_batch_set_option", "arapb200_batch_resident_count", "arapb200_debug_wide_sum", "arapb200_plan_error", "arapb200_plan_lm_info", "arapb200_plan_timing_report",
     "arapb200_batch_launch_info",
 ]
@@ -308,8 +308,9 @@ def debug_cost(X, A, U, Cn, M, wf, wr):
     return np.float32(c.value)
 
 
-def debug_resident_profile(mask_red, matches, nCont, nGN, nPCG):
-    """Cycle accounting of the resident kernel (thread 0 of every CTA).  Returns (prof[G, 8], info, ms)."""
+def debug_resident_profile(mask_red, matches, nCont, nGN, nPCG, copies=1):
+    """Cycle accounting of the resident kernel (thread 0 of every CTA) for one problem, or for the first of `copies`
+    identical problems sharing one cooperative launch.  Returns (prof[G, 16], info, ms)."""
     H, W = mask_red.shape
     m = _c(matches, np.int32).reshape(-1, 4)
     prof = np.zeros((160, 16), np.uint64)
@@ -318,8 +319,14 @@ def debug_resident_profile(mask_red, matches, nCont, nGN, nPCG):
     L = load()
     L.arapb200_debug_resident_profile.argtypes = [C.c_int, C.c_int, _u8p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int,
                                                   C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)]
-    _check(L.arapb200_debug_resident_profile(W, H, _c(mask_red, np.uint8), m, len(m), nCont, nGN, nPCG,
-                                             prof.ctypes.data, info, C.byref(ms)), "debug_resident_profile")
+    L.arapb200_debug_resident_profile_group.argtypes = [C.c_int, C.c_int, _u8p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                        C.c_int, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)]
+    if copies > 1:
+        _check(L.arapb200_debug_resident_profile_group(W, H, _c(mask_red, np.uint8), m, len(m), copies, nCont, nGN, nPCG,
+                                                       prof.ctypes.data, info, C.byref(ms)), "debug_resident_profile_group")
+    else:
+        _check(L.arapb200_debug_resident_profile(W, H, _c(mask_red, np.uint8), m, len(m), nCont, nGN, nPCG,
+                                                 prof.ctypes.data, info, C.byref(ms)), "debug_resident_profile")
     G = info[1]
     return prof[:G], dict(strips=info[0], ctas=info[1], warps=info[2]), ms.value
 

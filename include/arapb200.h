@@ -159,6 +159,11 @@ ARAPB200_API int arapb200_debug_cost(int W, int H, const float* X, const float* 
 ARAPB200_API int arapb200_debug_resident_profile(int W, int H, const uint8_t* mask_red, const int32_t* matches,
                                                  int n_matches, int nCont, int nGN, int nPCG,
                                                  unsigned long long* prof, int* info, float* ms);
+/* the same for the first of `copies` (1..16) identical problems that share ONE cooperative launch: what one problem's
+ * phases and barriers cost next to co-resident neighbours; returns 4 when they do not fit one launch */
+ARAPB200_API int arapb200_debug_resident_profile_group(int W, int H, const uint8_t* mask_red, const int32_t* matches,
+                                                       int n_matches, int copies, int nCont, int nGN, int nPCG,
+                                                       unsigned long long* prof, int* info, float* ms);
 /* contract sincos and exact sum on the device */
 ARAPB200_API int arapb200_debug_sincos(int n, const float* a, float* s, float* c);
 ARAPB200_API int arapb200_debug_exact_sum(size_t n, const float* t, float* sum);

@@ -7,13 +7,14 @@ from arap_flow_b200 import lib, synth
 
 cfg = sys.argv[1] if len(sys.argv) > 1 else "C1"
 nPCG = int(sys.argv[2]) if len(sys.argv) > 2 else 400
+copies = int(sys.argv[3]) if len(sys.argv) > 3 else 1   # > 1: the first of that many co-resident identical problems
 sp = synth.config(cfg)
 for rep in range(2):
-    prof, info, ms = lib.debug_resident_profile(sp.masks[0], sp.matches, 1, 2, nPCG)
+    prof, info, ms = lib.debug_resident_profile(sp.masks[0], sp.matches, 1, 2, nPCG, copies=copies)
 it = 2 * nPCG
 names = ["phase1(JTJ)", "phase2(update)", "phase3(p,halo)", "other", "bar:arrive", "bar:poll", "bar:fold", None,
          " arrive:limbs", " arrive:redux+stage", " arrive:cta-sync", " arrive:sum+red", " fold:decode"]
-print(f"{cfg}: {info}, launch {ms:.3f} ms, {ms * 1e3 / it:.2f} us per PCG iteration, barriers/CTA {int(prof[0, 7])}")
+print(f"{cfg} x{copies}: {info}, launch {ms:.3f} ms, {ms * 1e3 / it:.2f} us per PCG iteration, barriers/CTA {int(prof[0, 7])}")
 clk = 1.9e3  # cycles per us (approx.)
 for i, n in enumerate(names):
     if n is None:
