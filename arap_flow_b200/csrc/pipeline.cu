@@ -168,6 +168,7 @@ void BatchPipeline::solve_streaming(const HostProblem& hp, Dev& d)
     const long long l0 = solver_->launches();
     const float wf = sqrtf(100.0f), wr = sqrtf(0.01f); // CombinedSolver.h:172-177
     solver_->set_pcg_rtol(pcg_rtol_);
+    solver_->set_gn_rtol(gn_rtol_);
     solver_->bind(d.X, d.A, d.U, d.C, d.M, wf, wr, stream_);
     for (int t = 0; t < nCont_; ++t) {
         const float alpha = (float)(t + 1) / (float)nCont_; // CombinedSolver.h:199-201
@@ -301,11 +302,6 @@ int BatchPipeline::run(const HostProblem* problems, int count)
             continue;
         }
         if (!d.resident) {
-            if (gn_rtol_ > 0.0f && !warned_rtol_) { // never silently: the caller asked for an early exit
-                warned_rtol_ = true;
-                fprintf(stderr, "arapb200: warning: gn_rtol is honoured by the resident back-end only; a %dx%d problem streams "
-                                "and runs every Gauss-Newton step (pcg_rtol is honoured)\n", problems[i].W, problems[i].H);
-            }
             solve_streaming(problems[i], d);
             ++i;
             continue;

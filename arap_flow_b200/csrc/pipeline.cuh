@@ -58,7 +58,7 @@ public:
         for (int i = 0; i < 5; ++i) out[1 + i] = sh[i];
     }
     int max_problems() const { return (int)dev_.size(); }
-    // opt-in early exit of the PCG loops (resident back-end only; the streaming graph keeps the fixed budget)
+    // opt-in early exits of the PCG loops / of the Gauss-Newton steps (both back-ends)
     void set_pcg_rtol(float rtol);
     void set_gn_rtol(float rtol);
     void set_cluster_barrier(bool on) { if (resident_) resident_->set_cluster_barrier(on); }
@@ -95,7 +95,6 @@ private:
     float ms_total_ = 0, ms_solve_ = 0, ms_warp_ = 0;
     int n_resident_ = 0, group_size_ = 0;
     float pcg_rtol_ = 0.0f, gn_rtol_ = 0.0f;
-    bool warned_rtol_ = false;
 };
 
 // shared small kernels

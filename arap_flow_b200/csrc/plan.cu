@@ -134,10 +134,11 @@ void GnPlan::choose_backend(void** pp)
         stream_->set_general(general_);
         stream_->set_timer(collect_timing_ ? timer_.get() : nullptr);
         stream_->set_pcg_rtol(general_ ? 0.0f : pcg_rtol_);
-        if ((gn_rtol_ > 0.0f || (general_ && pcg_rtol_ > 0.0f)) && !warned_rtol_) {
+        stream_->set_gn_rtol(general_ ? 0.0f : gn_rtol_);
+        if (general_ && (gn_rtol_ > 0.0f || pcg_rtol_ > 0.0f) && !warned_rtol_) { // never silently
             warned_rtol_ = true;
-            fprintf(stderr, "arapb200: warning: gn_rtol (and, for a non-grid UrShape, pcg_rtol) is honoured by the resident "
-                            "back-end only; this %dx%d problem streams\n", W_, H_);
+            fprintf(stderr, "arapb200: warning: pcg_rtol / gn_rtol are not honoured for a non-grid UrShape (general-d kernels): "
+                            "this %dx%d problem runs the fixed budget\n", W_, H_);
         }
     }
 }

@@ -129,7 +129,9 @@ __global__ void __launch_bounds__(ST_THREADS) k_prep(const StreamDev* __restrict
     if (bad) atomicAdd(&dp.sc->bad_u, 1u);
     any = __syncthreads_or(any);
     if (threadIdx.x == 0) dp.tile_active[blockIdx.x] = any ? 1 : 0;
-    if (blockIdx.x == 0 && threadIdx.x == 0) { dp.sc->conv = 0u; dp.sc->stop = -1.0f; } // opt-in early exit: re-armed per GN step
+    // opt-in early exits: the PCG one is re-armed per Gauss-Newton step; a finished Gauss-Newton loop (gn_done) keeps the
+    // step's PCG kernels switched off
+    if (blockIdx.x == 0 && threadIdx.x == 0) { dp.sc->conv = dp.sc->gn_done ? 1u : 0u; dp.sc->stop = -1.0f; }
 }
 
 // Stage (X_x, X_y, cos, sin) of a tile + halo.  Inactive / out-of-image entries are never used.
@@ -615,7 +617,10 @@ __global__ void __launch_bounds__(SUB * 8, ARAP_ST_MINB_B) k_step_b(const __grid
             s_alpha = (den > 0.0f) ? num / den : 0.0f; // :456-459
             if (RT) {
                 // it == 0: num is r.p of PCGInit1 -> the threshold of this Gauss-Newton step; later: num is r.z of iteration it-1
-                if (it == 0) { if (blockIdx.x == 0) pl.sc->stop = (dpp->pcg_rtol2 > 0.0f) ? dpp->pcg_rtol2 * num : -1.0f; s_skip = 0; }
+                if (it == 0) {
+                    s_skip = pl.sc->conv != 0u ? 1 : 0; // set by k_prep: the Gauss-Newton loop has ended (gn_rtol)
+                    if (blockIdx.x == 0 && !s_skip) pl.sc->stop = (dpp->pcg_rtol2 > 0.0f) ? dpp->pcg_rtol2 * num : -1.0f;
+                }
                 else s_skip = (pl.sc->conv != 0u || num <= pl.sc->stop) ? 1 : 0;
             }
             if (blockIdx.x == 0 && dpp->trace && !(RT && s_skip)) {
@@ -921,11 +926,22 @@ __global__ void __launch_bounds__(ST_THREADS) k_cost_gen(const StreamDev* __rest
 }
 
 // Cost accumulator -> scalars; with tracing, also the last iteration's r.z
+// is_init: the cost of Opt_ProblemInit (a new Gauss-Newton loop starts); otherwise the cost after a step, which the opt-in
+// gn_rtol rule compares with the previous one (same rule as the resident kernel and oracle/arap_oracle.c)
 __global__ void __launch_bounds__(32) k_finish(const __grid_constant__ StreamPlanes pl, const StreamDev* __restrict__ dpp,
-                                               int last_it)
+                                               int last_it, int is_init)
 {
     const float v = wide_round(fetch2(pl, ST_ACC_COST, bn_set(last_it < 0 ? 0 : last_it)));
-    if (threadIdx.x == 0) pl.sc->cost = 0.5f * v;
+    if (threadIdx.x == 0) {
+        const float c = 0.5f * v;
+        StreamScalars* sc = pl.sc;
+        sc->cost = c;
+        if (is_init) { sc->gn_prev = c; sc->gn_done = 0u; }
+        else if (dpp->gn_rtol > 0.0f && !sc->gn_done) {
+            if (!((sc->gn_prev - c) > dpp->gn_rtol * sc->gn_prev)) sc->gn_done = 1u; // this step gained too little
+            sc->gn_prev = c;
+        }
+    }
     if (threadIdx.x == 16 && last_it >= 0 && dpp->trace) dpp->trace[3 * last_it + 2] = v;
 }
 
@@ -1034,6 +1050,7 @@ void StreamSolver::bind(float2* X, float* A, const float2* U, const float2* C, c
     h_.wf = wf; h_.wr = wr; h_.wf2 = wf * wf; h_.wr2 = wr * wr;
     h_.trace = nullptr;
     h_.pcg_rtol2 = pcg_rtol_ * pcg_rtol_;
+    h_.gn_rtol = general_ ? 0.0f : gn_rtol_;
     upload(stream);
 }
 
@@ -1058,7 +1075,7 @@ void StreamSolver::launch_step_a(bool first, int it, cudaStream_t stream)
         if (first) k_step_a_gen<true><<<h_.ntiles, ST_THREADS, 0, stream>>>(pl, d_, it);
         else k_step_a_gen<false><<<h_.ntiles, ST_THREADS, 0, stream>>>(pl, d_, it);
     } else {
-        const bool rt = pcg_rtol_ > 0.0f; // opt-in early exit: its own instantiations
+        const bool rt = this->rt(); // opt-in early exits: their own instantiations
         if (sub16_) {
             if (first) k_step_a<true, 16><<<2 * h_.ntiles, 128, 0, stream>>>(pl, d_, it);
             else if (rt) k_step_a<false, 16, true><<<2 * h_.ntiles, 128, 0, stream>>>(pl, d_, it);
@@ -1076,7 +1093,7 @@ void StreamSolver::launch_step_a(bool first, int it, cudaStream_t stream)
 void StreamSolver::launch_step_b(int it, cudaStream_t stream)
 {
     const StreamPlanes& pl = h_;
-    const bool rt = pcg_rtol_ > 0.0f && !general_;
+    const bool rt = this->rt();
     if (sub16_) {
         if (rt) k_step_b<16, true><<<2 * h_.ntiles, 128, 0, stream>>>(pl, d_, it);
         else k_step_b<16><<<2 * h_.ntiles, 128, 0, stream>>>(pl, d_, it);
@@ -1089,10 +1106,21 @@ void StreamSolver::launch_step_b(int it, cudaStream_t stream)
 void StreamSolver::set_pcg_rtol(float rtol)
 {
     rtol = rtol > 0.0f ? rtol : 0.0f;
-    if ((rtol > 0.0f) != (pcg_rtol_ > 0.0f) && graph_) { // other kernel instantiations: re-capture
+    const bool was = rt();
+    pcg_rtol_ = rtol;
+    if (rt() != was && graph_) { // other kernel instantiations: re-capture
         cudaGraphExecDestroy(graph_); graph_ = nullptr; graph_npcg_ = -1;
     }
-    pcg_rtol_ = rtol;
+}
+
+void StreamSolver::set_gn_rtol(float rtol)
+{
+    rtol = rtol > 0.0f ? rtol : 0.0f;
+    const bool was = rt();
+    gn_rtol_ = rtol;
+    if (rt() != was && graph_) {
+        cudaGraphExecDestroy(graph_); graph_ = nullptr; graph_npcg_ = -1;
+    }
 }
 
 void StreamSolver::set_general(bool general)
@@ -1117,7 +1145,7 @@ void StreamSolver::enqueue_init(cudaStream_t stream)
     ARAP_TIMED(timer_, "precompute", stream, enqueue_prep(stream));
     if (general_) ARAP_TIMED(timer_, "computeCost", stream, (k_cost_gen<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_)));
     else ARAP_TIMED(timer_, "computeCost", stream, (k_cost<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_)));
-    k_finish<<<1, 32, 0, stream>>>(pl, d_, -1);
+    k_finish<<<1, 32, 0, stream>>>(pl, d_, -1, 1);
     launches_ += 2;
     ARAP_CUDA_CHECK(cudaGetLastError());
 }
@@ -1139,7 +1167,7 @@ void StreamSolver::launch_gn_body(int nPCG, cudaStream_t stream, bool tracing)
     ARAP_TIMED(tm, "PCGLinearUpdate", stream, (k_update<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_)));
     if (general_) ARAP_TIMED(tm, "computeCost", stream, (k_cost_gen<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_)));
     else ARAP_TIMED(tm, "computeCost", stream, (k_cost<<<h_.ntiles, ST_THREADS, 0, stream>>>(d_)));
-    k_finish<<<1, 32, 0, stream>>>(pl, d_, nPCG - 1);
+    k_finish<<<1, 32, 0, stream>>>(pl, d_, nPCG - 1, 0);
 }
 
 void StreamSolver::enqueue_gn_step(int nPCG, cudaStream_t stream, float* d_trace)

@@ -20,7 +20,11 @@ struct StreamScalars {
     // "converged" flag that turns the remaining k_step_a / k_step_b launches of the captured graph into no-ops
     float stop;
     unsigned conv;
-    unsigned pad;
+    // opt-in early exit of the Gauss-Newton steps: once a step lowers the cost by less than gn_rtol (relative), gn_done makes
+    // every later step of the same Opt_ProblemSolve a no-op (k_prep raises conv, delta stays 0, the cost repeats)
+    unsigned gn_done;
+    float gn_prev;
+    unsigned pad[3];
 };
 
 // Accumulator sets (common.cuh: wide fixed-point accumulators).  r.z of PCG iteration j lives in set (j + 3) % 3
@@ -67,6 +71,7 @@ struct StreamDev : StreamPlanes {
     const float* M;       // Mask
     float wf, wr, wf2, wr2;
     float* trace;         // optional: (den, num, bnum) per PCG iteration of the current GN step
+    float gn_rtol;        // 0 = every Gauss-Newton step runs; > 0: see StreamScalars::gn_done
     float pcg_rtol2;      // 0 = fixed budget (reference behaviour); > 0: the PCG loop ends once r.z <= pcg_rtol2 * (r.z at PCGInit1)
 };
 
@@ -95,6 +100,7 @@ public:
     void set_general(bool general);
     // opt-in (never on the parity path): relative tolerance of the PCG loops; takes effect with the next bind()
     void set_pcg_rtol(float rtol);
+    void set_gn_rtol(float rtol);
     // per-kernel timing (Opt_InitializationParameters.collectPerKernelTimingInfo): every launch of a Gauss-Newton step is
     // bracketed by an event pair under the reference's kernel name; bypasses the graph.  Null = off.
     void set_timer(KernelTimer* t) { timer_ = t; }
@@ -116,7 +122,8 @@ private:
     void launch_step_b(int it, cudaStream_t stream);
     bool general_ = false;
     KernelTimer* timer_ = nullptr;
-    float pcg_rtol_ = 0.0f;
+    float pcg_rtol_ = 0.0f, gn_rtol_ = 0.0f;
+    bool rt() const { return (pcg_rtol_ > 0.0f || gn_rtol_ > 0.0f) && !general_; } // the early-exit kernel instantiations
     int tma_ = 0;       // ARAP_STREAM_TMA=1 / 2: k_step_a_tma<true / false> instead of k_step_a<false, 16>
     bool sub16_ = true; // two 128-thread blocks per tile in the PCG kernels (ARAP_STREAM_SUB=32: one 256-thread block)
     StreamDev h_{};

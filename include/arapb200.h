@@ -101,7 +101,7 @@ ARAPB200_API int arapb200_batch_launch_info(arapb200_batch* b, int* info6);
  *   streaming one turns the remaining kernels of its captured graph into no-ops).
  *   "gn_rtol": 0 <= value < 1.  > 0: the Gauss-Newton steps of a continuation step end as soon as one of them lowers
  *   the cost by less than value (relative) instead of always running nIterations steps; the skipped entries of
- *   out_costs repeat the last cost.  Same scope and caveats as "pcg_rtol".
+ *   out_costs repeat the last cost.  Same scope and caveats as "pcg_rtol" (both back-ends).
  *   "cluster_barrier": 1 = problems that fit one thread-block cluster (<= 16 CTAs of <= 12 strips) run with a cluster-scope
  *   barrier (limb sums pushed through distributed shared memory, mbarrier completion); 0 (default) = every resident
  *   problem uses the L2 barrier.  Same results bit for bit; measured slower on B200, kept as an option.

@@ -486,7 +486,21 @@ def test_opt_in_pcg_tolerance_n4(oracle):
     o = bs.submit(0, sp.rgb, sp.masks[0], sp.matches)
     bs.run()
     assert _eq(o["flow"], oracle.flow(Xe)) and _eq(o["costs"], ce)     # (no time bound: at this size the graph is launch-bound)
+    bs.set_option("gn_rtol", 1e-2)                                      # ... and gn_rtol, alone or with pcg_rtol
+    o = bs.submit(0, sp.rgb, sp.masks[0], sp.matches)
+    bs.run()
+    assert _eq(o["flow"], oracle.flow(Xe2)) and _eq(o["costs"], ce2)
     bs.set_option("pcg_rtol", 0.0)
+    o = bs.submit(0, sp.rgb, sp.masks[0], sp.matches)
+    bs.run()
+    try:
+        oracle.set_rtol(0.0, 1e-2)
+        Xe3, Ae3, ce3 = oracle.solve(sp.masks[0], sp.matches, **kw)
+    finally:
+        oracle.set_rtol(0.0, 0.0)
+    assert _eq(o["flow"], oracle.flow(Xe3)) and _eq(o["costs"], ce3)
+    assert not _eq(ce3, full["costs"])                                  # the rule did fire
+    bs.set_option("gn_rtol", 0.0)
     o = bs.submit(0, sp.rgb, sp.masks[0], sp.matches)
     bs.run()
     assert _eq(o["flow"], full["flow"]) and _eq(o["costs"], full["costs"])
