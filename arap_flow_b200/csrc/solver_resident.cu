@@ -65,6 +65,11 @@ constexpr int S_MIN = -100, S_MAX = 100;
 #ifndef ARAP_RS_SUM_UNROLL
 #define ARAP_RS_SUM_UNROLL 0 // 1: the CTA-level sum over the warps' limb sums is unrolled (all shared-memory loads in flight)
 #endif
+#ifndef ARAP_RS_DEFER_DELTA
+#define ARAP_RS_DEFER_DELTA 2 // delta += alpha p feeds no reduction: 1 = it is done AFTER the arrival at the second barrier, under the
+                              // barrier's latency, everywhere; 2 = in the 128-register variants only (fewer live values in
+                              // phase 2: C1s +1.4 %, C3 +1.3 %; at 168 registers it delays the poller: lone problem -1.4 %); 0 = never
+#endif
 #ifndef ARAP_RS_G1_LOCAL
 #define ARAP_RS_G1_LOCAL 0   // 1: a problem that runs in ONE CTA keeps its barrier in shared memory (no L2 round trip)
 #endif
@@ -825,6 +830,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
 
     constexpr bool LEAN = (MINB >= 3);               // the 128-register variants
     constexpr bool HOIST = ARAP_RS_HOIST && (!LEAN || ARAP_RS_HOIST_LEAN > 0);
+    constexpr bool DEFER = ARAP_RS_DEFER_DELTA == 1 || (ARAP_RS_DEFER_DELTA == 2 && LEAN);
     constexpr int HG = (LEAN && ARAP_RS_HOIST_LEAN > 0) ? ARAP_RS_HOIST_LEAN : RS_STRIP_H; // rows whose loads are issued together
     Cta c;
     c.u4 = ARAP_RS_SUM_UNROLL4 && (ARAP_RS_SUM_UNROLL4 > 1 || !LEAN);
@@ -1109,19 +1115,23 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
 #pragma unroll
                     for (int j = 0; j < HG; ++j) {
                         const int k = kb + j;
-                        const float4 e = s.own[(k + 1) * TW + lane + 1];
-                        const float* Dk = s.D + k * 32;
-                        hx[j] = e.x; hy[j] = e.y;
-                        hd0[j] = Dk[0 * RS_STRIP_H * 32]; hd1[j] = Dk[1 * RS_STRIP_H * 32]; hd2[j] = Dk[2 * RS_STRIP_H * 32];
+                        if constexpr (!DEFER) {
+                            const float4 e = s.own[(k + 1) * TW + lane + 1];
+                            const float* Dk = s.D + k * 32;
+                            hx[j] = e.x; hy[j] = e.y;
+                            hd0[j] = Dk[0 * RS_STRIP_H * 32]; hd1[j] = Dk[1 * RS_STRIP_H * 32]; hd2[j] = Dk[2 * RS_STRIP_H * 32];
+                        }
                         hpre[j] = s.pre[k * 32];
                     }
 #pragma unroll
                     for (int j = 0; j < HG; ++j) {
                         const int k = kb + j;
-                        float* Dk = s.D + k * 32;
-                        Dk[0 * RS_STRIP_H * 32] = fmaf(alpha, hx[j], hd0[j]);
-                        Dk[1 * RS_STRIP_H * 32] = fmaf(alpha, hy[j], hd1[j]);
-                        Dk[2 * RS_STRIP_H * 32] = fmaf(alpha, pa[k], hd2[j]);
+                        if constexpr (!DEFER) {
+                            float* Dk = s.D + k * 32;
+                            Dk[0 * RS_STRIP_H * 32] = fmaf(alpha, hx[j], hd0[j]);
+                            Dk[1 * RS_STRIP_H * 32] = fmaf(alpha, hy[j], hd1[j]);
+                            Dk[2 * RS_STRIP_H * 32] = fmaf(alpha, pa[k], hd2[j]);
+                        }
                         r0[k] = fmaf(-alpha, q0[k], r0[k]);
                         r1[k] = fmaf(-alpha, q1[k], r1[k]);
                         r2[k] = fmaf(-alpha, qa[k], r2[k]);
@@ -1135,11 +1145,13 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                 } else {
 #pragma unroll
                 for (int k = 0; k < RS_STRIP_H; ++k) {
-                    const float4 e = s.own[(k + 1) * TW + lane + 1];
-                    float* Dk = s.D + k * 32;
-                    Dk[0 * RS_STRIP_H * 32] = fmaf(alpha, e.x, Dk[0 * RS_STRIP_H * 32]);
-                    Dk[1 * RS_STRIP_H * 32] = fmaf(alpha, e.y, Dk[1 * RS_STRIP_H * 32]);
-                    Dk[2 * RS_STRIP_H * 32] = fmaf(alpha, pa[k], Dk[2 * RS_STRIP_H * 32]);
+                    if constexpr (!DEFER) {
+                        const float4 e = s.own[(k + 1) * TW + lane + 1];
+                        float* Dk = s.D + k * 32;
+                        Dk[0 * RS_STRIP_H * 32] = fmaf(alpha, e.x, Dk[0 * RS_STRIP_H * 32]);
+                        Dk[1 * RS_STRIP_H * 32] = fmaf(alpha, e.y, Dk[1 * RS_STRIP_H * 32]);
+                        Dk[2 * RS_STRIP_H * 32] = fmaf(alpha, pa[k], Dk[2 * RS_STRIP_H * 32]);
+                    }
                     r0[k] = fmaf(-alpha, q0[k], r0[k]);
                     r1[k] = fmaf(-alpha, q1[k], r1[k]);
                     r2[k] = fmaf(-alpha, qa[k], r2[k]);
@@ -1154,6 +1166,30 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                 RS_TICK(1);
                 long long tb0 = 0, tb1 = 0;
                 arrive_t<CL>(c, gs0, gs1, S_bnum, tb0, tb1);
+                if constexpr (DEFER) {
+                    // delta += alpha p feeds no reduction: it runs here, under the latency of the barrier just arrived at
+                    // (p -- the tile entries and pa -- does not change before phase 3)
+#pragma unroll
+                    for (int kb = 0; kb < RS_STRIP_H; kb += HG) {
+                        float hx[HG], hy[HG], hd0[HG], hd1[HG], hd2[HG];
+#pragma unroll
+                        for (int j = 0; j < HG; ++j) {
+                            const int k = kb + j;
+                            const float4 e = s.own[(k + 1) * TW + lane + 1];
+                            const float* Dk = s.D + k * 32;
+                            hx[j] = e.x; hy[j] = e.y;
+                            hd0[j] = Dk[0 * RS_STRIP_H * 32]; hd1[j] = Dk[1 * RS_STRIP_H * 32]; hd2[j] = Dk[2 * RS_STRIP_H * 32];
+                        }
+#pragma unroll
+                        for (int j = 0; j < HG; ++j) {
+                            const int k = kb + j;
+                            float* Dk = s.D + k * 32;
+                            Dk[0 * RS_STRIP_H * 32] = fmaf(alpha, hx[j], hd0[j]);
+                            Dk[1 * RS_STRIP_H * 32] = fmaf(alpha, hy[j], hd1[j]);
+                            Dk[2 * RS_STRIP_H * 32] = fmaf(alpha, pa[k], hd2[j]);
+                        }
+                    }
+                }
                 if (pub) fetch_halo(P, &ctl, s, lane, seq, false); // overlaps the barrier latency
                 const float bnum = grid_finish<CL>(c, gs0, gs1, S_bnum, ok, tb0, tb1);
                 RS_TOCK();

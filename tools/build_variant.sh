@@ -11,7 +11,7 @@ out=$root/arap_flow_b200/variants
 mkdir -p "$bld" "$out"
 flags="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -DARAP_RS_STRIP_H=${RS_H:-8} $defs -lineinfo -fmad=false -prec-div=true -prec-sqrt=true -Xcompiler -fPIC,-fvisibility=hidden"
 objs=""
-for f in solver_stream solver_resident plan pipeline warp composite opt_api arapb200_api; do
+for f in solver_stream solver_resident solver_lm plan pipeline warp composite opt_api arapb200_api; do
   ( /usr/local/cuda/bin/nvcc $flags -c -o "$bld/$f.o" "$src/$f.cu" 2> "$bld/$f.log" || { cat "$bld/$f.log"; exit 1; } ) &
   objs="$objs $bld/$f.o"
 done
