@@ -62,7 +62,7 @@ static void usage()
     puts("./arap_deform --serve SPOOLDIR [--warm WxH]   (resident worker: runs the list files that clients with ARAP_SERVER=SPOOLDIR");
     puts("                                               submit; --warm pre-builds the plan and buffers for that image size)");
     puts("Environment: ARAP_PLAN = path of the ARAP energy file (default ./arap_plan.t); CUDA_VISIBLE_DEVICES selects the GPU;");
-    puts("             ARAP_BATCH = problems solved together (default 9: three cooperative launches of three)");
+    puts("             ARAP_BATCH = problems solved together (default 8: two cooperative launches of four)");
     puts("             ARAP_PCG_RTOL = opt-in relative PCG tolerance, e.g. 1e-3 (default 0: fixed 400 iterations)");
     puts("             ARAP_SOLVER = gaussNewtonGPU (default) | LMGPU (opt-in: trust region + Q-based exit of the linear loops)");
     puts("             ARAP_GN_RTOL = opt-in relative cost-decrease tolerance of the Gauss-Newton steps (default 0: fixed 8 steps)");
@@ -101,7 +101,7 @@ static bool read_list(const char* path, std::vector<InputPaths>& lines)
 struct Settings {
     // the solver budget is a compile-time constant of the reference: main.cpp:215-221
     int nCont = 19, nGN = 8, nPCG = 400;
-    int batch = 9;
+    int batch = 8;
     // opt-in, off by default: convergence-aware PCG loops (changes results; include/arapb200.h)
     double pcg_rtol = 0.0, gn_rtol = 0.0;
     bool lm = false;     // ARAP_SOLVER=LMGPU: the reference's other solver kind (o.t:121-124), default gaussNewtonGPU

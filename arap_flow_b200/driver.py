@@ -53,7 +53,7 @@ class Server:
     para_gen.py keeps calling the binary with a list file (para_gen.py:190-195); with ARAP_SERVER set that call is a thin
     client of this worker."""
 
-    def __init__(self, gpu: int, spool: str, arap_bin: str = ARAP_BIN, plan: str = PLAN, batch: int = 9, timeout: float = 120.0,
+    def __init__(self, gpu: int, spool: str, arap_bin: str = ARAP_BIN, plan: str = PLAN, batch: int = 8, timeout: float = 120.0,
                  warm=None):
         """warm = (W, H): build the plan and the buffers for that image size at start-up (para_gen's --size), so that the
         first dispatch already runs at steady state."""
@@ -90,7 +90,7 @@ class Server:
         self.close()
 
 
-def do_arap(items: Sequence[Item], gpu: int, tmp_dir: str, arap_bin: str = ARAP_BIN, plan: str = PLAN, batch: int = 9,
+def do_arap(items: Sequence[Item], gpu: int, tmp_dir: str, arap_bin: str = ARAP_BIN, plan: str = PLAN, batch: int = 8,
             server: str = None):
     """para_gen.do_arap (para_gen.py:178-200): write a temporary list file, run the solver binary on one GPU, assert
     a zero exit code, always remove the list file.  Returns the elapsed seconds.  `server` = spool directory of a

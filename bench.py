@@ -311,7 +311,9 @@ def main():
     # resident back-end: 3 (168 registers) or 4 (128 registers) C1-sized problems share one cooperative launch; 9 = three
     # launches of three, measured 2 % faster than two launches of four (profiles/r1_batch_choice.txt).  Smaller problems: as
     # many as fill the CTA slots of ONE launch (profiles/r2_batch_sweep.txt): 3 multi-segment pairs = 12 problems, 14 C1s pairs
-    DEFAULT_B = {"C2": 3, "C1s": 14}
+    # C1: two launches of FOUR co-resident problems (128-register variant; 3 x 3 at 168 registers was the default until the
+    # lean variants got their own load hoisting and deferred delta update: profiles/r2_batch_sweep.txt)
+    DEFAULT_B = {"C1": 8, "C2": 3, "C1s": 14}
     B = args.batch if args.batch > 0 else (1 if (args.backend == "stream" or args.workload == "C4" or opt_h) else
                                            DEFAULT_B.get(args.workload, 9))
     pairs = make_pairs(args.workload, B, first=rank * B)
@@ -418,7 +420,7 @@ def main():
             h2d = int(len(problems) * (4 * N) + nseg * sum(16 * (len(p.matches) + 2 * (W + H)) for p in pairs))
             d2h = int(len(problems) * (12 * N + 4 * NCONT * (NGN + 1)))
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": (measured_traffic(3 if B % 3 == 0 else 4) if not streamed and not opt_h and (B % 3 == 0 or B % 4 == 0) and args.workload == "C1" else None),
+                "traffic": (measured_traffic(4 if B % 4 == 0 else 3) if not streamed and not opt_h and (B % 3 == 0 or B % 4 == 0) and args.workload == "C1" else None),
                 "peak_source": peak_src}
         if streamed:
             roof["kernel"] = "k_step_a + k_step_b (streaming PCG iteration; 156 B/active px/iteration algorithmic)"

@@ -77,7 +77,7 @@ def _run_and_check(wl, seeds, expect_variant=None, expect_grid_y=None, backend=l
 # Kernel variants are named by their launch bounds (max threads, min CTAs per SM): with 128-thread CTAs the (384, 1)
 # instantiation is the 168-register, spill-free one (three CTAs per SM) and (160, 3) the 128-register one (four).
 def test_c1_three_coresident_problems_168_register_variant():
-    """bench.py's default C1 line: launches of three co-resident problems, (G, 3) grid, 168 registers"""
+    """launches of three co-resident problems, (G, 3) grid, 168 registers (bench.py --batch 9)"""
     _run_and_check("C1", [1000, 1001, 1002], expect_variant=(384, 1), expect_grid_y=3)
 
 
@@ -85,8 +85,13 @@ def test_c1_four_coresident_problems_128_register_variant():
     _run_and_check("C1", [1000, 1001, 1002, 1003], expect_variant=(160, 3), expect_grid_y=4)
 
 
-def test_c1_default_bench_batch_of_nine():
-    """exactly bench.py --workload C1 (rank 0): Batch(854, 480, 9), seeds 1000..1008, three launches of three"""
+def test_c1_default_bench_batch_of_eight():
+    """exactly bench.py --workload C1 (rank 0): Batch(854, 480, 8), seeds 1000..1007, two launches of four (128 registers)"""
+    _run_and_check("C1", list(range(1000, 1008)), expect_variant=(160, 3), expect_grid_y=4)
+
+
+def test_c1_batch_of_nine():
+    """Batch(854, 480, 9), seeds 1000..1008: three launches of three (168 registers)"""
     _run_and_check("C1", list(range(1000, 1009)), expect_variant=(384, 1), expect_grid_y=3)
 
 

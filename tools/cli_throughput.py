@@ -55,7 +55,7 @@ def main():
             per = a.pairs or 8
             items = write_items(d, wl, a.dispatches * per)
             dispatches = [items[k * per:(k + 1) * per] for k in range(a.dispatches)]
-            batch = a.batch or (9 if per >= 9 else per)
+            batch = a.batch or (8 if per >= 8 else per)
             # (a) the reference's way: one process per dispatch
             if not a.served_only:
                 t0 = time.time()

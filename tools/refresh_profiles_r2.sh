@@ -16,10 +16,11 @@ timeout 900 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/
 python -c "import json;d=json.load(open('gpurun_out/r2_bench_reference.json'));print('reference',d['value'],d['ms_per_step'],d['extrapolated'],d['cpu_baseline']['cores'])"
 # launch list of the default bench command
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2_bench_launch_list.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/r2_ncu_bench.log 2>&1 || echo "ncu launch list failed"
-# the dominant kernel, full set, on the default bench's launch shape (3 co-resident C1 problems) at a reduced schedule
-timeout 200 python tools/ncu_target.py resident C1 50 3 > gpurun_out/r2_ncu_target_plain.log 2>&1 && \
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_resident --launch-skip 1 --launch-count 1 -f -o gpurun_out/r2_resident_b3 python tools/ncu_target.py resident C1 50 3 > gpurun_out/r2_ncu_full.log 2>&1 || echo "ncu full failed"
-# DRAM traffic of one FULL-schedule launch of 3 co-resident problems
-timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:k_resident --launch-skip 1 --launch-count 1 --csv --log-file gpurun_out/r2_traffic_resident3.csv python bench.py --steps 1 --warmup 1 --batch 3 --no-cpu-baseline > gpurun_out/r2_ncu_traffic3.log 2>&1 || echo "traffic capture failed"
-tail -2 gpurun_out/r2_traffic_resident3.csv
+# the dominant kernel, full set, on the default bench's launch shape (NP co-resident C1 problems) at a reduced schedule
+NP=${NP:-4}
+timeout 200 python tools/ncu_target.py resident C1 50 $NP > gpurun_out/r2_ncu_target_plain.log 2>&1 && \
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_resident --launch-skip 1 --launch-count 1 -f -o gpurun_out/r2_resident_b$NP python tools/ncu_target.py resident C1 50 $NP > gpurun_out/r2_ncu_full.log 2>&1 || echo "ncu full failed"
+# DRAM traffic of one FULL-schedule launch of NP co-resident problems
+timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:k_resident --launch-skip 1 --launch-count 1 --csv --log-file gpurun_out/r2_traffic_resident$NP.csv python bench.py --steps 1 --warmup 1 --batch $NP --no-cpu-baseline > gpurun_out/r2_ncu_traffic$NP.log 2>&1 || echo "traffic capture failed"
+tail -2 gpurun_out/r2_traffic_resident$NP.csv
 python tools/profile_resident.py C1 > gpurun_out/r2_prof_c1.log 2>&1; cat gpurun_out/r2_prof_c1.log
