@@ -30,6 +30,7 @@ namespace {
 using Dev = LmSolver::Dev;
 
 constexpr int LM_THREADS = 128;
+constexpr int LM_RING = 64; // PCG iterations whose accumulators are live at a time (solver_lm.cu: ensure_acc)
 // planes of N floats each
 enum : int {
     L_CS = 0,    // cos, sin of the angle the current linearisation uses
@@ -463,9 +464,12 @@ LmSolver::~LmSolver()
     delete d_;
 }
 
-void LmSolver::ensure_acc(int lIterations)
+// Accumulator sets: 0 / 1 = r.z and Q of PCGInit, then a ring of LM_RING iterations x (p.q, r.z, Q), then model cost and
+// cost.  A ring slot is cleared (stream-ordered memset) before its second use, so the footprint does not grow with
+// lIterations.
+void LmSolver::ensure_acc(int)
 {
-    const int need = 3 * (lIterations > 0 ? lIterations : 0) + 4;
+    const int need = 2 + 3 * LM_RING + 2;
     if (need <= acc_sets_) return;
     if (acc_) ARAP_CUDA_CHECK(cudaFree(acc_)); // cudaFree waits for the device
     acc_ = nullptr;
@@ -539,7 +543,7 @@ int LmSolver::step(int L, cudaStream_t s, float* prev_cost)
     const Dev& d = *d_;
     const unsigned nb = (unsigned)((d.N + 255) / 256);
     const dim3 grid((W_ + 31) / 32, (H_ + 15) / 16);
-    const int set_model = 2 + 3 * L, set_cost = set_model + 1;
+    const int set_model = 2 + 3 * LM_RING, set_cost = set_model + 1;
     ARAP_CUDA_CHECK(cudaMemsetAsync(acc_, 0, (size_t)(set_cost + 1) * WA_WORDS * sizeof(unsigned long long), s));
     k_lm_flags<<<nb, 256, 0, s>>>(d);
     ARAP_TIMED(timer_, "precompute", s, (k_lm_cs<<<nb, 256, 0, s>>>(d)));
@@ -550,7 +554,9 @@ int LmSolver::step(int L, cudaStream_t s, float* prev_cost)
     launches_ += 4;
     first_ = false;
     for (int it = 0; it < L; ++it) {
-        const int base = 2 + 3 * it;
+        const int base = 2 + 3 * (it % LM_RING);
+        if (it > 0 && it % LM_RING == 0) // the ring wraps: every consumer of these sets is behind us in the stream
+            ARAP_CUDA_CHECK(cudaMemsetAsync(acc_ + (size_t)2 * WA_WORDS, 0, (size_t)3 * LM_RING * WA_WORDS * sizeof(unsigned long long), s));
         ARAP_TIMED(timer_, "PCGStep1", s, (k_lm_apply<0><<<grid, LM_THREADS, 0, s>>>(d, base)));
         k_lm_alpha<<<1, 32, 0, s>>>(d, base);
         if (((it + 1) % sp_.residual_reset_period) == 0) { // :1077-1086

@@ -114,6 +114,9 @@ def test_lm_residual_refresh_and_full_linear_budget(oracle):
     co, so = _check(oracle, pr, 3, 50, residual_reset_period=3, q_tolerance=-1e30)
     assert list(so[:, 1]) == [50.0, 50.0, 50.0]
     _check(oracle, pr, 2, 33, residual_reset_period=1, q_tolerance=-1e30, trust_region_radius=10.0)
+    # more linear iterations than the accumulator ring holds (64): the ring wraps twice
+    co, so = _check(oracle, pr, 1, 150, q_tolerance=-1e30)
+    assert list(so[:, 1]) == [150.0]
 
 
 def test_lm_general_urshape_and_weights(oracle):
