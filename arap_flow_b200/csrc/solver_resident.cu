@@ -65,6 +65,11 @@ constexpr int S_MIN = -100, S_MAX = 100;
 #ifndef ARAP_RS_SUM_UNROLL
 #define ARAP_RS_SUM_UNROLL 0 // 1: the CTA-level sum over the warps' limb sums is unrolled (all shared-memory loads in flight)
 #endif
+#ifndef ARAP_RS_LEAN_CS_SMEM
+#define ARAP_RS_LEAN_CS_SMEM 0 // 1: the 128-register variants keep cos/sin of the own pixels in shared memory (the strip's `pre` array)
+                               // instead of 16 registers, and look the preconditioner up in a 15-entry table: on the pixel
+                               // grid it only depends on the number of valid neighbours and the fit flag
+#endif
 #ifndef ARAP_RS_DEFER_DELTA
 #define ARAP_RS_DEFER_DELTA 2 // delta += alpha p feeds no reduction: 1 = it is done AFTER the arrival at the second barrier, under the
                               // barrier's latency, everywhere; 2 = in the 128-register variants only (fewer live values in
@@ -80,6 +85,7 @@ struct __align__(16) StripSmem {
     float2 rcs[RS_OUTBOX_ENTRIES]; // cos/sin of the ring pixels (remote sides only)
     float stage[RS_OUTBOX_ENTRIES][4]; // remote ring pixels: [0..2] fetched z (parked until beta is known), [3] their p_a
     float2 pre[RS_STRIP_H][32];        // (1/(1+sqrt(D_X))^2, 1/(1+sqrt(D_a))^2) per pixel, constant during a GN step
+                                       // (ARAP_RS_LEAN_CS_SMEM, 128-register variants: (cos, sin) of the pixel instead)
 };
 
 struct __align__(16) Ctl {
@@ -95,6 +101,7 @@ struct __align__(16) Ctl {
     int bc_code;                   // 0 accept, 1 redo with bc_S
     int bc_S;
     int abort;
+    float preX[2][5], preA[5];     // ARAP_RS_LEAN_CS_SMEM: guarded-inverted diagonal by (fit, valid neighbours)
 };
 
 __device__ __forceinline__ unsigned long long ld_u64_volatile(const unsigned long long* p)
@@ -830,6 +837,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
 
     constexpr bool LEAN = (MINB >= 3);               // the 128-register variants
     constexpr bool HOIST = ARAP_RS_HOIST && (!LEAN || ARAP_RS_HOIST_LEAN > 0);
+    constexpr bool CSM = LEAN && ARAP_RS_LEAN_CS_SMEM != 0;
     constexpr bool DEFER = ARAP_RS_DEFER_DELTA == 1 || (ARAP_RS_DEFER_DELTA == 2 && LEAN);
     constexpr int HG = (LEAN && ARAP_RS_HOIST_LEAN > 0) ? ARAP_RS_HOIST_LEAN : RS_STRIP_H; // rows whose loads are issued together
     Cta c;
@@ -847,6 +855,16 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
 
     if (threadIdx.x == 0) ctl.abort = 0;
     if (threadIdx.x < 8) ctl.prev[threadIdx.x >> 2][threadIdx.x & 3] = 0ull; // the host zeroes P.bar before the launch
+    if constexpr (CSM) {
+        // jtf_finish's diagonal on the pixel grid: DX = (wr2 + wr2) * nv (+ wf2 with a constraint), DA = wr2 * nv
+        if (threadIdx.x < 15) {
+            const int nv = threadIdx.x % 5, which = threadIdx.x / 5;
+            float Dg = (which == 2) ? wr2 * (float)nv : (wr2 + wr2) * (float)nv;
+            if (which == 1) Dg = Dg + wf2;
+            const float v = guarded_invert(Dg);
+            if (which == 2) ctl.preA[nv] = v; else ctl.preX[which][nv] = v;
+        }
+    }
     if constexpr (CL) {
         // cluster launch: the problem IS the cluster (host: enqueue_cluster), rank in the cluster = CTA in the problem
         __shared__ ClusterCtl xc;
@@ -916,6 +934,24 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
     float q0[RS_STRIP_H], q1[RS_STRIP_H], qa[RS_STRIP_H];
 #pragma unroll
     for (int k = 0; k < RS_STRIP_H; ++k) { r0[k] = r1[k] = r2[k] = pa[k] = 0.f; cc[k] = 1.f; ss[k] = 0.f; q0[k] = q1[k] = qa[k] = 0.f; }
+    if constexpr (CSM) {
+#pragma unroll
+        for (int k = 0; k < RS_STRIP_H; ++k) s.pre[k * 32] = make_float2(1.f, 0.f); // (cos, sin) of a pixel that is never active
+    }
+    // (cos, sin) of own pixel k / its preconditioner entries (position, angle): registers + the per-pixel array, or --
+    // CSM -- the per-pixel array + a table lookup by (fit, number of valid neighbours)
+    auto cs_of = [&](int k) -> float2 {
+        if constexpr (CSM) return s.pre[k * 32];
+        else return make_float2(cc[k], ss[k]);
+    };
+    auto pre_of = [&](int k, unsigned f) -> float2 {
+        if constexpr (CSM) {
+            const int nv = __popc(f & 15u);
+            return make_float2(ctl.preX[(f & FLAG_FIT) ? 1 : 0][nv], ctl.preA[nv]);
+        } else {
+            return s.pre[k * 32];
+        }
+    };
     // every tile cell must hold finite data (the masked stencil multiplies invalid neighbours by 0)
     for (int e = lane; e < TH * TW; e += 32) s.own[e] = make_float4(0.f, 0.f, 0.f, 0.f);
     int S_cost = 0, S_num = 0, S_den = 0, S_bnum = 0, S_sep = 8;
@@ -936,7 +972,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                     const float2 X = P.X[i];
                     float sn, cs;
                     contract_sincos(P.A[i], sn, cs);
-                    cc[k] = cs; ss[k] = sn;
+                    if constexpr (CSM) s.pre[k * 32] = make_float2(cs, sn);
+                    else { cc[k] = cs; ss[k] = sn; }
                     e = make_float4(X.x, X.y, cs, sn);
                 }
                 s.own[(k + 1) * TW + lane + 1] = e;
@@ -999,7 +1036,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                     unsigned f = flag_of(flo, fhi, k) & ~FLAG_FIT;
                     r0[k] = r1[k] = r2[k] = 0.f;
                     pa[k] = 0.f;
-                    s.pre[k * 32] = make_float2(1.0f, 1.0f); // inactive pixels: r stays 0, any finite value works
+                    if constexpr (!CSM) s.pre[k * 32] = make_float2(1.0f, 1.0f); // inactive pixels: r stays 0, any finite value works
                     s.D[(0 * RS_STRIP_H + k) * 32] = 0.f;
                     s.D[(1 * RS_STRIP_H + k) * 32] = 0.f;
                     s.D[(2 * RS_STRIP_H + k) * 32] = 0.f;
@@ -1018,7 +1055,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                         float g0, g1, ga, DX, DA;
                         jtf_finish(a, cur.x, cur.y, fit, ct.x, ct.y, wr2, wf2, g0, g1, ga, DX, DA);
                         const float pX = guarded_invert(DX), pA = guarded_invert(DA);
-                        s.pre[k * 32] = make_float2(pX, pA);
+                        if constexpr (!CSM) s.pre[k * 32] = make_float2(pX, pA);
                         r0[k] = -g0; r1[k] = -g1; r2[k] = -ga;
                         const float z0 = pX * r0[k], z1 = pX * r1[k], z2 = pA * r2[k];
                         const float term = dot3(r0[k], r1[k], r2[k], z0, z1, z2);
@@ -1034,7 +1071,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
 #pragma unroll
                 for (int k = 0; k < RS_STRIP_H; ++k) {
                     if (any_rem) {
-                        const float2 pre = s.pre[k * 32];
+                        const float2 pre = pre_of(k, flag_of(flo, fhi, k));
                         publish_rowcol(s, lane, k, seq, pre.x * r0[k], pre.x * r1[k], pre.y * r2[k], 0.f);
                     }
                 }
@@ -1046,11 +1083,12 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                 // p_0 = z_0 into the tile (all warps are past their J^T F reads: grid_sum synchronised)
 #pragma unroll
                 for (int k = 0; k < RS_STRIP_H; ++k) {
-                    const float2 pre = s.pre[k * 32];
+                    const float2 pre = pre_of(k, flag_of(flo, fhi, k));
+                    const float2 csk = cs_of(k);
                     const float pX = pre.x, pA = pre.y;
                     const float p0 = pX * r0[k], p1 = pX * r1[k];
                     pa[k] = pA * r2[k];
-                    s.own[(k + 1) * TW + lane + 1] = make_float4(p0, p1, ss[k] * pa[k], cc[k] * pa[k]);
+                    s.own[(k + 1) * TW + lane + 1] = make_float4(p0, p1, csk.y * pa[k], csk.x * pa[k]);
                 }
                 if (any_rem) apply_p<true>(s, lane, 0.0f);
                 // N4 (opt-in, never on the parity path): relative tolerance on the preconditioned residual norm
@@ -1087,7 +1125,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                     jtj_nb_masked<1>(a, cur.x, cur.y, lf, m1);
                     jtj_nb_masked<2>(a, cur.x, cur.y, dn, m2);
                     jtj_nb_masked<3>(a, cur.x, cur.y, up, m3);
-                    jtj_finish(a, cc[k], ss[k], cur.x, cur.y, pa[k], (f & FLAG_FIT) != 0, wr2, wf2, q0[k], q1[k], qa[k]);
+                    const float2 csk = cs_of(k);
+                    jtj_finish(a, csk.x, csk.y, cur.x, cur.y, pa[k], (f & FLAG_FIT) != 0, wr2, wf2, q0[k], q1[k], qa[k]);
                     const float term = dot3(cur.x, cur.y, pa[k], q0[k], q1[k], qa[k]);
                     if (k < 4) gs0 = gs0 + term; else gs1 = gs1 + term;
                     up = cur;
@@ -1121,7 +1160,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                             hx[j] = e.x; hy[j] = e.y;
                             hd0[j] = Dk[0 * RS_STRIP_H * 32]; hd1[j] = Dk[1 * RS_STRIP_H * 32]; hd2[j] = Dk[2 * RS_STRIP_H * 32];
                         }
-                        hpre[j] = s.pre[k * 32];
+                        hpre[j] = pre_of(k, flag_of(flo, fhi, k));
                     }
 #pragma unroll
                     for (int j = 0; j < HG; ++j) {
@@ -1155,7 +1194,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                     r0[k] = fmaf(-alpha, q0[k], r0[k]);
                     r1[k] = fmaf(-alpha, q1[k], r1[k]);
                     r2[k] = fmaf(-alpha, qa[k], r2[k]);
-                    const float2 pre = s.pre[k * 32];
+                    const float2 pre = pre_of(k, flag_of(flo, fhi, k));
                     const float pX = pre.x, pA = pre.y;
                     const float z0 = pX * r0[k], z1 = pX * r1[k], z2 = pA * r2[k];
                     const float term = dot3(z0, z1, z2, r0[k], r1[k], r2[k]);
@@ -1213,7 +1252,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                         for (int j = 0; j < HG; ++j) {
                             const float4 e = s.own[(kb + j + 1) * TW + lane + 1];
                             hx[j] = e.x; hy[j] = e.y;
-                            hpre[j] = s.pre[(kb + j) * 32];
+                            hpre[j] = pre_of(kb + j, flag_of(flo, fhi, kb + j));
                         }
 #pragma unroll
                         for (int j = 0; j < HG; ++j) {
@@ -1222,19 +1261,21 @@ __global__ void __launch_bounds__(MAXT, MINB) k_resident_t(const ResProb* __rest
                             const float p0 = fmaf(beta, hx[j], pX * r0[k]);
                             const float p1 = fmaf(beta, hy[j], pX * r1[k]);
                             pa[k] = fmaf(beta, pa[k], pA * r2[k]);
-                            s.own[(k + 1) * TW + lane + 1] = make_float4(p0, p1, ss[k] * pa[k], cc[k] * pa[k]);
+                            const float2 csk = cs_of(k);
+                            s.own[(k + 1) * TW + lane + 1] = make_float4(p0, p1, csk.y * pa[k], csk.x * pa[k]);
                         }
                     }
                 } else {
 #pragma unroll
                 for (int k = 0; k < RS_STRIP_H; ++k) {
                     const float4 e = s.own[(k + 1) * TW + lane + 1];
-                    const float2 pre = s.pre[k * 32];
+                    const float2 pre = pre_of(k, flag_of(flo, fhi, k));
+                    const float2 csk = cs_of(k);
                     const float pX = pre.x, pA = pre.y;
                     const float p0 = fmaf(beta, e.x, pX * r0[k]);
                     const float p1 = fmaf(beta, e.y, pX * r1[k]);
                     pa[k] = fmaf(beta, pa[k], pA * r2[k]);
-                    s.own[(k + 1) * TW + lane + 1] = make_float4(p0, p1, ss[k] * pa[k], cc[k] * pa[k]);
+                    s.own[(k + 1) * TW + lane + 1] = make_float4(p0, p1, csk.y * pa[k], csk.x * pa[k]);
                 }
                 }
                 if (any_rem) apply_p<false>(s, lane, beta);
